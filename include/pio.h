@@ -1,0 +1,198 @@
+/*
+ * pio.h -- C ABI of libpio_sm100.so: the B200 (sm_100a) patch -> region -> caption hot path of
+ * Patch-ioner, as a drop-in below the reference's Python facade.
+ *
+ * The reference has no FFI / plugin interface: its seam is Python.  Every entry
+ * point below therefore cites the reference *call site* it replaces (file:line under
+ * /root/reference/Patch-ioner) -- this is what a maintainer would bind with ctypes (see
+ * INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer into caller-owned memory unless the
+ *     parameter name starts with h_ (host).  Row-major, innermost dimension contiguous.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing
+ *     on the hot path (workspaces are caller-provided; sizes from the *_workspace_bytes calls) and
+ *     returns 0 on success, a negative PIO_E* code otherwise; pio_last_error() gives the text.
+ *   - a handle belongs to one (process, device); calls on it are stream-ordered, not re-entrant.
+ *   - there is no CPU fallback and no backend dispatch: without a CUDA device every compute
+ *     entry point fails with PIO_ECUDA.
+ */
+#ifndef PIO_H_
+#define PIO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIO_OK 0
+#define PIO_EINVAL (-1)
+#define PIO_ECUDA (-2)
+#define PIO_EUNSUPPORTED (-3)
+
+/* arithmetic mode of the dense layers */
+#define PIO_FP32 0 /* fp32 operands, fp32 FFMA accumulate: the 'fp32 parity' mode            */
+#define PIO_BF16 1 /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM          */
+
+/* element types of loose buffers */
+#define PIO_DT_F32 0
+#define PIO_DT_BF16 1
+
+/* region weighting (bbox_utils.py:46-92) */
+#define PIO_POOL_MEAN 0
+#define PIO_POOL_GAUSS 1
+#define PIO_POOL_ATTN 2
+
+/* activations of the generic linear layer */
+#define PIO_ACT_NONE 0
+#define PIO_ACT_GELU_ERF 1 /* DINOv2 mlp (exact erf GELU)                 */
+#define PIO_ACT_GELU_NEW 2 /* GPT-2 'gelu_new' (tanh form)                */
+
+const char* pio_last_error(void);
+int pio_version(void);
+/* number of kernels this library launched since the last pio_reset_launch_count() (bench evidence) */
+long long pio_launch_count(void);
+void pio_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* generic dense layer:  C[map(m), n] = res + gamma[n] * act( alpha * colscale[n] * (A W^T)[m,n] + bias[n] ) */
+/* Replaces every nn.Linear / Conv1D on the path (DINOv2 qkv/proj/fc1/fc2, GPT-2 c_attn/c_proj/c_fc,   */
+/* lm_head, clip_project decap.py:71, the two GEMMs of im2txtprojection.py:370,377).                   */
+typedef struct {
+  const void* A;   /* [M, lda] K-contiguous, dtype a_dt                                         */
+  const void* W;   /* [N, ldw] K-contiguous (torch Linear layout), dtype a_dt                    */
+  void* C;         /* [*, ldc], dtype c_dt                                                        */
+  int M, N, K;
+  int lda, ldw, ldc;
+  int a_dt, c_dt;
+  const float* bias;      /* [N] or NULL                                                          */
+  const float* colscale;  /* [N] or NULL                                                          */
+  const float* gamma;     /* [N] or NULL (LayerScale)                                             */
+  const float* residual;  /* fp32 [*, ldres] or NULL; may alias C                                 */
+  const float* res_rowscale; /* [M] or NULL: residual row m is multiplied by res_rowscale[m]      */
+  int ldres;
+  float alpha;
+  int act;
+  /* optional row remap: output row = (m / rows_per_group) * group_stride + group_offset + m % rows_per_group */
+  int rows_per_group, group_stride, group_offset; /* rows_per_group == 0 -> identity             */
+} PioLinear;
+int pio_linear(const PioLinear* p, int mode, void* stream);
+
+/* LayerNorm over the last dim (DINOv2 eps 1e-6, GPT-2 eps 1e-5); x fp32 [rows, dim] with row stride ldx. */
+int pio_layernorm(const float* x, int ldx, const float* w, const float* b, void* out, int out_dt, int ldo,
+                  int rows, int dim, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* DINOv2 ViT-B/14-reg4 forward:  replaces  self.dino(imgs, is_training=True)  (src/model.py:783) and */
+/* the forward hook on blocks[-1].attn.qkv (src/model.py:589-590, src/dino_extraction.py:8-9).         */
+typedef struct {
+  const float *ln1_w, *ln1_b, *qkv_w, *qkv_b, *proj_w, *proj_b, *ls1;
+  const float *ln2_w, *ln2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b, *ls2;
+} PioVitBlock;
+typedef struct {
+  const float* cls_token;       /* [768]                                                         */
+  const float* register_tokens; /* [4,768]                                                       */
+  const float* patch_w;         /* [768, 3*14*14] (Conv2d weight flattened c,ky,kx)              */
+  const float* patch_b;         /* [768]                                                         */
+  PioVitBlock blk[12];
+  const float *norm_w, *norm_b;
+} PioVitWeights;
+typedef struct PioVit PioVit;
+/* Copies / repacks the weights into library-owned device memory (bf16 copies in PIO_BF16 mode). */
+int pio_vit_create(PioVit** out, const PioVitWeights* w, int mode, void* stream);
+void pio_vit_destroy(PioVit* h);
+size_t pio_vit_workspace_bytes(const PioVit* h, int B, int S);
+/* imgs fp32 [B,3,S,S]; pos_embed fp32 [1+g*g,768] already resized to this grid (host, once);       */
+/* out_tokens fp32 [B,N,768] = final LayerNorm of all tokens (cls | 4 reg | patches), N = 5+g*g;    */
+/* out_attn   fp32 [B,g*g]   = softmax_j(<q_cls,k_j>/128) of the LAST block (process_self_attention,  */
+/*                             dino_extraction.py:24-34) or NULL;                                   */
+/* out_qkv    fp32 [B,N,2304] raw hooked qkv of the last block or NULL (debug / parity only).       */
+int pio_vit_forward(PioVit* h, const float* imgs, int B, int S, const float* pos_embed, float* out_tokens,
+                    float* out_attn, float* out_qkv, void* workspace, size_t workspace_bytes, void* stream);
+
+/* CLS attention map alone, from a hooked qkv tensor [B,N,3*D] (dino_extraction.py:24-34). */
+int pio_cls_attention(const void* qkv, int qkv_dt, int B, int N, int D, int num_global, float* out_attn,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Region aggregation:  replaces extract_bboxes_feats (src/bbox_utils.py:8-109).                  */
+/* boxes: [B,R,4] xywh in crop pixels, float32 (boxes_dt = PIO_DT_F32) or int32 (boxes_dt = 2);    */
+/* tokens: fp32 patch tokens, image b at tokens + b*img_stride, patch p at + p*row_stride, D floats. */
+/* out_bounds int32 [B,R,4] = (y_lo,y_hi,x_lo,x_hi) slice actually pooled (hi exclusive) or NULL.   */
+/* attn_map fp32 [B,P] is only read for PIO_POOL_ATTN; it is NOT modified (the reference mutates     */
+/* its CPU copy; the sequential rescaling is reproduced on a private copy in `workspace`).          */
+/* set_mode = 0: out [B,R,D];  set_mode = 1 (get_single_embedding_per_image): out [B,D].            */
+#define PIO_DT_I32 2
+size_t pio_pool_workspace_bytes(int B, int R, int grid);
+int pio_pool_boxes(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D,
+                   const void* boxes, int boxes_dt, int R, int patch_size, int mode, float variance,
+                   const float* attn_map, int set_mode, float* out, int* out_bounds, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* Weighted pooling with explicit weights [B,R,grid*grid]: out[b,r,:] = scale * sum_p w[b,r,p] x[b,p,:].  */
+/* Replaces the trace branch src/model.py:1052-1054 (scale = 1/g^2), avg_self_attn_token :869 (1/P),   */
+/* compute_region_means :45-94 and the masks= generalisation.                                        */
+int pio_pool_grid(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D,
+                  const float* weights, int R, float scale, float* out, void* stream);
+/* map_traces_to_grid (src/bbox_utils.py:158-168): points double (x,y) pairs, trace t owns points      */
+/* [offsets[t], offsets[t+1]); counts fp32 [T,grid,grid] (zeroed here); optional attn multiply        */
+/* (model.py:1052-1053): counts *= attn[t].                                                          */
+int pio_trace_bins(const double* points_xy, const int* offsets, int T, int grid, const float* attn, float* counts,
+                   void* stream);
+/* Gaussian / uniform whole-image weights of compute_region_means (model.py:45-94) -> weights [grid*grid] */
+int pio_region_mean_weights(int grid, float variance, float* weights, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* DeCap caption-memory projection: replaces Im2TxtProjector.project (im2txtprojection.py:353-385).  */
+typedef struct PioBank PioBank;
+/* bank fp32 [M,D] (zero rows already dropped, :345).  Builds library-owned copies: the bank, its     */
+/* transpose, and 1/|row| (the reference re-normalises the whole bank on every call, :367).           */
+int pio_bank_create(PioBank** out, const float* bank, long long M, int D, int mode, void* stream);
+void pio_bank_destroy(PioBank* h);
+long long pio_bank_rows(const PioBank* h);
+size_t pio_project_workspace_bytes(const PioBank* h, int R);
+/* q fp32 [R,D] (not modified; the reference normalises it in place, :368); out fp32 [R,D].          */
+/* normalize != 0 -> out /= |out| (:379-380).  Partial form for a row-sharded bank:    */
+/* if part_m/part_l are non-NULL the un-normalised (m[R], l[R], O[R,D]) of THIS shard are written     */
+/* (O into out) and pio_project_finish() completes after the all-reduces.                             */
+int pio_project(PioBank* h, const float* q, int R, float temperature, int normalize, float* out, float* part_m,
+                float* part_l, void* workspace, size_t workspace_bytes, void* stream);
+/* rescale a shard's partial by exp(m_local - m_global): O *= f, l *= f (before the SUM all-reduce) */
+int pio_project_rescale(float* O, float* l, const float* m_local, const float* m_global, int R, int D, void* stream);
+/* O / l and optional L2 normalisation (after the SUM all-reduce) */
+int pio_project_finish(float* O, const float* l, int R, int D, int normalize, void* stream);
+/* revert_transformation (embedding_utils.py:17-24) is pio_linear with W = A_pinv, bias = -A_pinv b. */
+
+/* ------------------------------------------------------------------------------------------ */
+/* DeCap prefix decoder: replaces decoding_batched (src/decap/decap.py:116-160) up to token ids.     */
+typedef struct {
+  const float *ln1_w, *ln1_b, *attn_w /*[768,2304] Conv1D in,out*/, *attn_b, *proj_w /*[768,768]*/, *proj_b;
+  const float *ln2_w, *ln2_b, *fc_w /*[768,3072]*/, *fc_b, *fc2_w /*[3072,768]*/, *fc2_b;
+} PioGptBlock;
+typedef struct {
+  const float* wte; /* [50257,768] (tied lm_head)                                                 */
+  const float* wpe; /* [1024,768]                                                                 */
+  PioGptBlock blk[4];
+  const float *lnf_w, *lnf_b;
+  const float* prefix_w; /* clip_project.model.0.weight [768, prefix_size]                        */
+  const float* prefix_b; /* [768]                                                                 */
+  int prefix_size;
+} PioDecoderWeights;
+typedef struct PioDecoder PioDecoder;
+int pio_decoder_create(PioDecoder** out, const PioDecoderWeights* w, int mode, void* stream);
+void pio_decoder_destroy(PioDecoder* h);
+size_t pio_decode_workspace_bytes(const PioDecoder* h, int R, int steps);
+/* prefix fp32 [R,prefix_size]; out_ids int32 [R,steps]; out_logprob_sum fp32 [R] or NULL            */
+/* (compute_scores: sum_t log softmax(logits_t)[tok_t], decap.py:157-160).  Fixed `steps` (30) greedy  */
+/* steps with a KV cache, argmax first-index tie-break, no EOS early exit.                            */
+int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int* out_ids, float* out_logprob_sum,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* L2-normalise rows in place */
+int pio_l2_normalize(float* x, int rows, int dim, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIO_H_ */

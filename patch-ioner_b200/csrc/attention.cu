@@ -1,0 +1,231 @@
+// attention.cu -- (1) ViT multi-head self-attention in fp32 arithmetic (flash-style, no N x N
+// materialisation), (2) the single-query KV-cache attention of the greedy decoder.
+#include "common.cuh"
+
+namespace pio {
+namespace {
+
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&u.x), b = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ViT attention, head_dim 64.  qkv [B,N,3*H*64] ([q|k|v], head-major inside each), out [B,N,H*64].
+// CTA = 64 queries of one (b,h); loops over 64-key tiles with an online softmax.
+// Thread (ty,tx) owns rows ty+16i and score columns tx+16j (interleaved: conflict-free LDS.128),
+// output columns tx*4..tx*4+3.
+constexpr int BR = 64, BC = 64, HD = 64, LDS = HD + 4;
+
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) vit_attention_kernel(const TIn* __restrict__ qkv, TOut* __restrict__ out, int N, int H,
+                                                            float scale) {
+  extern __shared__ __align__(16) float smem[];
+  float* Qs = smem;               // [BR][LDS]
+  float* Ks = Qs + BR * LDS;      // [BC][LDS]
+  float* Vs = Ks + BC * LDS;      // [BC][LDS]
+  float* Ps = Vs + BC * LDS;      // [BR][LDS]
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BR;
+  const int C3 = 3 * H * HD;
+  const TIn* base = qkv + (long long)b * N * C3;
+  const TIn* qp = base + h * HD;
+  const TIn* kp = base + H * HD + h * HD;
+  const TIn* vp = base + 2 * H * HD + h * HD;
+
+  // Q tile (rows beyond N are zero)
+  for (int idx = tid; idx < BR * (HD / 4); idx += 256) {
+    int r = idx >> 4, d4 = (idx & 15) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < N) v = load4<TIn>(qp + (long long)(q0 + r) * C3 + d4);
+    *reinterpret_cast<float4*>(&Qs[r * LDS + d4]) = v;
+  }
+  float m[4], l[4], o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m[i] = -INFINITY;
+    l[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < N; k0 += BC) {
+    __syncthreads();  // previous tile's Ks/Vs/Ps fully consumed (and Qs visible on first pass)
+    for (int idx = tid; idx < BC * (HD / 4); idx += 256) {
+      int r = idx >> 4, d4 = (idx & 15) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (k0 + r < N) {
+        kv = load4<TIn>(kp + (long long)(k0 + r) * C3 + d4);
+        vv = load4<TIn>(vp + (long long)(k0 + r) * C3 + d4);
+      }
+      *reinterpret_cast<float4*>(&Ks[r * LDS + d4]) = kv;
+      *reinterpret_cast<float4*>(&Vs[r * LDS + d4]) = vv;
+    }
+    __syncthreads();
+    float s[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < HD; d += 4) {
+      float4 q[4], k[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q[i] = *reinterpret_cast<const float4*>(&Qs[(ty + 16 * i) * LDS + d]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) k[j] = *reinterpret_cast<const float4*>(&Ks[(tx + 16 * j) * LDS + d]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          s[i][j] += q[i].x * k[j].x + q[i].y * k[j].y + q[i].z * k[j].z + q[i].w * k[j].w;
+    }
+    // online softmax, rows shared by the 16 lanes with equal ty
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[i][j] = (k0 + tx + 16 * j < N) ? s[i][j] * scale : -INFINITY;
+        mx = fmaxf(mx, s[i][j]);
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const float mnew = fmaxf(m[i], mx);
+      const float corr = __expf(m[i] - mnew);  // m = -inf on first tile -> 0
+      float ps = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float p = __expf(s[i][j] - mnew);
+        ps += p;
+        Ps[(ty + 16 * i) * LDS + tx + 16 * j] = p;
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
+      l[i] = l[i] * corr + ps;
+      m[i] = mnew;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] *= corr;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int jj = 0; jj < BC; jj += 4) {
+      float4 p[4], v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = *reinterpret_cast<const float4*>(&Ps[(ty + 16 * i) * LDS + jj]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = *reinterpret_cast<const float4*>(&Vs[(jj + e) * LDS + tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        o[i][0] += p[i].x * v[0].x + p[i].y * v[1].x + p[i].z * v[2].x + p[i].w * v[3].x;
+        o[i][1] += p[i].x * v[0].y + p[i].y * v[1].y + p[i].z * v[2].y + p[i].w * v[3].y;
+        o[i][2] += p[i].x * v[0].z + p[i].y * v[1].z + p[i].z * v[2].z + p[i].w * v[3].z;
+        o[i][3] += p[i].x * v[0].w + p[i].y * v[1].w + p[i].z * v[2].w + p[i].w * v[3].w;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = q0 + ty + 16 * i;
+    if (r < N) {
+      float inv = 1.0f / l[i];
+      store4<TOut>(out + ((long long)b * N + r) * (H * HD) + h * HD + tx * 4,
+                   make_float4(o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder attention for ONE new position t: append this step's k,v to the cache, then
+// out[r, h*HDIM..] = softmax(q . K[0..t] / sqrt(HDIM)) V[0..t].   One warp per (region, head).
+// qkv [R, 3*H*HDIM] (this step), cache kc/vc [R][H][T][HDIM].
+template <typename TIn, typename TOut, typename TC, int HDIM>
+__global__ void __launch_bounds__(128) decode_attention_kernel(const TIn* __restrict__ qkv, TC* __restrict__ kc,
+                                                               TC* __restrict__ vc, TOut* __restrict__ out, int R, int H,
+                                                               int T, int t, float scale) {
+  constexpr int PER = HDIM / 32;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R * H) return;
+  const int r = warp / H, h = warp % H;
+  const TIn* row = qkv + (long long)r * 3 * H * HDIM;
+  TC* kbase = kc + ((long long)(r * H + h) * T) * HDIM;
+  TC* vbase = vc + ((long long)(r * H + h) * T) * HDIM;
+  float q[PER];
+#pragma unroll
+  for (int e = 0; e < PER; ++e) {
+    const int d = lane + 32 * e;
+    q[e] = (float)row[h * HDIM + d];
+    const float kv = (float)row[H * HDIM + h * HDIM + d], vv = (float)row[2 * H * HDIM + h * HDIM + d];
+    kbase[(long long)t * HDIM + d] = (TC)kv;
+    vbase[(long long)t * HDIM + d] = (TC)vv;
+  }
+  __syncwarp();
+  float my = -INFINITY;  // lane j keeps score j
+  for (int j = 0; j <= t; ++j) {
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) s += q[e] * (float)kbase[(long long)j * HDIM + lane + 32 * e];
+    s = warp_sum(s) * scale;
+    if (lane == j) my = s;
+  }
+  const float mx = warp_max(my);
+  const float p = (lane <= t) ? __expf(my - mx) : 0.f;
+  const float inv = 1.0f / warp_sum(p);
+  float acc[PER];
+#pragma unroll
+  for (int e = 0; e < PER; ++e) acc[e] = 0.f;
+  for (int j = 0; j <= t; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, p, j) * inv;
+#pragma unroll
+    for (int e = 0; e < PER; ++e) acc[e] += pj * (float)vbase[(long long)j * HDIM + lane + 32 * e];
+  }
+#pragma unroll
+  for (int e = 0; e < PER; ++e) out[(long long)r * H * HDIM + h * HDIM + lane + 32 * e] = (TOut)acc[e];
+}
+
+}  // namespace
+
+int vit_attention(const void* qkv, void* out, int dt, int B, int N, int H, cudaStream_t st) {
+  const size_t smem = (size_t)(3 * BC + BR) * LDS * sizeof(float);
+  dim3 grid(cdiv(N, BR), H, B);
+  const float scale = 0.125f;  // 64^-0.5
+  if (dt == PIO_DT_F32) {
+    static bool set = false;
+    if (!set) { PIO_CUDA(cudaFuncSetAttribute(vit_attention_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+    vit_attention_kernel<float, float><<<grid, 256, smem, st>>>((const float*)qkv, (float*)out, N, H, scale);
+  } else {
+    static bool set = false;
+    if (!set) { PIO_CUDA(cudaFuncSetAttribute(vit_attention_kernel<__nv_bfloat16, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+    vit_attention_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, N, H, scale);
+  }
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int R, int H, int T, int t, cudaStream_t st) {
+  PIO_CHECK(t < T && T <= 32, "decode attention: position %d outside cache of %d (max 32)", t, T);
+  const float scale = rsqrtf(192.0f);
+  const int blocks = cdiv((long long)R * H * 32, 128);
+  if (dt == PIO_DT_F32)
+    decode_attention_kernel<float, float, float, 192><<<blocks, 128, 0, st>>>((const float*)qkv, (float*)kc, (float*)vc, (float*)out, R, H, T, t, scale);
+  else
+    decode_attention_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, 192><<<blocks, 128, 0, st>>>(
+        (const __nv_bfloat16*)qkv, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, (__nv_bfloat16*)out, R, H, T, t, scale);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+}  // namespace pio

@@ -1,0 +1,148 @@
+// common.cuh -- shared helpers for libpio_sm100 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/pio.h"
+
+namespace pio {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+}  // namespace pio
+
+#include <stdarg.h>
+namespace pio {
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define PIO_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return pio::fail(PIO_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define PIO_CHECK(cond, ...)                                   \
+  do {                                                         \
+    if (!(cond)) return pio::fail(PIO_EINVAL, __VA_ARGS__);    \
+  } while (0)
+
+// after every kernel launch: count it and pick up launch-configuration errors
+#define PIO_LAUNCHED()                                                                          \
+  do {                                                                                          \
+    pio::g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess)                                                                      \
+      return pio::fail(PIO_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define PIO_TRY(expr)          \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != PIO_OK) return _r; \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+constexpr int kNumSMs = 148;  // B200
+
+// -------------------------------------------------------------------------------- device helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_new(float x) {
+  const float k = 0.79788456080286535588f;  // sqrt(2/pi)
+  return 0.5f * x * (1.0f + tanhf(k * (x + 0.044715f * x * x * x)));
+}
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == PIO_ACT_GELU_ERF) return gelu_erf(v);
+  if (act == PIO_ACT_GELU_NEW) return gelu_new(v);
+  return v;
+}
+
+// The epilogue shared by the SIMT and the tcgen05 GEMMs (see PioLinear in pio.h).
+struct Epilogue {
+  const float* bias;
+  const float* colscale;
+  const float* gamma;
+  const float* residual;
+  const float* res_rowscale;
+  int ldres;
+  float alpha;
+  int act;
+  int rows_per_group, group_stride, group_offset;
+  __device__ __forceinline__ long long out_row(int m) const {
+    if (rows_per_group == 0) return m;
+    return (long long)(m / rows_per_group) * group_stride + group_offset + (m % rows_per_group);
+  }
+  // value for output element (m, n); orow = out_row(m)
+  __device__ __forceinline__ float apply(float acc, int m, long long orow, int n) const {
+    float v = acc * alpha;
+    if (colscale) v *= __ldg(colscale + n);
+    if (bias) v += __ldg(bias + n);
+    v = apply_act(v, act);
+    if (gamma) v *= __ldg(gamma + n);
+    if (residual) {
+      float r = residual[orow * ldres + n];
+      if (res_rowscale) r *= __ldg(res_rowscale + m);
+      v += r;
+    }
+    return v;
+  }
+};
+
+inline Epilogue make_epilogue(const PioLinear& p) {
+  Epilogue e;
+  e.bias = p.bias;
+  e.colscale = p.colscale;
+  e.gamma = p.gamma;
+  e.residual = p.residual;
+  e.res_rowscale = p.res_rowscale;
+  e.ldres = p.ldres;
+  e.alpha = p.alpha;
+  e.act = p.act;
+  e.rows_per_group = p.rows_per_group;
+  e.group_stride = p.group_stride;
+  e.group_offset = p.group_offset;
+  return e;
+}
+
+// kernels implemented in other translation units
+int linear_simt(const PioLinear& p, cudaStream_t st);    // gemm_simt.cu  (fp32 FFMA)
+int linear_tc(const PioLinear& p, cudaStream_t st);      // gemm_sm100.cu (tcgen05 / TMA / TMEM)
+int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
+int transpose_f32(const float* in, float* out, int rows, int cols, cudaStream_t st);           // out[c][r] = in[r][c]
+int transpose_to_bf16(const float* in, __nv_bfloat16* out, int rows, int cols, cudaStream_t st);
+int layernorm(const float* x, int ldx, const float* w, const float* b, void* out, int out_dt, int ldo, int rows, int dim,
+              float eps, cudaStream_t st);
+int im2col14(const float* imgs, void* cols, int cols_dt, int B, int S, int g, int Kp, cudaStream_t st);
+int init_global_tokens(float* x, const float* cls, const float* reg, const float* pos, int B, int N, int D, cudaStream_t st);
+int l2norm_rows(float* x, int rows, int dim, cudaStream_t st);
+int softmax_rows(const float* in, float* out, int rows, int cols, float scale, cudaStream_t st);
+int cls_attention(const void* qkv, int dt, int B, int N, int D, int ng, float* out, float* logits_ws, cudaStream_t st);
+int vit_attention(const void* qkv, void* out, int dt, int B, int N, int H, cudaStream_t st);
+int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int R, int H, int T, int t, cudaStream_t st);
+
+}  // namespace pio

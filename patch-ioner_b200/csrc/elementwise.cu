@@ -1,0 +1,268 @@
+// elementwise.cu -- HBM-bound helpers: LayerNorm, dtype/layout repacks, im2col, token assembly,
+// row L2-normalisation, row softmax, row arg-max.  All vectorised 16-byte accesses, one warp per
+// row where a row reduction is needed (warp-shuffle reductions, no shared memory).
+#include "common.cuh"
+
+namespace pio {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+namespace {
+
+// ------------------------------------------------------------------------------ LayerNorm
+// One warp per row; dim % 128 == 0, dim <= 1024 -> each lane owns dim/128 float4.
+template <int VEC>  // float4 per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                        const float* __restrict__ b, void* out, int out_dt, int ldo,
+                                                        int rows, float eps) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  constexpr int DIM = VEC * 128;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)warp * ldx);
+  float4 v[VEC];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / DIM);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+    q += a * a + c * c + d * d + e * e;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / DIM) + eps);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+    float4 o;
+    o.x = (v[i].x - mean) * rstd * g.x + bb.x;
+    o.y = (v[i].y - mean) * rstd * g.y + bb.y;
+    o.z = (v[i].z - mean) * rstd * g.z + bb.z;
+    o.w = (v[i].w - mean) * rstd * g.w + bb.w;
+    if (out_dt == PIO_DT_F32) {
+      reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (long long)warp * ldo)[lane + 32 * i] = o;
+    } else {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + (long long)warp * ldo)[lane + 32 * i] = pk;
+    }
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(out)[i] = pk;
+  }
+}
+__global__ void f32_to_bf16_tail(const float* in, __nv_bfloat16* out, long long start, long long n) {
+  long long i = start + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+
+template <typename OutT>
+__global__ void transpose_kernel(const float* __restrict__ in, OutT* __restrict__ out, int rows, int cols) {
+  __shared__ float tile[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = r0 + i;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(long long)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  int orow0 = blockIdx.x * 32, ocol = blockIdx.y * 32 + threadIdx.x;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int orow = orow0 + i;
+    if (orow < cols && ocol < rows) {
+      float v = tile[threadIdx.x][i];
+      if constexpr (sizeof(OutT) == 4)
+        out[(long long)orow * rows + ocol] = v;
+      else
+        out[(long long)orow * rows + ocol] = __float2bfloat16(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ patch-embed im2col
+// imgs [B,3,S,S] -> cols [B*P, Kp] with k = c*196 + ky*14 + kx (Conv2d weight order), zero padded to Kp.
+template <typename OutT>
+__global__ void im2col14_kernel(const float* __restrict__ imgs, OutT* __restrict__ cols, int B, int S, int g, int Kp) {
+  const long long total = (long long)B * g * g * Kp;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int k = (int)(i % Kp);
+    long long row = i / Kp;
+    float v = 0.f;
+    if (k < 588) {
+      int p = (int)(row % (g * g));
+      int b = (int)(row / (g * g));
+      int c = k / 196, r = k % 196, ky = r / 14, kx = r % 14;
+      int py = p / g, px = p % g;
+      v = imgs[(((long long)b * 3 + c) * S + py * 14 + ky) * S + px * 14 + kx];
+    }
+    if constexpr (sizeof(OutT) == 4)
+      cols[i] = v;
+    else
+      cols[i] = __float2bfloat16(v);
+  }
+}
+
+// cls/register rows of the token matrix: x[b,0] = cls + pos[0]; x[b,1..4] = reg (no pos_embed)
+__global__ void init_global_tokens_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ reg,
+                                          const float* __restrict__ pos, int B, int N, int D) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 5 * D) return;
+  int d = i % D, t = (i / D) % 5, b = i / (5 * D);
+  float v = (t == 0) ? cls[d] + pos[d] : reg[(t - 1) * D + d];
+  x[((long long)b * N + t) * D + d] = v;
+}
+
+// ------------------------------------------------------------------------------ row ops
+__global__ void l2norm_kernel(float* __restrict__ x, int rows, int dim) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  float* r = x + (long long)warp * dim;
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) s += r[i] * r[i];
+  const float n = sqrtf(warp_sum(s));
+  for (int i = lane; i < dim; i += 32) r[i] = r[i] / n;
+}
+
+// one CTA per row: out = softmax(in * scale)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int cols,
+                                                           float scale) {
+  __shared__ float red[8];
+  const float* r = in + (long long)blockIdx.x * cols;
+  float* o = out + (long long)blockIdx.x * cols;
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < cols; i += 256) m = fmaxf(m, r[i] * scale);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < cols; i += 256) s += expf(r[i] * scale - m);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i];
+  for (int i = threadIdx.x; i < cols; i += 256) o[i] = expf(r[i] * scale - m) / s;
+}
+
+}  // namespace
+
+int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st) {
+  long long n4 = n / 4;
+  if (n4 > 0) {
+    int blocks = (int)std::min<long long>((n4 + 255) / 256, kNumSMs * 16);
+    f32_to_bf16_kernel<<<blocks, 256, 0, st>>>(in, out, n4);
+    PIO_LAUNCHED();
+  }
+  if (n4 * 4 < n) {
+    f32_to_bf16_tail<<<1, 32, 0, st>>>(in, out, n4 * 4, n);
+    PIO_LAUNCHED();
+  }
+  return PIO_OK;
+}
+int transpose_f32(const float* in, float* out, int rows, int cols, cudaStream_t st) {
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+  transpose_kernel<float><<<grid, dim3(32, 8), 0, st>>>(in, out, rows, cols);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+int transpose_to_bf16(const float* in, __nv_bfloat16* out, int rows, int cols, cudaStream_t st) {
+  dim3 grid(cdiv(cols, 32), cdiv(rows, 32));
+  transpose_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, st>>>(in, out, rows, cols);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+int layernorm(const float* x, int ldx, const float* w, const float* b, void* out, int out_dt, int ldo, int rows, int dim,
+              float eps, cudaStream_t st) {
+  PIO_CHECK(dim % 128 == 0 && dim <= 1024, "layernorm: dim %d must be a multiple of 128, <= 1024", dim);
+  PIO_CHECK(ldx % 4 == 0 && ldo % 4 == 0, "layernorm: strides must be multiples of 4");
+  if (rows == 0) return PIO_OK;
+  const int blocks = cdiv((long long)rows * 32, 256);
+#define LN_CASE(V)                                                                                   \
+  case V:                                                                                            \
+    layernorm_kernel<V><<<blocks, 256, 0, st>>>(x, ldx, w, b, out, out_dt, ldo, rows, eps);          \
+    break;
+  switch (dim / 128) {
+    LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
+  }
+#undef LN_CASE
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+int im2col14(const float* imgs, void* cols, int cols_dt, int B, int S, int g, int Kp, cudaStream_t st) {
+  const long long total = (long long)B * g * g * Kp;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, kNumSMs * 32);
+  if (cols_dt == PIO_DT_F32)
+    im2col14_kernel<float><<<blocks, 256, 0, st>>>(imgs, (float*)cols, B, S, g, Kp);
+  else
+    im2col14_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(imgs, (__nv_bfloat16*)cols, B, S, g, Kp);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+int init_global_tokens(float* x, const float* cls, const float* reg, const float* pos, int B, int N, int D, cudaStream_t st) {
+  init_global_tokens_kernel<<<cdiv((long long)B * 5 * D, 256), 256, 0, st>>>(x, cls, reg, pos, B, N, D);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+int l2norm_rows(float* x, int rows, int dim, cudaStream_t st) {
+  if (rows == 0) return PIO_OK;
+  l2norm_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(x, rows, dim);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+int softmax_rows(const float* in, float* out, int rows, int cols, float scale, cudaStream_t st) {
+  if (rows == 0) return PIO_OK;
+  softmax_rows_kernel<<<rows, 256, 0, st>>>(in, out, cols, scale);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+}  // namespace pio
+
+extern "C" {
+const char* pio_last_error(void) { return pio::g_err; }
+int pio_version(void) { return 100; }
+long long pio_launch_count(void) { return pio::g_launches.load(); }
+void pio_reset_launch_count(void) { pio::g_launches.store(0); }
+
+int pio_layernorm(const float* x, int ldx, const float* w, const float* b, void* out, int out_dt, int ldo, int rows,
+                  int dim, float eps, void* stream) {
+  return pio::layernorm(x, ldx, w, b, out, out_dt, ldo, rows, dim, eps, pio::as_stream(stream));
+}
+int pio_l2_normalize(float* x, int rows, int dim, void* stream) {
+  return pio::l2norm_rows(x, rows, dim, pio::as_stream(stream));
+}
+int pio_linear(const PioLinear* p, int mode, void* stream) {
+  if (!p) return pio::fail(PIO_EINVAL, "pio_linear: null descriptor");
+  if (mode == PIO_FP32) return pio::linear_simt(*p, pio::as_stream(stream));
+  if (mode == PIO_BF16) return pio::linear_tc(*p, pio::as_stream(stream));
+  return pio::fail(PIO_EINVAL, "pio_linear: unknown mode %d", mode);
+}
+}

@@ -1,0 +1,342 @@
+// gemm_sm100.cu -- bf16 x bf16 -> fp32 GEMM on the Blackwell 5th-gen tensor cores (sm_100a).
+//
+//   C[map(m), n] = epilogue( sum_k A[m,k] * W[n,k] )          A [M,K], W [N,K], both K-contiguous
+//
+// Structure (one persistent CTA per SM, 192 threads, warp specialised):
+//   warp 0      TMA producer : cp.async.bulk.tensor.2d (128-byte swizzle) of a 128 x 64 A tile and a
+//               BN x 64 W tile per stage into a STAGES-deep shared-memory ring, completion on mbarriers
+//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16)
+//               straight from shared memory into a TMEM accumulator; tcgen05.commit releases the ring slot
+//               and, after the last k-block, publishes the accumulator
+//   warps 2..5  epilogue     : tcgen05.ld the fp32 accumulator (lane == row), apply bias / activation /
+//               LayerScale / residual, store.  The accumulator is double buffered in TMEM (2 x BN columns)
+//               so the epilogue of tile i overlaps the MMAs of tile i+1.
+// No CUTLASS: descriptors are built by hand (field layout checked against cute/arch/mma_sm100_desc.hpp).
+#include "common.cuh"
+
+#include <cuda.h>  // CUtensorMap types only; the driver entry point is fetched at run time (no -lcuda)
+#include <mutex>
+
+namespace pio {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+template <int BN> struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // power of two: 128 / 256 / 512
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*manual 1024-byte alignment*/;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major, canonical 1) | [32,46) SBO >> 4 = 1024 B
+//   (8 rows x 128 B) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D fp32, A/B bf16, both K-major.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) /*c_format F32*/ | (1u << 7) /*a BF16*/ | (1u << 10) /*b BF16*/ | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void store_chunk(void* C, int c_dt, long long base, const float (&v)[32], int nvalid, bool vec_ok) {
+  if (c_dt == PIO_DT_F32) {
+    float* p = reinterpret_cast<float*>(C) + base;
+    if (nvalid == 32 && vec_ok) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) p[i] = v[i];
+    }
+  } else {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(C) + base;
+    if (nvalid == 32 && vec_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]), b = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+        __nv_bfloat162 c = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]), d = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+        pk.z = *reinterpret_cast<uint32_t*>(&c); pk.w = *reinterpret_cast<uint32_t*>(&d);
+        reinterpret_cast<uint4*>(p)[i] = pk;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) p[i] = __float2bfloat16(v[i]);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, void* C, int M, int N, int K,
+               int ldc, int c_dt, Epilogue epi) {
+  using cfg = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B-swizzle atoms
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * cfg::STAGES + 4];
+  __shared__ uint32_t tmem_slot_var;
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (cfg::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * cfg::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * cfg::STAGES + 2 + s); };
+  const uint32_t tmem_slot = smem_u32(&tmem_slot_var);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
+  const int num_tiles = m_blocks * n_blocks;
+  const int k_blocks = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_var);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * cfg::STAGE_BYTES, sb = sa + cfg::A_BYTES;
+          mbar_expect_tx(full_bar(stage), cfg::STAGE_BYTES);
+          tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m0);
+          tma_load_2d(sb, &map_w, full_bar(stage), kb * BK, n0);
+          if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * cfg::STAGE_BYTES, sb = sa + cfg::A_BYTES;
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));                       // ring slot reusable once these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(tfull_bar(as));  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const long long orow = epi.out_row(m < M ? m : 0);
+      const bool vec_ok = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + c, r);
+        tmem_ld_wait();
+        const int n = n0 + c;
+        if (m < M && n < N) {
+          const int nvalid = min(32, N - n);
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? epi.apply(__uint_as_float(r[i]), m, orow, n + i) : 0.f;
+          store_chunk(C, c_dt, orow * ldc + n, v, nvalid, vec_ok);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row stride ld elements; box = box_rows x 64 columns, 128-byte swizzle.
+int make_map(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(PIO_ECUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PIO_ECUDA, "cuTensorMapEncodeTiled failed with %d (rows %lld cols %lld ld %lld)", (int)r, rows, cols, ld);
+  return PIO_OK;
+}
+
+template <int BN>
+int launch(const PioLinear& p, cudaStream_t st) {
+  using cfg = Cfg<BN>;
+  CUtensorMap ma, mw;
+  PIO_TRY(make_map(&ma, p.A, p.M, p.K, p.lda, BM));
+  PIO_TRY(make_map(&mw, p.W, p.N, p.K, p.ldw, BN));
+  static bool attr_set = false;
+  if (!attr_set) {
+    PIO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = cdiv(p.M, BM) * cdiv(p.N, BN);
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, cfg::SMEM_BYTES, st>>>(ma, mw, p.C, p.M, p.N, p.K, p.ldc, p.c_dt, make_epilogue(p));
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+}  // namespace
+
+int linear_tc(const PioLinear& p, cudaStream_t st) {
+  PIO_CHECK(p.a_dt == PIO_DT_BF16, "tcgen05 GEMM needs bf16 operands");
+  PIO_CHECK(p.lda % 8 == 0 && p.ldw % 8 == 0, "tcgen05 GEMM: lda/ldw must be multiples of 8 (16-byte TMA strides)");
+  PIO_CHECK((((uintptr_t)p.A) & 15) == 0 && (((uintptr_t)p.W) & 15) == 0, "tcgen05 GEMM: operands must be 16-byte aligned");
+  PIO_CHECK(p.K > 0, "tcgen05 GEMM: K must be positive");
+  if (p.M == 0 || p.N == 0) return PIO_OK;
+  // widest N tile that still gives every SM at least one tile
+  const long long mt = cdiv(p.M, BM);
+  if (mt * cdiv(p.N, 256) >= kNumSMs) return launch<256>(p, st);
+  if (mt * cdiv(p.N, 128) >= kNumSMs) return launch<128>(p, st);
+  return launch<64>(p, st);
+}
+
+}  // namespace pio

@@ -1,0 +1,373 @@
+// pooling.cu -- region aggregation of patch tokens.
+//
+// HBM-bound byte work: each image's patch tokens are read from HBM exactly once per call.  A CTA
+// stages a [P x 32-channel] slab of one image in shared memory (128-byte row segments, fully
+// coalesced), then its 8 warps walk the regions of that image: lane = channel, weights are computed
+// 32 patches at a time (one per lane) and broadcast with warp shuffles, the slab is read
+// conflict-free (32 consecutive floats per patch).  Index arithmetic follows the reference exactly
+// (torch float floor-division, inclusive end, Python slice clamping) and is exported as int32
+// bounds so that tests can compare it bit-for-bit.
+#include "common.cuh"
+
+namespace pio {
+namespace {
+
+// torch `a //= b` for float32 (c10::div_floor_floating), see bbox_utils.py:19
+__device__ __forceinline__ float torch_floor_div(float a, float b) {
+  if (b == 0.f) return a / b;
+  float mod = fmodf(a, b);
+  float div = (a - mod) / b;
+  if ((mod != 0.f) && ((b < 0.f) != (mod < 0.f))) div -= 1.0f;
+  float floordiv;
+  if (div != 0.f) {
+    floordiv = floorf(div);
+    if (div - floordiv > 0.5f) floordiv += 1.0f;
+  } else {
+    floordiv = copysignf(0.f, a / b);
+  }
+  return floordiv;
+}
+__device__ __forceinline__ int py_floor_div(int a, int b) {
+  int q = a / b, r = a % b;
+  return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q;
+}
+// Python a[start:stop] on a dimension of `size` -> [lo, hi)
+__device__ __forceinline__ void py_slice(int start, int stop, int size, int& lo, int& hi) {
+  if (start < 0) { start += size; if (start < 0) start = 0; } else if (start > size) start = size;
+  if (stop < 0) { stop += size; if (stop < 0) stop = 0; } else if (stop > size) stop = size;
+  lo = start;
+  hi = stop < start ? start : stop;
+}
+
+// boxes [n,4] xywh px -> bounds [n,4] (y_lo,y_hi,x_lo,x_hi) and skip[n] (patch-unit sum < 0: dummy box)
+__global__ void box_bounds_kernel(const void* __restrict__ boxes, int boxes_dt, int n, int patch, int grid,
+                                  int* __restrict__ bounds, int* __restrict__ skip) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int pu[4];
+  if (boxes_dt == PIO_DT_F32) {
+    const float* bx = reinterpret_cast<const float*>(boxes) + 4 * i;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float q = torch_floor_div(bx[e], (float)patch);
+      pu[e] = isfinite(q) ? (int)q : 0;
+    }
+  } else {
+    const int* bx = reinterpret_cast<const int*>(boxes) + 4 * i;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pu[e] = py_floor_div(bx[e], patch);
+  }
+  int x1 = pu[0], y1 = pu[1], w = pu[2], h = pu[3];
+  int ylo, yhi, xlo, xhi;
+  py_slice(y1, y1 + h + 1, grid, ylo, yhi);
+  py_slice(x1, x1 + w + 1, grid, xlo, xhi);
+  bounds[4 * i + 0] = ylo; bounds[4 * i + 1] = yhi; bounds[4 * i + 2] = xlo; bounds[4 * i + 3] = xhi;
+  skip[i] = (x1 + y1 + w + h) < 0 ? 1 : 0;
+}
+
+// torch.linspace(-1, 1, n)[i] in fp32
+__device__ __forceinline__ float linspace_m1_1(int i, int n) {
+  if (n == 1) return -1.0f;
+  const float step = 2.0f / (float)(n - 1);
+  return (i < n / 2) ? (-1.0f + step * (float)i) : (1.0f - step * (float)(n - 1 - i));
+}
+__device__ __forceinline__ float gauss_w(int iy, int hs, int ix, int ws, float variance) {
+  const float y = linspace_m1_1(iy, hs), x = linspace_m1_1(ix, ws);
+  return expf(-(x * x + y * y) / variance);
+}
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float s = 0.f;
+  for (int i = 0; i < nw; ++i) s += red[i];
+  return s;
+}
+
+// One CTA per image, boxes in order (the attention-map rescale is sequential and order dependent,
+// bbox_utils.py:46-48).  Writes per-box dense weights (per_box, [B,R,P], zero outside the box) and /
+// or the normalised box-set map (set_out, [B,P], bbox_utils.py:49,82,89,100).
+__global__ void __launch_bounds__(256) box_weights_kernel(const int* __restrict__ bounds, const int* __restrict__ skip, int R,
+                                                          int grid, int mode, float variance,
+                                                          const float* __restrict__ attn_map, float* __restrict__ per_box,
+                                                          float* __restrict__ set_out, int set_mode) {
+  extern __shared__ float sm[];
+  const int P = grid * grid;
+  float* A = sm;          // private copy of the attention map
+  float* total = sm + P;  // box-set accumulation
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    A[p] = (mode == PIO_POOL_ATTN) ? attn_map[(long long)b * P + p] : 0.f;
+    total[p] = 0.f;
+  }
+  __syncthreads();
+  for (int j = 0; j < R; ++j) {
+    const int bi = b * R + j;
+    if (set_mode && skip[bi]) continue;  // dummy box (bbox_utils.py:40-42)
+    const int y0 = bounds[4 * bi], y1 = bounds[4 * bi + 1], x0 = bounds[4 * bi + 2], x1 = bounds[4 * bi + 3];
+    const int hs = y1 - y0, ws = x1 - x0, area = hs * ws;
+    float part = 0.f;
+    for (int i = threadIdx.x; i < area; i += blockDim.x) {
+      const int iy = i / ws, ix = i % ws;
+      if (mode == PIO_POOL_ATTN) part += A[(y0 + iy) * grid + x0 + ix];
+      else if (mode == PIO_POOL_GAUSS) part += gauss_w(iy, hs, ix, ws, variance);
+      else part += 1.0f;
+    }
+    const float s = block_sum(part, red);
+    if (per_box)
+      for (int p = threadIdx.x; p < P; p += blockDim.x) per_box[((long long)bi) * P + p] = 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < area; i += blockDim.x) {
+      const int iy = i / ws, ix = i % ws, p = (y0 + iy) * grid + x0 + ix;
+      float w;
+      if (mode == PIO_POOL_ATTN) { w = A[p] / s; A[p] = w; }
+      else if (mode == PIO_POOL_GAUSS) w = gauss_w(iy, hs, ix, ws, variance) / s;
+      else w = 1.0f / (float)area;
+      total[p] += w;
+      if (per_box) per_box[((long long)bi) * P + p] = w;
+    }
+    __syncthreads();
+  }
+  if (set_out) {
+    float part = 0.f;
+    for (int p = threadIdx.x; p < P; p += blockDim.x) part += total[p];
+    const float s = block_sum(part, red);
+    for (int p = threadIdx.x; p < P; p += blockDim.x) set_out[(long long)b * P + p] = total[p] / s;
+  }
+}
+
+// Slab pooling.  grid = (D/32, B).  SRC 0: mean over the box, 1: gaussian over the box,
+// 2: explicit weights w[b,r,P] restricted to `bounds` (or the whole grid when bounds == NULL), times `scale`.
+template <int SRC>
+__global__ void __launch_bounds__(256) pool_slab_kernel(const float* __restrict__ tokens, long long img_stride,
+                                                        long long row_stride, int grid, int D, const int* __restrict__ bounds,
+                                                        int R, float variance, const float* __restrict__ weights, float scale,
+                                                        float* __restrict__ out) {
+  extern __shared__ __align__(16) float slab[];  // [P][32]
+  const int P = grid * grid;
+  const int b = blockIdx.y, c0 = blockIdx.x * 32;
+  const float* src = tokens + (long long)b * img_stride + c0;
+  // 8 lanes x float4 cover one 128-byte row segment; a warp loads 4 rows per instruction
+  for (int i = threadIdx.x; i < P * 8; i += blockDim.x) {
+    const int p = i >> 3, q = (i & 7) * 4;
+    *reinterpret_cast<float4*>(&slab[p * 32 + q]) = *reinterpret_cast<const float4*>(src + (long long)p * row_stride + q);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int j = warp; j < R; j += nw) {
+    const int bi = b * R + j;
+    int y0 = 0, y1 = grid, x0 = 0, x1 = grid;
+    if (bounds) { y0 = bounds[4 * bi]; y1 = bounds[4 * bi + 1]; x0 = bounds[4 * bi + 2]; x1 = bounds[4 * bi + 3]; }
+    const int hs = y1 - y0, ws = x1 - x0, area = hs * ws;
+    float acc = 0.f, wsum = 0.f;
+    for (int base = 0; base < area; base += 32) {
+      const int i = base + lane;
+      int p = 0;
+      float w = 0.f;
+      if (i < area) {
+        const int iy = i / ws, ix = i - iy * ws;
+        p = (y0 + iy) * grid + x0 + ix;
+        if (SRC == 0) w = 1.0f;
+        else if (SRC == 1) w = gauss_w(iy, hs, ix, ws, variance);
+        else w = __ldg(weights + (long long)bi * P + p);
+      }
+      wsum += w;
+      const int cnt = min(32, area - base);
+      if (SRC == 2) {
+        // sparse grids (trace histograms): skip the whole chunk when every weight is zero
+        if (__ballot_sync(0xffffffffu, w != 0.f) == 0u) continue;
+      }
+      for (int k = 0; k < cnt; ++k) {
+        const float wk = __shfl_sync(0xffffffffu, w, k);
+        const int pk = __shfl_sync(0xffffffffu, p, k);
+        acc = fmaf(wk, slab[pk * 32 + lane], acc);
+      }
+    }
+    float r;
+    if (SRC == 0) r = acc / (float)area;               // empty box -> 0/0 = NaN like tensor.mean()
+    else if (SRC == 1) { wsum = warp_sum(wsum); r = (area > 0) ? acc / wsum : 0.f; }
+    else r = acc * scale;
+    out[(long long)bi * D + c0 + lane] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------- traces
+// One CTA per trace; Python-double binning of bbox_utils.py:158-168.
+__global__ void __launch_bounds__(256) trace_bins_kernel(const double* __restrict__ pts, const int* __restrict__ offsets, int grid,
+                                                         const float* __restrict__ attn, float* __restrict__ counts) {
+  extern __shared__ int hist[];
+  const int P = grid * grid, t = blockIdx.x;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) hist[p] = 0;
+  __syncthreads();
+  const double patch_size = 1.0 / (double)grid;
+  for (int i = offsets[t] + threadIdx.x; i < offsets[t + 1]; i += blockDim.x) {
+    const double x = pts[2 * i], y = pts[2 * i + 1];
+    if (0.0 <= x && x <= 1.0 && 0.0 <= y && y <= 1.0) {
+      int gx = (int)(x / patch_size), gy = (int)(y / patch_size);
+      gx = min(gx, grid - 1);
+      gy = min(gy, grid - 1);
+      atomicAdd(&hist[gy * grid + gx], 1);
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < P; p += blockDim.x) {
+    float c = (float)hist[p];
+    if (attn) c = attn[(long long)t * P + p] * c;  // model.py:1053
+    counts[(long long)t * P + p] = c;
+  }
+}
+
+// ---------------------------------------------------------------------------------- CLS attention map
+// logits[b,j] = <q_cls[b], k[b,5+j]> / 128  -- one warp per (b, patch); softmax afterwards.
+template <typename T>
+__global__ void __launch_bounds__(256) cls_logits_kernel(const T* __restrict__ qkv, int B, int N, int D, int ng,
+                                                         float* __restrict__ logits) {
+  const int P = N - ng;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)B * P) return;
+  const int b = (int)(warp / P), j = (int)(warp % P);
+  const T* q = qkv + (long long)b * N * 3 * D;
+  const T* k = qkv + ((long long)b * N + ng + j) * 3 * D + D;
+  float s = 0.f;
+  for (int d = lane * 4; d < D; d += 128) {
+    float4 a, c;
+    if constexpr (sizeof(T) == 4) {
+      a = *reinterpret_cast<const float4*>(q + d);
+      c = *reinterpret_cast<const float4*>(k + d);
+    } else {
+      uint2 ua = *reinterpret_cast<const uint2*>(q + d), uc = *reinterpret_cast<const uint2*>(k + d);
+      float2 a0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&ua.x)), a1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&ua.y));
+      float2 c0 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&uc.x)), c1 = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&uc.y));
+      a = make_float4(a0.x, a0.y, a1.x, a1.y);
+      c = make_float4(c0.x, c0.y, c1.x, c1.y);
+    }
+    s += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+  }
+  s = warp_sum(s);
+  if (lane == 0) logits[warp] = s * (0.125f / 16.0f);
+}
+
+__global__ void __launch_bounds__(256) region_mean_weights_kernel(int grid, float variance, float* __restrict__ w) {
+  __shared__ float red[8];
+  const int P = grid * grid;
+  if (variance >= 100.f) {
+    for (int p = threadIdx.x; p < P; p += blockDim.x) w[p] = 1.0f / (float)P;
+    return;
+  }
+  float part = 0.f;
+  for (int p = threadIdx.x; p < P; p += blockDim.x) part += gauss_w(p / grid, grid, p % grid, grid, variance);
+  const float s = block_sum(part, red);
+  for (int p = threadIdx.x; p < P; p += blockDim.x) w[p] = gauss_w(p / grid, grid, p % grid, grid, variance) / s;
+}
+
+template <int SRC>
+int launch_slab(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D, const int* bounds,
+                int R, float variance, const float* weights, float scale, float* out, cudaStream_t st) {
+  const size_t smem = (size_t)grid * grid * 32 * sizeof(float);
+  PIO_CHECK(smem <= 227 * 1024, "pooling: grid %d too large for the shared-memory slab", grid);
+  PIO_CUDA(cudaFuncSetAttribute(pool_slab_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 g(D / 32, B);
+  pool_slab_kernel<SRC><<<g, 256, smem, st>>>(tokens, img_stride, row_stride, grid, D, bounds, R, variance, weights, scale, out);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+}  // namespace
+
+int cls_attention(const void* qkv, int dt, int B, int N, int D, int ng, float* out, float* logits_ws, cudaStream_t st) {
+  const int P = N - ng;
+  PIO_CHECK(D % 128 == 0, "cls attention: D %d must be a multiple of 128", D);
+  const int blocks = cdiv((long long)B * P * 32, 256);
+  if (dt == PIO_DT_F32)
+    cls_logits_kernel<float><<<blocks, 256, 0, st>>>((const float*)qkv, B, N, D, ng, logits_ws);
+  else
+    cls_logits_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)qkv, B, N, D, ng, logits_ws);
+  PIO_LAUNCHED();
+  return softmax_rows(logits_ws, out, B, P, 1.0f, st);
+}
+
+}  // namespace pio
+
+extern "C" {
+
+size_t pio_pool_workspace_bytes(int B, int R, int grid) {
+  const size_t P = (size_t)grid * grid;
+  return pio::align_up((size_t)B * R * 4 * sizeof(int), 256) + pio::align_up((size_t)B * R * sizeof(int), 256) +
+         pio::align_up((size_t)B * R * P * sizeof(float), 256) + pio::align_up((size_t)B * P * sizeof(float), 256) + 1024;
+}
+
+int pio_pool_boxes(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D, const void* boxes,
+                   int boxes_dt, int R, int patch_size, int mode, float variance, const float* attn_map, int set_mode,
+                   float* out, int* out_bounds, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace pio;
+  cudaStream_t st = as_stream(stream);
+  PIO_CHECK(D % 32 == 0 && row_stride % 4 == 0 && img_stride % 4 == 0 && (((uintptr_t)tokens) & 15) == 0,
+            "pool_boxes: D must be a multiple of 32 and tokens 16-byte aligned");
+  PIO_CHECK(boxes_dt == PIO_DT_F32 || boxes_dt == PIO_DT_I32, "pool_boxes: boxes must be float32 or int32");
+  PIO_CHECK(mode == PIO_POOL_MEAN || mode == PIO_POOL_GAUSS || mode == PIO_POOL_ATTN, "pool_boxes: bad mode %d", mode);
+  PIO_CHECK(mode != PIO_POOL_ATTN || attn_map, "pool_boxes: attention mode needs attn_map");
+  PIO_CHECK(!(mode == PIO_POOL_GAUSS && variance == 0.f),
+            "pool_boxes: gaussian variance 0 (python-random centre, bbox_utils.py:62-71) is not supported");
+  PIO_CHECK(workspace_bytes >= pio_pool_workspace_bytes(B, R, grid), "pool_boxes: workspace too small");
+  if (B == 0 || R == 0) return PIO_OK;
+  const size_t P = (size_t)grid * grid;
+  char* ws = (char*)workspace;
+  int* bounds = (int*)ws; ws += align_up((size_t)B * R * 4 * sizeof(int), 256);
+  int* skip = (int*)ws;   ws += align_up((size_t)B * R * sizeof(int), 256);
+  float* per_box = (float*)ws; ws += align_up((size_t)B * R * P * sizeof(float), 256);
+  float* set_map = (float*)ws;
+  box_bounds_kernel<<<cdiv(B * R, 128), 128, 0, st>>>(boxes, boxes_dt, B * R, patch_size, grid, bounds, skip);
+  PIO_LAUNCHED();
+  if (out_bounds) PIO_CUDA(cudaMemcpyAsync(out_bounds, bounds, (size_t)B * R * 4 * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  const size_t wsmem = 2 * P * sizeof(float);
+  if (set_mode) {
+    box_weights_kernel<<<B, 256, wsmem, st>>>(bounds, skip, R, grid, mode, variance, attn_map, nullptr, set_map, 1);
+    PIO_LAUNCHED();
+    return launch_slab<2>(tokens, img_stride, row_stride, B, grid, D, nullptr, 1, 0.f, set_map, 1.0f, out, st);
+  }
+  if (mode == PIO_POOL_ATTN) {
+    box_weights_kernel<<<B, 256, wsmem, st>>>(bounds, skip, R, grid, mode, variance, attn_map, per_box, nullptr, 0);
+    PIO_LAUNCHED();
+    return launch_slab<2>(tokens, img_stride, row_stride, B, grid, D, bounds, R, 0.f, per_box, 1.0f, out, st);
+  }
+  if (mode == PIO_POOL_GAUSS)
+    return launch_slab<1>(tokens, img_stride, row_stride, B, grid, D, bounds, R, variance, nullptr, 1.0f, out, st);
+  return launch_slab<0>(tokens, img_stride, row_stride, B, grid, D, bounds, R, 0.f, nullptr, 1.0f, out, st);
+}
+
+int pio_pool_grid(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D,
+                  const float* weights, int R, float scale, float* out, void* stream) {
+  using namespace pio;
+  PIO_CHECK(D % 32 == 0 && row_stride % 4 == 0 && img_stride % 4 == 0 && (((uintptr_t)tokens) & 15) == 0,
+            "pool_grid: D must be a multiple of 32 and tokens 16-byte aligned");
+  if (B == 0 || R == 0) return PIO_OK;
+  return launch_slab<2>(tokens, img_stride, row_stride, B, grid, D, nullptr, R, 0.f, weights, scale, out, as_stream(stream));
+}
+
+int pio_trace_bins(const double* points_xy, const int* offsets, int T, int grid, const float* attn, float* counts, void* stream) {
+  using namespace pio;
+  if (T == 0) return PIO_OK;
+  trace_bins_kernel<<<T, 256, (size_t)grid * grid * sizeof(int), as_stream(stream)>>>(points_xy, offsets, grid, attn, counts);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+int pio_region_mean_weights(int grid, float variance, float* weights, void* stream) {
+  using namespace pio;
+  PIO_CHECK(variance != 0.f, "region_mean_weights: variance 0 (python-random centre, model.py:71-77) is not supported");
+  region_mean_weights_kernel<<<1, 256, 0, as_stream(stream)>>>(grid, variance, weights);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+int pio_cls_attention(const void* qkv, int qkv_dt, int B, int N, int D, int num_global, float* out_attn, void* stream) {
+  using namespace pio;
+  // logits are staged in out_attn itself (softmax_rows is safe in place: each CTA owns one row)
+  return cls_attention(qkv, qkv_dt, B, N, D, num_global, out_attn, out_attn, as_stream(stream));
+}
+}

@@ -1,0 +1,500 @@
+// text.cu -- the DeCap text side: caption-memory projection and the KV-cached greedy prefix decoder.
+//   pio_project*        replaces Im2TxtProjector.project   (im2txtprojection.py:353-385)
+//   pio_decode_greedy   replaces decoding_batched          (src/decap/decap.py:116-160)
+#include "common.cuh"
+#include <vector>
+
+namespace pio {
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// Online-softmax step over one bank chunk (one CTA per query row).
+//   S[r, 0:mc] holds  <q^, k^_j> / T  for the chunk;  running (m, l) are updated,
+//   P = exp(S - m_new) is written (fp32 in place or bf16 to P16), columns [mc, mc_pad) are zeroed,
+//   alpha[r] = exp(m_old - m_new) rescales the running output in the following GEMM.
+__global__ void __launch_bounds__(256) softmax_chunk_kernel(float* __restrict__ S, int lds, __nv_bfloat16* __restrict__ P16,
+                                                            int ldp, int mc, int mc_pad, float* __restrict__ m,
+                                                            float* __restrict__ l, float* __restrict__ alpha) {
+  __shared__ float red[8];
+  const int r = blockIdx.x;
+  float* row = S + (long long)r * lds;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < mc; i += 256) mx = fmaxf(mx, row[i]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  const float mold = m[r];
+  const float mnew = fmaxf(mold, mx);
+  float s = 0.f;
+  for (int i = threadIdx.x; i < mc_pad; i += 256) {
+    float p = (i < mc) ? expf(row[i] - mnew) : 0.f;
+    s += p;
+    if (P16) P16[(long long)r * ldp + i] = __float2bfloat16(p);
+    else row[i] = p;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    const float a = expf(mold - mnew);  // mold = -inf on the first chunk -> 0
+    alpha[r] = a;
+    l[r] = l[r] * a + t;
+    m[r] = mnew;
+  }
+}
+
+__global__ void fill_kernel(float* p, float v, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+__global__ void row_inv_norm_kernel(const float* __restrict__ x, float* __restrict__ inv, long long rows, int dim) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* r = x + warp * dim;
+  float s = 0.f;
+  for (int i = lane; i < dim; i += 32) s += r[i] * r[i];
+  s = warp_sum(s);
+  if (lane == 0) inv[warp] = 1.0f / sqrtf(s);
+}
+
+// O[r,:] *= f, l[r] *= f with f = exp(m_local - m_global)
+__global__ void rescale_rows_kernel(float* __restrict__ O, float* __restrict__ l, const float* __restrict__ ml,
+                                    const float* __restrict__ mg, int R, int D) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const float f = expf(ml[warp] - mg[warp]);
+  for (int i = lane; i < D; i += 32) O[(long long)warp * D + i] *= f;
+  if (lane == 0) l[warp] *= f;
+}
+// O[r,:] /= l[r]; optional L2 normalisation
+__global__ void finish_rows_kernel(float* __restrict__ O, const float* __restrict__ l, int R, int D, int normalize) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  float* r = O + (long long)warp * D;
+  const float inv = 1.0f / l[warp];
+  float s = 0.f;
+  for (int i = lane; i < D; i += 32) { float v = r[i] * inv; r[i] = v; s += v * v; }
+  if (normalize) {
+    const float n = sqrtf(warp_sum(s));
+    for (int i = lane; i < D; i += 32) r[i] = r[i] / n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Row arg-max of the logits (first index wins ties, like torch.argmax) + log softmax at the arg-max.
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ logits, int ld, int V, int* __restrict__ ids,
+                                                          int ids_ld, int t, float* __restrict__ logprob_sum) {
+  __shared__ float rv[8];
+  __shared__ int ri[8];
+  __shared__ float rs[8];
+  const float* row = logits + (long long)blockIdx.x * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += 256) {
+    float v = row[i];
+    if (v > best) { best = v; bi = i; }   // strided ascending: first index kept on ties
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { rv[threadIdx.x >> 5] = best; ri[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  best = rv[0]; bi = ri[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+    if (rv[i] > best || (rv[i] == best && ri[i] < bi)) { best = rv[i]; bi = ri[i]; }
+  if (logprob_sum) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < V; i += 256) s += expf(row[i] - best);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) rs[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tot += rs[i];
+      logprob_sum[blockIdx.x] += -logf(tot);  // log softmax(logits)[argmax] = -log sum exp(l - max)
+    }
+  }
+  if (threadIdx.x == 0) ids[(long long)blockIdx.x * ids_ld + t] = bi;
+}
+
+// x[r,:] = wte[ids[r,t],:] + wpe[pos,:]
+__global__ void embed_kernel(const float* __restrict__ wte, const float* __restrict__ wpe, const int* __restrict__ ids,
+                             int ids_ld, int t, int pos, float* __restrict__ x, int R, int D) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const int tok = ids[(long long)warp * ids_ld + t];
+  const float4* a = reinterpret_cast<const float4*>(wte + (long long)tok * D);
+  const float4* b = reinterpret_cast<const float4*>(wpe + (long long)pos * D);
+  float4* o = reinterpret_cast<float4*>(x + (long long)warp * D);
+  for (int i = lane; i < D / 4; i += 32) {
+    float4 u = __ldg(a + i), v = __ldg(b + i);
+    o[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) o[i] = a[i] + b[i];
+}
+
+int linear(int mode, const void* A, const void* W, void* C, int M, int N, int K, int lda, int ldw, int ldc, int a_dt, int c_dt,
+           const float* bias, const float* residual, int act, cudaStream_t st) {
+  PioLinear p;
+  memset(&p, 0, sizeof(p));
+  p.A = A; p.W = W; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw; p.ldc = ldc; p.a_dt = a_dt; p.c_dt = c_dt;
+  p.bias = bias; p.residual = residual; p.ldres = ldc; p.alpha = 1.0f; p.act = act;
+  return mode == PIO_FP32 ? linear_simt(p, st) : linear_tc(p, st);
+}
+
+}  // namespace
+}  // namespace pio
+
+// ==========================================================================================
+struct PioBank {
+  int mode, act_dt, D;
+  long long M, Mp;       // rows, padded row count (leading dimension of the transpose)
+  void* bank;            // act [M, D]
+  void* bankT;           // act [D, Mp], zero padded
+  float* inv_norm;       // [M]
+};
+
+namespace pio {
+namespace {
+// bankT[c, r] = bank[r, c] with leading dimension ldt; also the straight copy in the activation dtype
+template <typename T>
+__global__ void bank_transpose_kernel(const float* __restrict__ in, T* __restrict__ outT, T* __restrict__ outC, long long rows,
+                                      int cols, long long ldt) {
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long long r = r0 + i;
+    const int c = c0 + threadIdx.x;
+    float v = (r < rows && c < cols) ? in[r * cols + c] : 0.f;
+    tile[i][threadIdx.x] = v;
+    if (r < rows && c < cols) outC[r * cols + c] = (T)v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    const long long r = r0 + threadIdx.x;
+    if (c < cols && r < rows) outT[(long long)c * ldt + r] = (T)tile[threadIdx.x][i];
+  }
+}
+}  // namespace
+}  // namespace pio
+
+static int pio_bank_fill_(PioBank* h, const float* bank, cudaStream_t st) {
+  using namespace pio;
+  dim3 grid((unsigned)((h->M + 31) / 32), (unsigned)(h->D / 32));
+  if (h->act_dt == PIO_DT_F32)
+    bank_transpose_kernel<float><<<grid, dim3(32, 8), 0, st>>>(bank, (float*)h->bankT, (float*)h->bank, h->M, h->D, h->Mp);
+  else
+    bank_transpose_kernel<__nv_bfloat16><<<grid, dim3(32, 8), 0, st>>>(bank, (__nv_bfloat16*)h->bankT, (__nv_bfloat16*)h->bank, h->M, h->D, h->Mp);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+extern "C" {
+
+int pio_bank_create(PioBank** out, const float* bank, long long M, int D, int mode, void* stream) {
+  using namespace pio;
+  PIO_CHECK(out && bank && M > 0, "bank_create: bad arguments");
+  PIO_CHECK(D % 128 == 0, "bank_create: D %d must be a multiple of 128", D);
+  PIO_CHECK(M < (1ll << 31) - 1024, "bank_create: too many rows for one shard");
+  cudaStream_t st = as_stream(stream);
+  PioBank* h = new PioBank();
+  memset(h, 0, sizeof(*h));
+  h->mode = mode; h->act_dt = mode == PIO_FP32 ? PIO_DT_F32 : PIO_DT_BF16; h->D = D; h->M = M;
+  h->Mp = (M + 127) / 128 * 128;
+  const size_t e = h->act_dt == PIO_DT_F32 ? 4 : 2;
+  auto go = [&]() -> int {
+    PIO_CUDA(cudaMalloc(&h->bank, (size_t)M * D * e));
+    PIO_CUDA(cudaMalloc(&h->bankT, (size_t)D * h->Mp * e));
+    PIO_CUDA(cudaMalloc((void**)&h->inv_norm, (size_t)M * sizeof(float)));
+    PIO_CUDA(cudaMemsetAsync(h->bankT, 0, (size_t)D * h->Mp * e, st));
+    row_inv_norm_kernel<<<cdiv(M * 32, 256), 256, 0, st>>>(bank, h->inv_norm, M, D);
+    PIO_LAUNCHED();
+    return PIO_OK;
+  };
+  int rc = go();
+  if (rc != PIO_OK) { pio_bank_destroy(h); return rc; }
+  rc = pio_bank_fill_(h, bank, st);  // bank + transposed copy in the activation dtype
+  if (rc != PIO_OK) { pio_bank_destroy(h); return rc; }
+  *out = h;
+  return PIO_OK;
+}
+}
+
+extern "C" {
+
+void pio_bank_destroy(PioBank* h) {
+  if (!h) return;
+  cudaFree(h->bank); cudaFree(h->bankT); cudaFree(h->inv_norm);
+  delete h;
+}
+long long pio_bank_rows(const PioBank* h) { return h ? h->M : 0; }
+
+static int project_chunk_rows(int R) {
+  // keep the S chunk (R x Mc fp32) around 64 MB so that it stays L2 resident between the two GEMMs
+  long long mc = (16ll << 20) / (R > 0 ? R : 1);
+  mc = mc / 128 * 128;
+  if (mc < 1024) mc = 1024;
+  if (mc > 16384) mc = 16384;
+  return (int)mc;
+}
+
+size_t pio_project_workspace_bytes(const PioBank* h, int R) {
+  using namespace pio;
+  const size_t Mc = project_chunk_rows(R), e = h->act_dt == PIO_DT_F32 ? 4 : 2;
+  return align_up((size_t)R * h->D * e, 1024) /*qn*/ + align_up((size_t)R * h->D * 4, 1024) /*qn fp32*/ +
+         align_up((size_t)R * Mc * 4, 1024) /*S*/ + align_up((size_t)R * Mc * 2, 1024) /*P16*/ + 3 * align_up((size_t)R * 4, 1024) + 4096;
+}
+
+int pio_project(PioBank* h, const float* q, int R, float temperature, int normalize, float* out, float* part_m, float* part_l,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace pio;
+  PIO_CHECK(h && q && out && workspace, "project: null argument");
+  PIO_CHECK(temperature > 0.f, "project: temperature must be positive");
+  PIO_CHECK(workspace_bytes >= pio_project_workspace_bytes(h, R), "project: workspace too small");
+  PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "project: workspace must be 1024-byte aligned");
+  PIO_CHECK((part_m == nullptr) == (part_l == nullptr), "project: part_m and part_l go together");
+  if (R == 0) return PIO_OK;
+  cudaStream_t st = as_stream(stream);
+  const int D = h->D, Mc = project_chunk_rows(R), adt = h->act_dt;
+  const size_t e = adt == PIO_DT_F32 ? 4 : 2;
+  char* ws = (char*)workspace;
+  void* qn = ws;            ws += align_up((size_t)R * D * e, 1024);
+  float* qn32 = (float*)ws; ws += align_up((size_t)R * D * 4, 1024);
+  float* S = (float*)ws;    ws += align_up((size_t)R * Mc * 4, 1024);
+  __nv_bfloat16* P16 = (__nv_bfloat16*)ws; ws += align_up((size_t)R * Mc * 2, 1024);
+  float* m = (float*)ws;    ws += align_up((size_t)R * 4, 1024);
+  float* l = (float*)ws;    ws += align_up((size_t)R * 4, 1024);
+  float* alpha = (float*)ws;
+
+  PIO_CUDA(cudaMemcpyAsync(qn32, q, (size_t)R * D * 4, cudaMemcpyDeviceToDevice, st));
+  PIO_TRY(l2norm_rows(qn32, R, D, st));                       // q / |q|  (im2txtprojection.py:368)
+  if (adt == PIO_DT_F32) qn = qn32; else PIO_TRY(f32_to_bf16(qn32, (__nv_bfloat16*)qn, (long long)R * D, st));
+  fill_kernel<<<cdiv(R, 256), 256, 0, st>>>(m, -INFINITY, R); PIO_LAUNCHED();
+  PIO_CUDA(cudaMemsetAsync(l, 0, (size_t)R * 4, st));
+  PIO_CUDA(cudaMemsetAsync(out, 0, (size_t)R * D * 4, st));
+
+  for (long long c0 = 0; c0 < h->M; c0 += Mc) {
+    const int mc = (int)std::min<long long>(Mc, h->M - c0);
+    const int mc_pad = (mc + 63) / 64 * 64;
+    PioLinear p;
+    memset(&p, 0, sizeof(p));
+    // S = (q^ . bank_j) * inv_norm_j / T                       (:367,370,376)
+    p.A = qn; p.W = (const char*)h->bank + (size_t)c0 * D * e; p.C = S; p.M = R; p.N = mc; p.K = D;
+    p.lda = D; p.ldw = D; p.ldc = Mc; p.a_dt = adt; p.c_dt = PIO_DT_F32; p.colscale = h->inv_norm + c0;
+    p.alpha = 1.0f / temperature;
+    PIO_TRY(h->mode == PIO_FP32 ? linear_simt(p, st) : linear_tc(p, st));
+    softmax_chunk_kernel<<<R, 256, 0, st>>>(S, Mc, adt == PIO_DT_F32 ? nullptr : P16, Mc, mc, mc_pad, m, l, alpha);
+    PIO_LAUNCHED();
+    // O = alpha * O + P . bank[c0:c0+mc]  (raw rows, :377) -- K-contiguous through the transposed copy
+    memset(&p, 0, sizeof(p));
+    p.A = adt == PIO_DT_F32 ? (const void*)S : (const void*)P16;
+    p.W = (const char*)h->bankT + (size_t)c0 * e; p.C = out; p.M = R; p.N = D; p.K = mc_pad;
+    p.lda = Mc; p.ldw = (int)h->Mp; p.ldc = D; p.a_dt = adt; p.c_dt = PIO_DT_F32; p.residual = out; p.ldres = D;
+    p.res_rowscale = alpha; p.alpha = 1.0f;
+    PIO_TRY(h->mode == PIO_FP32 ? linear_simt(p, st) : linear_tc(p, st));
+  }
+  if (part_m) {
+    PIO_CUDA(cudaMemcpyAsync(part_m, m, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+    PIO_CUDA(cudaMemcpyAsync(part_l, l, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+    return PIO_OK;
+  }
+  finish_rows_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(out, l, R, D, normalize);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+int pio_project_rescale(float* O, float* l, const float* m_local, const float* m_global, int R, int D, void* stream) {
+  using namespace pio;
+  if (R == 0) return PIO_OK;
+  rescale_rows_kernel<<<cdiv((long long)R * 32, 256), 256, 0, as_stream(stream)>>>(O, l, m_local, m_global, R, D);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+int pio_project_finish(float* O, const float* l, int R, int D, int normalize, void* stream) {
+  using namespace pio;
+  if (R == 0) return PIO_OK;
+  finish_rows_kernel<<<cdiv((long long)R * 32, 256), 256, 0, as_stream(stream)>>>(O, l, R, D, normalize);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+}
+
+// ==========================================================================================
+namespace pio {
+constexpr int gD = 768, gH = 4, gL = 4, gV = 50257, gVld = 50264, gFF = 3072, gT = 32;
+}
+struct PioDecoder {
+  int mode, act_dt, prefix_size;
+  std::vector<void*> owned;
+  const float *wte32, *wpe, *lnf_w, *lnf_b, *prefix_b0;  // prefix_b0 = prefix bias + wpe[0]
+  const void *wte, *prefix_w;                             // act dtype
+  struct Blk {
+    const float *ln1_w, *ln1_b, *attn_b, *proj_b, *ln2_w, *ln2_b, *fc_b, *fc2_b;
+    const void *attn_w, *proj_w, *fc_w, *fc2_w;  // act dtype, transposed to [out, in]
+  } blk[4];
+};
+
+namespace pio {
+namespace {
+int d_own(PioDecoder* h, void** p, size_t bytes) {
+  PIO_CUDA(cudaMalloc(p, bytes));
+  h->owned.push_back(*p);
+  return PIO_OK;
+}
+int d_f32(PioDecoder* h, const float** dst, const float* src, size_t n, cudaStream_t st) {
+  void* p;
+  PIO_TRY(d_own(h, &p, n * 4));
+  PIO_CUDA(cudaMemcpyAsync(p, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  *dst = (const float*)p;
+  return PIO_OK;
+}
+// Conv1D weight [in, out] -> Linear layout [out, in] in the activation dtype
+int d_matT(PioDecoder* h, const void** dst, const float* src, int in, int outn, cudaStream_t st) {
+  void* p;
+  PIO_TRY(d_own(h, &p, (size_t)in * outn * (h->act_dt == PIO_DT_F32 ? 4 : 2)));
+  if (h->act_dt == PIO_DT_F32) PIO_TRY(transpose_f32(src, (float*)p, in, outn, st));
+  else PIO_TRY(transpose_to_bf16(src, (__nv_bfloat16*)p, in, outn, st));
+  *dst = p;
+  return PIO_OK;
+}
+int d_mat(PioDecoder* h, const void** dst, const float* src, size_t n, cudaStream_t st) {
+  void* p;
+  if (h->act_dt == PIO_DT_F32) return d_f32(h, (const float**)dst, src, n, st);
+  PIO_TRY(d_own(h, &p, n * 2));
+  PIO_TRY(f32_to_bf16(src, (__nv_bfloat16*)p, (long long)n, st));
+  *dst = p;
+  return PIO_OK;
+}
+}  // namespace
+}  // namespace pio
+
+extern "C" {
+
+int pio_decoder_create(PioDecoder** out, const PioDecoderWeights* w, int mode, void* stream) {
+  using namespace pio;
+  PIO_CHECK(out && w, "decoder_create: null argument");
+  PIO_CHECK(mode == PIO_FP32 || mode == PIO_BF16, "decoder_create: unknown mode %d", mode);
+  PIO_CHECK(w->prefix_size > 0 && w->prefix_size % 64 == 0, "decoder_create: prefix_size %d must be a multiple of 64", w->prefix_size);
+  cudaStream_t st = as_stream(stream);
+  PioDecoder* h = new PioDecoder();
+  h->mode = mode; h->act_dt = mode == PIO_FP32 ? PIO_DT_F32 : PIO_DT_BF16; h->prefix_size = w->prefix_size;
+  auto go = [&]() -> int {
+    PIO_TRY(d_f32(h, &h->wte32, w->wte, (size_t)gV * gD, st));
+    if (h->act_dt == PIO_DT_F32) h->wte = h->wte32; else PIO_TRY(d_mat(h, &h->wte, w->wte, (size_t)gV * gD, st));
+    PIO_TRY(d_f32(h, &h->wpe, w->wpe, (size_t)1024 * gD, st));
+    PIO_TRY(d_f32(h, &h->lnf_w, w->lnf_w, gD, st)); PIO_TRY(d_f32(h, &h->lnf_b, w->lnf_b, gD, st));
+    PIO_TRY(d_mat(h, &h->prefix_w, w->prefix_w, (size_t)gD * w->prefix_size, st));
+    void* pb;
+    PIO_TRY(d_own(h, &pb, gD * 4));
+    add_vec_kernel<<<cdiv(gD, 256), 256, 0, st>>>(w->prefix_b, w->wpe, (float*)pb, gD);
+    PIO_LAUNCHED();
+    h->prefix_b0 = (const float*)pb;
+    for (int i = 0; i < gL; ++i) {
+      const PioGptBlock& s = w->blk[i];
+      PioDecoder::Blk& d = h->blk[i];
+      PIO_TRY(d_f32(h, &d.ln1_w, s.ln1_w, gD, st)); PIO_TRY(d_f32(h, &d.ln1_b, s.ln1_b, gD, st));
+      PIO_TRY(d_f32(h, &d.attn_b, s.attn_b, 3 * gD, st)); PIO_TRY(d_f32(h, &d.proj_b, s.proj_b, gD, st));
+      PIO_TRY(d_f32(h, &d.ln2_w, s.ln2_w, gD, st)); PIO_TRY(d_f32(h, &d.ln2_b, s.ln2_b, gD, st));
+      PIO_TRY(d_f32(h, &d.fc_b, s.fc_b, gFF, st)); PIO_TRY(d_f32(h, &d.fc2_b, s.fc2_b, gD, st));
+      PIO_TRY(d_matT(h, &d.attn_w, s.attn_w, gD, 3 * gD, st));
+      PIO_TRY(d_matT(h, &d.proj_w, s.proj_w, gD, gD, st));
+      PIO_TRY(d_matT(h, &d.fc_w, s.fc_w, gD, gFF, st));
+      PIO_TRY(d_matT(h, &d.fc2_w, s.fc2_w, gFF, gD, st));
+    }
+    return PIO_OK;
+  };
+  int rc = go();
+  if (rc != PIO_OK) { pio_decoder_destroy(h); return rc; }
+  *out = h;
+  return PIO_OK;
+}
+
+void pio_decoder_destroy(PioDecoder* h) {
+  if (!h) return;
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+}
+
+size_t pio_decode_workspace_bytes(const PioDecoder* h, int R, int steps) {
+  using namespace pio;
+  (void)steps;
+  const size_t e = h->act_dt == PIO_DT_F32 ? 4 : 2;
+  return align_up((size_t)R * gD * 4, 1024) /*x*/ + align_up((size_t)R * gD * e, 1024) /*h*/ +
+         align_up((size_t)R * 3 * gD * e, 1024) /*qkv*/ + align_up((size_t)R * gFF * e, 1024) /*f*/ +
+         align_up((size_t)R * gVld * 4, 1024) /*logits*/ + 2 * align_up((size_t)gL * R * gH * gT * (gD / gH) * e, 1024) /*kv*/ +
+         align_up((size_t)R * h->prefix_size * e, 1024) + 4096;
+}
+
+int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int* out_ids, float* out_logprob_sum,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace pio;
+  PIO_CHECK(h && prefix && out_ids && workspace, "decode_greedy: null argument");
+  PIO_CHECK(steps >= 1 && steps <= gT, "decode_greedy: steps %d outside [1,%d]", steps, gT);
+  PIO_CHECK(workspace_bytes >= pio_decode_workspace_bytes(h, R, steps), "decode_greedy: workspace too small");
+  PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "decode_greedy: workspace must be 1024-byte aligned");
+  if (R == 0) return PIO_OK;
+  cudaStream_t st = as_stream(stream);
+  const int adt = h->act_dt, mode = h->mode;
+  const size_t e = adt == PIO_DT_F32 ? 4 : 2;
+  const size_t kv_layer = (size_t)R * gH * gT * (gD / gH) * e;
+  char* ws = (char*)workspace;
+  float* x = (float*)ws;      ws += align_up((size_t)R * gD * 4, 1024);
+  void* hb = ws;              ws += align_up((size_t)R * gD * e, 1024);
+  void* qkv = ws;             ws += align_up((size_t)R * 3 * gD * e, 1024);
+  void* f = ws;               ws += align_up((size_t)R * gFF * e, 1024);
+  float* logits = (float*)ws; ws += align_up((size_t)R * gVld * 4, 1024);
+  char* kc = ws;              ws += align_up(gL * kv_layer, 1024);
+  char* vc = ws;              ws += align_up(gL * kv_layer, 1024);
+  void* pfx = ws;
+
+  // prefix embedding at position 0: clip_project(feats) + wpe[0]   (decap.py:124; GPT-2 adds wpe)
+  const void* pA = prefix;
+  if (adt != PIO_DT_F32) { PIO_TRY(f32_to_bf16(prefix, (__nv_bfloat16*)pfx, (long long)R * h->prefix_size, st)); pA = pfx; }
+  PIO_TRY(linear(mode, pA, h->prefix_w, x, R, gD, h->prefix_size, h->prefix_size, h->prefix_size, gD, adt, PIO_DT_F32,
+                 h->prefix_b0, nullptr, PIO_ACT_NONE, st));
+  if (out_logprob_sum) PIO_CUDA(cudaMemsetAsync(out_logprob_sum, 0, (size_t)R * 4, st));
+
+  for (int t = 0; t < steps; ++t) {
+    for (int i = 0; i < gL; ++i) {
+      const PioDecoder::Blk& w = h->blk[i];
+      PIO_TRY(layernorm(x, gD, w.ln1_w, w.ln1_b, hb, adt, gD, R, gD, 1e-5f, st));
+      PIO_TRY(linear(mode, hb, w.attn_w, qkv, R, 3 * gD, gD, gD, gD, 3 * gD, adt, adt, w.attn_b, nullptr, PIO_ACT_NONE, st));
+      PIO_TRY(decode_attention(qkv, kc + i * kv_layer, vc + i * kv_layer, hb, adt, R, gH, gT, t, st));
+      PIO_TRY(linear(mode, hb, w.proj_w, x, R, gD, gD, gD, gD, gD, adt, PIO_DT_F32, w.proj_b, x, PIO_ACT_NONE, st));
+      PIO_TRY(layernorm(x, gD, w.ln2_w, w.ln2_b, hb, adt, gD, R, gD, 1e-5f, st));
+      PIO_TRY(linear(mode, hb, w.fc_w, f, R, gFF, gD, gD, gD, gFF, adt, adt, w.fc_b, nullptr, PIO_ACT_GELU_NEW, st));
+      PIO_TRY(linear(mode, f, w.fc2_w, x, R, gD, gFF, gFF, gFF, gD, adt, PIO_DT_F32, w.fc2_b, x, PIO_ACT_NONE, st));
+    }
+    PIO_TRY(layernorm(x, gD, h->lnf_w, h->lnf_b, hb, adt, gD, R, gD, 1e-5f, st));
+    PIO_TRY(linear(mode, hb, h->wte, logits, R, gV, gD, gD, gD, gVld, adt, PIO_DT_F32, nullptr, nullptr, PIO_ACT_NONE, st));
+    argmax_rows_kernel<<<R, 256, 0, st>>>(logits, gVld, gV, out_ids, steps, t, out_logprob_sum);
+    PIO_LAUNCHED();
+    if (t + 1 < steps) {
+      embed_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(h->wte32, h->wpe, out_ids, steps, t, t + 1, x, R, gD);
+      PIO_LAUNCHED();
+    }
+  }
+  return PIO_OK;
+}
+}

@@ -1,0 +1,357 @@
+"""``Patchioner`` -- drop-in for the reference's model facade on the talk2dino (DINOv2 ViT-B/14-reg) path.
+
+Mirrors Patch-ioner/src/model.py: ``Patchioner.from_config`` (:666-715), ``forward`` (:718-1058, same keyword
+names, same output keys), ``caption_tokens`` (:1392-1423).  Underneath, every numeric step runs in
+libpio_sm100.so (hand-written sm_100a CUDA) -- there is no PyTorch compute path and no CPU fallback.
+
+Scope: DINOv2-reg backbone + DeCap / CapDec text side.  The alternative backbones and
+captioners of the reference (ProxyCLIP, RegionCLIP, INViTE, DenseCLIP, AlphaCLIP, ViECap, MeaCap, ClipCap),
+``double_DINO_for_bboxes``, ``cleaning_type``, ``caption_bboxes_type`` and ``get_attn_heads_capt`` are out of
+scope for this round and raise ``NotImplementedError`` instead of silently doing something else.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .detok import default_detokenizer
+
+EOT = "<|endoftext|>"
+SOT = "<|startoftext|>"
+
+
+def _load_tensor_file(path: str):
+    if path.endswith((".pt", ".pth", ".bin")):
+        return torch.load(path, map_location="cpu", weights_only=False)
+    if path.endswith(".npy"):
+        import numpy as np
+
+        return torch.from_numpy(np.load(path))
+    if path.endswith((".h5", ".hdf5")):
+        try:
+            import h5py  # the reference's bank format (im2txtprojection.py:320-323)
+        except ImportError as e:  # pragma: no cover - h5py is absent from this image
+            raise RuntimeError("reading an HDF5 memory bank needs h5py") from e
+        with h5py.File(path, "r") as hf:
+            key = [k for k in hf.keys() if k.endswith("-embeddings")][0]
+            return torch.from_numpy(hf[key][:])
+    raise ValueError(f"do not know how to read {path}")
+
+
+class Patchioner:
+    """See module docstring.  Not an ``nn.Module``: the weights live in library-owned device memory."""
+
+    def __init__(self, decoder_weights, device, prefix_size, linear_talk2dino=False, support_memory_size=0,
+                 projection_type=None, dino_model=None, proxyclip_clipmodel=None, proxyclip_vfm=None,
+                 use_talk2dino_project=True, normalize=True, attention_type="qkv", talk2dino_config=None,
+                 talk2dino_weights=None, resize_dim=518, crop_dim=518, talk2dino_attn_type="qkv",
+                 calculate_argmax_text=False, online_texts=None, clip_model_name=None, use_open_clip=False,
+                 viecap_config=None, regionclip_config=None, invite_config=None, denseclip_config=None,
+                 alphaclip_config=None, clipcap_config=None, hf_repo_id=None,
+                 # extensions (no network in this image: weights are given as files / state dicts)
+                 dino_weights=None, memory_bank=None, precision="fp32", **kwargs):
+        for name, val in (("proxyclip_clipmodel", proxyclip_clipmodel), ("viecap", viecap_config),
+                          ("regionclip_config", regionclip_config), ("invite_config", invite_config),
+                          ("denseclip_config", denseclip_config), ("alphaclip_config", alphaclip_config),
+                          ("clipcap", clipcap_config)):
+            if val is not None:
+                raise NotImplementedError(f"'{name}' selects a backbone/captioner outside the B200 hot path (SURVEY.md 8)")
+        if calculate_argmax_text or online_texts is not None:
+            raise NotImplementedError("calculate_argmax_text / online_texts need the bank's texts (out of scope)")
+        if dino_model is None or "dinov2" not in dino_model or "vitb14" not in dino_model or "reg" not in dino_model:
+            raise NotImplementedError(f"dino_model={dino_model!r}: only 'dinov2_vitb14_reg' is built (model.py:342-343)")
+        if attention_type != "qkv":
+            raise NotImplementedError("attention_type != 'qkv' re-wires the last block (model.py:557-582): out of scope")
+        if precision not in ops.MODES:
+            raise ValueError(f"precision must be one of {list(ops.MODES)}")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.PioError("patchioner_b200 runs on CUDA (sm_100a) only: there is no CPU fallback")
+        L.lib()  # fail loudly now if the CUDA library has not been built
+        self.precision = precision
+        self.decoding_method: Optional[Callable[[List[int]], str]] = None  # model.py:105
+        self.normalize = normalize
+        self.resize_dim, self.crop_dim = resize_dim, crop_dim
+        self.model_name = dino_model
+        self.num_global_tokens = 5
+        self.patch_size = 14
+        self.embed_dim = 768
+        self.num_attn_heads = 16  # sic (model.py:336); only get_attn_heads_capt depends on it
+        self.num_patch_tokens = crop_dim // 14 * crop_dim // 14
+        self.num_tokens = self.num_global_tokens + self.num_patch_tokens
+        self.backbone_type = "DINO"
+        self.viecap = self.clipcap = None
+        self.calculate_argmax_text = False
+
+        # --- backbone (model.py:342-343 loads it from torch.hub; here: a state dict with the hub's key names)
+        if isinstance(dino_weights, str):
+            dino_weights = torch.load(dino_weights, map_location="cpu", weights_only=False)
+        if dino_weights is None:
+            raise ValueError("dino_weights (state dict or path) is required: torch.hub needs the network")
+        self.dino = ops.Vit(dino_weights, self.device, precision)
+
+        # --- decoder (model.py:165-166 -> decap.py:188-222)
+        if isinstance(decoder_weights, str):
+            decoder_weights = torch.load(decoder_weights, map_location="cpu", weights_only=False)
+        if decoder_weights is None:
+            raise ValueError("decap_weights is required")
+        self.decoder = ops.Decoder(decoder_weights, self.device, precision)
+        if self.decoder.prefix_size != prefix_size:
+            raise ValueError(f"prefix_size {prefix_size} != clip_project input {self.decoder.prefix_size}")
+
+        # --- caption memory (model.py:144-186).  support_memory_size == 0 -> CapDec, no bank.
+        self.im_proj = None
+        if support_memory_size > 0:
+            bank = memory_bank
+            if bank is None and isinstance(projection_type, str) and os.path.exists(projection_type):
+                bank = projection_type
+            if isinstance(bank, str):
+                bank = _load_tensor_file(bank)
+            if bank is None:
+                raise ValueError("support_memory_size > 0 needs memory_bank (tensor or file); building banks from "
+                                 "captions needs CLIP text encoders + network (out of scope)")
+            self.im_proj = ops.Bank(bank, self.device, precision)
+
+        # --- Talk2DINO inversion (model.py:618-627)
+        self.embed_inversion = False
+        if talk2dino_weights is not None:
+            from .talk2dino import pseudo_inverse
+
+            sd = torch.load(talk2dino_weights, map_location="cpu", weights_only=False) if isinstance(talk2dino_weights, str) else talk2dino_weights
+            A = sd["linear_layer.weight"].float()
+            b = sd["linear_layer.bias"].float()
+            A_pinv = pseudo_inverse(A)                      # init-time SVD on the host (embedding_utils.py:3-15)
+            self.talk2dino_A_pinv = A_pinv.to(self.device).contiguous()          # [512, 768]
+            self.talk2dino_b = b.to(self.device)
+            # (x - b) @ A_pinv^T  ==  x @ A_pinv^T - A_pinv b   -> one dense layer with a folded bias
+            self._inv_bias = (-(A_pinv @ b)).to(self.device).contiguous()
+            self._inv_w = self.talk2dino_A_pinv.to(torch.bfloat16) if precision == "bf16" else self.talk2dino_A_pinv
+            self.embed_inversion = True
+
+        self._transforms = None
+
+    # ------------------------------------------------------------------------------------------ config
+    @classmethod
+    def from_config(cls, config, device="cuda", online_texts=None, **overrides):
+        """model.py:666-715: ``config`` is a dict or a YAML path with the reference's keys."""
+        if isinstance(config, str):
+            if not os.path.exists(config):
+                raise FileNotFoundError(f"{config}: HuggingFace repo ids need the network (hf_utils.py) -- not available")
+            import yaml
+
+            with open(config, "r") as f:
+                config = yaml.safe_load(f)
+        config = dict(config)
+        config.update(overrides)
+        return cls(
+            projection_type=config.get("projection_type", "coco"),
+            decoder_weights=config.get("decap_weights", None),
+            device=device,
+            prefix_size=config["prefix_size"],
+            linear_talk2dino=config.get("linear_talk2dino", False),
+            support_memory_size=config["support_memory_size"],
+            dino_model=config.get("dino_model", None),
+            proxyclip_clipmodel=config.get("proxyclip_clipmodel", None),
+            proxyclip_vfm=config.get("proxyclip_vfm", None),
+            use_talk2dino_project=config.get("use_talk2dino_project", True),
+            normalize=config.get("normalize", True),
+            attention_type=config.get("attention_type", "qkv"),
+            talk2dino_config=config.get("talk2dino_config", None),
+            talk2dino_weights=config.get("talk2dino_weights", None),
+            resize_dim=config.get("resize_dim", 518),
+            crop_dim=config.get("crop_dim", 518),
+            talk2dino_attn_type=config.get("talk2dino_attn_type", "qkv"),
+            calculate_argmax_text=config.get("calculate_argmax_text", False),
+            clip_model_name=config.get("clip_model_name", None),
+            online_texts=online_texts,
+            use_open_clip=config.get("use_open_clip", False),
+            viecap_config=config.get("viecap", None),
+            regionclip_config=config.get("regionclip_config", None),
+            invite_config=config.get("invite_config", None),
+            denseclip_config=config.get("denseclip_config", None),
+            alphaclip_config=config.get("alphaclip_config", None),
+            clipcap_config=config.get("clipcap", None),
+            hf_repo_id=config.get("hf_repo_id", None),
+            dino_weights=config.get("dino_weights", None),
+            memory_bank=config.get("memory_bank", None),
+            precision=config.get("precision", "fp32"),
+        )
+
+    # image transforms the eval drivers read (model.py:347-357); built lazily (torchvision is host-side only)
+    def _build_transforms(self):
+        import torchvision.transforms as T
+
+        norm = T.Normalize(mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225))
+        self._transforms = (
+            T.Compose([T.Resize(self.resize_dim, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(self.crop_dim),
+                       T.ToTensor(), norm]),
+            T.Compose([T.Resize((self.resize_dim, self.resize_dim), interpolation=T.InterpolationMode.BICUBIC),
+                       T.ToTensor(), norm]))
+
+    @property
+    def image_transforms(self):
+        if self._transforms is None:
+            self._build_transforms()
+        return self._transforms[0]
+
+    @property
+    def image_transforms_no_crop(self):
+        if self._transforms is None:
+            self._build_transforms()
+        return self._transforms[1]
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        if torch.device(device) != self.device and torch.device(device).type != self.device.type:
+            raise L.PioError("weights live in library-owned memory on the construction device")
+        return self
+
+    def parameters(self):
+        yield torch.empty(0, device=self.device)
+
+    # ------------------------------------------------------------------------------------------ text side
+    def embed_tokens(self, dino_tokens: torch.Tensor, project: bool = True) -> torch.Tensor:
+        """model.py:1406-1422 up to the decoder input: memory projection iff a bank exists, optional inversion."""
+        x = dino_tokens
+        if self.im_proj is not None and project:
+            x = self.im_proj.project(x, normalize=self.normalize)
+        if self.embed_inversion:
+            a = x.to(torch.bfloat16) if self.precision == "bf16" else x.float().contiguous()
+            x = ops.linear(a, self._inv_w, self.precision, bias=self._inv_bias)
+        return x
+
+    def caption_token_ids(self, dino_tokens: torch.Tensor, project: bool = True, compute_scores: bool = False):
+        """ids int32 [R,30] on the device (+ scores).  Chunked only to bound the decoder workspace."""
+        feats = dino_tokens.reshape(-1, dino_tokens.shape[-1])
+        ids, scores = [], []
+        chunk = 8192
+        for s in range(0, max(feats.shape[0], 1), chunk):
+            f = feats[s:s + chunk]
+            if f.shape[0] == 0:
+                break
+            pre = self.embed_tokens(f, project)
+            r = self.decoder.decode(pre, 30, compute_scores)
+            if compute_scores:
+                ids.append(r[0])
+                scores.append(torch.exp(r[1]))  # decap.py:159-160
+            else:
+                ids.append(r)
+        ids = torch.cat(ids, 0) if ids else torch.empty(0, 30, dtype=torch.int32, device=self.device)
+        return (ids, torch.cat(scores, 0)) if compute_scores else ids
+
+    def _ids_to_text(self, ids: torch.Tensor) -> List[str]:
+        """decap.py:162-181: detokenise (``decoding_method`` hook or CLIP-BPE), cut at <|endoftext|>."""
+        rows = ids.cpu().tolist()  # the one device->host read of a caption batch
+        fn = self.decoding_method or default_detokenizer()
+        outs = []
+        for r in rows:
+            s = fn(r)
+            s = s.split(EOT)[0].replace(SOT, "")
+            outs.append(s)
+        return outs
+
+    def caption_tokens(self, dino_tokens, project=True, return_n_best_sims=None, compute_scores: bool = False):
+        """model.py:1392-1423."""
+        if return_n_best_sims:
+            raise NotImplementedError("return_n_best_sims (im2txtprojection.py:382-383) is a 'next' row (SURVEY.md 8f.4)")
+        r = self.caption_token_ids(dino_tokens, project, compute_scores)
+        if compute_scores:
+            return self._ids_to_text(r[0]), r[1].cpu().tolist()
+        return self._ids_to_text(r)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def region_embeddings(self, imgs, bboxes=None, traces=None, masks=None, get_controllable_capts=False, gaussian_avg=False,
+                          gaussian_bbox_variance=0.5, use_attn_map_for_bboxes=False, use_attention_tracing=False):
+        """ViT + pooling only: dict of region embeddings on the device (what ``forward`` captions)."""
+        tokens, attn, _ = self.dino.forward(imgs, want_attn=True)
+        patch = tokens[:, self.num_global_tokens:]
+        out: Dict[str, torch.Tensor] = {"cls": tokens[:, 0], "registers": tokens[:, 1:5], "patch": patch, "self_attn": attn}
+        bs, P, _ = patch.shape
+        g = int(P ** 0.5)
+        if bboxes is not None:
+            amap = attn if use_attn_map_for_bboxes else None
+            out["set" if get_controllable_capts else "bbox"] = ops.pool_boxes(
+                patch, bboxes, self.patch_size, gaussian_avg, gaussian_bbox_variance, amap,
+                get_single_embedding_per_image=get_controllable_capts)
+        if traces is not None:
+            w = ops.trace_bins(traces, g, patch.device, attn if use_attention_tracing else None)
+            out["trace"] = ops.pool_grid(patch, w.reshape(bs, 1, P), 1.0 / P)[:, 0]       # model.py:1054 (.mean over g*g)
+        if masks is not None:
+            m = masks.to(patch.device, torch.float32)
+            out["mask"] = ops.pool_grid(patch, m.reshape(bs, -1, P), 1.0 / P)
+        return out
+
+    @torch.no_grad()
+    def forward(self, imgs, get_cls_capt=True, get_avg_self_attn_capt=False, get_attn_heads_capt=False, get_patch_capts=False,
+                get_register_capts=False, bboxes=None, traces=None, get_controllable_capts=False, bs_factor=4,
+                gaussian_avg=False, gaussian_bbox_variance=0.5, get_avg_patch_capt=False, gaussian_img_variance=1,
+                use_attn_map_for_bboxes=False, use_attention_tracing=False, double_DINO_for_bboxes=False,
+                double_DINO_for_bboxes_return_type="avg", double_DINO_use_cls=False, cleaning_type=None,
+                clean_after_projection=True, alpha=1.0, clean_from="cls", caption_bboxes_type: str = None,
+                return_n_best_sims=None, compute_scores: bool = False, masks=None, return_ids: bool = False):
+        """Same keywords and output keys as the reference (model.py:718-1058).  Extensions: ``masks`` [B,R,g,g]
+         -> ``mask_capts``; ``return_ids=True`` returns int32 id tensors instead of strings."""
+        assert clean_from in ["cls", "avg_self_attn"]
+        assert cleaning_type in [None, "orthogonal_projection", "contrastive_mask"]
+        if double_DINO_for_bboxes or cleaning_type is not None or caption_bboxes_type is not None or get_attn_heads_capt:
+            raise NotImplementedError("double_DINO / cleaning_type / caption_bboxes_type / get_attn_heads_capt are "
+                                      "'next' rows (SURVEY.md 8f.4), not built in this round")
+        if return_n_best_sims is not None:
+            raise NotImplementedError("return_n_best_sims is a 'next' row (SURVEY.md 8f.4)")
+        imgs = imgs.to(self.device, non_blocking=True)
+        outs: Dict[str, object] = {}
+        bs = imgs.shape[0]
+        tokens, self_attn, _ = self.dino.forward(imgs, want_attn=True)
+        cls, reg, patch = tokens[:, 0], tokens[:, 1:5], tokens[:, 5:]
+        P, D = patch.shape[1], patch.shape[2]
+        g = int(P ** 0.5)
+
+        def emit(key, feats, group=None):
+            r = self.caption_token_ids(feats, compute_scores=compute_scores)
+            ids, sc = (r if compute_scores else (r, None))
+            vals = ids if return_ids else self._ids_to_text(ids)
+            if group is not None:
+                vals = ids.reshape(bs, group, -1) if return_ids else [vals[i * group:(i + 1) * group] for i in range(bs)]
+            outs[key] = vals
+            if compute_scores:
+                s = sc.cpu().tolist()
+                skey = {"bbox_capts": "bbox_scores", "patch_tokens_capts": "patch_tokens_scores",
+                        "register_capts": "register_scores"}.get(key, key + "_scores")
+                outs[skey] = s if group is None else [s[i * group:(i + 1) * group] for i in range(bs)]
+
+        if get_cls_capt:
+            emit("cls_capt", cls)
+        if get_avg_self_attn_capt:  # model.py:869
+            emit("avg_self_attn_capt", ops.pool_grid(patch, self_attn.reshape(bs, 1, P), 1.0 / P)[:, 0])
+        if get_avg_patch_capt:      # model.py:45-94
+            w = ops.region_mean_weights(g, gaussian_img_variance, patch.device)
+            emit("avg_patch_capt", ops.pool_grid(patch, w.reshape(1, 1, P).expand(bs, 1, P), 1.0)[:, 0])
+        if get_patch_capts:
+            emit("patch_tokens_capts", patch.reshape(-1, D), group=P)
+        if get_register_capts:
+            emit("register_capts", reg.reshape(-1, D), group=4)
+        if bboxes is not None and not get_controllable_capts:
+            amap = self_attn if use_attn_map_for_bboxes else None
+            feats = ops.pool_boxes(patch, bboxes, self.patch_size, gaussian_avg, gaussian_bbox_variance, amap)
+            emit("bbox_capts", feats.reshape(-1, D), group=bboxes.shape[1])
+        elif bboxes is not None and get_controllable_capts:
+            amap = self_attn if use_attn_map_for_bboxes else None
+            feats = ops.pool_boxes(patch, bboxes, self.patch_size, gaussian_avg, gaussian_bbox_variance, amap,
+                                   get_single_embedding_per_image=True)
+            emit("set_controllable_capts", feats)
+        if traces is not None:
+            w = ops.trace_bins(traces, g, patch.device, self_attn if use_attention_tracing else None)
+            emit("trace_capts", ops.pool_grid(patch, w.reshape(bs, 1, P), 1.0 / P)[:, 0])
+        if masks is not None:
+            m = masks.to(patch.device, torch.float32).reshape(bs, -1, P)
+            emit("mask_capts", ops.pool_grid(patch, m, 1.0 / P).reshape(-1, D), group=m.shape[1])
+        return outs
+
+    __call__ = forward

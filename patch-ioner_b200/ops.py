@@ -1,0 +1,371 @@
+"""Thin torch-tensor wrappers over the C ABI.  torch is plumbing here: device memory, streams."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib as L
+
+MODES = {"fp32": L.PIO_FP32, "bf16": L.PIO_BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.PioError("libpio_sm100 works on CUDA tensors only (there is no CPU fallback)")
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return L.DT_F32
+    if t.dtype == torch.bfloat16:
+        return L.DT_BF16
+    raise L.PioError(f"unsupported dtype {t.dtype}")
+
+
+_ws_cache: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def workspace(nbytes: int, device, tag: str = "") -> torch.Tensor:
+    """A cached, 1024-byte aligned scratch buffer per (device, tag); grows monotonically."""
+    key = (torch.device(device).index or 0, tag)
+    buf = _ws_cache.get(key)
+    need = nbytes + 1024
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    off = (-buf.data_ptr()) % 1024
+    return buf[off:off + nbytes]
+
+
+def launch_count() -> int:
+    return int(L.lib().pio_launch_count())
+
+
+def reset_launch_count() -> None:
+    L.lib().pio_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------ dense layer
+def linear(A: torch.Tensor, W: torch.Tensor, mode: str = "fp32", bias=None, act: int = L.ACT_NONE, gamma=None,
+           residual=None, out: Optional[torch.Tensor] = None, out_dtype=None, alpha: float = 1.0, colscale=None,
+           res_rowscale=None) -> torch.Tensor:
+    """out = residual * res_rowscale[:,None] + gamma * act(alpha * colscale * (A @ W.T) + bias)."""
+    _need_cuda(A, W)
+    assert A.dim() == 2 and W.dim() == 2 and A.shape[1] == W.shape[1]
+    assert A.stride(1) == 1 and W.stride(1) == 1
+    M, K = A.shape
+    N = W.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype or torch.float32, device=A.device)
+    p = L.PioLinear()
+    p.A, p.W, p.C = A.data_ptr(), W.data_ptr(), out.data_ptr()
+    p.M, p.N, p.K = M, N, K
+    p.lda, p.ldw, p.ldc = A.stride(0), W.stride(0), out.stride(0)
+    p.a_dt, p.c_dt = _dt(A), _dt(out)
+    p.bias, p.colscale, p.gamma = _ptr(bias), _ptr(colscale), _ptr(gamma)
+    p.residual, p.res_rowscale = _ptr(residual), _ptr(res_rowscale)
+    p.ldres = residual.stride(0) if residual is not None else 0
+    p.alpha, p.act = alpha, act
+    L.check(L.lib().pio_linear(C.byref(p), MODES[mode], _stream()))
+    return out
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out_dtype=torch.float32) -> torch.Tensor:
+    _need_cuda(x, w, b)
+    rows, dim = x.shape
+    out = torch.empty(rows, dim, dtype=out_dtype, device=x.device)
+    L.check(L.lib().pio_layernorm(x.data_ptr(), x.stride(0), w.data_ptr(), b.data_ptr(), out.data_ptr(), _dt(out),
+                                  out.stride(0), rows, dim, eps, _stream()))
+    return out
+
+
+def l2_normalize_(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    assert x.is_contiguous() and x.dtype == torch.float32
+    L.check(L.lib().pio_l2_normalize(x.data_ptr(), x.shape[0], x.shape[1], _stream()))
+    return x
+
+
+# ------------------------------------------------------------------------------------------ ViT
+def interpolate_pos_embed(pos_embed: torch.Tensor, grid: int) -> torch.Tensor:
+    """DINOv2 ``interpolate_pos_encoding`` (offset 0.0): size-based bicubic, antialias, fp32; done once per
+    grid on the host side of the boundary (init-time, cached) -- SURVEY.md section 7 'hard parts'."""
+    pe = pos_embed.float().reshape(1, -1, pos_embed.shape[-1])
+    n = pe.shape[1] - 1
+    if grid * grid == n:
+        return pe[0].contiguous()
+    m = int(math.sqrt(n))
+    patch = pe[:, 1:].reshape(1, m, m, -1).permute(0, 3, 1, 2)
+    patch = F.interpolate(patch.cpu(), size=(grid, grid), mode="bicubic", antialias=True, align_corners=False)
+    patch = patch.permute(0, 2, 3, 1).reshape(1, grid * grid, -1).to(pe.device)
+    return torch.cat([pe[:, :1], patch], dim=1)[0].contiguous()
+
+
+class Vit:
+    """DINOv2 ViT-B/14-reg4 on the device; weights by torch.hub state-dict key names."""
+
+    D, NG, PATCH = 768, 5, 14
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, mode: str = "fp32"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.PioError("the ViT engine needs a CUDA device (there is no CPU fallback)")
+        self.mode = mode
+        sd = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items()}
+        self._keep = sd
+        w = L.PioVitWeights()
+        w.cls_token = sd["cls_token"].data_ptr()
+        w.register_tokens = sd["register_tokens"].data_ptr()
+        self._patch_w = sd["patch_embed.proj.weight"].reshape(768, -1).contiguous()
+        w.patch_w = self._patch_w.data_ptr()
+        w.patch_b = sd["patch_embed.proj.bias"].data_ptr()
+        names = {"ln1_w": "norm1.weight", "ln1_b": "norm1.bias", "qkv_w": "attn.qkv.weight", "qkv_b": "attn.qkv.bias",
+                 "proj_w": "attn.proj.weight", "proj_b": "attn.proj.bias", "ls1": "ls1.gamma", "ln2_w": "norm2.weight",
+                 "ln2_b": "norm2.bias", "fc1_w": "mlp.fc1.weight", "fc1_b": "mlp.fc1.bias", "fc2_w": "mlp.fc2.weight",
+                 "fc2_b": "mlp.fc2.bias", "ls2": "ls2.gamma"}
+        for i in range(12):
+            for f, n in names.items():
+                setattr(w.blk[i], f, sd[f"blocks.{i}.{n}"].data_ptr())
+        w.norm_w, w.norm_b = sd["norm.weight"].data_ptr(), sd["norm.bias"].data_ptr()
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().pio_vit_create(C.byref(h), C.byref(w), MODES[mode], _stream()))
+            torch.cuda.current_stream().synchronize()
+        self._h = h
+        self._pos_src = sd["pos_embed"]
+        self._pos: Dict[int, torch.Tensor] = {}
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            L.lib().pio_vit_destroy(h)
+            self._h = None
+
+    def pos_embed(self, grid: int) -> torch.Tensor:
+        if grid not in self._pos:
+            self._pos[grid] = interpolate_pos_embed(self._pos_src, grid)
+        return self._pos[grid]
+
+    def forward(self, imgs: torch.Tensor, want_attn: bool = True, want_qkv: bool = False):
+        """imgs fp32 [B,3,S,S] -> (tokens [B,N,768] = final LN of [cls | 4 reg | patches], attn [B,P] | None, qkv | None)."""
+        _need_cuda(imgs)
+        imgs = imgs.contiguous().float()
+        B, _, S, S2 = imgs.shape
+        assert S == S2, "square crops only (the reference center-crops / resizes to crop_dim x crop_dim)"
+        g = S // self.PATCH
+        N = self.NG + g * g
+        tokens = torch.empty(B, N, self.D, dtype=torch.float32, device=imgs.device)
+        attn = torch.empty(B, g * g, dtype=torch.float32, device=imgs.device) if want_attn else None
+        qkv = torch.empty(B, N, 3 * self.D, dtype=torch.float32, device=imgs.device) if want_qkv else None
+        nbytes = L.lib().pio_vit_workspace_bytes(self._h, B, S)
+        ws = workspace(nbytes, imgs.device, "vit")
+        L.check(L.lib().pio_vit_forward(self._h, imgs.data_ptr(), B, S, self.pos_embed(g).data_ptr(), tokens.data_ptr(),
+                                        _ptr(attn), _ptr(qkv), ws.data_ptr(), nbytes, _stream()))
+        return tokens, attn, qkv
+
+
+def cls_attention(qkv: torch.Tensor, num_global: int = 5) -> torch.Tensor:
+    _need_cuda(qkv)
+    B, N, C3 = qkv.shape
+    out = torch.empty(B, N - num_global, dtype=torch.float32, device=qkv.device)
+    L.check(L.lib().pio_cls_attention(qkv.contiguous().data_ptr(), _dt(qkv), B, N, C3 // 3, num_global, out.data_ptr(), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ pooling
+def _token_view(patch_tokens: torch.Tensor):
+    """patch tokens [B,P,D] (possibly a view into [B,N,D]) -> (ptr, img_stride, row_stride)."""
+    assert patch_tokens.dtype == torch.float32 and patch_tokens.stride(2) == 1
+    return patch_tokens.data_ptr(), patch_tokens.stride(0), patch_tokens.stride(1)
+
+
+def pool_boxes(patch_tokens: torch.Tensor, bboxes: torch.Tensor, patch_size: int = 14, gaussian_avg: bool = False,
+               gaussian_bbox_variance: float = 0.5, attention_map: Optional[torch.Tensor] = None,
+               get_single_embedding_per_image: bool = False, return_bounds: bool = False):
+    """extract_bboxes_feats (bbox_utils.py:8-109) on the device.  ``bboxes`` is not modified."""
+    _need_cuda(patch_tokens)
+    B, P, D = patch_tokens.shape
+    g = int(P ** 0.5)
+    R = bboxes.shape[1]
+    if bboxes.dtype.is_floating_point:
+        bx, bdt = bboxes.to(patch_tokens.device, torch.float32).contiguous(), L.DT_F32
+    else:
+        bx, bdt = bboxes.to(patch_tokens.device, torch.int32).contiguous(), L.DT_I32
+    mode = L.POOL_ATTN if attention_map is not None else (L.POOL_GAUSS if gaussian_avg else L.POOL_MEAN)
+    amap = attention_map.to(patch_tokens.device, torch.float32).contiguous() if attention_map is not None else None
+    out = torch.empty((B, D) if get_single_embedding_per_image else (B, R, D), dtype=torch.float32, device=patch_tokens.device)
+    bounds = torch.empty(B, R, 4, dtype=torch.int32, device=patch_tokens.device) if return_bounds else None
+    nbytes = L.lib().pio_pool_workspace_bytes(B, R, g)
+    ws = workspace(nbytes, patch_tokens.device, "pool")
+    ptr, istr, rstr = _token_view(patch_tokens)
+    L.check(L.lib().pio_pool_boxes(ptr, istr, rstr, B, g, D, bx.data_ptr(), bdt, R, patch_size, mode,
+                                   float(gaussian_bbox_variance), _ptr(amap), int(get_single_embedding_per_image),
+                                   out.data_ptr(), _ptr(bounds), ws.data_ptr(), nbytes, _stream()))
+    return (out, bounds) if return_bounds else out
+
+
+def pool_grid(patch_tokens: torch.Tensor, weights: torch.Tensor, scale: float) -> torch.Tensor:
+    """out[b,r] = scale * sum_p weights[b,r,p] * x[b,p]   (traces, masks, avg_self_attn, whole-image means)."""
+    _need_cuda(patch_tokens, weights)
+    B, P, D = patch_tokens.shape
+    g = int(P ** 0.5)
+    w = weights.reshape(B, -1, P).float().contiguous()
+    R = w.shape[1]
+    out = torch.empty(B, R, D, dtype=torch.float32, device=patch_tokens.device)
+    ptr, istr, rstr = _token_view(patch_tokens)
+    L.check(L.lib().pio_pool_grid(ptr, istr, rstr, B, g, D, w.data_ptr(), R, float(scale), out.data_ptr(), _stream()))
+    return out
+
+
+def pack_traces(traces: Sequence[Sequence[dict]]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """list (per image) of lists of {'x','y','t'} dicts -> pinned (points float64 [n,2], offsets int32 [T+1])."""
+    offs = [0]
+    flat: List[float] = []
+    for tr in traces:
+        for p in tr:
+            flat.append(float(p["x"]))
+            flat.append(float(p["y"]))
+        offs.append(len(flat) // 2)
+    pts = torch.tensor(flat, dtype=torch.float64).reshape(-1, 2)
+    off = torch.tensor(offs, dtype=torch.int32)
+    if torch.cuda.is_available():
+        pts, off = pts.pin_memory(), off.pin_memory()
+    return pts, off
+
+
+def trace_bins(traces, grid: int, device, attn: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """map_traces_to_grid (bbox_utils.py:158-168) for a batch of traces -> counts fp32 [T,grid,grid] (x attn)."""
+    pts, off = traces if isinstance(traces, tuple) else pack_traces(traces)
+    T = off.numel() - 1
+    pts_d = pts.to(device, non_blocking=True)
+    off_d = off.to(device, non_blocking=True)
+    if pts_d.numel() == 0:
+        pts_d = torch.zeros(1, 2, dtype=torch.float64, device=device)
+    counts = torch.empty(T, grid, grid, dtype=torch.float32, device=device)
+    a = attn.contiguous() if attn is not None else None
+    L.check(L.lib().pio_trace_bins(pts_d.data_ptr(), off_d.data_ptr(), T, grid, _ptr(a), counts.data_ptr(), _stream()))
+    return counts
+
+
+def region_mean_weights(grid: int, variance: float, device) -> torch.Tensor:
+    w = torch.empty(grid * grid, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        L.check(L.lib().pio_region_mean_weights(grid, float(variance), w.data_ptr(), _stream()))
+    return w
+
+
+# ------------------------------------------------------------------------------------------ memory bank
+class Bank:
+    """Caption memory on the device (zero rows are dropped like im2txtprojection.py:345)."""
+
+    def __init__(self, bank: torch.Tensor, device, mode: str = "fp32"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.PioError("the memory bank needs a CUDA device (there is no CPU fallback)")
+        self.mode = mode
+        bank = bank.detach().to(torch.float32)
+        bank = bank[bank.norm(dim=-1) != 0]
+        b = bank.to(self.device).contiguous()
+        self.M, self.D = b.shape
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().pio_bank_create(C.byref(h), b.data_ptr(), self.M, self.D, MODES[mode], _stream()))
+            torch.cuda.current_stream().synchronize()
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            L.lib().pio_bank_destroy(h)
+            self._h = None
+
+    def project(self, q: torch.Tensor, temperature: float = 0.01, normalize: bool = False, partial: bool = False):
+        """Im2TxtProjector.project (im2txtprojection.py:353-385).  ``q`` is not modified.
+        partial=True returns the un-normalised shard partial (m [R], l [R], O [R,D])."""
+        _need_cuda(q)
+        q = q.float().contiguous()
+        R = q.shape[0]
+        out = torch.empty(R, self.D, dtype=torch.float32, device=q.device)
+        m = torch.empty(R, dtype=torch.float32, device=q.device) if partial else None
+        l = torch.empty(R, dtype=torch.float32, device=q.device) if partial else None
+        nbytes = L.lib().pio_project_workspace_bytes(self._h, R)
+        ws = workspace(nbytes, q.device, "project")
+        L.check(L.lib().pio_project(self._h, q.data_ptr(), R, float(temperature), int(normalize), out.data_ptr(), _ptr(m),
+                                    _ptr(l), ws.data_ptr(), nbytes, _stream()))
+        return (m, l, out) if partial else out
+
+
+def project_rescale_(O, l, m_local, m_global):
+    L.check(L.lib().pio_project_rescale(O.data_ptr(), l.data_ptr(), m_local.data_ptr(), m_global.data_ptr(), O.shape[0],
+                                        O.shape[1], _stream()))
+
+
+def project_finish_(O, l, normalize: bool):
+    L.check(L.lib().pio_project_finish(O.data_ptr(), l.data_ptr(), O.shape[0], O.shape[1], int(normalize), _stream()))
+    return O
+
+
+# ------------------------------------------------------------------------------------------ decoder
+class Decoder:
+    """DeCap prefix decoder (GPT-2 4x4x768 + Linear prefix); weights by the reference's state-dict key names."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, mode: str = "fp32"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.PioError("the decoder needs a CUDA device (there is no CPU fallback)")
+        self.mode = mode
+        T = "decoder.transformer."
+        sd = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items()
+              if k.startswith(T) or k.startswith("clip_project.")}
+        self._keep = sd
+        w = L.PioDecoderWeights()
+        w.wte, w.wpe = sd[T + "wte.weight"].data_ptr(), sd[T + "wpe.weight"].data_ptr()
+        names = {"ln1_w": "ln_1.weight", "ln1_b": "ln_1.bias", "attn_w": "attn.c_attn.weight", "attn_b": "attn.c_attn.bias",
+                 "proj_w": "attn.c_proj.weight", "proj_b": "attn.c_proj.bias", "ln2_w": "ln_2.weight", "ln2_b": "ln_2.bias",
+                 "fc_w": "mlp.c_fc.weight", "fc_b": "mlp.c_fc.bias", "fc2_w": "mlp.c_proj.weight", "fc2_b": "mlp.c_proj.bias"}
+        for i in range(4):
+            for f, n in names.items():
+                setattr(w.blk[i], f, sd[f"{T}h.{i}.{n}"].data_ptr())
+        w.lnf_w, w.lnf_b = sd[T + "ln_f.weight"].data_ptr(), sd[T + "ln_f.bias"].data_ptr()
+        w.prefix_w = sd["clip_project.model.0.weight"].data_ptr()
+        w.prefix_b = sd["clip_project.model.0.bias"].data_ptr()
+        self.prefix_size = w.prefix_size = sd["clip_project.model.0.weight"].shape[1]
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().pio_decoder_create(C.byref(h), C.byref(w), MODES[mode], _stream()))
+            torch.cuda.current_stream().synchronize()
+        self._h = h
+        self._keep = None  # the library owns repacked copies
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            L.lib().pio_decoder_destroy(h)
+            self._h = None
+
+    def decode(self, prefix: torch.Tensor, steps: int = 30, compute_scores: bool = False):
+        """decoding_batched (decap.py:116-160) up to the ids: int32 [R,steps] (+ sum of log-probs [R])."""
+        _need_cuda(prefix)
+        prefix = prefix.float().contiguous()
+        R = prefix.shape[0]
+        assert prefix.shape[1] == self.prefix_size
+        ids = torch.empty(R, steps, dtype=torch.int32, device=prefix.device)
+        lp = torch.empty(R, dtype=torch.float32, device=prefix.device) if compute_scores else None
+        nbytes = L.lib().pio_decode_workspace_bytes(self._h, R, steps)
+        ws = workspace(nbytes, prefix.device, "decode")
+        L.check(L.lib().pio_decode_greedy(self._h, prefix.data_ptr(), R, steps, ids.data_ptr(), _ptr(lp), ws.data_ptr(),
+                                          nbytes, _stream()))
+        return (ids, lp) if compute_scores else ids

@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/pio.h declares; host logic."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+
+    ge.build()
+    from patchioner_b200 import _lib
+
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "pio.h")).read()
+    declared = set(re.findall(r"\b(pio_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in pio.h but not exported"
+    assert declared == set(built.SIGNATURES), declared ^ set(built.SIGNATURES)
+
+
+def test_library_loads_without_gpu_and_reports_version(built):
+    L = built.lib()
+    assert L.pio_version() >= 100
+    L.pio_reset_launch_count()
+    assert L.pio_launch_count() == 0
+
+
+def test_struct_layouts_match_header(built):
+    # pointers + ints as declared in pio.h (x86-64): PioLinear = 3 ptr + 8 int + 5 ptr + int + float + int + 3 int
+    assert ctypes.sizeof(built.PioVitBlock) == 14 * 8
+    assert ctypes.sizeof(built.PioVitWeights) == (4 + 12 * 14 + 2) * 8
+    assert ctypes.sizeof(built.PioGptBlock) == 12 * 8
+    assert ctypes.sizeof(built.PioDecoderWeights) == (2 + 4 * 12 + 2 + 2) * 8 + 8
+    assert ctypes.sizeof(built.PioLinear) == 24 + 32 + 40 + 4 + 4 + 4 + 12
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")
+def test_product_path_fails_loudly_without_gpu(built):
+    from patchioner_b200 import Patchioner, PioError, ops
+
+    with pytest.raises(PioError):
+        Patchioner.from_config({"prefix_size": 768, "support_memory_size": 0, "dino_model": "dinov2_vitb14_reg",
+                                "decap_weights": {}, "dino_weights": {}}, device="cpu")
+    with pytest.raises(PioError):
+        ops.linear(torch.zeros(4, 4), torch.zeros(4, 4))
+    with pytest.raises(PioError):
+        ops.Bank(torch.randn(10, 768), "cpu")
+
+
+def test_unsupported_backbones_raise(built):
+    from patchioner_b200 import Patchioner
+
+    with pytest.raises(NotImplementedError):
+        Patchioner.from_config({"prefix_size": 768, "support_memory_size": 0, "dino_model": "dinov2_vitb14_reg",
+                                "viecap": {"x": 1}}, device="cuda")
+    with pytest.raises(NotImplementedError):
+        Patchioner.from_config({"prefix_size": 768, "support_memory_size": 0, "dino_model": "dinov2_vitl14"}, device="cuda")
+
+
+def test_pack_traces_and_pos_embed_host_logic(built):
+    from oracle import dinov2 as o_vit
+    from patchioner_b200 import ops
+
+    pts, off = ops.pack_traces([[{"x": 0.1, "y": 0.2, "t": 0}], [], [{"x": 1, "y": 0, "t": 1}, {"x": 0.5, "y": 0.25, "t": 2}]])
+    assert off.tolist() == [0, 1, 1, 3] and pts.dtype == torch.float64 and pts.shape == (3, 2)
+    pe = torch.randn(1, 1 + 37 * 37, 768, generator=torch.Generator().manual_seed(0))
+    for g in (16, 37):
+        assert torch.equal(ops.interpolate_pos_embed(pe, g), o_vit.interpolate_pos_embed(pe, g)[0])
+
+
+def test_detokenizer_hook():
+    from patchioner_b200.detok import _id_renderer
+
+    assert _id_renderer([5, 49407, 7]).split("<|endoftext|>")[0].strip() == "5"
