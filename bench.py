@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- region captions / second of the patch -> region -> caption hot path on B200.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                    # our arm (libpio_sm100, CUDA)
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1   # the reference's CPU algorithm on the host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                        # one rank per GPU, images sharded, no collective
+
+A *step* is one pass of the hot path over one batch of synthetic input of BASELINE.json configs[1]
+("talk2dino_decap dense captioning: 518px images, 64 synthetic bboxes/image, batch 64"): DINOv2 ViT-B/14-reg
+forward -> CLS attention map -> box pooling -> caption-memory projection (M = 591 753) -> 30-step greedy decode,
+4096 region captions per GPU per step.  Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "region captions/sec"
+UNIT = "captions/s"
+BANK_ROWS = 591_753  # configs/mlp.k.yaml: support_memory_size
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--boxes", type=int, default=64)
+    ap.add_argument("--size", type=int, default=518)
+    ap.add_argument("--bank-rows", type=int, default=BANK_ROWS)
+    ap.add_argument("--pool", default="gauss", choices=["mean", "gauss", "attn"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-images", type=int, default=1)
+    ap.add_argument("--cpu-sample-boxes", type=int, default=8)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+def cpu_sample(args, steps: int, warmup: int):
+    """The reference's own algorithm (oracle port: no KV cache, bank re-normalised per call, Python box loop) on the
+    host cores, on a bounded sample of the same workload.  Returns (captions/s, seconds per step, description)."""
+    from oracle import decap as o_decap
+    from oracle import dinov2 as o_vit
+    from oracle import pipeline as o_pipe
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    B, R, S = args.cpu_sample_images, args.cpu_sample_boxes, args.size
+    vit_w, dec_w = o_vit.make_weights(1234), o_decap.make_weights(1234)
+    bank = o_pipe.synth_bank(args.bank_rows, 768, seed=7)
+    model = o_pipe.OracleModel(vit_w, dec_w, bank)
+    kw = dict(gaussian_avg=args.pool == "gauss", gaussian_bbox_variance=1.0, use_attn_map_for_bboxes=args.pool == "attn")
+    times = []
+    for i in range(warmup + steps):
+        imgs = o_pipe.synth_images(B, S, seed=100 + i)
+        boxes = o_pipe.synth_boxes(B, R, S, seed=100 + i, pad="dense")
+        t0 = time.perf_counter()
+        model.forward(imgs, get_cls_capt=False, bboxes=boxes, use_cache=False, **kw)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    sample = (f"{B} x {S}px image(s), {R} boxes each = {B * R} regions/step, bank M={args.bank_rows}, fp32, reference algorithm "
+              f"(no KV cache, 30 steps), {len(times)} timed step(s) after {warmup} warm-up")
+    return B * R / sec, sec, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, sec, sample = cpu_sample(args, max(1, args.steps), max(0, args.warmup))
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, per_step_note="each step is a bounded sample of the workload (see cpu_baseline.sample)"),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_step_note=None):
+    cfg = {"workload": f"talk2dino_decap dense captioning: {args.size}px images, {args.boxes} synthetic bboxes/image, batch {args.batch} per GPU "
+                       f"(BASELINE.json configs[1])",
+           "images_per_gpu": args.batch, "boxes_per_image": args.boxes, "regions_per_gpu_per_step": args.batch * args.boxes,
+           "image_size": args.size, "bank_rows": args.bank_rows, "pooling": args.pool, "decode_steps": 30,
+           "parallelism": f"dp{args.gpus} over images, no collective",
+           "cache": "per-step inputs (206 MB of images) and activations (> 1 GB) exceed the 126 MB L2; no explicit flush"}
+    if per_step_note:
+        cfg["note"] = per_step_note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------ our arm (CUDA)
+def run_ours(args):
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as ge
+
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from patchioner_b200 import Patchioner, ops, synth
+
+    B, R, S = args.batch, args.boxes, args.size
+    vit_w, dec_w = synth.make_vit_weights(1234), synth.make_decoder_weights(1234)
+    bank = synth.synth_bank(args.bank_rows, 768, seed=7)
+    model = Patchioner.from_config({"decap_weights": dec_w, "prefix_size": 768, "support_memory_size": args.bank_rows,
+                                    "dino_model": "dinov2_vitb14_reg", "normalize": True, "resize_dim": S, "crop_dim": S,
+                                    "dino_weights": vit_w, "memory_bank": bank, "precision": args.precision}, device=dev)
+    del bank, vit_w, dec_w
+    kw = dict(gaussian_avg=args.pool == "gauss", gaussian_bbox_variance=1.0, use_attn_map_for_bboxes=args.pool == "attn")
+
+    # distinct synthetic batches per rank (data-parallel shards), pinned on the host for the e2e leg
+    n_sets = 2
+    host_imgs = [synth.synth_images(B, S, seed=1000 * rank + i).pin_memory() for i in range(n_sets)]
+    host_boxes = [synth.synth_boxes(B, R, S, seed=1000 * rank + i, pad="dense").pin_memory() for i in range(n_sets)]
+    dev_imgs = [t.to(dev) for t in host_imgs]
+    dev_boxes = [t.to(dev) for t in host_boxes]
+    stream = torch.cuda.current_stream()
+
+    def step_resident(i):
+        return model(dev_imgs[i % n_sets], get_cls_capt=False, bboxes=dev_boxes[i % n_sets], return_ids=True, **kw)["bbox_capts"]
+
+    def step_e2e(i):
+        imgs = host_imgs[i % n_sets].to(dev, non_blocking=True)
+        boxes = host_boxes[i % n_sets].to(dev, non_blocking=True)
+        ids = model(imgs, get_cls_capt=False, bboxes=boxes, return_ids=True, **kw)["bbox_capts"]
+        return ids.cpu()  # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ms_total = timed(step_resident, args.steps, args.warmup)
+    launches = ops.launch_count()
+    # launches counted include the warm-up steps: keep the timed share
+    launches = launches * args.steps // (args.steps + args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+
+    regions = B * R * world
+    value = regions * args.steps / (ms_total / 1e3)
+    e2e_value = regions * args.steps / (ms_e2e / 1e3)
+
+    extra = {}
+    if rank == 0:
+        extra = stage_breakdown(model, ops, dev_imgs[0], dev_boxes[0], kw, args, stream)
+    line = None
+    if rank == 0:
+        pk = peaks()
+        gm = extra.pop("_gemm")
+        roof = {"kernel": gm["kernel"], "bound": "tensor", "achieved": gm["tflops"], "peak": pk["bf16_tflops"] if args.precision == "bf16" else None,
+                "unit": "TFLOP/s", "frac": (gm["tflops"] / pk["bf16_tflops"]) if args.precision == "bf16" else None,
+                "traffic": None, "peak_source": pk["source"] + " (burst figure: kernel timed alone, back to back)",
+                "shape": gm["shape"], "avg_launch_ms": gm["ms"], "algorithmic_flops_per_launch": gm["flops"]}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.precision, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(host_imgs[0].numel() * 4 + host_boxes[0].numel() * 4) * world,
+                        "d2h_bytes_per_step": int(B * R * 30 * 4) * world},
+                "gpu_launches": int(launches), "roofline": roof, "stages": extra,
+                "vit_images_per_s": extra.get("vit_images_per_s")}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                v, sec, sample = cpu_sample(args, 1, 1)
+                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample,
+                                        "seconds_per_sample_step": sec}
+            except Exception as e:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def stage_breakdown(model, ops, imgs, boxes, kw, args, stream):
+    """One extra instrumented step (not the timed one): CUDA-event time per stage and for the dominant kernel."""
+    from patchioner_b200 import _lib as L
+
+    def flops_per_image(size):  # 12*(24*N*D^2 + 4*N^2*D) + 2*P*588*D
+        p_ = (size // 14) ** 2
+        n_ = p_ + 5
+        return 12 * (24 * n_ * 768 ** 2 + 4 * n_ * n_ * 768) + 2 * p_ * 588 * 768
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    B, R, S = args.batch, args.boxes, args.size
+    marks = [ev() for _ in range(5)]
+    torch.cuda.synchronize()
+    marks[0].record(stream)
+    tokens, attn, _ = model.dino.forward(imgs, want_attn=True)
+    marks[1].record(stream)
+    patch = tokens[:, 5:]
+    feats = ops.pool_boxes(patch, boxes, 14, kw["gaussian_avg"], kw["gaussian_bbox_variance"], attn if kw["use_attn_map_for_bboxes"] else None)
+    marks[2].record(stream)
+    pre = model.embed_tokens(feats.reshape(-1, 768))
+    marks[3].record(stream)
+    model.decoder.decode(pre, 30)
+    marks[4].record(stream)
+    torch.cuda.synchronize()
+    t = [marks[i].elapsed_time(marks[i + 1]) for i in range(4)]
+    pk = peaks()
+    vit_flops = flops_per_image(S) * B
+    P = (S // 14) ** 2
+    pool_bytes = B * (P * 768 * 4 + R * 768 * 4 + R * 16)
+    proj_flops = 4.0 * model.im_proj.M * 768 * B * R if model.im_proj is not None else 0.0
+    dec_flops = 2 * (4 * 12 * 768 * 768 + 50257 * 768) * 30 * B * R
+    out = {"vit_ms": t[0], "pool_ms": t[1], "project_ms": t[2], "decode_ms": t[3],
+           "vit_images_per_s": B / (t[0] / 1e3), "vit_tflops": vit_flops / t[0] / 1e9,
+           "pool_gbs": pool_bytes / t[1] / 1e6, "pool_frac_of_hbm": pool_bytes / t[1] / 1e6 / pk["hbm_gbs"],
+           "project_tflops": proj_flops / t[2] / 1e9 if t[2] > 0 else None, "decode_tflops": dec_flops / t[3] / 1e9}
+    # dominant kernel: the dense layers (tcgen05 GEMM in bf16 mode).  Time the ViT fc1 shape alone.
+    N = 5 + P
+    M = B * N
+    dt = torch.bfloat16 if args.precision == "bf16" else torch.float32
+    A = torch.randn(M, 768, device=imgs.device).to(dt)
+    W = torch.randn(3072, 768, device=imgs.device).to(dt) / 28
+    bias = torch.zeros(3072, device=imgs.device)
+    Cbuf = torch.empty(M, 3072, device=imgs.device, dtype=dt)
+    for _ in range(3):
+        ops.linear(A, W, args.precision, bias=bias, act=L.ACT_GELU_ERF, out=Cbuf)
+    e0, e1 = ev(), ev()
+    reps = 10
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        ops.linear(A, W, args.precision, bias=bias, act=L.ACT_GELU_ERF, out=Cbuf)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * M * 3072 * 768
+    out["_gemm"] = {"kernel": "gemm_tc_kernel<256> (ViT fc1 + GELU)" if args.precision == "bf16" else "sgemm_tn_kernel (ViT fc1 + GELU)",
+                    "shape": [M, 3072, 768], "ms": ms, "flops": flops, "tflops": flops / ms / 1e9}
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
