@@ -8,9 +8,11 @@
 //   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16)
 //               straight from shared memory into a TMEM accumulator; tcgen05.commit releases the ring slot
 //               and, after the last k-block, publishes the accumulator
-//   warps 2..5  epilogue     : tcgen05.ld the fp32 accumulator (lane == row), apply bias / activation /
-//               LayerScale / residual, store.  The accumulator is double buffered in TMEM (2 x BN columns)
-//               so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 2..9  epilogue     : tcgen05.ld the fp32 accumulator (lane == row; warp w reads TMEM lane quarter w%4 and
+//               one half of the columns), apply the epilogue and store.  Per-column vectors (colscale, bias, LayerScale)
+//               are staged once per tile in shared memory; residual rows are fetched with 16-byte loads issued ahead of
+//               the TMEM wait.  The accumulator is double buffered in TMEM (2 x BN columns) so the epilogue of tile i
+//               overlaps the MMAs of tile i+1.
 // No CUTLASS: descriptors are built by hand (field layout checked against cute/arch/mma_sm100_desc.hpp).
 #include "common.cuh"
 
@@ -23,7 +25,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;          // 2 per TMEM lane quarter, each owning half of the tile's columns
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
 template <int BN> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -119,8 +122,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
          ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void store_chunk(void* C, int c_dt, long long base, const float (&v)[32], int nvalid, bool vec_ok) {
-  if (c_dt == PIO_DT_F32) {
+template <bool OUT_BF16>
+__device__ __forceinline__ void store_chunk(void* C, long long base, const float (&v)[32], int nvalid, bool vec_ok) {
+  if constexpr (!OUT_BF16) {
     float* p = reinterpret_cast<float*>(C) + base;
     if (nvalid == 32 && vec_ok) {
 #pragma unroll
@@ -150,6 +154,65 @@ __device__ __forceinline__ void store_chunk(void* C, int c_dt, long long base, c
   }
 }
 
+// One epilogue warp, one tile: columns [c_begin, c_end) of TMEM lane quarter `quarter`.
+//   out = residual * rowscale + gamma * act(acc * (alpha * colscale) + bias); vectors come from shared memory.
+template <int ACT, bool HAS_RES, bool OUT_BF16>
+__device__ __forceinline__ void epilogue_cols(uint32_t tmem_acc, int quarter, int lane, int c_begin, int c_end, int m, int M,
+                                              int n0, int N, void* C, int ldc, const Epilogue& epi, const float* s_scale,
+                                              const float* s_bias, const float* s_gamma) {
+  const long long orow = epi.out_row(m < M ? m : 0);
+  const bool row_ok = m < M;
+  const bool vec_ok = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  float rs = 1.0f;
+  if constexpr (HAS_RES) {
+    if (epi.res_rowscale && row_ok) rs = __ldg(epi.res_rowscale + m);
+  }
+  const bool res_vec = HAS_RES && (epi.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0);
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; c += 32) {
+    const int n = n0 + c;
+    const int nvalid = min(32, N - n);
+    float res[32];
+    if constexpr (HAS_RES) {
+      // issue the residual loads before waiting on tensor memory
+      const float* rp = epi.residual + orow * epi.ldres + n;
+      if (row_ok && nvalid == 32 && res_vec) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 t = *reinterpret_cast<const float4*>(rp + 4 * i);
+          res[4 * i] = t.x; res[4 * i + 1] = t.y; res[4 * i + 2] = t.z; res[4 * i + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) res[i] = (row_ok && i < nvalid) ? rp[i] : 0.f;
+      }
+    }
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + c, r);
+    tmem_ld_wait();
+    if (row_ok && nvalid > 0) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 sc = *reinterpret_cast<const float4*>(s_scale + c + i);
+        const float4 bi = *reinterpret_cast<const float4*>(s_bias + c + i);
+        const float4 ga = *reinterpret_cast<const float4*>(s_gamma + c + i);
+        const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, biv[4] = {bi.x, bi.y, bi.z, bi.w}, gav[4] = {ga.x, ga.y, ga.z, ga.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = fmaf(__uint_as_float(r[i + j]), scv[j], biv[j]);
+          if constexpr (ACT == PIO_ACT_GELU_ERF) t = gelu_erf(t);
+          if constexpr (ACT == PIO_ACT_GELU_NEW) t = gelu_new(t);
+          t *= gav[j];
+          if constexpr (HAS_RES) t = fmaf(res[i + j], rs, t);
+          v[i + j] = t;
+        }
+      }
+      store_chunk<OUT_BF16>(C, orow * ldc + n, v, nvalid, vec_ok);
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, void* C, int M, int N, int K,
@@ -160,6 +223,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[2 * cfg::STAGES + 4];
   __shared__ uint32_t tmem_slot_var;
+  __shared__ __align__(16) float s_scale[BN], s_bias[BN], s_gamma[BN];  // per-tile column vectors of the epilogue
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (cfg::STAGES + s); };
@@ -176,7 +240,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < cfg::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NUM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, cfg::TMEM_COLS);
@@ -234,32 +298,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    const int quarter = warp & 3;              // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;          // which half of the tile's columns
+    const int et = threadIdx.x - 64;           // 0..255 among the epilogue threads
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
+      // stage this tile's column vectors (defaults make every epilogue the same arithmetic)
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done
+      for (int c = et; c < BN; c += NUM_EPI_WARPS * 32) {
+        const int n = n0 + c;
+        const bool ok = n < N;
+        s_scale[c] = epi.alpha * ((epi.colscale && ok) ? __ldg(epi.colscale + n) : 1.0f);
+        s_bias[c] = (epi.bias && ok) ? __ldg(epi.bias + n) : 0.0f;
+        s_gamma[c] = (epi.gamma && ok) ? __ldg(epi.gamma + n) : 1.0f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
-      const long long orow = epi.out_row(m < M ? m : 0);
-      const bool vec_ok = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + c, r);
-        tmem_ld_wait();
-        const int n = n0 + c;
-        if (m < M && n < N) {
-          const int nvalid = min(32, N - n);
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = (i < nvalid) ? epi.apply(__uint_as_float(r[i]), m, orow, n + i) : 0.f;
-          store_chunk(C, c_dt, orow * ldc + n, v, nvalid, vec_ok);
-        }
-      }
+      const uint32_t tacc = tmem_base + as * BN;
+      const int cb = half * (BN / 2), ce = cb + BN / 2;
+      const bool bf = c_dt == PIO_DT_BF16;
+      const bool hr = epi.residual != nullptr;
+#define PIO_EPI(ACTV, HR, BF) epilogue_cols<ACTV, HR, BF>(tacc, quarter, lane, cb, ce, m, M, n0, N, C, ldc, epi, s_scale, s_bias, s_gamma)
+#define PIO_EPI_ACT(ACTV)                                                      \
+  do {                                                                         \
+    if (hr) { if (bf) PIO_EPI(ACTV, true, true); else PIO_EPI(ACTV, true, false); }   \
+    else    { if (bf) PIO_EPI(ACTV, false, true); else PIO_EPI(ACTV, false, false); } \
+  } while (0)
+      if (epi.act == PIO_ACT_GELU_ERF) PIO_EPI_ACT(PIO_ACT_GELU_ERF);
+      else if (epi.act == PIO_ACT_GELU_NEW) PIO_EPI_ACT(PIO_ACT_GELU_NEW);
+      else PIO_EPI_ACT(PIO_ACT_NONE);
+#undef PIO_EPI_ACT
+#undef PIO_EPI
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
