@@ -112,6 +112,13 @@ size_t pio_vit_workspace_bytes(const PioVit* h, int B, int S);
 int pio_vit_forward(PioVit* h, const float* imgs, int B, int S, const float* pos_embed, float* out_tokens,
                     float* out_attn, float* out_qkv, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Multi-head self-attention of one ViT block (head_dim 64): qkv [B,N,3*H*64] = [q|k|v] -> out [B,N,H*64], same dtype  */
+/* (PIO_DT_F32: fp32 FFMA flash kernel; PIO_DT_BF16: tcgen05 kernel, needs a workspace for the transposed V copy).      */
+/* Replaces dinov2 Attention.forward inside self.dino(...) (src/model.py:783).                                          */
+size_t pio_attention_workspace_bytes(int dt, int B, int N, int H);
+int pio_vit_attention(const void* qkv, void* out, int dt, int B, int N, int H, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* CLS attention map alone, from a hooked qkv tensor [B,N,3*D] (dino_extraction.py:24-34). */
 int pio_cls_attention(const void* qkv, int qkv_dt, int B, int N, int D, int num_global, float* out_attn,
                       void* stream);

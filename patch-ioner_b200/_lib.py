@@ -65,6 +65,8 @@ SIGNATURES = {
     "pio_vit_destroy": (None, [_fp]),
     "pio_vit_workspace_bytes": (C.c_size_t, [_fp, C.c_int, C.c_int]),
     "pio_vit_forward": (C.c_int, [_fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "pio_attention_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pio_vit_attention": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_size_t, _fp]),
     "pio_cls_attention": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp]),
     "pio_pool_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "pio_pool_boxes": (C.c_int, [_fp, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int,

@@ -143,6 +143,8 @@ int l2norm_rows(float* x, int rows, int dim, cudaStream_t st);
 int softmax_rows(const float* in, float* out, int rows, int cols, float scale, cudaStream_t st);
 int cls_attention(const void* qkv, int dt, int B, int N, int D, int ng, float* out, float* logits_ws, cudaStream_t st);
 int vit_attention(const void* qkv, void* out, int dt, int B, int N, int H, cudaStream_t st);
+size_t vit_attention_tc_workspace(int B, int N, int H);
+int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int H, cudaStream_t st);  // attention_sm100.cu
 int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int R, int H, int T, int t, cudaStream_t st);
 
 }  // namespace pio

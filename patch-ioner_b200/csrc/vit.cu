@@ -155,8 +155,9 @@ void pio_vit_destroy(PioVit* h) {
 size_t pio_vit_workspace_bytes(const PioVit* h, int B, int S) {
   using namespace pio;
   const size_t g = S / 14, N = kNG + g * g, M = (size_t)B * N, e = h->act_dt == PIO_DT_F32 ? 4 : 2;
+  const size_t vt = h->act_dt == PIO_DT_BF16 ? align_up(vit_attention_tc_workspace(B, (int)N, kHeads), 1024) : 0;
   return align_up(M * kD * 4, 1024) + align_up(M * kD * e, 1024) + align_up(M * 3 * kD * e, 1024) +
-         align_up(M * kMlp * e, 1024) + 4096;
+         align_up(M * kMlp * e, 1024) + vt + 4096;
 }
 
 int pio_vit_forward(PioVit* h, const float* imgs, int B, int S, const float* pos_embed, float* out_tokens, float* out_attn,
@@ -175,7 +176,8 @@ int pio_vit_forward(PioVit* h, const float* imgs, int B, int S, const float* pos
   float* x = (float*)ws;  ws += align_up((size_t)M * kD * 4, 1024);
   void* hb = ws;          ws += align_up((size_t)M * kD * e, 1024);
   void* qkv = ws;         ws += align_up((size_t)M * 3 * kD * e, 1024);
-  void* f = ws;
+  void* f = ws;            ws += align_up((size_t)M * kMlp * e, 1024);
+  void* vt = ws;           // transposed V copy for the tensor-core attention (bf16 mode only)
 
   // tokens: [cls + pos0 | registers | pos[1+p]] then accumulate the patch embedding onto the patch rows
   PIO_TRY(init_global_tokens(x, h->cls, h->reg, pos_embed, B, N, kD, st));
@@ -200,7 +202,8 @@ int pio_vit_forward(PioVit* h, const float* imgs, int B, int S, const float* pos
         }
       }
     }
-    PIO_TRY(vit_attention(qkv, hb, adt, B, N, kHeads, st));
+    if (adt == PIO_DT_BF16) PIO_TRY(vit_attention_tc(qkv, hb, vt, B, N, kHeads, st));
+    else PIO_TRY(vit_attention(qkv, hb, adt, B, N, kHeads, st));
     PIO_TRY(gemm(mode, hb, w.proj_w, x, M, kD, kD, kD, kD, kD, adt, PIO_DT_F32, w.proj_b, w.ls1, x, PIO_ACT_NONE, st));
     PIO_TRY(layernorm(x, kD, w.ln2_w, w.ln2_b, hb, adt, kD, M, kD, 1e-6f, st));
     PIO_TRY(gemm(mode, hb, w.fc1_w, f, M, kMlp, kD, kD, kD, kMlp, adt, adt, w.fc1_b, nullptr, nullptr, PIO_ACT_GELU_ERF, st));
@@ -208,5 +211,22 @@ int pio_vit_forward(PioVit* h, const float* imgs, int B, int S, const float* pos
   }
   PIO_TRY(layernorm(x, kD, h->norm_w, h->norm_b, out_tokens, PIO_DT_F32, kD, M, kD, 1e-6f, st));
   return PIO_OK;
+}
+
+size_t pio_attention_workspace_bytes(int dt, int B, int N, int H) {
+  return dt == PIO_DT_BF16 ? pio::align_up(pio::vit_attention_tc_workspace(B, N, H), 1024) : 0;
+}
+
+int pio_vit_attention(const void* qkv, void* out, int dt, int B, int N, int H, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  using namespace pio;
+  PIO_CHECK(qkv && out, "vit_attention: null argument");
+  PIO_CHECK(dt == PIO_DT_F32 || dt == PIO_DT_BF16, "vit_attention: dtype must be fp32 or bf16");
+  if (B == 0 || N == 0) return PIO_OK;
+  if (dt == PIO_DT_BF16) {
+    PIO_CHECK(workspace && workspace_bytes >= pio_attention_workspace_bytes(dt, B, N, H), "vit_attention: workspace too small");
+    return vit_attention_tc(qkv, out, workspace, B, N, H, as_stream(stream));
+  }
+  return vit_attention(qkv, out, dt, B, N, H, as_stream(stream));
 }
 }

@@ -177,6 +177,18 @@ class Vit:
         return tokens, attn, qkv
 
 
+def vit_attention(qkv: torch.Tensor, heads: int = 12) -> torch.Tensor:
+    """One block's multi-head self-attention: qkv [B,N,3*heads*64] (fp32 or bf16) -> [B,N,heads*64]."""
+    _need_cuda(qkv)
+    qkv = qkv.contiguous()
+    B, N, C3 = qkv.shape
+    out = torch.empty(B, N, C3 // 3, dtype=qkv.dtype, device=qkv.device)
+    nbytes = L.lib().pio_attention_workspace_bytes(_dt(qkv), B, N, heads)
+    ws = workspace(max(nbytes, 16), qkv.device, "attn")
+    L.check(L.lib().pio_vit_attention(qkv.data_ptr(), out.data_ptr(), _dt(qkv), B, N, heads, ws.data_ptr(), nbytes, _stream()))
+    return out
+
+
 def cls_attention(qkv: torch.Tensor, num_global: int = 5) -> torch.Tensor:
     _need_cuda(qkv)
     B, N, C3 = qkv.shape

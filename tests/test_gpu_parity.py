@@ -234,6 +234,31 @@ def test_cls_attention_against_golden(dev, ops, golden):
     torch.testing.assert_close(sa.cpu(), rec["self_attn"], rtol=1e-4, atol=1e-7)
 
 
+# ----------------------------------------------------------------------------------------- attention
+def _attn_ref(qkv, H=12):
+    B, N, C3 = qkv.shape
+    D = C3 // 3
+    t = qkv.float().reshape(B, N, 3, H, D // H).permute(2, 0, 3, 1, 4)
+    a = ((t[0] * (D // H) ** -0.5) @ t[1].transpose(-2, -1)).softmax(dim=-1)
+    return (a @ t[2]).transpose(1, 2).reshape(B, N, D)
+
+
+@pytest.mark.parametrize("B,N", [(2, 261), (1, 1374), (3, 128), (1, 77)])
+def test_vit_attention_fp32(dev, ops, B, N):
+    qkv = torch.randn(B, N, 2304, generator=torch.Generator().manual_seed(N))
+    out = ops.vit_attention(qkv.to(dev)).cpu()
+    torch.testing.assert_close(out, _attn_ref(qkv), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,N", [(2, 261), (1, 1374), (3, 128), (1, 77), (2, 300)])
+def test_vit_attention_bf16_tcgen05(dev, ops, B, N):
+    qkv = (torch.randn(B, N, 2304, generator=torch.Generator().manual_seed(N)) * 1.5).bfloat16()
+    out = ops.vit_attention(qkv.to(dev)).float().cpu()
+    ref = _attn_ref(qkv)
+    torch.testing.assert_close(out, ref, rtol=2e-2, atol=2e-2)
+    assert cos_min(out, ref) >= 0.9995
+
+
 # ----------------------------------------------------------------------------------------- ViT
 @pytest.fixture(scope="module")
 def vit_w():
