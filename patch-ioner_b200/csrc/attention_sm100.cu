@@ -2,12 +2,14 @@
 //
 // One CTA = 128 queries of one (image, head); it walks the keys in tiles of 128 with an online softmax:
 //   warp 0      TMA producer : Q tile once, then per key tile K [128 keys x 64] and V^T [64 x 128 keys] into a
-//               3-stage shared-memory ring (128-byte swizzle, mbarrier completion)
-//   warp 1      MMA issuer   : S_j = Q K_j^T   (UMMA 128x128x16 x4, fp32 in TMEM, double buffered)
+//               2-stage shared-memory ring (128-byte swizzle, mbarrier completion)
+//   warp 1      MMA issuer   : S_j = Q K_j^T   (UMMA 128x128x16 x4, fp32 in TMEM)
 //                              PV_j = P_j V_j  (UMMA 128x64x16 x8, A = P_j from shared memory, fresh accumulator)
-//   warps 2..5  softmax      : thread == query row.  tcgen05.ld S_j, running max / sum in fp32 with exp2,
-//               P_j -> bf16 -> shared memory in the UMMA K-major swizzled layout, then O = (O + PV_{j-1}) * alpha_j
-//               in registers (no TMEM read-modify-write of the output).
+//   warps 2..5  softmax      : thread == query row.  tcgen05.ld S_j, running max / sum in fp32 with ex2.approx,
+//               O = (O + PV_{j-1}) * alpha_j in registers (no TMEM read-modify-write of the output), then
+//               P_j -> bf16 -> shared memory in the UMMA K-major swizzled layout.
+// Footprint is trimmed to 112.3 KB of shared memory, 256 TMEM columns and <= 168 registers so that TWO CTAs are
+// resident per SM: one CTA's softmax (MUFU/FMA bound) overlaps the other's tensor-core and TMA work.
 // V is consumed K-major (keys contiguous) from a transposed copy V^T [B, H, 64, Np] written by transpose_v_kernel,
 // so both GEMMs use the same, verified, K-major 128B-swizzle descriptors as gemm_sm100.cu.
 #include "tc_ptx.cuh"
@@ -19,15 +21,16 @@ namespace {
 constexpr int HD = 64;        // head dim
 constexpr int BQ = 128;       // queries per CTA
 constexpr int BKV = 128;      // keys per tile
-constexpr int KV_STAGES = 3;
+constexpr int KV_STAGES = 2;
 constexpr int Q_BYTES = BQ * HD * 2;            // 16 KB
 constexpr int K_BYTES = BKV * HD * 2;           // 16 KB
 constexpr int V_BYTES = HD * BKV * 2;           // 16 KB (two [64 d x 64 keys] sub-tiles)
 constexpr int KV_BYTES = K_BYTES + V_BYTES;
 constexpr int P_BYTES = BQ * BKV * 2;           // 32 KB (two [128 q x 64 keys] sub-tiles)
-constexpr int ATT_SMEM = Q_BYTES + KV_STAGES * KV_BYTES + 2 * P_BYTES + 1024;
+constexpr int NUM_BARS = 1 + 2 * KV_STAGES + 3;
+constexpr int ATT_SMEM = Q_BYTES + KV_STAGES * KV_BYTES + P_BYTES + NUM_BARS * 8 + 16;  // no static smem: base stays 1024-aligned
 constexpr int ATT_THREADS = 192;
-constexpr uint32_t TM_S0 = 0, TM_PV0 = 256, TM_COLS = 512;  // S[2] at cols 0/128, PV[2] at cols 256/320
+constexpr uint32_t TM_S0 = 0, TM_PV0 = 128, TM_COLS = 256;  // S at cols 0..127, PV at cols 128..191
 
 // V^T[b,h,d,n] = V[b,n,h,d]; columns [N, Np) are zero.  grid (ceil(Np/64), H, B), block (64, 4)
 __global__ void __launch_bounds__(256) transpose_v_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vt,
@@ -50,26 +53,90 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const __nv_bfloat16* _
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// One query row against one 128-key tile, in 32-column tcgen05.ld chunks (TMEM loads are cheap: re-reading S
+// beats keeping 128 values live in registers).  MASK only for the last, partial key tile.
+template <bool MASK>
+__device__ __forceinline__ float row_max(uint32_t s_addr, int kbase, int N) {
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < BKV; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(s_addr + c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]), v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
+      if (MASK) {
+        if (kbase + c + i >= N) v0 = -INFINITY;
+        if (kbase + c + i + 1 >= N) v1 = -INFINITY;
+        if (kbase + c + i + 2 >= N) v2 = -INFINITY;
+        if (kbase + c + i + 3 >= N) v3 = -INFINITY;
+      }
+      mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1); mx2 = fmaxf(mx2, v2); mx3 = fmaxf(mx3, v3);
+    }
+  }
+  return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+}
+
+// S (fp32, TMEM) -> P = exp2(S * c - m_new) (bf16, swizzled K-major shared memory); returns the row sum.
+template <bool MASK>
+__device__ __forceinline__ float write_probs(uint32_t s_addr, uint8_t* prow, int row, int kbase, int N, float scale_log2e,
+                                             float m_new) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < BKV; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(s_addr + c, r);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2e, -m_new));
+      float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2e, -m_new));
+      if (MASK) {
+        if (kbase + c + i >= N) p0 = 0.f;
+        if (kbase + c + i + 1 >= N) p1 = 0.f;
+      }
+      s0 += p0;
+      s1 += p1;
+      __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
+      pk[i >> 1] = *reinterpret_cast<uint32_t*>(&q2);
+    }
+    // 32 keys = 4 chunks of 16 bytes; sub-tile (c / 64), chunk index ((c % 64) / 8 + q) ^ (row % 8)
+    uint8_t* sub = prow + (c >> 6) * (BQ * 128);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int chunk = (((c & 63) >> 3) + q) ^ (row & 7);
+      *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    }
+  }
+  return s0 + s1;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_vt,
                         __nv_bfloat16* __restrict__ out, int N, int H, float scale_log2e) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();  // the 128B-swizzle atoms need 1024-byte alignment
   const uint32_t sQ = smem_base;
   const uint32_t sKV = sQ + Q_BYTES;
   const uint32_t sP = sKV + KV_STAGES * KV_BYTES;
-  uint8_t* sP_gen = smem_gen + Q_BYTES + KV_STAGES * KV_BYTES;
-
-  __shared__ __align__(8) uint64_t bars[1 + 2 * KV_STAGES + 6];
-  __shared__ uint32_t tmem_slot_var;
-  const uint32_t bar0 = smem_u32(bars);
+  uint8_t* sP_gen = smem_raw + Q_BYTES + KV_STAGES * KV_BYTES;
+  const uint32_t bar0 = sP + P_BYTES;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + Q_BYTES + KV_STAGES * KV_BYTES + P_BYTES + NUM_BARS * 8);
   const uint32_t q_full = bar0;
   auto kv_full = [&](int s) { return bar0 + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bar0 + 8u * (1 + KV_STAGES + s); };
-  auto s_ready = [&](int s) { return bar0 + 8u * (1 + 2 * KV_STAGES + s); };
-  auto p_ready = [&](int s) { return bar0 + 8u * (3 + 2 * KV_STAGES + s); };
-  auto pv_done = [&](int s) { return bar0 + 8u * (5 + 2 * KV_STAGES + s); };
+  const uint32_t s_ready = bar0 + 8u * (1 + 2 * KV_STAGES);
+  const uint32_t p_ready = s_ready + 8u;
+  const uint32_t pv_done = s_ready + 16u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -81,14 +148,16 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_vt) : "memory");
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(s_ready(s), 1); mbar_init(p_ready(s), 4); mbar_init(pv_done(s), 1); }
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot_var), TM_COLS);
+  if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot_ptr)), TM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_var);
+  const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -102,9 +171,9 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
         mbar_wait(kv_empty(s), ph ^ 1);
         const uint32_t dst = sKV + s * KV_BYTES;
         mbar_expect_tx(kv_full(s), KV_BYTES);
-        tma_load_2d(dst, &map_qk, kv_full(s), H * HD + h * HD, row_base + j * BKV);        // K_j  [128 keys x 64]
-        tma_load_2d(dst + K_BYTES, &map_vt, kv_full(s), j * BKV, vt_row);                  // V^T  [64 x keys 0..63]
-        tma_load_2d(dst + K_BYTES + V_BYTES / 2, &map_vt, kv_full(s), j * BKV + 64, vt_row);  // V^T [64 x keys 64..127]
+        tma_load_2d(dst, &map_qk, kv_full(s), H * HD + h * HD, row_base + j * BKV);           // K_j  [128 keys x 64]
+        tma_load_2d(dst + K_BYTES, &map_vt, kv_full(s), j * BKV, vt_row);                     // V^T  [64 x keys 0..63]
+        tma_load_2d(dst + K_BYTES + V_BYTES / 2, &map_vt, kv_full(s), j * BKV + 64, vt_row);  // V^T  [64 x keys 64..127]
       }
     }
     __syncwarp();
@@ -119,98 +188,57 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
       if (lane == 0) {
         const uint64_t adesc = make_smem_desc(sQ), bdesc = make_smem_desc(sKV + s * KV_BYTES);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_base + TM_S0 + (j & 1) * BKV, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(s_ready(j & 1));
+        for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_base + TM_S0, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_ready);
       }
       __syncwarp();
     };
     mbar_wait(q_full, 0);
     issue_qk(0);
-    if (nt > 1) issue_qk(1);
     for (int j = 0; j < nt; ++j) {
       const int s = j % KV_STAGES;
-      mbar_wait(p_ready(j & 1), (j >> 1) & 1);
+      mbar_wait(p_ready, j & 1);   // P_j is in shared memory; S_j and PV_{j-1} have been read
       tc_fence_after();
+      if (j + 1 < nt) issue_qk(j + 1);  // S first: the softmax warps need it next
       if (lane == 0) {
-        const uint32_t pbase = sP + (j & 1) * P_BYTES, vbase = sKV + s * KV_BYTES + K_BYTES;
+        const uint32_t vbase = sKV + s * KV_BYTES + K_BYTES;
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
-          const uint64_t adesc = make_smem_desc(pbase + (k >> 2) * (BQ * 128)) + 2 * (k & 3);
+          const uint64_t adesc = make_smem_desc(sP + (k >> 2) * (BQ * 128)) + 2 * (k & 3);
           const uint64_t bdesc = make_smem_desc(vbase + (k >> 2) * (HD * 128)) + 2 * (k & 3);
-          umma_f16(tmem_base + TM_PV0 + (j & 1) * HD, adesc, bdesc, idesc_o, k != 0);
+          umma_f16(tmem_base + TM_PV0, adesc, bdesc, idesc_o, k != 0);
         }
-        umma_commit(pv_done(j & 1));
+        umma_commit(pv_done);
         umma_commit(kv_empty(s));
       }
       __syncwarp();
-      if (j + 2 < nt) issue_qk(j + 2);
     }
   } else {
     // ------------------------------------------------------------------ softmax / output (warps 2..5)
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;           // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr + TM_S0;
+    const uint32_t pv_addr = tmem_base + lane_addr + TM_PV0;
+    uint8_t* prow = sP_gen + row * 128;
     float m = -INFINITY, l = 0.f;
     float o[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) o[i] = 0.f;
 
     for (int j = 0; j < nt; ++j) {
-      mbar_wait(s_ready(j & 1), (j >> 1) & 1);
+      mbar_wait(s_ready, j & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_base + lane_addr + TM_S0 + (j & 1) * BKV;
+      const bool mask = (j + 1) * BKV > N;
       const int kbase = j * BKV;
       // pass 1: row max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(s_addr + c, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = (kbase + c + i < N) ? __uint_as_float(r[i]) : -INFINITY;
-          mx = fmaxf(mx, v);
-        }
-      }
-      const float m_new = fmaxf(m, mx * scale_log2e);   // every tile has >= 1 valid key, so m_new is finite
-      const float alpha = exp2f(m - m_new);
-      // pass 2: probabilities -> bf16 -> swizzled K-major shared memory
-      float ls = 0.f;
-      uint8_t* prow = sP_gen + (j & 1) * P_BYTES + row * 128;
-#pragma unroll 1
-      for (int c = 0; c < BKV; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(s_addr + c, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = (kbase + c + i < N) ? exp2f(fmaf(__uint_as_float(r[i]), scale_log2e, -m_new)) : 0.f;
-          const float p1 = (kbase + c + i + 1 < N) ? exp2f(fmaf(__uint_as_float(r[i + 1]), scale_log2e, -m_new)) : 0.f;
-          __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
-          // accumulate the row sum from the ROUNDED probabilities: it is what the PV product sees
-          const float2 back = __bfloat1622float2(q2);
-          ls += back.x + back.y;
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&q2);
-        }
-        // 32 keys = 4 chunks of 16 bytes; sub-tile (c / 64), chunk index ((c % 64) / 8 + q) ^ (row % 8)
-        uint8_t* sub = prow + (c >> 6) * (BQ * 128);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (((c & 63) >> 3) + q) ^ (row & 7);
-          *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-      }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready(j & 1));
-      // fold in the previous tile's PV, then rescale to the new reference max
+      const float mx = mask ? row_max<true>(s_addr, kbase, N) : row_max<false>(s_addr, kbase, N);
+      const float m_new = fmaxf(m, mx * scale_log2e);  // every tile has >= 1 valid key, so m_new is finite
+      const float alpha = ex2_approx(m - m_new);       // m = -inf on the first tile -> 0
+      // fold in the previous tile's PV (its P buffer and PV accumulator are then free), rescale to the new max
       if (j > 0) {
-        mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1);
+        mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
-        const uint32_t pv_addr = tmem_base + lane_addr + TM_PV0 + ((j - 1) & 1) * HD;
 #pragma unroll
         for (int c = 0; c < HD; c += 32) {
           uint32_t r[32];
@@ -220,14 +248,19 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
           for (int i = 0; i < 32; ++i) o[c + i] = (o[c + i] + __uint_as_float(r[i])) * alpha;
         }
       }
+      // pass 2: probabilities -> bf16 -> swizzled shared memory
+      const float ls = mask ? write_probs<true>(s_addr, prow, row, kbase, N, scale_log2e, m_new)
+                            : write_probs<false>(s_addr, prow, row, kbase, N, scale_log2e, m_new);
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
       l = l * alpha + ls;
       m = m_new;
     }
     {
-      const int jl = nt - 1;
-      mbar_wait(pv_done(jl & 1), (jl >> 1) & 1);
+      mbar_wait(pv_done, (nt - 1) & 1);
       tc_fence_after();
-      const uint32_t pv_addr = tmem_base + lane_addr + TM_PV0 + (jl & 1) * HD;
       const float inv = 1.0f / l;
 #pragma unroll
       for (int c = 0; c < HD; c += 32) {
@@ -251,7 +284,6 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
         *reinterpret_cast<uint4*>(dst + i) = pk;
       }
     }
-    tc_fence_before();
   }
 
   tc_fence_before();

@@ -150,8 +150,8 @@ class Vit:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            L.lib().pio_vit_destroy(h)
+        if h and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.pio_vit_destroy(h)
             self._h = None
 
     def pos_embed(self, grid: int) -> torch.Tensor:
@@ -300,8 +300,8 @@ class Bank:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            L.lib().pio_bank_destroy(h)
+        if h and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.pio_bank_destroy(h)
             self._h = None
 
     def project(self, q: torch.Tensor, temperature: float = 0.01, normalize: bool = False, partial: bool = False):
@@ -364,8 +364,8 @@ class Decoder:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
-            L.lib().pio_decoder_destroy(h)
+        if h and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.pio_decoder_destroy(h)
             self._h = None
 
     def decode(self, prefix: torch.Tensor, steps: int = 30, compute_scores: bool = False):
