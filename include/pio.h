@@ -77,7 +77,19 @@ typedef struct {
   int act;
   /* optional row remap: output row = (m / rows_per_group) * group_stride + group_offset + m % rows_per_group */
   int rows_per_group, group_stride, group_offset; /* rows_per_group == 0 -> identity             */
+  /* fused row arg-max (PIO_BF16 mode only): when argmax_val != NULL nothing is written to C; instead every  */
+  /* (row, column-slab) pair s writes its maximum, the FIRST column index reaching it and sum exp(v - max)    */
+  /* to argmax_*[row * argmax_ld + s]; pio_argmax_slabs() tells how many slabs a call produces and          */
+  /* pio_argmax_finish() reduces them.  Replaces logits -> softmax -> argmax of decap.py:133-141.           */
+  float* argmax_val;
+  int* argmax_idx;
+  float* argmax_sumexp;
+  int argmax_ld;
 } PioLinear;
+int pio_argmax_slabs(int M, int N);
+/* ids[row*ids_ld + t] = arg-max over the slabs (first index wins ties); logprob_sum[row] += log softmax at it (or NULL) */
+int pio_argmax_finish(const float* val, const int* idx, const float* sumexp, int ld, int slabs, int M, int* ids, int ids_ld,
+                      int t, float* logprob_sum, void* stream);
 int pio_linear(const PioLinear* p, int mode, void* stream);
 
 /* LayerNorm over the last dim (DINOv2 eps 1e-6, GPT-2 eps 1e-5); x fp32 [rows, dim] with row stride ldx. */

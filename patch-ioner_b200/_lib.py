@@ -24,7 +24,8 @@ class PioLinear(C.Structure):
                 ("lda", C.c_int), ("ldw", C.c_int), ("ldc", C.c_int), ("a_dt", C.c_int), ("c_dt", C.c_int),
                 ("bias", _fp), ("colscale", _fp), ("gamma", _fp), ("residual", _fp), ("res_rowscale", _fp),
                 ("ldres", C.c_int), ("alpha", C.c_float), ("act", C.c_int),
-                ("rows_per_group", C.c_int), ("group_stride", C.c_int), ("group_offset", C.c_int)]
+                ("rows_per_group", C.c_int), ("group_stride", C.c_int), ("group_offset", C.c_int),
+                ("argmax_val", _fp), ("argmax_idx", _fp), ("argmax_sumexp", _fp), ("argmax_ld", C.c_int)]
 
 
 VIT_BLOCK_FIELDS = ["ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ls1",
@@ -60,6 +61,8 @@ SIGNATURES = {
     "pio_launch_count": (C.c_longlong, []),
     "pio_reset_launch_count": (None, []),
     "pio_linear": (C.c_int, [C.POINTER(PioLinear), C.c_int, _fp]),
+    "pio_argmax_slabs": (C.c_int, [C.c_int, C.c_int]),
+    "pio_argmax_finish": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp, _fp]),
     "pio_layernorm": (C.c_int, [_fp, C.c_int, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),
     "pio_vit_create": (C.c_int, [C.POINTER(_fp), C.POINTER(PioVitWeights), C.c_int, _fp]),
     "pio_vit_destroy": (None, [_fp]),

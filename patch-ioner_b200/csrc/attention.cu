@@ -196,6 +196,76 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const TIn* __rest
   for (int e = 0; e < PER; ++e) out[(long long)r * H * HDIM + h * HDIM + lane + 32 * e] = (TOut)acc[e];
 }
 
+
+// bf16 variant with 16-byte loads: head_dim 192 = 24 lanes x 8 elements (lanes 24..31 only help in the reductions).
+// KV-cache rows are 384 contiguous bytes, so a warp reads each key / value row with one coalesced request.
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__global__ void __launch_bounds__(128) decode_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kc,
+                                                                    __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out,
+                                                                    int R, int H, int T, int t, float scale) {
+  constexpr int HDIM = 192;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R * H) return;
+  const int r = warp / H, h = warp % H;
+  const bool act = lane < HDIM / 8;
+  const __nv_bfloat16* row = qkv + (long long)r * 3 * H * HDIM + h * HDIM + lane * 8;
+  __nv_bfloat16* kbase = kc + ((long long)(r * H + h) * T) * HDIM + lane * 8;
+  __nv_bfloat16* vbase = vc + ((long long)(r * H + h) * T) * HDIM + lane * 8;
+  float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint4 knew = make_uint4(0, 0, 0, 0), vnew = knew;
+  if (act) {
+    const uint4 qu = *reinterpret_cast<const uint4*>(row);
+    knew = *reinterpret_cast<const uint4*>(row + H * HDIM);
+    vnew = *reinterpret_cast<const uint4*>(row + 2 * H * HDIM);
+    unpack8(qu, q);
+    *reinterpret_cast<uint4*>(kbase + (long long)t * HDIM) = knew;   // append this step's key / value
+    *reinterpret_cast<uint4*>(vbase + (long long)t * HDIM) = vnew;
+  }
+  float my = -INFINITY;  // lane j keeps score j
+  for (int j = 0; j <= t; ++j) {
+    float s = 0.f;
+    if (act) {
+      const uint4 ku = (j == t) ? knew : *reinterpret_cast<const uint4*>(kbase + (long long)j * HDIM);
+      float kf[8];
+      unpack8(ku, kf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s = fmaf(q[e], kf[e], s);
+    }
+    s = warp_sum(s) * scale;
+    if (lane == j) my = s;
+  }
+  const float mx = warp_max(my);
+  const float p = (lane <= t) ? __expf(my - mx) : 0.f;
+  const float inv = 1.0f / warp_sum(p);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j <= t; ++j) {
+    const float pj = __shfl_sync(0xffffffffu, p, j) * inv;
+    if (act) {
+      const uint4 vu = (j == t) ? vnew : *reinterpret_cast<const uint4*>(vbase + (long long)j * HDIM);
+      float vf[8];
+      unpack8(vu, vf);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vf[e], acc[e]);
+    }
+  }
+  if (act) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(acc[0], acc[1]), b = __floats2bfloat162_rn(acc[2], acc[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(acc[4], acc[5]), d = __floats2bfloat162_rn(acc[6], acc[7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+    pk.z = *reinterpret_cast<uint32_t*>(&c); pk.w = *reinterpret_cast<uint32_t*>(&d);
+    *reinterpret_cast<uint4*>(out + (long long)r * H * HDIM + h * HDIM + lane * 8) = pk;
+  }
+}
+
 }  // namespace
 
 int vit_attention(const void* qkv, void* out, int dt, int B, int N, int H, cudaStream_t st) {
@@ -222,8 +292,8 @@ int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int
   if (dt == PIO_DT_F32)
     decode_attention_kernel<float, float, float, 192><<<blocks, 128, 0, st>>>((const float*)qkv, (float*)kc, (float*)vc, (float*)out, R, H, T, t, scale);
   else
-    decode_attention_kernel<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16, 192><<<blocks, 128, 0, st>>>(
-        (const __nv_bfloat16*)qkv, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, (__nv_bfloat16*)out, R, H, T, t, scale);
+    decode_attention_bf16_kernel<<<blocks, 128, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc,
+                                                         (__nv_bfloat16*)out, R, H, T, t, scale);
   PIO_LAUNCHED();
   return PIO_OK;
 }

@@ -93,6 +93,10 @@ struct Epilogue {
   float alpha;
   int act;
   int rows_per_group, group_stride, group_offset;
+  float* argmax_val;
+  int* argmax_idx;
+  float* argmax_sumexp;
+  int argmax_ld;
   __device__ __forceinline__ long long out_row(int m) const {
     if (rows_per_group == 0) return m;
     return (long long)(m / rows_per_group) * group_stride + group_offset + (m % rows_per_group);
@@ -126,12 +130,17 @@ inline Epilogue make_epilogue(const PioLinear& p) {
   e.rows_per_group = p.rows_per_group;
   e.group_stride = p.group_stride;
   e.group_offset = p.group_offset;
+  e.argmax_val = p.argmax_val;
+  e.argmax_idx = p.argmax_idx;
+  e.argmax_sumexp = p.argmax_sumexp;
+  e.argmax_ld = p.argmax_ld;
   return e;
 }
 
 // kernels implemented in other translation units
 int linear_simt(const PioLinear& p, cudaStream_t st);    // gemm_simt.cu  (fp32 FFMA)
 int linear_tc(const PioLinear& p, cudaStream_t st);      // gemm_sm100.cu (tcgen05 / TMA / TMEM)
+int argmax_slabs_tc(int M, int N);                       // column slabs a fused arg-max call writes per row
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);
 int transpose_f32(const float* in, float* out, int rows, int cols, cudaStream_t st);           // out[c][r] = in[r][c]
 int transpose_to_bf16(const float* in, __nv_bfloat16* out, int rows, int cols, cudaStream_t st);

@@ -128,6 +128,45 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_acc, int quarter, in
   }
 }
 
+// Fused arg-max epilogue: this warp's columns [c_begin, c_end) of its row -> (max, first arg-max, sum exp(v - max)).
+__device__ __forceinline__ void epilogue_argmax(uint32_t tmem_acc, int quarter, int c_begin, int c_end, int m, int M, int n0, int N,
+                                                int slab, const Epilogue& epi, const float* s_scale, const float* s_bias) {
+  float best = -INFINITY, sum = 0.f;
+  int bidx = 0x7fffffff;
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + c, r);
+    tmem_ld_wait();
+    const int n = n0 + c;
+    float v[32];
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      v[i] = (n + i < N) ? fmaf(__uint_as_float(r[i]), s_scale[c + i], s_bias[c + i]) : -INFINITY;
+      cmax = fmaxf(cmax, v[i]);
+    }
+    if (cmax == -INFINITY) continue;  // chunk entirely beyond N
+    if (cmax > best) {  // strictly greater: earlier chunks keep ties (first index wins)
+      int ci = 0;
+#pragma unroll
+      for (int i = 31; i >= 0; --i)
+        if (v[i] == cmax) ci = i;
+      sum *= __expf(best - cmax);
+      best = cmax;
+      bidx = n + ci;
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) sum += __expf(v[i] - best);
+  }
+  if (m < M) {
+    const long long o = (long long)m * epi.argmax_ld + slab;
+    epi.argmax_val[o] = best;
+    epi.argmax_idx[o] = bidx;
+    epi.argmax_sumexp[o] = sum;
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, void* C, int M, int N, int K,
@@ -239,6 +278,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int cb = half * (BN / 2), ce = cb + BN / 2;
       const bool bf = c_dt == PIO_DT_BF16;
       const bool hr = epi.residual != nullptr;
+      if (epi.argmax_val != nullptr) {
+        epilogue_argmax(tacc, quarter, cb, ce, m, M, n0, N, (tile % n_blocks) * 2 + half, epi, s_scale, s_bias);
+      } else
 #define PIO_EPI(ACTV, HR, BF) epilogue_cols<ACTV, HR, BF>(tacc, quarter, lane, cb, ce, m, M, n0, N, C, ldc, epi, s_scale, s_bias, s_gamma)
 #define PIO_EPI_ACT(ACTV)                                                      \
   do {                                                                         \
@@ -285,12 +327,17 @@ int launch(const PioLinear& p, cudaStream_t st) {
 
 }  // namespace
 
+int argmax_slabs_tc(int M, int N) { (void)M; return 2 * cdiv(N, 256); }
+
 int linear_tc(const PioLinear& p, cudaStream_t st) {
   PIO_CHECK(p.a_dt == PIO_DT_BF16, "tcgen05 GEMM needs bf16 operands");
   PIO_CHECK(p.lda % 8 == 0 && p.ldw % 8 == 0, "tcgen05 GEMM: lda/ldw must be multiples of 8 (16-byte TMA strides)");
   PIO_CHECK((((uintptr_t)p.A) & 15) == 0 && (((uintptr_t)p.W) & 15) == 0, "tcgen05 GEMM: operands must be 16-byte aligned");
   PIO_CHECK(p.K > 0, "tcgen05 GEMM: K must be positive");
   if (p.M == 0 || p.N == 0) return PIO_OK;
+  PIO_CHECK(p.argmax_val == nullptr || (p.argmax_idx && p.argmax_sumexp && p.argmax_ld >= argmax_slabs_tc(p.M, p.N)),
+            "tcgen05 GEMM: fused arg-max needs val/idx/sumexp buffers with ld >= pio_argmax_slabs()");
+  if (p.argmax_val != nullptr) return launch<256>(p, st);  // slab count is defined for the 256-wide tile
   // widest N tile that still gives every SM at least one tile
   const long long mt = cdiv(p.M, BM);
   if (mt * cdiv(p.N, 256) >= kNumSMs) return launch<256>(p, st);

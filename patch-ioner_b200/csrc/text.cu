@@ -132,6 +132,37 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
   if (threadIdx.x == 0) ids[(long long)blockIdx.x * ids_ld + t] = bi;
 }
 
+// Reduce the per-slab (max, first index, sum exp) triples of the fused lm-head epilogue: one warp per row.
+__global__ void __launch_bounds__(256) argmax_finish_kernel(const float* __restrict__ val, const int* __restrict__ idx,
+                                                            const float* __restrict__ sumexp, int ld, int slabs, int M,
+                                                            int* __restrict__ ids, int ids_ld, int t, float* __restrict__ logprob_sum) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int s = lane; s < slabs; s += 32) {
+    const float v = val[(long long)row * ld + s];
+    const int i = idx[(long long)row * ld + s];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (logprob_sum) {
+    float s = 0.f;
+    for (int k = lane; k < slabs; k += 32) {
+      const float v = val[(long long)row * ld + k];
+      if (v != -INFINITY) s += sumexp[(long long)row * ld + k] * expf(v - best);  // slabs beyond N carry no mass
+    }
+    s = warp_sum(s);
+    if (lane == 0) logprob_sum[row] += -logf(s);
+  }
+  if (lane == 0) ids[(long long)row * ids_ld + t] = bi;
+}
+
 // x[r,:] = wte[ids[r,t],:] + wpe[pos,:]
 __global__ void embed_kernel(const float* __restrict__ wte, const float* __restrict__ wpe, const int* __restrict__ ids,
                              int ids_ld, int t, int pos, float* __restrict__ x, int R, int D) {
@@ -487,14 +518,43 @@ int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int*
       PIO_TRY(linear(mode, f, w.fc2_w, x, R, gD, gFF, gFF, gFF, gD, adt, PIO_DT_F32, w.fc2_b, x, PIO_ACT_NONE, st));
     }
     PIO_TRY(layernorm(x, gD, h->lnf_w, h->lnf_b, hb, adt, gD, R, gD, 1e-5f, st));
-    PIO_TRY(linear(mode, hb, h->wte, logits, R, gV, gD, gD, gD, gVld, adt, PIO_DT_F32, nullptr, nullptr, PIO_ACT_NONE, st));
-    argmax_rows_kernel<<<R, 256, 0, st>>>(logits, gVld, gV, out_ids, steps, t, out_logprob_sum);
-    PIO_LAUNCHED();
+    if (mode == PIO_BF16) {
+      // lm_head with the arg-max fused in the epilogue: the R x 50257 logits are never materialised
+      const int slabs = argmax_slabs_tc(R, gV);
+      float* av = logits;
+      int* ai = (int*)(logits + (size_t)R * slabs);
+      float* as = logits + 2 * (size_t)R * slabs;
+      PioLinear p;
+      memset(&p, 0, sizeof(p));
+      p.A = hb; p.W = h->wte; p.C = nullptr; p.M = R; p.N = gV; p.K = gD; p.lda = gD; p.ldw = gD; p.ldc = gVld;
+      p.a_dt = adt; p.c_dt = PIO_DT_F32; p.alpha = 1.0f;
+      p.argmax_val = av; p.argmax_idx = ai; p.argmax_sumexp = as; p.argmax_ld = slabs;
+      PIO_TRY(linear_tc(p, st));
+      argmax_finish_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(av, ai, as, slabs, slabs, R, out_ids, steps, t, out_logprob_sum);
+      PIO_LAUNCHED();
+    } else {
+      PIO_TRY(linear(mode, hb, h->wte, logits, R, gV, gD, gD, gD, gVld, adt, PIO_DT_F32, nullptr, nullptr, PIO_ACT_NONE, st));
+      argmax_rows_kernel<<<R, 256, 0, st>>>(logits, gVld, gV, out_ids, steps, t, out_logprob_sum);
+      PIO_LAUNCHED();
+    }
     if (t + 1 < steps) {
       embed_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(h->wte32, h->wpe, out_ids, steps, t, t + 1, x, R, gD);
       PIO_LAUNCHED();
     }
   }
+  return PIO_OK;
+}
+
+int pio_argmax_slabs(int M, int N) { return pio::argmax_slabs_tc(M, N); }
+
+int pio_argmax_finish(const float* val, const int* idx, const float* sumexp, int ld, int slabs, int M, int* ids, int ids_ld,
+                      int t, float* logprob_sum, void* stream) {
+  using namespace pio;
+  PIO_CHECK(val && idx && sumexp && ids, "argmax_finish: null argument");
+  if (M == 0) return PIO_OK;
+  argmax_finish_kernel<<<cdiv((long long)M * 32, 256), 256, 0, as_stream(stream)>>>(val, idx, sumexp, ld, slabs, M, ids, ids_ld, t,
+                                                                                    logprob_sum);
+  PIO_LAUNCHED();
   return PIO_OK;
 }
 }

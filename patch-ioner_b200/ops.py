@@ -83,6 +83,32 @@ def linear(A: torch.Tensor, W: torch.Tensor, mode: str = "fp32", bias=None, act:
     return out
 
 
+def linear_argmax(A: torch.Tensor, W: torch.Tensor, bias=None, with_logprob: bool = False):
+    """argmax_n (A @ W.T + bias)[m, n] with the arg-max fused into the tcgen05 GEMM epilogue (bf16 operands):
+    returns int32 ids [M] (first index on ties) and, optionally, log softmax at the arg-max [M]."""
+    _need_cuda(A, W)
+    M, K = A.shape
+    N = W.shape[0]
+    slabs = L.lib().pio_argmax_slabs(M, N)
+    val = torch.empty(M, slabs, dtype=torch.float32, device=A.device)
+    idx = torch.empty(M, slabs, dtype=torch.int32, device=A.device)
+    se = torch.empty(M, slabs, dtype=torch.float32, device=A.device)
+    p = L.PioLinear()
+    p.A, p.W, p.C = A.data_ptr(), W.data_ptr(), None
+    p.M, p.N, p.K = M, N, K
+    p.lda, p.ldw, p.ldc = A.stride(0), W.stride(0), N
+    p.a_dt, p.c_dt = _dt(A), L.DT_F32
+    p.bias = _ptr(bias)
+    p.alpha = 1.0
+    p.argmax_val, p.argmax_idx, p.argmax_sumexp, p.argmax_ld = val.data_ptr(), idx.data_ptr(), se.data_ptr(), slabs
+    L.check(L.lib().pio_linear(C.byref(p), L.PIO_BF16, _stream()))
+    ids = torch.empty(M, 1, dtype=torch.int32, device=A.device)
+    lp = torch.zeros(M, dtype=torch.float32, device=A.device) if with_logprob else None
+    L.check(L.lib().pio_argmax_finish(val.data_ptr(), idx.data_ptr(), se.data_ptr(), slabs, slabs, M, ids.data_ptr(), 1, 0,
+                                      _ptr(lp), _stream()))
+    return (ids[:, 0], lp) if with_logprob else ids[:, 0]
+
+
 def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, out_dtype=torch.float32) -> torch.Tensor:
     _need_cuda(x, w, b)
     rows, dim = x.shape

@@ -86,6 +86,21 @@ def test_linear_inplace_residual_and_rowscale(dev, ops):
         torch.testing.assert_close(Od.cpu(), ref, rtol=tol, atol=tol)
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 5003, 256), (4096, 50257, 768), (33, 700, 64)])
+def test_linear_fused_argmax(dev, ops, M, N, K):
+    g = torch.Generator().manual_seed(N)
+    A = torch.randn(M, K, generator=g).bfloat16()
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16()
+    W[7] = W[3]  # exact ties: the first index must win
+    Ad, Wd = A.to(dev), W.to(dev)
+    logits = ops.linear(Ad, Wd, "bf16")          # same kernel, materialised
+    ids, lp = ops.linear_argmax(Ad, Wd, with_logprob=True)
+    want = logits.argmax(dim=-1)
+    assert torch.equal(ids.long(), want)
+    ref_lp = torch.log_softmax(logits.double(), -1).gather(1, want[:, None])[:, 0].float()
+    torch.testing.assert_close(lp, ref_lp, rtol=1e-4, atol=1e-4)
+
+
 def test_layernorm(dev, ops):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(1000, 768, generator=g) * 3 + 1
