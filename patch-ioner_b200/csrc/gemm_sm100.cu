@@ -379,6 +379,21 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
   return PIO_OK;
 }
 
+int make_map_f32_3d(CUtensorMap* map, const void* ptr, long long d0, long long d1, long long d2, long long stride1_bytes,
+                    long long stride2_bytes, int box0, int box1) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(PIO_ECUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+  cuuint64_t strides[2] = {(cuuint64_t)stride1_bytes, (cuuint64_t)stride2_bytes};
+  cuuint32_t box[3] = {(cuuint32_t)box0, (cuuint32_t)box1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PIO_ECUDA, "cuTensorMapEncodeTiled (f32 3d) failed with %d", (int)r);
+  return PIO_OK;
+}
+
 }  // namespace tc
 
 }  // namespace pio

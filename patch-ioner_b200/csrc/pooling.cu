@@ -1,13 +1,14 @@
 // pooling.cu -- region aggregation of patch tokens.
 //
 // HBM-bound byte work: each image's patch tokens are read from HBM exactly once per call.  A CTA
-// stages a [P x 32-channel] slab of one image in shared memory (128-byte row segments, fully
-// coalesced), then its 8 warps walk the regions of that image: lane = channel, weights are computed
+// stages a [P x 32-channel] slab of one image in shared memory with cp.async (128-byte row
+// segments, the whole slab in flight at once -- narrow TMA boxes measured 4x slower), then its 32 warps walk the
+// regions of that image: lane = channel, weights are computed
 // 32 patches at a time (one per lane) and broadcast with warp shuffles, the slab is read
 // conflict-free (32 consecutive floats per patch).  Index arithmetic follows the reference exactly
 // (torch float floor-division, inclusive end, Python slice clamping) and is exported as int32
 // bounds so that tests can compare it bit-for-bit.
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace pio {
 namespace {
@@ -142,56 +143,118 @@ __global__ void __launch_bounds__(256) box_weights_kernel(const int* __restrict_
 
 // Slab pooling.  grid = (D/32, B).  SRC 0: mean over the box, 1: gaussian over the box,
 // 2: explicit weights w[b,r,P] restricted to `bounds` (or the whole grid when bounds == NULL), times `scale`.
+constexpr int POOL_THREADS = 1024;
+constexpr int POOL_RGROUP = 64;  // boxes accumulated per shared-memory pass
+
 template <int SRC>
-__global__ void __launch_bounds__(256) pool_slab_kernel(const float* __restrict__ tokens, long long img_stride,
-                                                        long long row_stride, int grid, int D, const int* __restrict__ bounds,
-                                                        int R, float variance, const float* __restrict__ weights, float scale,
-                                                        float* __restrict__ out) {
-  extern __shared__ __align__(16) float slab[];  // [P][32]
+__global__ void __launch_bounds__(POOL_THREADS) pool_slab_kernel(const float* __restrict__ tokens, long long img_stride,
+                                                                 long long row_stride, int grid, int D,
+                                                                 const int* __restrict__ bounds, int R, float variance,
+                                                                 const float* __restrict__ weights, float scale,
+                                                                 float* __restrict__ out) {
+  extern __shared__ __align__(128) float slab[];  // [P][32] | s_out [POOL_RGROUP][32] | s_norm [POOL_RGROUP] | s_bounds [POOL_RGROUP][4]
   const int P = grid * grid;
   const int b = blockIdx.y, c0 = blockIdx.x * 32;
-  const float* src = tokens + (long long)b * img_stride + c0;
-  // 8 lanes x float4 cover one 128-byte row segment; a warp loads 4 rows per instruction
-  for (int i = threadIdx.x; i < P * 8; i += blockDim.x) {
-    const int p = i >> 3, q = (i & 7) * 4;
-    *reinterpret_cast<float4*>(&slab[p * 32 + q]) = *reinterpret_cast<const float4*>(src + (long long)p * row_stride + q);
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int j = warp; j < R; j += nw) {
-    const int bi = b * R + j;
-    int y0 = 0, y1 = grid, x0 = 0, x1 = grid;
-    if (bounds) { y0 = bounds[4 * bi]; y1 = bounds[4 * bi + 1]; x0 = bounds[4 * bi + 2]; x1 = bounds[4 * bi + 3]; }
-    const int hs = y1 - y0, ws = x1 - x0, area = hs * ws;
-    float acc = 0.f, wsum = 0.f;
-    for (int base = 0; base < area; base += 32) {
-      const int i = base + lane;
-      int p = 0;
-      float w = 0.f;
-      if (i < area) {
-        const int iy = i / ws, ix = i - iy * ws;
-        p = (y0 + iy) * grid + x0 + ix;
-        if (SRC == 0) w = 1.0f;
-        else if (SRC == 1) w = gauss_w(iy, hs, ix, ws, variance);
-        else w = __ldg(weights + (long long)bi * P + p);
-      }
-      wsum += w;
-      const int cnt = min(32, area - base);
-      if (SRC == 2) {
-        // sparse grids (trace histograms): skip the whole chunk when every weight is zero
-        if (__ballot_sync(0xffffffffu, w != 0.f) == 0u) continue;
-      }
-      for (int k = 0; k < cnt; ++k) {
-        const float wk = __shfl_sync(0xffffffffu, w, k);
-        const int pk = __shfl_sync(0xffffffffu, p, k);
-        acc = fmaf(wk, slab[pk * 32 + lane], acc);
-      }
+  float* s_out = slab + (size_t)P * 32;
+  float* s_norm = s_out + POOL_RGROUP * 32;
+  int* s_bounds = reinterpret_cast<int*>(s_norm + POOL_RGROUP);
+  {
+    // stage the slab with cp.async: 8 lanes x 16 bytes cover one 128-byte row segment, ~11 copies in flight per
+    // thread and 1024 threads -> the whole 175 KB slab is requested at once (no register staging, full MLP)
+    const float* src = tokens + (long long)b * img_stride + c0;
+    const uint32_t dst0 = tc::smem_u32(slab);
+    for (int i = threadIdx.x; i < P * 8; i += POOL_THREADS) {
+      const int p = i >> 3, q = (i & 7) * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(p * 32 + q) * 4),
+                   "l"(src + (long long)p * row_stride + q)
+                   : "memory");
     }
-    float r;
-    if (SRC == 0) r = acc / (float)area;               // empty box -> 0/0 = NaN like tensor.mean()
-    else if (SRC == 1) { wsum = warp_sum(wsum); r = (area > 0) ? acc / wsum : 0.f; }
-    else r = acc * scale;
-    out[(long long)bi * D + c0 + lane] = r;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+  // Region walk: work unit = (box j, grid row y of the box).  Warp w takes the rows r of box j with
+  // (r + j) % 32 == w, so large boxes are spread over all warps and the rotation by j balances small ones.
+  // lane = channel; per row the lane-distributed x-weights are broadcast with one shuffle per patch, four
+  // independent accumulators break the FMA dependency chain; partial sums meet in shared memory.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int jg = 0; jg < R; jg += POOL_RGROUP) {
+    const int rg = min(POOL_RGROUP, R - jg);
+    for (int i = threadIdx.x; i < rg * 32; i += POOL_THREADS) s_out[i] = 0.f;
+    for (int i = threadIdx.x; i < rg * 4; i += POOL_THREADS)  // this group's slice bounds -> shared memory
+      s_bounds[i] = bounds ? bounds[4 * (b * R + jg) + i] : ((i & 1) ? grid : 0);
+    __syncthreads();
+    // per-box normalisation (one warp per box)
+    for (int jj = warp; jj < rg; jj += POOL_THREADS / 32) {
+      const int y0 = s_bounds[4 * jj], y1 = s_bounds[4 * jj + 1], x0 = s_bounds[4 * jj + 2], x1 = s_bounds[4 * jj + 3];
+      const int hs = y1 - y0, ws = x1 - x0;
+      float nrm;
+      if (SRC == 0) nrm = 1.0f / (float)(hs * ws);  // empty box -> inf -> 0 * inf = NaN like tensor.mean()
+      else if (SRC == 1) {
+        float sy = 0.f, sx = 0.f;
+        for (int i = lane; i < hs; i += 32) { const float y = linspace_m1_1(i, hs); sy += expf(-(y * y) / variance); }
+        for (int i = lane; i < ws; i += 32) { const float x = linspace_m1_1(i, ws); sx += expf(-(x * x) / variance); }
+        nrm = (hs > 0 && ws > 0) ? 1.0f / (warp_sum(sy) * warp_sum(sx)) : 0.f;  // empty box -> zeros, like the reference
+      } else nrm = scale;
+      if (lane == 0) s_norm[jj] = nrm;
+    }
+    __syncthreads();
+    for (int it = 0; it < rg; ++it) {
+      // every warp starts at a different box, so concurrent shared-memory accumulations rarely collide
+      int jj = it + 2 * warp;
+      jj -= (jj >= rg) ? rg * (jj / rg) : 0;
+      const int bi = b * R + jg + jj;
+      const int y0 = s_bounds[4 * jj], y1 = s_bounds[4 * jj + 1], x0 = s_bounds[4 * jj + 2], x1 = s_bounds[4 * jj + 3];
+      const int hs = y1 - y0, ws = x1 - x0;
+      const int r0 = (warp - jj) & 31;
+      if (r0 >= hs || ws <= 0) continue;  // no row of this box for this warp
+      float wx0 = 0.f, wx1 = 0.f;       // separable gaussian: x-factors for columns lane and lane + 32 (grid <= 64)
+      if (SRC == 1) {
+        if (lane < ws) { const float x = linspace_m1_1(lane, ws); wx0 = expf(-(x * x) / variance); }
+        if (lane + 32 < ws) { const float x = linspace_m1_1(lane + 32, ws); wx1 = expf(-(x * x) / variance); }
+      }
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      for (int r = r0; r < hs; r += 32) {
+        const int prow = (y0 + r) * grid + x0;
+        float wy = 1.0f;
+        if (SRC == 1) { const float y = linspace_m1_1(r, hs); wy = expf(-(y * y) / variance); }
+        for (int xb = 0; xb < ws; xb += 32) {
+          const int cnt = min(32, ws - xb);
+          float w = 0.f;  // this lane's weight for patch (row r, column xb + lane)
+          if (lane < cnt) {
+            if (SRC == 0) w = 1.0f;
+            else if (SRC == 1) w = wy * (xb == 0 ? wx0 : wx1);
+            else w = __ldg(weights + (long long)bi * P + prow + xb + lane);
+          }
+          const float* sp = slab + (prow + xb) * 32 + lane;
+          if (SRC == 2) {
+            // explicit weights are often sparse (trace histograms): visit only the non-zero patches
+            unsigned nz = __ballot_sync(0xffffffffu, w != 0.f);
+            while (nz) {
+              const int k = __ffs(nz) - 1;
+              nz &= nz - 1;
+              acc0 = fmaf(__shfl_sync(0xffffffffu, w, k), sp[k * 32], acc0);
+            }
+          } else {
+            int k = 0;
+            for (; k + 4 <= cnt; k += 4) {
+              acc0 = fmaf(__shfl_sync(0xffffffffu, w, k), sp[k * 32], acc0);
+              acc1 = fmaf(__shfl_sync(0xffffffffu, w, k + 1), sp[(k + 1) * 32], acc1);
+              acc2 = fmaf(__shfl_sync(0xffffffffu, w, k + 2), sp[(k + 2) * 32], acc2);
+              acc3 = fmaf(__shfl_sync(0xffffffffu, w, k + 3), sp[(k + 3) * 32], acc3);
+            }
+            for (; k < cnt; ++k) acc0 = fmaf(__shfl_sync(0xffffffffu, w, k), sp[k * 32], acc0);
+          }
+        }
+      }
+      atomicAdd(&s_out[jj * 32 + lane], (acc0 + acc1) + (acc2 + acc3));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < rg * 32; i += POOL_THREADS) {
+      const int jj = i >> 5, l = i & 31;
+      out[(long long)(b * R + jg + jj) * D + c0 + l] = s_out[i] * s_norm[jj];
+    }
+    __syncthreads();
   }
 }
 
@@ -268,11 +331,11 @@ __global__ void __launch_bounds__(256) region_mean_weights_kernel(int grid, floa
 template <int SRC>
 int launch_slab(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D, const int* bounds,
                 int R, float variance, const float* weights, float scale, float* out, cudaStream_t st) {
-  const size_t smem = (size_t)grid * grid * 32 * sizeof(float);
+  const size_t smem = ((size_t)grid * grid * 32 + POOL_RGROUP * 37) * sizeof(float);
   PIO_CHECK(smem <= 227 * 1024, "pooling: grid %d too large for the shared-memory slab", grid);
   PIO_CUDA(cudaFuncSetAttribute(pool_slab_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 g(D / 32, B);
-  pool_slab_kernel<SRC><<<g, 256, smem, st>>>(tokens, img_stride, row_stride, grid, D, bounds, R, variance, weights, scale, out);
+  pool_slab_kernel<SRC><<<g, POOL_THREADS, smem, st>>>(tokens, img_stride, row_stride, grid, D, bounds, R, variance, weights, scale, out);
   PIO_LAUNCHED();
   return PIO_OK;
 }

@@ -94,6 +94,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 }
 
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// 3-D fp32 tensor map [d2, d1, d0] (d0 contiguous) with byte strides, box = 1 x box1 x box0, no swizzle.
+int make_map_f32_3d(CUtensorMap* map, const void* ptr, long long d0, long long d1, long long d2, long long stride1_bytes,
+                    long long stride2_bytes, int box0, int box1);
+
 // 2-D bf16 tensor map [rows, cols] with row stride ld elements; box = box_rows x box_cols, 128-byte swizzle.
 int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int box_rows, int box_cols);
 
