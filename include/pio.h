@@ -85,6 +85,14 @@ typedef struct {
   int* argmax_idx;
   float* argmax_sumexp;
   int argmax_ld;
+  /* fused exponential (PIO_BF16 mode only, C must be bf16): when exp_ref != NULL the epilogue stores           */
+  /*   C[m,n] = exp2( alpha*colscale[n]*acc - exp_ref[m] )   and writes, per (row, column-slab) pair s,           */
+  /*   exp_psum[m*exp_ld+s] = sum of those values, exp_pmax[m*exp_ld+s] = max of alpha*colscale[n]*acc.           */
+  /* This is the streaming softmax numerator of im2txtprojection.py:376 with a lagging reference maximum.        */
+  const float* exp_ref;
+  float* exp_psum;
+  float* exp_pmax;
+  int exp_ld;
 } PioLinear;
 int pio_argmax_slabs(int M, int N);
 /* ids[row*ids_ld + t] = arg-max over the slabs (first index wins ties); logprob_sum[row] += log softmax at it (or NULL) */

@@ -25,7 +25,8 @@ class PioLinear(C.Structure):
                 ("bias", _fp), ("colscale", _fp), ("gamma", _fp), ("residual", _fp), ("res_rowscale", _fp),
                 ("ldres", C.c_int), ("alpha", C.c_float), ("act", C.c_int),
                 ("rows_per_group", C.c_int), ("group_stride", C.c_int), ("group_offset", C.c_int),
-                ("argmax_val", _fp), ("argmax_idx", _fp), ("argmax_sumexp", _fp), ("argmax_ld", C.c_int)]
+                ("argmax_val", _fp), ("argmax_idx", _fp), ("argmax_sumexp", _fp), ("argmax_ld", C.c_int),
+                ("exp_ref", _fp), ("exp_psum", _fp), ("exp_pmax", _fp), ("exp_ld", C.c_int)]
 
 
 VIT_BLOCK_FIELDS = ["ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ls1",

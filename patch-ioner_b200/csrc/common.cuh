@@ -97,6 +97,10 @@ struct Epilogue {
   int* argmax_idx;
   float* argmax_sumexp;
   int argmax_ld;
+  const float* exp_ref;
+  float* exp_psum;
+  float* exp_pmax;
+  int exp_ld;
   __device__ __forceinline__ long long out_row(int m) const {
     if (rows_per_group == 0) return m;
     return (long long)(m / rows_per_group) * group_stride + group_offset + (m % rows_per_group);
@@ -134,6 +138,10 @@ inline Epilogue make_epilogue(const PioLinear& p) {
   e.argmax_idx = p.argmax_idx;
   e.argmax_sumexp = p.argmax_sumexp;
   e.argmax_ld = p.argmax_ld;
+  e.exp_ref = p.exp_ref;
+  e.exp_psum = p.exp_psum;
+  e.exp_pmax = p.exp_pmax;
+  e.exp_ld = p.exp_ld;
   return e;
 }
 

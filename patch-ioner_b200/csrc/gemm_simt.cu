@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(THREADS) sgemm_tn_kernel(const float* __restri
 
 int linear_simt(const PioLinear& p, cudaStream_t st) {
   PIO_CHECK(p.a_dt == PIO_DT_F32, "fp32 GEMM needs fp32 operands");
-  PIO_CHECK(p.argmax_val == nullptr, "the fused arg-max epilogue exists in PIO_BF16 mode only");
+  PIO_CHECK(p.argmax_val == nullptr && p.exp_ref == nullptr, "the fused arg-max / exp epilogues exist in PIO_BF16 mode only");
   PIO_CHECK(p.K % 4 == 0 && p.lda % 4 == 0 && p.ldw % 4 == 0, "fp32 GEMM needs K, lda, ldw multiples of 4 (K=%d)", p.K);
   PIO_CHECK((((uintptr_t)p.A) & 15) == 0 && (((uintptr_t)p.W) & 15) == 0, "fp32 GEMM operands must be 16-byte aligned");
   if (p.M == 0 || p.N == 0) return PIO_OK;

@@ -128,6 +128,49 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_acc, int quarter, in
   }
 }
 
+__device__ __forceinline__ float ex2_approx_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Fused exponential epilogue (streaming softmax numerator): this warp's columns [c_begin, c_end) of its row.
+__device__ __forceinline__ void epilogue_exp(uint32_t tmem_acc, int quarter, int c_begin, int c_end, int m, int M, int n0, int N,
+                                             int slab, void* C, int ldc, const Epilogue& epi, const float* s_scale) {
+  const bool row_ok = m < M;
+  const float ref = row_ok ? __ldg(epi.exp_ref + m) : 0.f;
+  const bool vec_ok = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  float sum0 = 0.f, sum1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll 1
+  for (int c = c_begin; c < c_end; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + c, r);
+    tmem_ld_wait();
+    const int n = n0 + c;
+    const int nvalid = min(32, N - n);
+    if (row_ok && nvalid > 0) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float a = __uint_as_float(r[i]) * s_scale[c + i], b = __uint_as_float(r[i + 1]) * s_scale[c + i + 1];
+        const bool va = i < nvalid, vb = i + 1 < nvalid;
+        mx0 = fmaxf(mx0, va ? a : -INFINITY);
+        mx1 = fmaxf(mx1, vb ? b : -INFINITY);
+        v[i] = va ? ex2_approx_ftz(a - ref) : 0.f;
+        v[i + 1] = vb ? ex2_approx_ftz(b - ref) : 0.f;
+        sum0 += v[i];
+        sum1 += v[i + 1];
+      }
+      store_chunk<true>(C, (long long)m * ldc + n, v, nvalid, vec_ok);
+    }
+  }
+  if (row_ok) {
+    const long long o = (long long)m * epi.exp_ld + slab;
+    epi.exp_psum[o] = sum0 + sum1;
+    epi.exp_pmax[o] = fmaxf(mx0, mx1);
+  }
+}
+
 // Fused arg-max epilogue: this warp's columns [c_begin, c_end) of its row -> (max, first arg-max, sum exp(v - max)).
 __device__ __forceinline__ void epilogue_argmax(uint32_t tmem_acc, int quarter, int c_begin, int c_end, int m, int M, int n0, int N,
                                                 int slab, const Epilogue& epi, const float* s_scale, const float* s_bias) {
@@ -280,6 +323,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool hr = epi.residual != nullptr;
       if (epi.argmax_val != nullptr) {
         epilogue_argmax(tacc, quarter, cb, ce, m, M, n0, N, (tile % n_blocks) * 2 + half, epi, s_scale, s_bias);
+      } else if (epi.exp_ref != nullptr) {
+        epilogue_exp(tacc, quarter, cb, ce, m, M, n0, N, (tile % n_blocks) * 2 + half, C, ldc, epi, s_scale);
       } else
 #define PIO_EPI(ACTV, HR, BF) epilogue_cols<ACTV, HR, BF>(tacc, quarter, lane, cb, ce, m, M, n0, N, C, ldc, epi, s_scale, s_bias, s_gamma)
 #define PIO_EPI_ACT(ACTV)                                                      \
@@ -337,7 +382,9 @@ int linear_tc(const PioLinear& p, cudaStream_t st) {
   if (p.M == 0 || p.N == 0) return PIO_OK;
   PIO_CHECK(p.argmax_val == nullptr || (p.argmax_idx && p.argmax_sumexp && p.argmax_ld >= argmax_slabs_tc(p.M, p.N)),
             "tcgen05 GEMM: fused arg-max needs val/idx/sumexp buffers with ld >= pio_argmax_slabs()");
-  if (p.argmax_val != nullptr) return launch<256>(p, st);  // slab count is defined for the 256-wide tile
+  PIO_CHECK(p.exp_ref == nullptr || (p.exp_psum && p.exp_pmax && p.c_dt == PIO_DT_BF16 && p.exp_ld >= argmax_slabs_tc(p.M, p.N)),
+            "tcgen05 GEMM: fused exp needs bf16 C and psum/pmax buffers with ld >= pio_argmax_slabs()");
+  if (p.argmax_val != nullptr || p.exp_ref != nullptr) return launch<256>(p, st);  // slab count is defined for the 256-wide tile
   // widest N tile that still gives every SM at least one tile
   const long long mt = cdiv(p.M, BM);
   if (mt * cdiv(p.N, 256) >= kNumSMs) return launch<256>(p, st);

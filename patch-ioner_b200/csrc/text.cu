@@ -2,6 +2,7 @@
 //   pio_project*        replaces Im2TxtProjector.project   (im2txtprojection.py:353-385)
 //   pio_decode_greedy   replaces decoding_batched          (src/decap/decap.py:116-160)
 #include "common.cuh"
+#include <stdlib.h>
 #include <vector>
 
 namespace pio {
@@ -48,6 +49,34 @@ __global__ void __launch_bounds__(256) softmax_chunk_kernel(float* __restrict__ 
     l[r] = l[r] * a + t;
     m[r] = mnew;
   }
+}
+
+// Streaming-softmax bookkeeping after one bank chunk of the fused path (everything in log2 units):
+//   l = alpha * l + sum(psum);  m' = max(m, max(pmax));  alpha' = 2^(m - m');  m = m'
+__global__ void project_update_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int ld, int slabs, int R,
+                                      float* __restrict__ mref, float* __restrict__ m_used, float* __restrict__ l,
+                                      float* __restrict__ alpha) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  float s = 0.f, mx = -INFINITY;
+  for (int k = lane; k < slabs; k += 32) {
+    s += psum[(long long)warp * ld + k];
+    mx = fmaxf(mx, pmax[(long long)warp * ld + k]);
+  }
+  s = warp_sum(s);
+  mx = warp_max(mx);
+  if (lane == 0) {
+    const float m_old = mref[warp], m_new = fmaxf(m_old, mx);
+    m_used[warp] = m_old;  // the reference this chunk's P, and hence O and l, are expressed in
+    l[warp] = alpha[warp] * l[warp] + s;
+    alpha[warp] = exp2f(m_old - m_new);
+    mref[warp] = m_new;
+  }
+}
+// after the last chunk: natural-log running max for the sharded interface
+__global__ void scale_vec_kernel(const float* in, float* out, float f, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i] * f;
 }
 
 __global__ void fill_kernel(float* p, float v, long long n) {
@@ -281,6 +310,12 @@ void pio_bank_destroy(PioBank* h) {
 }
 long long pio_bank_rows(const PioBank* h) { return h ? h->M : 0; }
 
+static bool project_exact_requested() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PIO_PROJECT_EXACT"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 static int project_chunk_rows(int R) {
   // keep the S chunk (R x Mc fp32) around 64 MB so that it stays L2 resident between the two GEMMs
   long long mc = (16ll << 20) / (R > 0 ? R : 1);
@@ -294,7 +329,8 @@ size_t pio_project_workspace_bytes(const PioBank* h, int R) {
   using namespace pio;
   const size_t Mc = project_chunk_rows(R), e = h->act_dt == PIO_DT_F32 ? 4 : 2;
   return align_up((size_t)R * h->D * e, 1024) /*qn*/ + align_up((size_t)R * h->D * 4, 1024) /*qn fp32*/ +
-         align_up((size_t)R * Mc * 4, 1024) /*S*/ + align_up((size_t)R * Mc * 2, 1024) /*P16*/ + 3 * align_up((size_t)R * 4, 1024) + 4096;
+         align_up((size_t)R * Mc * 4, 1024) /*S, or P + partials on the fused path*/ + align_up((size_t)R * Mc * 2, 1024) /*P16*/ +
+         4 * align_up((size_t)R * 4, 1024) + 4096;
 }
 
 int pio_project(PioBank* h, const float* q, int R, float temperature, int normalize, float* out, float* part_m, float* part_l,
@@ -316,7 +352,8 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
   __nv_bfloat16* P16 = (__nv_bfloat16*)ws; ws += align_up((size_t)R * Mc * 2, 1024);
   float* m = (float*)ws;    ws += align_up((size_t)R * 4, 1024);
   float* l = (float*)ws;    ws += align_up((size_t)R * 4, 1024);
-  float* alpha = (float*)ws;
+  float* alpha = (float*)ws; ws += align_up((size_t)R * 4, 1024);
+  float* m_used = (float*)ws;
 
   PIO_CUDA(cudaMemcpyAsync(qn32, q, (size_t)R * D * 4, cudaMemcpyDeviceToDevice, st));
   PIO_TRY(l2norm_rows(qn32, R, D, st));                       // q / |q|  (im2txtprojection.py:368)
@@ -324,6 +361,50 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
   fill_kernel<<<cdiv(R, 256), 256, 0, st>>>(m, -INFINITY, R); PIO_LAUNCHED();
   PIO_CUDA(cudaMemsetAsync(l, 0, (size_t)R * 4, st));
   PIO_CUDA(cudaMemsetAsync(out, 0, (size_t)R * D * 4, st));
+
+  if (adt == PIO_DT_BF16 && !project_exact_requested()) {
+    // ---- fused path: P = exp2(s - m_ref) straight from the similarity GEMM's epilogue (no fp32 score matrix,
+    // no separate softmax pass).  m_ref lags by one chunk and never drops below log2e * (1/T - 70), so with
+    // |s| <= 1/T the exponent stays <= 70 / ln 2: no overflow for any input; accurate while max cosine >= -0.4.
+    const float log2e = 1.4426950408889634f;
+    // the S region (R x Mc fp32) hosts P (bf16, R x 2Mc columns) on this path: twice the chunk, same bytes
+    const int Mf = 2 * Mc;
+    __nv_bfloat16* P = (__nv_bfloat16*)S;
+    const int slabs_max = argmax_slabs_tc(R, Mf);
+    float* psum = (float*)P16;                       // [R, slabs_max]
+    float* pmax = psum + (size_t)R * slabs_max;      // [R, slabs_max]   (R*Mc*2 bytes are available: plenty)
+    PIO_CUDA(cudaMemsetAsync(P, 0, (size_t)R * Mf * 2, st));
+    fill_kernel<<<cdiv(R, 256), 256, 0, st>>>(m, log2e * (1.0f / temperature - 70.0f), R); PIO_LAUNCHED();
+    fill_kernel<<<cdiv(R, 256), 256, 0, st>>>(alpha, 1.0f, R); PIO_LAUNCHED();
+    for (long long c0 = 0; c0 < h->M; c0 += Mf) {
+      const int mc = (int)std::min<long long>(Mf, h->M - c0);
+      const int mc_pad = (mc + 63) / 64 * 64;
+      const int slabs = argmax_slabs_tc(R, mc);
+      PioLinear p;
+      memset(&p, 0, sizeof(p));
+      p.A = qn; p.W = (const char*)h->bank + (size_t)c0 * D * e; p.C = P; p.M = R; p.N = mc; p.K = D;
+      p.lda = D; p.ldw = D; p.ldc = Mf; p.a_dt = adt; p.c_dt = PIO_DT_BF16; p.colscale = h->inv_norm + c0;
+      p.alpha = log2e / temperature;
+      p.exp_ref = m; p.exp_psum = psum; p.exp_pmax = pmax; p.exp_ld = slabs_max;
+      PIO_TRY(linear_tc(p, st));
+      memset(&p, 0, sizeof(p));
+      p.A = P; p.W = (const char*)h->bankT + (size_t)c0 * e; p.C = out; p.M = R; p.N = D; p.K = mc_pad;
+      p.lda = Mf; p.ldw = (int)h->Mp; p.ldc = D; p.a_dt = adt; p.c_dt = PIO_DT_F32; p.residual = out; p.ldres = D;
+      p.res_rowscale = alpha; p.alpha = 1.0f;
+      PIO_TRY(linear_tc(p, st));
+      project_update_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(psum, pmax, slabs_max, slabs, R, m, m_used, l, alpha);
+      PIO_LAUNCHED();
+    }
+    // O and l are relative to the reference the LAST chunk used (m_used); the ratio O / l does not depend on it
+    if (part_m) {
+      scale_vec_kernel<<<cdiv(R, 256), 256, 0, st>>>(m_used, part_m, 1.0f / log2e, R); PIO_LAUNCHED();  // natural-log units
+      PIO_CUDA(cudaMemcpyAsync(part_l, l, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+      return PIO_OK;
+    }
+    finish_rows_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(out, l, R, D, normalize);
+    PIO_LAUNCHED();
+    return PIO_OK;
+  }
 
   for (long long c0 = 0; c0 < h->M; c0 += Mc) {
     const int mc = (int)std::min<long long>(Mc, h->M - c0);

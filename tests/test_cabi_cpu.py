@@ -42,7 +42,7 @@ def test_struct_layouts_match_header(built):
     assert ctypes.sizeof(built.PioVitWeights) == (4 + 12 * 14 + 2) * 8
     assert ctypes.sizeof(built.PioGptBlock) == 12 * 8
     assert ctypes.sizeof(built.PioDecoderWeights) == (2 + 4 * 12 + 2 + 2) * 8 + 8
-    assert ctypes.sizeof(built.PioLinear) == 24 + 32 + 40 + 4 + 4 + 4 + 12 + 24 + 8
+    assert ctypes.sizeof(built.PioLinear) == 24 + 32 + 40 + 4 + 4 + 4 + 12 + 24 + 8 + 24 + 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only behaviour")

@@ -347,6 +347,29 @@ def test_project_multi_chunk_and_sharded(dev, ops):
     assert cos_min(merged, ref) >= 0.9999
 
 
+def test_project_bf16_fused_multi_chunk_and_sharded(dev, ops):
+    """bf16 fast path (exp fused in the GEMM epilogue, lagging reference max): several chunks, a near-duplicate query
+    (logit ~ 1/T = 100 -> the overflow guard), opposite-direction queries, and the sharded (m, l, O) merge."""
+    bank = o_pipe.synth_bank(70000, 768, seed=23, zero_frac=0.001)
+    gen = torch.Generator().manual_seed(24)
+    q = torch.randn(200, 768, generator=gen)
+    q[5] = bank[60001] * 3.0 + 0.02 * torch.randn(768, generator=gen)   # match late in the bank: reference max jumps
+    q[6] = bank[17] * 0.5
+    q[7] = -bank[100]
+    ref = o_mem.project(q, o_mem.drop_zero_rows(bank), normalize=True)
+    full = ops.Bank(bank, dev, "bf16")
+    out = full.project(q.to(dev), normalize=True).cpu()
+    assert torch.isfinite(out).all()
+    assert cos_min(out, ref) >= 0.999, cos_min(out, ref)
+    shards = [ops.Bank(s, dev, "bf16") for s in bank.chunk(3)]
+    parts = [s.project(q.to(dev), partial=True) for s in shards]
+    m = torch.stack([p[0] for p in parts]).max(dim=0).values
+    for pm, pl, pO in parts:
+        ops.project_rescale_(pO, pl, pm, m)
+    merged = ops.project_finish_(sum(p[2] for p in parts), sum(p[1] for p in parts), True).cpu()
+    assert cos_min(merged, ref) >= 0.999, cos_min(merged, ref)
+
+
 # ----------------------------------------------------------------------------------------- decoder
 def test_decode_fp32_against_golden(dev, ops, golden):
     rec = golden("decoder")
