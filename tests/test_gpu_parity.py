@@ -52,7 +52,7 @@ def test_linear_fp32(dev, ops, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 64, 128), (300, 200, 192), (1030, 768, 768), (257, 2304, 768),
-                                   (4096, 768, 3072), (70, 1000, 640), (20000, 768, 768), (513, 5003, 768)])
+                                   (4096, 768, 3072), (70, 1000, 640), (20000, 768, 768), (513, 5003, 768), (2000, 5003, 192), (19000, 2304, 768)])
 def test_linear_bf16_tcgen05(dev, ops, M, N, K):
     """tcgen05 GEMM: products of bf16 inputs are exact in fp32, so only the accumulation order differs."""
     g = torch.Generator().manual_seed(M + N + K)

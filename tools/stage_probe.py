@@ -34,7 +34,7 @@ if what in ("text", "all"):
         e0.record()
         pre = bank.project(q, normalize=True)
         e1.record()
-        ids = dec.decode(pre, 30)
+        ids = dec.decode(pre, int(os.environ.get("PIO_STEPS", "30")))
         e2.record()
         torch.cuda.synchronize()
         print(f"project R={R}: {e0.elapsed_time(e1):.2f} ms   decode: {e1.elapsed_time(e2):.2f} ms", flush=True)
