@@ -19,12 +19,13 @@ constexpr int BM2 = 128;            // rows per CTA (256 per pair)
 constexpr int BN2 = 256;            // columns per pair tile
 constexpr int BNH = 128;            // W rows each CTA loads
 constexpr int BK2 = 64;
-constexpr int STAGES2 = 6;
+constexpr int STAGES2 = 5;
 constexpr int A2_BYTES = BM2 * BK2 * 2;   // 16 KB
 constexpr int B2_BYTES = BNH * BK2 * 2;   // 16 KB
 constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
-constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024;
 constexpr int NUM_EPI_WARPS2 = 8;
+constexpr int OUT_STAGE_BYTES = 4096;     // one 32-row x 128-byte TMA-store box per epilogue warp
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + NUM_EPI_WARPS2 * OUT_STAGE_BYTES + 1024;
 constexpr int NUM_THREADS2 = 64 + NUM_EPI_WARPS2 * 32;
 constexpr uint32_t TMEM_COLS2 = 512;      // 2 accumulators x 256 columns
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0
@@ -76,8 +77,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, void* C, int M, int N, int K,
-                int ldc, int c_dt, Epilogue epi) {
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_c, int store_mode, void* C, int M, int N, int K, int ldc, int c_dt, Epilogue epi) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[2 * STAGES2 + 4];
@@ -100,6 +101,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     for (int s = 0; s < STAGES2; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * NUM_EPI_WARPS2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -164,6 +166,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int quarter = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;
+    const TmaOut to{&map_c, smem_base + STAGES2 * STAGE2_BYTES + (warp - 2) * OUT_STAGE_BYTES, store_mode};
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int as = it & 1;
@@ -181,8 +184,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
-      epilogue_tile(tmem_base + as * BN2, quarter, lane, half, BN2, m, M, n0, N, (tile % n_blocks) * 2 + half, C, ldc, c_dt, epi,
-                    s_scale, s_bias, s_gamma);
+      epilogue_tile<BN2>(tmem_base + as * BN2, quarter, lane, half, m, M, n0, N, (tile % n_blocks) * 2 + half, C, ldc, c_dt, epi,
+                    s_scale, s_bias, s_gamma, to);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -190,6 +193,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         else mbar_arrive_remote(tempty_bar(as), 0);
       }
     }
+    stage_drain(lane);
   }
 
   tc_fence_before();
@@ -208,9 +212,12 @@ bool linear_tc2_eligible(const PioLinear& p) {
 }
 
 int linear_tc2(const PioLinear& p, cudaStream_t st) {
-  CUtensorMap ma, mw;
+  CUtensorMap ma, mw, mc;
   PIO_TRY(make_map_2d(&ma, p.A, p.M, p.K, p.lda, BM2, BK2));
   PIO_TRY(make_map_2d(&mw, p.W, p.N, p.K, p.ldw, BNH, BK2));
+  const int store_mode = tma_store_enabled() ? pick_store_mode(p) : STORE_DIRECT;
+  if (store_mode != STORE_DIRECT) PIO_TRY(make_map_out(&mc, p.C, p.M, p.N, p.ldc, p.c_dt));
+  else mc = ma;
   static bool attr_set = false;
   if (!attr_set) {
     PIO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
@@ -218,7 +225,7 @@ int linear_tc2(const PioLinear& p, cudaStream_t st) {
   }
   const int tiles = cdiv(p.M, 2 * BM2) * cdiv(p.N, BN2);
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
-  gemm_tc2_kernel<<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, st>>>(ma, mw, p.C, p.M, p.N, p.K, p.ldc, p.c_dt, make_epilogue(p));
+  gemm_tc2_kernel<<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, st>>>(ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc, p.c_dt, make_epilogue(p));
   PIO_LAUNCHED();
   return PIO_OK;
 }

@@ -39,12 +39,108 @@ __device__ __forceinline__ void store_chunk(void* C, long long base, const float
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-store output path.  An epilogue warp owns one 32-row x 128-byte staging box in shared memory (4 KB, 1024-byte
+// aligned, 128-byte swizzle: 16-byte chunk j of row r sits at r * 128 + ((j ^ (r & 7)) << 4), which makes the
+// lane-per-row st.shared.v4 conflict free).  One lane then issues cp.async.bulk.tensor (or cp.reduce ... .add for the
+// in-place residual  x += t) for the whole box: fully coalesced global writes, rows >= M / columns >= N clipped by the
+// tensor map, and no global load/store instructions in the epilogue warps at all.
+struct TmaOut {
+  const CUtensorMap* map;  // tensor map of C: box = 32 rows x 128 bytes, SWIZZLE_128B
+  uint32_t smem;           // this warp's staging box
+  int mode;                // 0 = direct stores, 1 = TMA store, 2 = TMA reduce-add (C += value)
+};
+enum { STORE_DIRECT = 0, STORE_TMA = 1, STORE_TMA_ADD = 2 };
+
+__device__ __forceinline__ void stage_wait_free(int lane) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// 32 consecutive output columns of this lane's row -> staging box.  bf16: 64 bytes = chunks [4 * part, 4 * part + 4);
+// fp32: 128 bytes = the whole row.
+template <bool OUT_BF16>
+__device__ __forceinline__ void stage_write(uint32_t smem, int lane, int part, const float (&v)[32]) {
+  const uint32_t row = smem + lane * 128;
+  const uint32_t x = lane & 7;
+  if constexpr (OUT_BF16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      st_shared_v4(row + (((uint32_t)(part * 4 + i) ^ x) << 4), pack_bf16x2(v[8 * i], v[8 * i + 1]), pack_bf16x2(v[8 * i + 2], v[8 * i + 3]),
+                   pack_bf16x2(v[8 * i + 4], v[8 * i + 5]), pack_bf16x2(v[8 * i + 6], v[8 * i + 7]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      st_shared_v4(row + (((uint32_t)i ^ x) << 4), __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]),
+                   __float_as_uint(v[4 * i + 3]));
+  }
+}
+// make the generic-proxy writes visible to the async proxy, then one lane issues the bulk tensor store of the box
+// whose first element is C[m_base, n]
+__device__ __forceinline__ void stage_commit(const TmaOut& to, int lane, int n, int m_base, bool add) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    if (add)
+      asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(to.map),
+                   "r"(to.smem), "r"(n), "r"(m_base)
+                   : "memory");
+    else
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(to.map), "r"(to.smem),
+                   "r"(n), "r"(m_base)
+                   : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+// before the kernel exits: every bulk store this thread issued has completed
+__device__ __forceinline__ void stage_drain(int lane) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  __syncwarp();
+}
+
+// Activations of the bf16 tensor-core path.  The exact erff / tanhf of the fp32 path cost 25-30 instructions per element,
+// more than the MMA time of the tile they follow; these use the SFU (rcp / ex2 / tanh.approx) instead.
+//   erf: Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 (far below the bf16 rounding of the result)
+//   tanh.approx.f32: relative error 2^-11, below the bf16 rounding (2^-9) of the activation it feeds
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float ax = fabsf(x), z = ax * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float erf_abs = fmaf(-p, ex2_approx(-1.4426950408889634f * z * z), 1.0f);  // erf(|x| / sqrt 2)
+  return 0.5f * fmaf(ax, erf_abs, x);                                              // 0.5 x (1 + sign(x) erf_abs)
+}
+__device__ __forceinline__ float gelu_new_fast(float x) {
+  const float u = 0.79788456080286535588f * fmaf(0.044715f * x * x, x, x);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
+
 // One epilogue warp, one tile: columns [c_begin, c_end) of TMEM lane quarter `quarter`.
 //   out = residual * rowscale + gamma * act(acc * (alpha * colscale) + bias); vectors come from shared memory.
-template <int ACT, bool HAS_RES, bool OUT_BF16>
-__device__ __forceinline__ void epilogue_cols(uint32_t tmem_acc, int quarter, int lane, int c_begin, int c_end, int m, int M,
+// STORE_TMA_ADD is the in-place residual (residual == C, no row scale): the value is reduced into C by the copy engine.
+template <int ACT, bool HAS_RES, bool OUT_BF16, int STORE, int NCOLS>
+__device__ __forceinline__ void epilogue_cols(uint32_t tmem_acc, int quarter, int lane, int c_begin, int m, int M,
                                               int n0, int N, void* C, int ldc, const Epilogue& epi, const float* s_scale,
-                                              const float* s_bias, const float* s_gamma) {
+                                              const float* s_bias, const float* s_gamma, const TmaOut& to) {
   const long long orow = epi.out_row(m < M ? m : 0);
   const bool row_ok = m < M;
   const bool vec_ok = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
@@ -57,12 +153,17 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_acc, int quarter, in
   }
   const bool res_vec = HAS_RES && (epi.ldres % 4 == 0) && ((reinterpret_cast<uintptr_t>(epi.residual) & 15) == 0);
   const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+  const int c_end = c_begin + NCOLS;  // NCOLS is a compile-time constant: the chunk loop below unrolls completely
   auto process = [&](const uint32_t (&r)[32], int c) {
     const int n = n0 + c;
     const int nvalid = min(32, N - n);
-    if (!(row_ok && nvalid > 0)) return;
+    if constexpr (STORE != STORE_DIRECT) {
+      if (nvalid <= 0) return;  // uniform: the whole chunk lies beyond N (rows >= M are clipped by the tensor map)
+    } else {
+      if (!(row_ok && nvalid > 0)) return;
+    }
     float res[32];
-    if constexpr (HAS_RES) {
+    if constexpr (HAS_RES && STORE == STORE_DIRECT) {
       const float* rp = epi.residual + orow * epi.ldres + n;
       if (nvalid == 32 && res_vec) {
 #pragma unroll
@@ -86,27 +187,36 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_acc, int quarter, in
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float t = fmaf(__uint_as_float(r[i + j]), scv[j], biv[j]);
-        if constexpr (ACT == PIO_ACT_GELU_ERF) t = gelu_erf(t);
-        if constexpr (ACT == PIO_ACT_GELU_NEW) t = gelu_new(t);
+        if constexpr (ACT == PIO_ACT_GELU_ERF) t = gelu_erf_fast(t);
+        if constexpr (ACT == PIO_ACT_GELU_NEW) t = gelu_new_fast(t);
         t *= gav[j];
-        if constexpr (HAS_RES) t = fmaf(res[i + j], rs, t);
+        if constexpr (HAS_RES && STORE == STORE_DIRECT) t = fmaf(res[i + j], rs, t);
         v[i + j] = t;
       }
     }
-    store_chunk<OUT_BF16>(C, orow * ldc + n, v, nvalid, vec_ok);
+    if constexpr (STORE == STORE_DIRECT) {
+      store_chunk<OUT_BF16>(C, orow * ldc + n, v, nvalid, vec_ok);
+    } else {
+      const int part = OUT_BF16 ? (((c - c_begin) >> 5) & 1) : 0;
+      if (part == 0) stage_wait_free(lane);  // the previous box has been read out of shared memory
+      stage_write<OUT_BF16>(to.smem, lane, part, v);
+      if (!OUT_BF16 || part == 1 || c + 32 >= c_end || n + 32 >= N)
+        stage_commit(to, lane, n - 32 * part, m - lane, STORE == STORE_TMA_ADD);
+    }
   };
   // software pipeline over two register buffers: the tcgen05.ld of the next chunk is in flight while this one
   // is processed (static buffer names -- dynamic indexing would push the arrays to local memory)
   uint32_t ra[32], rb[32];
   tmem_ld32(taddr + c_begin, ra);
 #pragma unroll
-  for (int c = c_begin; c < c_end; c += 64) {
+  for (int j = 0; j < NCOLS; j += 64) {
+    const int c = c_begin + j;
     tmem_ld_wait();
-    if (c + 32 < c_end) tmem_ld32(taddr + c + 32, rb);
+    if (j + 32 < NCOLS) tmem_ld32(taddr + c + 32, rb);
     process(ra, c);
-    if (c + 32 < c_end) {
+    if (j + 32 < NCOLS) {
       tmem_ld_wait();
-      if (c + 64 < c_end) tmem_ld32(taddr + c + 64, ra);
+      if (j + 64 < NCOLS) tmem_ld32(taddr + c + 64, ra);
       process(rb, c + 32);
     }
   }
@@ -119,8 +229,9 @@ __device__ __forceinline__ float ex2_approx_ftz(float x) {
 }
 
 // Fused exponential epilogue (streaming softmax numerator): this warp's columns [c_begin, c_end) of its row.
-__device__ __forceinline__ void epilogue_exp(uint32_t tmem_acc, int quarter, int c_begin, int c_end, int m, int M, int n0, int N,
-                                             int slab, void* C, int ldc, const Epilogue& epi, const float* s_scale) {
+__device__ __forceinline__ void epilogue_exp(uint32_t tmem_acc, int quarter, int lane, int c_begin, int c_end, int m, int M, int n0,
+                                             int N, int slab, void* C, int ldc, const Epilogue& epi, const float* s_scale,
+                                             const TmaOut& to) {
   const bool row_ok = m < M;
   const float ref = row_ok ? __ldg(epi.exp_ref + m) : 0.f;
   const bool vec_ok = (ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
@@ -132,7 +243,8 @@ __device__ __forceinline__ void epilogue_exp(uint32_t tmem_acc, int quarter, int
     tmem_ld_wait();
     const int n = n0 + c;
     const int nvalid = min(32, N - n);
-    if (row_ok && nvalid > 0) {
+    if (nvalid <= 0) break;  // uniform
+    if (row_ok || to.mode != STORE_DIRECT) {
       float v[32];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
@@ -145,7 +257,14 @@ __device__ __forceinline__ void epilogue_exp(uint32_t tmem_acc, int quarter, int
         sum0 += v[i];
         sum1 += v[i + 1];
       }
-      store_chunk<true>(C, (long long)m * ldc + n, v, nvalid, vec_ok);
+      if (to.mode == STORE_DIRECT) {
+        store_chunk<true>(C, (long long)m * ldc + n, v, nvalid, vec_ok);
+      } else {
+        const int part = ((c - c_begin) >> 5) & 1;
+        if (part == 0) stage_wait_free(lane);
+        stage_write<true>(to.smem, lane, part, v);
+        if (part == 1 || c + 32 >= c_end || n + 32 >= N) stage_commit(to, lane, n - 32 * part, m - lane, false);
+      }
     }
   }
   if (row_ok) {
@@ -196,29 +315,60 @@ __device__ __forceinline__ void epilogue_argmax(uint32_t tmem_acc, int quarter, 
 
 
 // One epilogue warp, one tile: dispatch on the (uniform) epilogue kind.  `half` selects this warp's column half.
-__device__ __forceinline__ void epilogue_tile(uint32_t tacc, int quarter, int lane, int half, int BN, int m, int M, int n0, int N,
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(uint32_t tacc, int quarter, int lane, int half, int m, int M, int n0, int N,
                                               int slab, void* C, int ldc, int c_dt, const Epilogue& epi, const float* s_scale,
-                                              const float* s_bias, const float* s_gamma) {
-  const int cb = half * (BN / 2), ce = cb + BN / 2;
+                                              const float* s_bias, const float* s_gamma, const TmaOut& to) {
   const bool bf = c_dt == PIO_DT_BF16;
+  // this warp's columns: half of the tile (the 192-wide tile is cut 128 + 64 for bf16 output: 64-column staging boxes)
+  const int cb = half * (BN / 2), ce = cb + BN / 2;
   const bool hr = epi.residual != nullptr;
   if (epi.argmax_val != nullptr) {
     epilogue_argmax(tacc, quarter, cb, ce, m, M, n0, N, slab, epi, s_scale, s_bias);
   } else if (epi.exp_ref != nullptr) {
-    epilogue_exp(tacc, quarter, cb, ce, m, M, n0, N, slab, C, ldc, epi, s_scale);
+    epilogue_exp(tacc, quarter, lane, cb, ce, m, M, n0, N, slab, C, ldc, epi, s_scale, to);
   } else
-#define PIO_EPI(ACTV, HR, BF) epilogue_cols<ACTV, HR, BF>(tacc, quarter, lane, cb, ce, m, M, n0, N, C, ldc, epi, s_scale, s_bias, s_gamma)
-#define PIO_EPI_ACT(ACTV)                  \
-  do {                         \
-    if (hr) { if (bf) PIO_EPI(ACTV, true, true); else PIO_EPI(ACTV, true, false); }   \
-    else    { if (bf) PIO_EPI(ACTV, false, true); else PIO_EPI(ACTV, false, false); } \
+#define PIO_EPI_N(ACTV, HR, BF, ST, NC, CB) \
+  epilogue_cols<ACTV, HR, BF, ST, NC>(tacc, quarter, lane, CB, m, M, n0, N, C, ldc, epi, s_scale, s_bias, s_gamma, to)
+#define PIO_EPI(ACTV, HR, BF, ST)                                                              \
+  do {                                                                                         \
+    if constexpr (BN == 192 && BF) {                                                           \
+      if (half == 0) PIO_EPI_N(ACTV, HR, BF, ST, 128, 0); else PIO_EPI_N(ACTV, HR, BF, ST, 64, 128); \
+    } else {                                                                                   \
+      PIO_EPI_N(ACTV, HR, BF, ST, BN / 2, cb);                                                 \
+    }                                                                                          \
+  } while (0)
+#define PIO_EPI_ACT(ACTV)                                                                         \
+  do {                                                                                            \
+    if (to.mode == STORE_TMA_ADD) PIO_EPI(ACTV, true, false, STORE_TMA_ADD); /* fp32, C += value */ \
+    else if (to.mode == STORE_TMA) { if (bf) PIO_EPI(ACTV, false, true, STORE_TMA); else PIO_EPI(ACTV, false, false, STORE_TMA); } \
+    else if (hr) { if (bf) PIO_EPI(ACTV, true, true, STORE_DIRECT); else PIO_EPI(ACTV, true, false, STORE_DIRECT); }   \
+    else         { if (bf) PIO_EPI(ACTV, false, true, STORE_DIRECT); else PIO_EPI(ACTV, false, false, STORE_DIRECT); } \
   } while (0)
   if (epi.act == PIO_ACT_GELU_ERF) PIO_EPI_ACT(PIO_ACT_GELU_ERF);
   else if (epi.act == PIO_ACT_GELU_NEW) PIO_EPI_ACT(PIO_ACT_GELU_NEW);
   else PIO_EPI_ACT(PIO_ACT_NONE);
 #undef PIO_EPI_ACT
 #undef PIO_EPI
+#undef PIO_EPI_N
 }
+
+// Host side: which output path a launch may use (the staging boxes need `tma_capable` kernels: see Cfg / gemm2).
+inline int pick_store_mode(const PioLinear& p) {
+  const size_t es = p.c_dt == PIO_DT_BF16 ? 2 : 4;
+  if (p.argmax_val != nullptr || p.C == nullptr || p.rows_per_group != 0) return STORE_DIRECT;
+  if ((reinterpret_cast<uintptr_t>(p.C) & 15) != 0 || ((size_t)p.ldc * es) % 16 != 0) return STORE_DIRECT;
+  // measured on B200: the bulk tensor store clips the inner dimension in 16-byte units (a chunk that straddles N is
+  // written whole), so N must end on a 16-byte boundary
+  if (((size_t)p.N * es) % 16 != 0) return STORE_DIRECT;
+  if (p.residual == nullptr) return STORE_TMA;
+  if (p.residual == p.C && p.ldres == p.ldc && p.res_rowscale == nullptr && p.c_dt == PIO_DT_F32 && p.exp_ref == nullptr)
+    return STORE_TMA_ADD;
+  return STORE_DIRECT;
+}
+// tensor map of C for the staging boxes: 32 rows x 128 bytes, 128-byte swizzle
+int make_map_out(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int c_dt);
+bool tma_store_enabled();  // PIO_GEMM_TMA_STORE=0 forces the direct-store epilogue (A/B testing)
 
 }  // namespace tc
 }  // namespace pio

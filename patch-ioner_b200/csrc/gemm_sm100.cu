@@ -17,6 +17,7 @@
 #include "tc_ptx.cuh"
 #include "gemm_epilogue.cuh"
 
+#include <algorithm>
 #include <mutex>
 #include <stdlib.h>
 
@@ -34,15 +35,19 @@ template <int BN> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // power of two: 128 / 256 / 512
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*manual 1024-byte alignment*/;
+  // the 256-wide tile keeps 4 x 48 KB of operand ring and therefore direct stores; the narrower tiles trade one ring
+  // slot for the TMA-store staging boxes (one 4 KB box per epilogue warp)
+  static constexpr bool TMA_OUT = BN != 256;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 5 : 7));
+  static constexpr int TMEM_COLS = BN == 192 ? 512 : 2 * BN;  // power of two: 128 / 256 / 512
+  static constexpr int OUT_BYTES = TMA_OUT ? NUM_EPI_WARPS * 4096 : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BYTES + 1024 /*manual 1024-byte alignment*/;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, void* C, int M, int N, int K,
-               int ldc, int c_dt, Epilogue epi) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+               const __grid_constant__ CUtensorMap map_c, int store_mode, void* C, int M, int N, int K, int ldc, int c_dt, Epilogue epi) {
   using cfg = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms
@@ -128,6 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int quarter = warp & 3;              // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;          // which half of the tile's columns
     const int et = threadIdx.x - 64;           // 0..255 among the epilogue threads
+    const TmaOut to{&map_c, smem_base + cfg::STAGES * cfg::STAGE_BYTES + (warp - 2) * 4096, cfg::TMA_OUT ? store_mode : STORE_DIRECT};
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
@@ -147,11 +153,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
       const uint32_t tacc = tmem_base + as * BN;
-      epilogue_tile(tacc, quarter, lane, half, BN, m, M, n0, N, (tile % n_blocks) * 2 + half, C, ldc, c_dt, epi, s_scale, s_bias, s_gamma);
+      epilogue_tile<BN>(tacc, quarter, lane, half, m, M, n0, N, (tile % n_blocks) * 2 + half, C, ldc, c_dt, epi, s_scale, s_bias, s_gamma, to);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
     }
+    stage_drain(lane);
   }
 
   tc_fence_before();
@@ -166,9 +173,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 template <int BN>
 int launch(const PioLinear& p, cudaStream_t st) {
   using cfg = Cfg<BN>;
-  CUtensorMap ma, mw;
+  CUtensorMap ma, mw, mc;
   PIO_TRY(make_map_2d(&ma, p.A, p.M, p.K, p.lda, BM, BK));
   PIO_TRY(make_map_2d(&mw, p.W, p.N, p.K, p.ldw, BN, BK));
+  // a bf16 staging box is 64 columns wide; with the 64-wide tile an epilogue warp owns only 32 columns
+  const bool box_fits = BN >= 128 || p.c_dt != PIO_DT_BF16;
+  const int store_mode = (cfg::TMA_OUT && box_fits && tma_store_enabled()) ? pick_store_mode(p) : STORE_DIRECT;
+  if (store_mode != STORE_DIRECT) PIO_TRY(make_map_out(&mc, p.C, p.M, p.N, p.ldc, p.c_dt));
+  else mc = ma;
   static bool attr_set = false;
   if (!attr_set) {
     PIO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
@@ -176,7 +188,7 @@ int launch(const PioLinear& p, cudaStream_t st) {
   }
   const int tiles = cdiv(p.M, BM) * cdiv(p.N, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, cfg::SMEM_BYTES, st>>>(ma, mw, p.C, p.M, p.N, p.K, p.ldc, p.c_dt, make_epilogue(p));
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, cfg::SMEM_BYTES, st>>>(ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc, p.c_dt, make_epilogue(p));
   PIO_LAUNCHED();
   return PIO_OK;
 }
@@ -196,12 +208,19 @@ int linear_tc(const PioLinear& p, cudaStream_t st) {
   PIO_CHECK(p.exp_ref == nullptr || (p.exp_psum && p.exp_pmax && p.c_dt == PIO_DT_BF16 && p.exp_ld >= argmax_slabs_tc(p.M, p.N)),
             "tcgen05 GEMM: fused exp needs bf16 C and psum/pmax buffers with ld >= pio_argmax_slabs()");
   static const bool use_2cta = [] { const char* e = getenv("PIO_GEMM_2CTA"); return !(e && e[0] == '0'); }();
-  if (use_2cta && linear_tc2_eligible(p)) return linear_tc2(p, st);  // big shapes: CTA pairs, 256 x 256 tiles
-  if (p.argmax_val != nullptr || p.exp_ref != nullptr) return launch<256>(p, st);  // slab count is defined for the 256-wide tile
-  // widest N tile that still gives every SM at least one tile
+  const bool slabs256 = p.argmax_val != nullptr || p.exp_ref != nullptr;  // slab count is defined for 256-wide tiles
+  // Tile shape: fewest (waves x per-tile MMA time), with a small penalty for the narrower, less efficient tiles.
+  // per-SM cost of one tile ~ its width (every CTA owns 128 rows); 74 CTA pairs or 148 CTAs work per wave.
   const long long mt = cdiv(p.M, BM);
-  if (mt * cdiv(p.N, 256) >= kNumSMs) return launch<256>(p, st);
-  if (mt * cdiv(p.N, 128) >= kNumSMs) return launch<128>(p, st);
+  auto cost = [&](int bn, double penalty) { return (double)cdiv(mt * cdiv(p.N, bn), kNumSMs) * bn * penalty; };
+  const double c2 = (use_2cta && linear_tc2_eligible(p)) ? (double)cdiv((long long)cdiv(p.M, 256) * cdiv(p.N, 256), kNumSMs / 2) * 256 * 0.95 : 1e30;
+  const double c256 = cost(256, 1.0), c192 = slabs256 ? 1e30 : cost(192, 1.03), c128 = slabs256 ? 1e30 : cost(128, 1.10),
+               c64 = slabs256 ? 1e30 : cost(64, 1.30);
+  const double best = std::min(std::min(std::min(c2, c256), std::min(c192, c128)), c64);
+  if (best == c2) return linear_tc2(p, st);
+  if (best == c256) return launch<256>(p, st);
+  if (best == c192) return launch<192>(p, st);
+  if (best == c128) return launch<128>(p, st);
   return launch<64>(p, st);
 }
 
@@ -237,6 +256,25 @@ int make_map_2d(CUtensorMap* map, const void* ptr, long long rows, long long col
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(PIO_ECUDA, "cuTensorMapEncodeTiled failed with %d (rows %lld cols %lld ld %lld)", (int)r, rows, cols, ld);
   return PIO_OK;
+}
+
+int make_map_out(CUtensorMap* map, const void* ptr, long long rows, long long cols, long long ld, int c_dt) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(PIO_ECUDA, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  const bool bf = c_dt == PIO_DT_BF16;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (bf ? 2 : 4)};
+  cuuint32_t box[2] = {(cuuint32_t)(bf ? 64 : 32), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(PIO_ECUDA, "cuTensorMapEncodeTiled (output) failed with %d (rows %lld cols %lld ld %lld)", (int)r, rows, cols, ld);
+  return PIO_OK;
+}
+bool tma_store_enabled() {
+  static const bool on = [] { const char* e = getenv("PIO_GEMM_TMA_STORE"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 int make_map_f32_3d(CUtensorMap* map, const void* ptr, long long d0, long long d1, long long d2, long long stride1_bytes,

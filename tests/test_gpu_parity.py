@@ -70,6 +70,16 @@ def test_linear_bf16_tcgen05(dev, ops, M, N, K):
     torch.testing.assert_close(out2.cpu(), ref2, rtol=2e-3, atol=2e-3)
     out3 = ops.linear(A.to(dev), W.to(dev), "bf16", bias=bias.to(dev), out_dtype=torch.bfloat16)
     torch.testing.assert_close(out3.float().cpu(), ref + bias, rtol=2e-2, atol=2e-2)
+    # in-place residual stream  x += gamma * (A W^T + bias)  (the copy engine's reduce-add when the layout allows it)
+    X = res.clone().to(dev)
+    ops.linear(A.to(dev), W.to(dev), "bf16", bias=bias.to(dev), gamma=gamma.to(dev), residual=X, out=X)
+    torch.testing.assert_close(X.cpu(), res + gamma * (ref + bias), rtol=2e-3, atol=2e-3)
+    # gelu to bf16 through a padded leading dimension (what the ViT's fc1 does)
+    ld = (N + 63) // 64 * 64 + 64
+    buf = torch.full((M, ld), 7.0, dtype=torch.bfloat16, device=dev)
+    ops.linear(A.to(dev), W.to(dev), "bf16", bias=bias.to(dev), act=1, out=buf[:, :N])
+    torch.testing.assert_close(buf[:, :N].float().cpu(), torch.nn.functional.gelu(ref + bias), rtol=2e-2, atol=2e-2)
+    assert (buf[:, N:] == 7.0).all(), "columns beyond N must not be written"
 
 
 def test_linear_inplace_residual_and_rowscale(dev, ops):
