@@ -208,10 +208,23 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
     f[2 * i + 1] = t.y;
   }
 }
+// streaming 16-byte load: the KV cache is read once per step and never reused inside a launch
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// scheduling fence: keeps ptxas from sinking the loads of a batch next to their uses (which leaves one load in flight)
+__device__ __forceinline__ void hold8(uint4 (&v)[8]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) asm volatile("" : "+r"(v[u].x), "+r"(v[u].y), "+r"(v[u].z), "+r"(v[u].w));
+}
+// Keys / values are walked in batches of 8 rows: the 8 loads are issued back to back (8 x 384 B in flight per warp, enough
+// to cover the HBM latency at 32 resident warps per SM) and the 8 warp reductions interleave.
 __global__ void __launch_bounds__(128) decode_attention_bf16_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ kc,
                                                                     __nv_bfloat16* __restrict__ vc, __nv_bfloat16* __restrict__ out,
                                                                     int R, int H, int T, int t, float scale) {
-  constexpr int HDIM = 192;
+  constexpr int HDIM = 192, KB = 8;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= R * H) return;
   const int r = warp / H, h = warp % H;
@@ -220,7 +233,8 @@ __global__ void __launch_bounds__(128) decode_attention_bf16_kernel(const __nv_b
   __nv_bfloat16* kbase = kc + ((long long)(r * H + h) * T) * HDIM + lane * 8;
   __nv_bfloat16* vbase = vc + ((long long)(r * H + h) * T) * HDIM + lane * 8;
   float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  uint4 knew = make_uint4(0, 0, 0, 0), vnew = knew;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  uint4 knew = zero, vnew = zero;
   if (act) {
     const uint4 qu = *reinterpret_cast<const uint4*>(row);
     knew = *reinterpret_cast<const uint4*>(row + H * HDIM);
@@ -229,29 +243,63 @@ __global__ void __launch_bounds__(128) decode_attention_bf16_kernel(const __nv_b
     *reinterpret_cast<uint4*>(kbase + (long long)t * HDIM) = knew;   // append this step's key / value
     *reinterpret_cast<uint4*>(vbase + (long long)t * HDIM) = vnew;
   }
+  const int tl = t > 0 ? t - 1 : 0;  // last row that older steps wrote (row t itself comes from registers)
   float my = -INFINITY;  // lane j keeps score j
-  for (int j = 0; j <= t; ++j) {
-    float s = 0.f;
-    if (act) {
-      const uint4 ku = (j == t) ? knew : *reinterpret_cast<const uint4*>(kbase + (long long)j * HDIM);
-      float kf[8];
-      unpack8(ku, kf);
+  for (int j0 = 0; j0 <= t; j0 += KB) {
+    uint4 ku[KB];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s = fmaf(q[e], kf[e], s);
+    for (int u = 0; u < KB; ++u) {
+      const int j = j0 + u;
+      ku[u] = ld_stream16(kbase + (long long)min(j, tl) * HDIM);  // unconditional (always inside this head's T rows)
     }
-    s = warp_sum(s) * scale;
-    if (lane == j) my = s;
+    hold8(ku);  // all 8 loads are issued before the first use
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+      const int j = j0 + u;
+      ku[u] = (act && j < t) ? ku[u] : (j == t ? knew : zero);
+    }
+    float sc[KB];
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+      float kf[8];
+      unpack8(ku[u], kf);
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a = fmaf(q[e], kf[e], a);
+      sc[u] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < KB; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < KB; ++u)
+      if (lane == j0 + u) my = sc[u] * scale;
   }
+  my = (lane <= t) ? my : -INFINITY;
   const float mx = warp_max(my);
-  const float p = (lane <= t) ? __expf(my - mx) : 0.f;
-  const float inv = 1.0f / warp_sum(p);
+  const float pe = (lane <= t) ? __expf(my - mx) : 0.f;
+  const float p = pe * (1.0f / warp_sum(pe));
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int j = 0; j <= t; ++j) {
-    const float pj = __shfl_sync(0xffffffffu, p, j) * inv;
-    if (act) {
-      const uint4 vu = (j == t) ? vnew : *reinterpret_cast<const uint4*>(vbase + (long long)j * HDIM);
+  for (int j0 = 0; j0 <= t; j0 += KB) {
+    uint4 vu[KB];
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+      const int j = j0 + u;
+      vu[u] = ld_stream16(vbase + (long long)min(j, tl) * HDIM);
+    }
+    hold8(vu);
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+      const int j = j0 + u;
+      vu[u] = (act && j < t) ? vu[u] : (j == t ? vnew : zero);
+    }
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+      const float pj = __shfl_sync(0xffffffffu, p, (j0 + u) & 31);  // lanes beyond t hold p = 0
       float vf[8];
-      unpack8(vu, vf);
+      unpack8(vu[u], vf);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vf[e], acc[e]);
     }
