@@ -226,6 +226,8 @@ __global__ void __launch_bounds__(128) decode_attention_bf16_kernel(const __nv_b
                                                                     int R, int H, int T, int t, float scale) {
   constexpr int HDIM = 192, KB = 8;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch_dependents();
   if (warp >= R * H) return;
   const int r = warp / H, h = warp % H;
   const bool act = lane < HDIM / 8;
@@ -340,8 +342,8 @@ int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int
   if (dt == PIO_DT_F32)
     decode_attention_kernel<float, float, float, 192><<<blocks, 128, 0, st>>>((const float*)qkv, (float*)kc, (float*)vc, (float*)out, R, H, T, t, scale);
   else
-    decode_attention_bf16_kernel<<<blocks, 128, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc,
-                                                         (__nv_bfloat16*)out, R, H, T, t, scale);
+    launch_pdl(decode_attention_bf16_kernel, dim3(blocks), dim3(128), 0, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)kc,
+               (__nv_bfloat16*)vc, (__nv_bfloat16*)out, R, H, T, t, scale);
   PIO_LAUNCHED();
   return PIO_OK;
 }

@@ -36,6 +36,8 @@ constexpr uint32_t TM_S0 = 0, TM_PV0 = 128, TM_COLS = 256;  // S at cols 0..127,
 __global__ void __launch_bounds__(256) transpose_v_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vt,
                                                           int N, int Np, int H) {
   __shared__ __nv_bfloat16 tile[64][HD + 2];
+  pdl_wait();
+  pdl_launch_dependents();
   const int n0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
   const int C3 = 3 * H * HD;
   const __nv_bfloat16* src = qkv + (long long)b * N * C3 + 2 * H * HD + h * HD;
@@ -158,6 +160,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -306,7 +310,7 @@ int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int 
   const int Np = (N + 7) / 8 * 8;
   {
     dim3 grid(cdiv(Np, 64), H, B);
-    transpose_v_kernel<<<grid, dim3(64, 4), 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)vt_ws, N, Np, H);
+    launch_pdl(transpose_v_kernel, grid, dim3(64, 4), 0, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)vt_ws, N, Np, H);
     PIO_LAUNCHED();
   }
   CUtensorMap mqk, mvt;
@@ -319,7 +323,7 @@ int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int 
   }
   dim3 grid(cdiv(N, BQ), H, B);
   const float scale_log2e = 0.125f * 1.4426950408889634f;
-  vit_attention_tc_kernel<<<grid, ATT_THREADS, ATT_SMEM, st>>>(mqk, mvt, (__nv_bfloat16*)out, N, H, scale_log2e);
+  launch_pdl(vit_attention_tc_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, st, mqk, mvt, (__nv_bfloat16*)out, N, H, scale_log2e);
   PIO_LAUNCHED();
   return PIO_OK;
 }

@@ -60,6 +60,28 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl() may start while its predecessor in
+// the stream is still draining; it must execute pdl_wait() before it touches anything a predecessor wrote (or before it
+// overwrites anything a predecessor reads).  Everything ahead of pdl_wait() -- barrier init, tensor-memory allocation,
+// tensor-map prefetch -- then overlaps the predecessor's tail.  PIO_PDL=0 restores plain stream order.
+bool pdl_enabled();  // elementwise.cu
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // -------------------------------------------------------------------------------- device helpers
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -2,11 +2,16 @@
 // row L2-normalisation, row softmax, row arg-max.  All vectorised 16-byte accesses, one warp per
 // row where a row reduction is needed (warp-shuffle reductions, no shared memory).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace pio {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("PIO_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 namespace {
 
@@ -17,6 +22,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ b, void* out, int out_dt, int ldo,
                                                         int rows, float eps) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch_dependents();
   if (warp >= rows) return;
   constexpr int DIM = VEC * 128;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)warp * ldx);
@@ -203,7 +210,7 @@ int layernorm(const float* x, int ldx, const float* w, const float* b, void* out
   const int blocks = cdiv((long long)rows * 32, 256);
 #define LN_CASE(V)                                                                                   \
   case V:                                                                                            \
-    layernorm_kernel<V><<<blocks, 256, 0, st>>>(x, ldx, w, b, out, out_dt, ldo, rows, eps);          \
+    launch_pdl(layernorm_kernel<V>, dim3(blocks), dim3(256), 0, st, x, ldx, w, b, out, out_dt, ldo, rows, eps); \
     break;
   switch (dim / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)

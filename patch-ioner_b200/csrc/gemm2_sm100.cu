@@ -111,6 +111,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   cluster_sync_all();  // barriers and tensor memory of BOTH CTAs are ready
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_var);
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
@@ -225,7 +227,8 @@ int linear_tc2(const PioLinear& p, cudaStream_t st) {
   }
   const int tiles = cdiv(p.M, 2 * BM2) * cdiv(p.N, BN2);
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
-  gemm_tc2_kernel<<<2 * pairs, NUM_THREADS2, SMEM2_BYTES, st>>>(ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc, p.c_dt, make_epilogue(p));
+  launch_pdl(gemm_tc2_kernel, dim3(2 * pairs), dim3(NUM_THREADS2), SMEM2_BYTES, st, ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc,
+             p.c_dt, make_epilogue(p));
   PIO_LAUNCHED();
   return PIO_OK;
 }

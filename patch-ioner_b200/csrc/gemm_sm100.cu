@@ -79,6 +79,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_var);
+  pdl_wait();               // everything above overlapped the previous kernel's tail
+  pdl_launch_dependents();  // the next kernel may start its own prologue as soon as this grid's CTAs retire
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -188,7 +190,8 @@ int launch(const PioLinear& p, cudaStream_t st) {
   }
   const int tiles = cdiv(p.M, BM) * cdiv(p.N, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
-  gemm_tc_kernel<BN><<<grid, NUM_THREADS, cfg::SMEM_BYTES, st>>>(ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc, p.c_dt, make_epilogue(p));
+  launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), cfg::SMEM_BYTES, st, ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc,
+             p.c_dt, make_epilogue(p));
   PIO_LAUNCHED();
   return PIO_OK;
 }
@@ -217,6 +220,13 @@ int linear_tc(const PioLinear& p, cudaStream_t st) {
   const double c256 = cost(256, 1.0), c192 = slabs256 ? 1e30 : cost(192, 1.03), c128 = slabs256 ? 1e30 : cost(128, 1.10),
                c64 = slabs256 ? 1e30 : cost(64, 1.30);
   const double best = std::min(std::min(std::min(c2, c256), std::min(c192, c128)), c64);
+  if (const char* force = getenv("PIO_GEMM_TILE")) {  // A/B testing: 2cta | 256 | 192 | 128 | 64
+    if (!strcmp(force, "2cta")) return linear_tc2(p, st);
+    if (!strcmp(force, "256") || slabs256) return launch<256>(p, st);
+    if (!strcmp(force, "192")) return launch<192>(p, st);
+    if (!strcmp(force, "128")) return launch<128>(p, st);
+    if (!strcmp(force, "64")) return launch<64>(p, st);
+  }
   if (best == c2) return linear_tc2(p, st);
   if (best == c256) return launch<256>(p, st);
   if (best == c192) return launch<192>(p, st);

@@ -57,6 +57,8 @@ __global__ void project_update_kernel(const float* __restrict__ psum, const floa
                                       float* __restrict__ mref, float* __restrict__ m_used, float* __restrict__ l,
                                       float* __restrict__ alpha) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch_dependents();
   if (warp >= R) return;
   float s = 0.f, mx = -INFINITY;
   for (int k = lane; k < slabs; k += 32) {
@@ -166,6 +168,8 @@ __global__ void __launch_bounds__(256) argmax_finish_kernel(const float* __restr
                                                             const float* __restrict__ sumexp, int ld, int slabs, int M,
                                                             int* __restrict__ ids, int ids_ld, int t, float* __restrict__ logprob_sum) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch_dependents();
   if (row >= M) return;
   float best = -INFINITY;
   int bi = 0x7fffffff;
@@ -196,6 +200,8 @@ __global__ void __launch_bounds__(256) argmax_finish_kernel(const float* __restr
 __global__ void embed_kernel(const float* __restrict__ wte, const float* __restrict__ wpe, const int* __restrict__ ids,
                              int ids_ld, int t, int pos, float* __restrict__ x, int R, int D) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch_dependents();
   if (warp >= R) return;
   const int tok = ids[(long long)warp * ids_ld + t];
   const float4* a = reinterpret_cast<const float4*>(wte + (long long)tok * D);
@@ -392,7 +398,8 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
       p.lda = Mf; p.ldw = (int)h->Mp; p.ldc = D; p.a_dt = adt; p.c_dt = PIO_DT_F32; p.residual = out; p.ldres = D;
       p.res_rowscale = alpha; p.alpha = 1.0f;
       PIO_TRY(linear_tc(p, st));
-      project_update_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(psum, pmax, slabs_max, slabs, R, m, m_used, l, alpha);
+      launch_pdl(project_update_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, psum, pmax, slabs_max, slabs, R, m, m_used, l,
+                 alpha);
       PIO_LAUNCHED();
     }
     // O and l are relative to the reference the LAST chunk used (m_used); the ratio O / l does not depend on it
@@ -611,7 +618,8 @@ int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int*
       p.a_dt = adt; p.c_dt = PIO_DT_F32; p.alpha = 1.0f;
       p.argmax_val = av; p.argmax_idx = ai; p.argmax_sumexp = as; p.argmax_ld = slabs;
       PIO_TRY(linear_tc(p, st));
-      argmax_finish_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(av, ai, as, slabs, slabs, R, out_ids, steps, t, out_logprob_sum);
+      launch_pdl(argmax_finish_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, av, ai, as, slabs, slabs, R, out_ids, steps, t,
+                 out_logprob_sum);
       PIO_LAUNCHED();
     } else {
       PIO_TRY(linear(mode, hb, h->wte, logits, R, gV, gD, gD, gD, gVld, adt, PIO_DT_F32, nullptr, nullptr, PIO_ACT_NONE, st));
@@ -619,7 +627,7 @@ int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int*
       PIO_LAUNCHED();
     }
     if (t + 1 < steps) {
-      embed_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(h->wte32, h->wpe, out_ids, steps, t, t + 1, x, R, gD);
+      launch_pdl(embed_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, h->wte32, h->wpe, out_ids, steps, t, t + 1, x, R, gD);
       PIO_LAUNCHED();
     }
   }
