@@ -5,14 +5,20 @@
 //               2-stage shared-memory ring (128-byte swizzle, mbarrier completion)
 //   warp 1      MMA issuer   : S_j = Q K_j^T   (UMMA 128x128x16 x4, fp32 in TMEM)
 //                              PV_j = P_j V_j  (UMMA 128x64x16 x8, A = P_j from shared memory, fresh accumulator)
-//   warps 2..5  softmax      : thread == query row.  tcgen05.ld S_j, running max / sum in fp32 with ex2.approx,
-//               O = (O + PV_{j-1}) * alpha_j in registers (no TMEM read-modify-write of the output), then
-//               P_j -> bf16 -> shared memory in the UMMA K-major swizzled layout.
+//   warps 2..5  softmax      : thread == query row.  ONE pass over S_j (tcgen05.ld in 16-column chunks, the next chunk in
+//               flight while this one is processed): P_j = exp2(S_j c - ref_j) -> bf16 -> shared memory in the UMMA K-major
+//               swizzled layout, row sum and raw row max on the way.  ref_j is a LAGGING reference: the running max over
+//               tiles 0..j-1 (tile 0 takes an exact max pass), so no second read of S is needed; entries of P may exceed 1,
+//               and a warp whose tile max runs more than 2^64 above its reference simply redoes the tile (never seen in
+//               practice: the first tile holds the CLS / register keys).  After P_j is published the warp folds PV_{j-1}
+//               (double buffered in TMEM) into its register accumulator, O = (O + PV_{j-1}) 2^(ref_{j-1} - ref_j), while
+//               the tensor core is busy with S_{j+1} and PV_j: the fold is off the S -> P -> S critical path.
 // Footprint is trimmed to 112.3 KB of shared memory, 256 TMEM columns and <= 168 registers so that TWO CTAs are
 // resident per SM: one CTA's softmax (MUFU/FMA bound) overlaps the other's tensor-core and TMA work.
 // V is consumed K-major (keys contiguous) from a transposed copy V^T [B, H, 64, Np] written by transpose_v_kernel,
 // so both GEMMs use the same, verified, K-major 128B-swizzle descriptors as gemm_sm100.cu.
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace pio {
 using namespace tc;
@@ -27,10 +33,10 @@ constexpr int K_BYTES = BKV * HD * 2;           // 16 KB
 constexpr int V_BYTES = HD * BKV * 2;           // 16 KB (two [64 d x 64 keys] sub-tiles)
 constexpr int KV_BYTES = K_BYTES + V_BYTES;
 constexpr int P_BYTES = BQ * BKV * 2;           // 32 KB (two [128 q x 64 keys] sub-tiles)
-constexpr int NUM_BARS = 1 + 2 * KV_STAGES + 3;
+constexpr int NUM_BARS = 1 + 2 * KV_STAGES + 4;
 constexpr int ATT_SMEM = Q_BYTES + KV_STAGES * KV_BYTES + P_BYTES + NUM_BARS * 8 + 16;  // no static smem: base stays 1024-aligned
 constexpr int ATT_THREADS = 192;
-constexpr uint32_t TM_S0 = 0, TM_PV0 = 128, TM_COLS = 256;  // S at cols 0..127, PV at cols 128..191
+constexpr uint32_t TM_S0 = 0, TM_PV0 = 128, TM_COLS = 256;  // S at cols 0..127, PV double buffered at cols 128..191 / 192..255
 
 // V^T[b,h,d,n] = V[b,n,h,d]; columns [N, Np) are zero.  grid (ceil(Np/64), H, B), block (64, 4)
 __global__ void __launch_bounds__(256) transpose_v_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vt,
@@ -61,66 +67,94 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// One query row against one 128-key tile, in 32-column tcgen05.ld chunks (TMEM loads are cheap: re-reading S
-// beats keeping 128 values live in registers).  MASK only for the last, partial key tile.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Exact row max of one 128-key tile (only the first tile needs it).  MASK for a partial tile.
 template <bool MASK>
 __device__ __forceinline__ float row_max(uint32_t s_addr, int kbase, int N) {
-  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < BKV; c += 32) {
-    uint32_t r[32];
-    tmem_ld32(s_addr + c, r);
-    tmem_ld_wait();
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+  uint32_t ra[16], rb[16];
+  tmem_ld16(s_addr, ra);
+  auto take = [&](const uint32_t (&r)[16], int c) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]), v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
+    for (int i = 0; i < 16; i += 2) {
+      float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
       if (MASK) {
         if (kbase + c + i >= N) v0 = -INFINITY;
         if (kbase + c + i + 1 >= N) v1 = -INFINITY;
-        if (kbase + c + i + 2 >= N) v2 = -INFINITY;
-        if (kbase + c + i + 3 >= N) v3 = -INFINITY;
       }
-      mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1); mx2 = fmaxf(mx2, v2); mx3 = fmaxf(mx3, v3);
+      mx0 = fmaxf(mx0, v0);
+      mx1 = fmaxf(mx1, v1);
     }
+  };
+#pragma unroll
+  for (int c = 0; c < BKV; c += 32) {
+    tmem_ld_wait();
+    tmem_ld16(s_addr + c + 16, rb);
+    take(ra, c);
+    tmem_ld_wait();
+    if (c + 32 < BKV) tmem_ld16(s_addr + c + 32, ra);
+    take(rb, c + 16);
   }
-  return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+  return fmaxf(mx0, mx1);
 }
 
-// S (fp32, TMEM) -> P = exp2(S * c - m_new) (bf16, swizzled K-major shared memory); returns the row sum.
+// One pass over S (fp32, TMEM): P = exp2(S * c - ref) -> bf16 -> swizzled K-major shared memory.
+// Returns the row sum; tmax receives the raw row max of the tile (for the next tile's reference).
 template <bool MASK>
-__device__ __forceinline__ float write_probs(uint32_t s_addr, uint8_t* prow, int row, int kbase, int N, float scale_log2e,
-                                             float m_new) {
-  float s0 = 0.f, s1 = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < BKV; c += 32) {
-    uint32_t r[32];
-    tmem_ld32(s_addr + c, r);
-    tmem_ld_wait();
-    uint32_t pk[16];
+__device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, int row, int kbase, int N, float scale_log2e,
+                                              float ref, float& tmax) {
+  float s0 = 0.f, s1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
+  uint32_t ra[16], rb[16];
+  tmem_ld16(s_addr, ra);
+  // 16 keys = 2 chunks of 16 bytes: sub-tile (c / 64), chunk index ((c % 64) / 8 + q) ^ (row % 8)
+  auto take = [&](const uint32_t (&r)[16], int c) {
+    uint32_t pk[8];
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale_log2e, -m_new));
-      float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale_log2e, -m_new));
+    for (int i = 0; i < 16; i += 2) {
+      float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
+      float p0 = ex2_approx(fmaf(v0, scale_log2e, -ref));
+      float p1 = ex2_approx(fmaf(v1, scale_log2e, -ref));
       if (MASK) {
-        if (kbase + c + i >= N) p0 = 0.f;
-        if (kbase + c + i + 1 >= N) p1 = 0.f;
+        if (kbase + c + i >= N) { p0 = 0.f; v0 = -INFINITY; }
+        if (kbase + c + i + 1 >= N) { p1 = 0.f; v1 = -INFINITY; }
       }
+      mx0 = fmaxf(mx0, v0);
+      mx1 = fmaxf(mx1, v1);
       s0 += p0;
       s1 += p1;
       __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
       pk[i >> 1] = *reinterpret_cast<uint32_t*>(&q2);
     }
-    // 32 keys = 4 chunks of 16 bytes; sub-tile (c / 64), chunk index ((c % 64) / 8 + q) ^ (row % 8)
     uint8_t* sub = prow + (c >> 6) * (BQ * 128);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
       const int chunk = (((c & 63) >> 3) + q) ^ (row & 7);
       *reinterpret_cast<uint4*>(sub + chunk * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
     }
+  };
+#pragma unroll
+  for (int c = 0; c < BKV; c += 32) {
+    tmem_ld_wait();
+    tmem_ld16(s_addr + c + 16, rb);
+    take(ra, c);
+    tmem_ld_wait();
+    if (c + 32 < BKV) tmem_ld16(s_addr + c + 32, ra);
+    take(rb, c + 16);
   }
+  tmax = fmaxf(mx0, mx1);
   return s0 + s1;
 }
 
+template <bool V_MN>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_vt,
                         __nv_bfloat16* __restrict__ out, int N, int H, float scale_log2e) {
@@ -138,7 +172,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
   auto kv_empty = [&](int s) { return bar0 + 8u * (1 + KV_STAGES + s); };
   const uint32_t s_ready = bar0 + 8u * (1 + 2 * KV_STAGES);
   const uint32_t p_ready = s_ready + 8u;
-  const uint32_t pv_done = s_ready + 16u;
+  auto pv_done = [&](int buf) { return s_ready + 16u + 8u * buf; };  // one per PV buffer: a barrier never runs two phases ahead
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -152,7 +186,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_init(s_ready, 1);
     mbar_init(p_ready, 4);
-    mbar_init(pv_done, 1);
+    mbar_init(pv_done(0), 1);
+    mbar_init(pv_done(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot_ptr)), TM_COLS);
@@ -176,15 +211,20 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
         const uint32_t dst = sKV + s * KV_BYTES;
         mbar_expect_tx(kv_full(s), KV_BYTES);
         tma_load_2d(dst, &map_qk, kv_full(s), H * HD + h * HD, row_base + j * BKV);           // K_j  [128 keys x 64]
-        tma_load_2d(dst + K_BYTES, &map_vt, kv_full(s), j * BKV, vt_row);                     // V^T  [64 x keys 0..63]
-        tma_load_2d(dst + K_BYTES + V_BYTES / 2, &map_vt, kv_full(s), j * BKV + 64, vt_row);  // V^T  [64 x keys 64..127]
+        if (V_MN) {
+          tma_load_2d(dst + K_BYTES, &map_qk, kv_full(s), 2 * H * HD + h * HD, row_base + j * BKV);  // V_j  [128 keys x 64], as stored
+        } else {
+          tma_load_2d(dst + K_BYTES, &map_vt, kv_full(s), j * BKV, vt_row);                     // V^T  [64 x keys 0..63]
+          tma_load_2d(dst + K_BYTES + V_BYTES / 2, &map_vt, kv_full(s), j * BKV + 64, vt_row);  // V^T  [64 x keys 64..127]
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = make_idesc(BQ, BKV);  // 128 x 128
-    constexpr uint32_t idesc_o = make_idesc(BQ, HD);   // 128 x 64
+    // 128 x 64; with V consumed as stored (keys x dims, dims contiguous) the B operand is MN-major: idesc bit 16
+    constexpr uint32_t idesc_o = make_idesc(BQ, HD) | (V_MN ? (1u << 16) : 0u);
     auto issue_qk = [&](int j) {
       const int s = j % KV_STAGES;
       mbar_wait(kv_full(s), (j / KV_STAGES) & 1);
@@ -201,7 +241,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
     issue_qk(0);
     for (int j = 0; j < nt; ++j) {
       const int s = j % KV_STAGES;
-      mbar_wait(p_ready, j & 1);   // P_j is in shared memory; S_j and PV_{j-1} have been read
+      mbar_wait(p_ready, j & 1);   // P_j is in shared memory; S_j and PV_{j-2} have been read
       tc_fence_after();
       if (j + 1 < nt) issue_qk(j + 1);  // S first: the softmax warps need it next
       if (lane == 0) {
@@ -209,10 +249,12 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t adesc = make_smem_desc(sP + (k >> 2) * (BQ * 128)) + 2 * (k & 3);
-          const uint64_t bdesc = make_smem_desc(vbase + (k >> 2) * (HD * 128)) + 2 * (k & 3);
-          umma_f16(tmem_base + TM_PV0, adesc, bdesc, idesc_o, k != 0);
+          // K-major V^T: two [64 d x 64 keys] sub-tiles, 32 bytes per K step inside the swizzle row.
+          // MN-major V: rows are keys (128 B = 64 dims each), 8-key groups 1024 B apart (SBO); K = 16 keys = 2048 B per step.
+          const uint64_t bdesc = V_MN ? make_smem_desc(vbase + k * 2048) : make_smem_desc(vbase + (k >> 2) * (HD * 128)) + 2 * (k & 3);
+          umma_f16(tmem_base + TM_PV0 + (j & 1) * HD, adesc, bdesc, idesc_o, k != 0);
         }
-        umma_commit(pv_done);
+        umma_commit(pv_done(j & 1));
         umma_commit(kv_empty(s));
       }
       __syncwarp();
@@ -225,56 +267,60 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
     const uint32_t s_addr = tmem_base + lane_addr + TM_S0;
     const uint32_t pv_addr = tmem_base + lane_addr + TM_PV0;
     uint8_t* prow = sP_gen + row * 128;
-    float m = -INFINITY, l = 0.f;
+    float ref = 0.f, ref_prev = 0.f, l = 0.f, tmax = -INFINITY;
     float o[HD];
 #pragma unroll
     for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    // O = (O + PV_k) * f, PV_k from TMEM buffer k & 1 (both 32-column loads in flight together)
+    auto fold = [&](int k, float f) {
+      mbar_wait(pv_done(k & 1), (k >> 1) & 1);
+      tc_fence_after();
+      uint32_t ra[16], rb[16];  // 16-column chunks, the next one in flight while this one is added
+      const uint32_t a = pv_addr + (k & 1) * HD;
+      tmem_ld16(a, ra);
+#pragma unroll
+      for (int c = 0; c < HD; c += 32) {
+        tmem_ld_wait();
+        tmem_ld16(a + c + 16, rb);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c + i] = (o[c + i] + __uint_as_float(ra[i])) * f;
+        tmem_ld_wait();
+        if (c + 32 < HD) tmem_ld16(a + c + 32, ra);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c + 16 + i] = (o[c + 16 + i] + __uint_as_float(rb[i])) * f;
+      }
+    };
 
     for (int j = 0; j < nt; ++j) {
       mbar_wait(s_ready, j & 1);
       tc_fence_after();
       const bool mask = (j + 1) * BKV > N;
       const int kbase = j * BKV;
-      // pass 1: row max
-      const float mx = mask ? row_max<true>(s_addr, kbase, N) : row_max<false>(s_addr, kbase, N);
-      const float m_new = fmaxf(m, mx * scale_log2e);  // every tile has >= 1 valid key, so m_new is finite
-      const float alpha = ex2_approx(m - m_new);       // m = -inf on the first tile -> 0
-      // fold in the previous tile's PV (its P buffer and PV accumulator are then free), rescale to the new max
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < HD; c += 32) {
-          uint32_t r[32];
-          tmem_ld32(pv_addr + c, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c + i] = (o[c + i] + __uint_as_float(r[i])) * alpha;
-        }
+      ref_prev = ref;
+      if (j == 0) {
+        ref = (mask ? row_max<true>(s_addr, kbase, N) : row_max<false>(s_addr, kbase, N)) * scale_log2e;  // finite: >= 1 valid key
+        ref_prev = ref;
+      } else {
+        ref = fmaxf(ref, tmax * scale_log2e);  // running max over tiles 0..j-1
       }
-      // pass 2: probabilities -> bf16 -> swizzled shared memory
-      const float ls = mask ? write_probs<true>(s_addr, prow, row, kbase, N, scale_log2e, m_new)
-                            : write_probs<false>(s_addr, prow, row, kbase, N, scale_log2e, m_new);
+      float ls;
+      for (;;) {
+        ls = mask ? softmax_pass<true>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax)
+                  : softmax_pass<false>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax);
+        // exponent headroom: a row whose tile max sits more than 2^64 above its reference redoes the tile (warp-uniform)
+        if (!__any_sync(0xffffffffu, fmaf(tmax, scale_log2e, -ref) > 64.f)) break;
+        ref = fmaxf(ref, tmax * scale_log2e);
+      }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
-      l = l * alpha + ls;
-      m = m_new;
+      // off the critical path: bring O and l to the units of ref_j while the tensor core works on S_{j+1} and PV_j
+      const float f = ex2_approx(ref_prev - ref);
+      if (j > 0) fold(j - 1, f);
+      l = l * f + ls;
     }
-    {
-      mbar_wait(pv_done, (nt - 1) & 1);
-      tc_fence_after();
-      const float inv = 1.0f / l;
-#pragma unroll
-      for (int c = 0; c < HD; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(pv_addr + c, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] = (o[c + i] + __uint_as_float(r[i])) * inv;
-      }
-    }
+    fold(nt - 1, 1.0f / l);
     const int q = q0 + row;
     if (q < N) {
       __nv_bfloat16* dst = out + ((long long)(row_base + q)) * (H * HD) + h * HD;
@@ -308,22 +354,26 @@ size_t vit_attention_tc_workspace(int B, int N, int H) {
 // qkv bf16 [B,N,3*H*64] -> out bf16 [B,N,H*64]; vt_ws holds the transposed V copy.
 int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int H, cudaStream_t st) {
   const int Np = (N + 7) / 8 * 8;
-  {
-    dim3 grid(cdiv(Np, 64), H, B);
-    launch_pdl(transpose_v_kernel, grid, dim3(64, 4), 0, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)vt_ws, N, Np, H);
-    PIO_LAUNCHED();
-  }
+  static const bool v_mn = [] { const char* e = getenv("PIO_ATTN_VT"); return !(e && e[0] == '1'); }();  // PIO_ATTN_VT=1: old V^T path
   CUtensorMap mqk, mvt;
   PIO_TRY(make_map_2d(&mqk, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, BQ, HD));
-  PIO_TRY(make_map_2d(&mvt, vt_ws, (long long)B * H * HD, Np, Np, HD, 64));
   static bool attr_set = false;
   if (!attr_set) {
-    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
   dim3 grid(cdiv(N, BQ), H, B);
   const float scale_log2e = 0.125f * 1.4426950408889634f;
-  launch_pdl(vit_attention_tc_kernel, grid, dim3(ATT_THREADS), ATT_SMEM, st, mqk, mvt, (__nv_bfloat16*)out, N, H, scale_log2e);
+  if (v_mn) {
+    launch_pdl(vit_attention_tc_kernel<true>, grid, dim3(ATT_THREADS), ATT_SMEM, st, mqk, mqk, (__nv_bfloat16*)out, N, H, scale_log2e);
+  } else {
+    dim3 tgrid(cdiv(Np, 64), H, B);
+    launch_pdl(transpose_v_kernel, tgrid, dim3(64, 4), 0, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)vt_ws, N, Np, H);
+    PIO_LAUNCHED();
+    PIO_TRY(make_map_2d(&mvt, vt_ws, (long long)B * H * HD, Np, Np, HD, 64));
+    launch_pdl(vit_attention_tc_kernel<false>, grid, dim3(ATT_THREADS), ATT_SMEM, st, mqk, mvt, (__nv_bfloat16*)out, N, H, scale_log2e);
+  }
   PIO_LAUNCHED();
   return PIO_OK;
 }
