@@ -6,13 +6,15 @@
 //   warp 1      MMA issuer   : S_j = Q K_j^T   (UMMA 128x128x16 x4, fp32 in TMEM)
 //                              PV_j = P_j V_j  (UMMA 128x64x16 x8, A = P_j from shared memory, fresh accumulator)
 //   warps 2..5  softmax      : thread == query row.  ONE pass over S_j (tcgen05.ld in 16-column chunks, the next chunk in
-//               flight while this one is processed): P_j = exp2(S_j c - ref_j) -> bf16 -> shared memory in the UMMA K-major
-//               swizzled layout, row sum and raw row max on the way.  ref_j is a LAGGING reference: the running max over
-//               tiles 0..j-1 (tile 0 takes an exact max pass), so no second read of S is needed; entries of P may exceed 1,
-//               and a warp whose tile max runs more than 2^64 above its reference simply redoes the tile (never seen in
-//               practice: the first tile holds the CLS / register keys).  After P_j is published the warp folds PV_{j-1}
-//               (double buffered in TMEM) into its register accumulator, O = (O + PV_{j-1}) 2^(ref_{j-1} - ref_j), while
-//               the tensor core is busy with S_{j+1} and PV_j: the fold is off the S -> P -> S critical path.
+//               flight while this one is processed): P_j = exp2(S_j c - ref) -> bf16 -> shared memory in the UMMA K-major
+//               swizzled layout, row sum and raw row max on the way.  Tensor-memory reads run at 64 B/clk per SM, so the
+//               128 x 128 fp32 S tile costs 1024 clk to read ONCE -- the same as its 16384 ex2 on the SFU -- and every
+//               further read (a separate max pass, a per-tile read of PV) is paid in full.  Hence:
+//                 * O accumulates in tensor memory across key tiles (MMA accumulate), it is read once at the end;
+//                 * ref is a lazily updated reference (FlashAttention-4 style): exact row max of tile 0, then raised
+//                   only when the running max has moved more than 2^8 above it.  Entries of P may exceed 1 (<= 2^8, or
+//                   <= 2^64 inside the tile that discovers a new max), harmless in bf16 / fp32.  Raising ref rescales
+//                   the O rows in tensor memory (tcgen05.ld / st) and l -- rare, warp-uniform, exact.
 // Footprint is trimmed to 112.3 KB of shared memory, 256 TMEM columns and <= 168 registers so that TWO CTAs are
 // resident per SM: one CTA's softmax (MUFU/FMA bound) overlaps the other's tensor-core and TMA work.
 // V is consumed K-major (keys contiguous) from a transposed copy V^T [B, H, 64, Np] written by transpose_v_kernel,
@@ -33,10 +35,10 @@ constexpr int K_BYTES = BKV * HD * 2;           // 16 KB
 constexpr int V_BYTES = HD * BKV * 2;           // 16 KB (two [64 d x 64 keys] sub-tiles)
 constexpr int KV_BYTES = K_BYTES + V_BYTES;
 constexpr int P_BYTES = BQ * BKV * 2;           // 32 KB (two [128 q x 64 keys] sub-tiles)
-constexpr int NUM_BARS = 1 + 2 * KV_STAGES + 4;
+constexpr int NUM_BARS = 1 + 2 * KV_STAGES + 3;
 constexpr int ATT_SMEM = Q_BYTES + KV_STAGES * KV_BYTES + P_BYTES + NUM_BARS * 8 + 16;  // no static smem: base stays 1024-aligned
 constexpr int ATT_THREADS = 192;
-constexpr uint32_t TM_S0 = 0, TM_PV0 = 128, TM_COLS = 256;  // S at cols 0..127, PV double buffered at cols 128..191 / 192..255
+constexpr uint32_t TM_S0 = 0, TM_PV0 = 128, TM_COLS = 256;  // S at cols 0..127, O (sum of P V) at cols 128..191
 
 // V^T[b,h,d,n] = V[b,n,h,d]; columns [N, Np) are zero.  grid (ceil(Np/64), H, B), block (64, 4)
 __global__ void __launch_bounds__(256) transpose_v_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vt,
@@ -76,6 +78,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Exact row max of one 128-key tile (only the first tile needs it).  MASK for a partial tile.
 template <bool MASK>
@@ -172,7 +184,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
   auto kv_empty = [&](int s) { return bar0 + 8u * (1 + KV_STAGES + s); };
   const uint32_t s_ready = bar0 + 8u * (1 + 2 * KV_STAGES);
   const uint32_t p_ready = s_ready + 8u;
-  auto pv_done = [&](int buf) { return s_ready + 16u + 8u * buf; };  // one per PV buffer: a barrier never runs two phases ahead
+  const uint32_t pv_step = s_ready + 16u;  // one phase per key tile; waited on only by a rescale and at the end (never > 1 phase ahead)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -186,8 +198,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_init(s_ready, 1);
     mbar_init(p_ready, 4);
-    mbar_init(pv_done(0), 1);
-    mbar_init(pv_done(1), 1);
+    mbar_init(pv_step, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot_ptr)), TM_COLS);
@@ -241,7 +252,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
     issue_qk(0);
     for (int j = 0; j < nt; ++j) {
       const int s = j % KV_STAGES;
-      mbar_wait(p_ready, j & 1);   // P_j is in shared memory; S_j and PV_{j-2} have been read
+      mbar_wait(p_ready, j & 1);   // P_j is in shared memory, S_j has been read, O carries the units P_j is in
       tc_fence_after();
       if (j + 1 < nt) issue_qk(j + 1);  // S first: the softmax warps need it next
       if (lane == 0) {
@@ -252,9 +263,9 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
           // K-major V^T: two [64 d x 64 keys] sub-tiles, 32 bytes per K step inside the swizzle row.
           // MN-major V: rows are keys (128 B = 64 dims each), 8-key groups 1024 B apart (SBO); K = 16 keys = 2048 B per step.
           const uint64_t bdesc = V_MN ? make_smem_desc(vbase + k * 2048) : make_smem_desc(vbase + (k >> 2) * (HD * 128)) + 2 * (k & 3);
-          umma_f16(tmem_base + TM_PV0 + (j & 1) * HD, adesc, bdesc, idesc_o, k != 0);
+          umma_f16(tmem_base + TM_PV0, adesc, bdesc, idesc_o, (j | k) != 0);  // O accumulates across key tiles
         }
-        umma_commit(pv_done(j & 1));
+        umma_commit(pv_step);
         umma_commit(kv_empty(s));
       }
       __syncwarp();
@@ -267,28 +278,27 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
     const uint32_t s_addr = tmem_base + lane_addr + TM_S0;
     const uint32_t pv_addr = tmem_base + lane_addr + TM_PV0;
     uint8_t* prow = sP_gen + row * 128;
-    float ref = 0.f, ref_prev = 0.f, l = 0.f, tmax = -INFINITY;
-    float o[HD];
+    float ref = 0.f, l = 0.f, seen = -INFINITY, tmax = -INFINITY;
+    // Raise the reference to new_ref (>= ref; equal for rows that keep theirs): O rows in tensor memory and l move to the
+    // new units.  j = the tile about to be (re)done: O then holds P V of tiles 0..j-1.  Warp-uniform.
+    auto rescale = [&](int j, float new_ref) {
+      const float f = ex2_approx(ref - new_ref);
+      if (j > 0) {
+        mbar_wait(pv_step, (j - 1) & 1);  // P_{j-1} V_{j-1} has landed
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < HD; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(pv_addr + c, r);
+          tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
-    // O = (O + PV_k) * f, PV_k from TMEM buffer k & 1 (both 32-column loads in flight together)
-    auto fold = [&](int k, float f) {
-      mbar_wait(pv_done(k & 1), (k >> 1) & 1);
-      tc_fence_after();
-      uint32_t ra[16], rb[16];  // 16-column chunks, the next one in flight while this one is added
-      const uint32_t a = pv_addr + (k & 1) * HD;
-      tmem_ld16(a, ra);
-#pragma unroll
-      for (int c = 0; c < HD; c += 32) {
-        tmem_ld_wait();
-        tmem_ld16(a + c + 16, rb);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o[c + i] = (o[c + i] + __uint_as_float(ra[i])) * f;
-        tmem_ld_wait();
-        if (c + 32 < HD) tmem_ld16(a + c + 32, ra);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o[c + 16 + i] = (o[c + 16 + i] + __uint_as_float(rb[i])) * f;
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          tmem_st16(pv_addr + c, r);
+        }
+        tmem_st_wait();
       }
+      l *= f;
+      ref = new_ref;
     };
 
     for (int j = 0; j < nt; ++j) {
@@ -296,43 +306,53 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
       tc_fence_after();
       const bool mask = (j + 1) * BKV > N;
       const int kbase = j * BKV;
-      ref_prev = ref;
       if (j == 0) {
         ref = (mask ? row_max<true>(s_addr, kbase, N) : row_max<false>(s_addr, kbase, N)) * scale_log2e;  // finite: >= 1 valid key
-        ref_prev = ref;
-      } else {
-        ref = fmaxf(ref, tmax * scale_log2e);  // running max over tiles 0..j-1
+      } else if (__any_sync(0xffffffffu, fmaf(seen, scale_log2e, -ref) > 8.f)) {
+        rescale(j, fmaxf(ref, seen * scale_log2e));
       }
       float ls;
       for (;;) {
         ls = mask ? softmax_pass<true>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax)
                   : softmax_pass<false>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax);
-        // exponent headroom: a row whose tile max sits more than 2^64 above its reference redoes the tile (warp-uniform)
+        // exponent headroom: a row whose tile max sits more than 2^64 above its reference redoes the tile
         if (!__any_sync(0xffffffffu, fmaf(tmax, scale_log2e, -ref) > 64.f)) break;
-        ref = fmaxf(ref, tmax * scale_log2e);
+        rescale(j, fmaxf(ref, tmax * scale_log2e));
       }
+      seen = fmaxf(seen, tmax);
+      l += ls;
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
-      // off the critical path: bring O and l to the units of ref_j while the tensor core works on S_{j+1} and PV_j
-      const float f = ex2_approx(ref_prev - ref);
-      if (j > 0) fold(j - 1, f);
-      l = l * f + ls;
     }
-    fold(nt - 1, 1.0f / l);
+    // O / l -> bf16 -> global (the only full read of the output accumulator)
+    mbar_wait(pv_step, (nt - 1) & 1);
+    tc_fence_after();
+    const float inv = 1.0f / l;
     const int q = q0 + row;
-    if (q < N) {
-      __nv_bfloat16* dst = out + ((long long)(row_base + q)) * (H * HD) + h * HD;
+    __nv_bfloat16* dst = out + ((long long)(row_base + q)) * (H * HD) + h * HD;
+    uint32_t ra[16], rb[16];
+    auto emit = [&](const uint32_t (&r)[16], int c) {
+      if (q >= N) return;
+      uint32_t pk[8];
 #pragma unroll
-      for (int i = 0; i < HD; i += 8) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(o[i], o[i + 1]), c2 = __floats2bfloat162_rn(o[i + 2], o[i + 3]);
-        __nv_bfloat162 d = __floats2bfloat162_rn(o[i + 4], o[i + 5]), e = __floats2bfloat162_rn(o[i + 6], o[i + 7]);
-        uint4 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&c2);
-        pk.z = *reinterpret_cast<uint32_t*>(&d); pk.w = *reinterpret_cast<uint32_t*>(&e);
-        *reinterpret_cast<uint4*>(dst + i) = pk;
+      for (int i = 0; i < 16; i += 2) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
       }
+      *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    };
+    tmem_ld16(pv_addr, ra);
+#pragma unroll
+    for (int c = 0; c < HD; c += 32) {
+      tmem_ld_wait();
+      tmem_ld16(pv_addr + c + 16, rb);
+      emit(ra, c);
+      tmem_ld_wait();
+      if (c + 32 < HD) tmem_ld16(pv_addr + c + 32, ra);
+      emit(rb, c + 16);
     }
   }
 

@@ -284,6 +284,24 @@ def test_vit_attention_bf16_tcgen05(dev, ops, B, N):
     assert cos_min(out, ref) >= 0.9995
 
 
+@pytest.mark.parametrize("late_gain", [6.0, 40.0, 400.0])
+def test_vit_attention_bf16_rising_max(dev, ops, late_gain):
+    """Scores that keep growing along the key axis: the lazily updated softmax reference must be raised
+    (> 2^8 above it: rescale of the tensor-memory accumulator; > 2^64: the tile is redone) and stay exact."""
+    B, N = 2, 700
+    g = torch.Generator().manual_seed(int(late_gain))
+    qkv = torch.randn(B, N, 2304, generator=g)
+    ramp = torch.linspace(1.0, late_gain, N)[None, :, None]
+    qkv[:, :, 768:1536] *= ramp            # keys grow with their position
+    qkv[:, 350:, 768:1536] *= 3.0          # and jump in the middle of a key tile
+    qkv = qkv.bfloat16()
+    out = ops.vit_attention(qkv.to(dev)).float().cpu()
+    ref = _attn_ref(qkv)
+    assert torch.isfinite(out).all()
+    torch.testing.assert_close(out, ref, rtol=3e-2, atol=3e-2)
+    assert cos_min(out, ref) >= 0.999
+
+
 # ----------------------------------------------------------------------------------------- ViT
 @pytest.fixture(scope="module")
 def vit_w():
