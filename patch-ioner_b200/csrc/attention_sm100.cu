@@ -17,8 +17,10 @@
 //                   the O rows in tensor memory (tcgen05.ld / st) and l -- rare, warp-uniform, exact.
 // Footprint is trimmed to 112.3 KB of shared memory, 256 TMEM columns and <= 168 registers so that TWO CTAs are
 // resident per SM: one CTA's softmax (MUFU/FMA bound) overlaps the other's tensor-core and TMA work.
-// V is consumed K-major (keys contiguous) from a transposed copy V^T [B, H, 64, Np] written by transpose_v_kernel,
-// so both GEMMs use the same, verified, K-major 128B-swizzle descriptors as gemm_sm100.cu.
+// V is consumed exactly as the qkv GEMM stored it ([key, dim], dims contiguous): for P V the B operand is MN-major
+// (instruction-descriptor bit 16; shared-memory descriptor with 8-key groups 1024 B apart), so no transposed copy exists.
+// One in POLY exponentials is evaluated on the FMA pipe (Cody-Waite split + cubic, |rel err| < 7.5e-5, far below the
+// bf16 rounding of P) instead of the SFU, which is the busiest pipe of this kernel (ncu: XU 60 % at POLY = 0).
 #include "tc_ptx.cuh"
 #include <stdlib.h>
 
@@ -39,27 +41,6 @@ constexpr int NUM_BARS = 1 + 2 * KV_STAGES + 3;
 constexpr int ATT_SMEM = Q_BYTES + KV_STAGES * KV_BYTES + P_BYTES + NUM_BARS * 8 + 16;  // no static smem: base stays 1024-aligned
 constexpr int ATT_THREADS = 192;
 constexpr uint32_t TM_S0 = 0, TM_PV0 = 128, TM_COLS = 256;  // S at cols 0..127, O (sum of P V) at cols 128..191
-
-// V^T[b,h,d,n] = V[b,n,h,d]; columns [N, Np) are zero.  grid (ceil(Np/64), H, B), block (64, 4)
-__global__ void __launch_bounds__(256) transpose_v_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ vt,
-                                                          int N, int Np, int H) {
-  __shared__ __nv_bfloat16 tile[64][HD + 2];
-  pdl_wait();
-  pdl_launch_dependents();
-  const int n0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
-  const int C3 = 3 * H * HD;
-  const __nv_bfloat16* src = qkv + (long long)b * N * C3 + 2 * H * HD + h * HD;
-  for (int r = threadIdx.y; r < 64; r += 4) {
-    const int n = n0 + r;
-    tile[r][threadIdx.x] = (n < N) ? src[(long long)n * C3 + threadIdx.x] : __float2bfloat16(0.f);
-  }
-  __syncthreads();
-  __nv_bfloat16* dst = vt + ((long long)(b * H + h) * HD) * Np;
-  for (int d = threadIdx.y; d < HD; d += 4) {
-    const int n = n0 + threadIdx.x;
-    if (n < Np) dst[(long long)d * Np + n] = tile[threadIdx.x][d];
-  }
-}
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -121,7 +102,18 @@ __device__ __forceinline__ float row_max(uint32_t s_addr, int kbase, int N) {
 
 // One pass over S (fp32, TMEM): P = exp2(S * c - ref) -> bf16 -> swizzled K-major shared memory.
 // Returns the row sum; tmax receives the raw row max of the tile (for the next tile's reference).
-template <bool MASK>
+// 2^x on the FMA pipe: n = round(x) through the 1.5 * 2^23 trick, cubic minimax for 2^f on [-0.5, 0.5], exponent add.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(0.05517132f, f, 0.24261054f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992812f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <bool MASK, int POLY>
 __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, int row, int kbase, int N, float scale_log2e,
                                               float ref, float& tmax) {
   float s0 = 0.f, s1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
@@ -133,8 +125,9 @@ __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, in
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
       float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
-      float p0 = ex2_approx(fmaf(v0, scale_log2e, -ref));
-      float p1 = ex2_approx(fmaf(v1, scale_log2e, -ref));
+      const float x0 = fmaf(v0, scale_log2e, -ref), x1 = fmaf(v1, scale_log2e, -ref);
+      float p0 = ex2_approx(x0);
+      float p1 = (POLY > 0 && ((i >> 1) % POLY) == POLY - 1) ? exp2_poly(x1) : ex2_approx(x1);  // one in 2 * POLY off the SFU
       if (MASK) {
         if (kbase + c + i >= N) { p0 = 0.f; v0 = -INFINITY; }
         if (kbase + c + i + 1 >= N) { p1 = 0.f; v1 = -INFINITY; }
@@ -166,10 +159,9 @@ __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, in
   return s0 + s1;
 }
 
-template <bool V_MN>
+template <int POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 2)
-vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_vt,
-                        __nv_bfloat16* __restrict__ out, int N, int H, float scale_log2e) {
+vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, __nv_bfloat16* __restrict__ out, int N, int H, float scale_log2e) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();  // the 128B-swizzle atoms need 1024-byte alignment
@@ -193,7 +185,6 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qk) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_vt) : "memory");
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_init(s_ready, 1);
@@ -214,7 +205,6 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
     if (lane == 0) {
       mbar_expect_tx(q_full, Q_BYTES);
       tma_load_2d(sQ, &map_qk, q_full, h * HD, row_base + q0);
-      const int vt_row = (b * H + h) * HD;
       for (int j = 0; j < nt; ++j) {
         const int s = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
@@ -222,12 +212,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
         const uint32_t dst = sKV + s * KV_BYTES;
         mbar_expect_tx(kv_full(s), KV_BYTES);
         tma_load_2d(dst, &map_qk, kv_full(s), H * HD + h * HD, row_base + j * BKV);           // K_j  [128 keys x 64]
-        if (V_MN) {
-          tma_load_2d(dst + K_BYTES, &map_qk, kv_full(s), 2 * H * HD + h * HD, row_base + j * BKV);  // V_j  [128 keys x 64], as stored
-        } else {
-          tma_load_2d(dst + K_BYTES, &map_vt, kv_full(s), j * BKV, vt_row);                     // V^T  [64 x keys 0..63]
-          tma_load_2d(dst + K_BYTES + V_BYTES / 2, &map_vt, kv_full(s), j * BKV + 64, vt_row);  // V^T  [64 x keys 64..127]
-        }
+        tma_load_2d(dst + K_BYTES, &map_qk, kv_full(s), 2 * H * HD + h * HD, row_base + j * BKV);  // V_j  [128 keys x 64], as stored
       }
     }
     __syncwarp();
@@ -235,7 +220,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc_s = make_idesc(BQ, BKV);  // 128 x 128
     // 128 x 64; with V consumed as stored (keys x dims, dims contiguous) the B operand is MN-major: idesc bit 16
-    constexpr uint32_t idesc_o = make_idesc(BQ, HD) | (V_MN ? (1u << 16) : 0u);
+    constexpr uint32_t idesc_o = make_idesc(BQ, HD) | (1u << 16);
     auto issue_qk = [&](int j) {
       const int s = j % KV_STAGES;
       mbar_wait(kv_full(s), (j / KV_STAGES) & 1);
@@ -260,9 +245,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t adesc = make_smem_desc(sP + (k >> 2) * (BQ * 128)) + 2 * (k & 3);
-          // K-major V^T: two [64 d x 64 keys] sub-tiles, 32 bytes per K step inside the swizzle row.
           // MN-major V: rows are keys (128 B = 64 dims each), 8-key groups 1024 B apart (SBO); K = 16 keys = 2048 B per step.
-          const uint64_t bdesc = V_MN ? make_smem_desc(vbase + k * 2048) : make_smem_desc(vbase + (k >> 2) * (HD * 128)) + 2 * (k & 3);
+          const uint64_t bdesc = make_smem_desc(vbase + k * 2048);
           umma_f16(tmem_base + TM_PV0, adesc, bdesc, idesc_o, (j | k) != 0);  // O accumulates across key tiles
         }
         umma_commit(pv_step);
@@ -313,8 +297,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
       }
       float ls;
       for (;;) {
-        ls = mask ? softmax_pass<true>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax)
-                  : softmax_pass<false>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax);
+        ls = mask ? softmax_pass<true, POLY>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax)
+                  : softmax_pass<false, POLY>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax);
         // exponent headroom: a row whose tile max sits more than 2^64 above its reference redoes the tile
         if (!__any_sync(0xffffffffu, fmaf(tmax, scale_log2e, -ref) > 64.f)) break;
         rescale(j, fmaxf(ref, tmax * scale_log2e));
@@ -367,33 +351,29 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
 }  // namespace
 
 size_t vit_attention_tc_workspace(int B, int N, int H) {
-  const size_t Np = (size_t)(N + 7) / 8 * 8;
-  return (size_t)B * H * HD * Np * 2;
+  (void)B; (void)N; (void)H;
+  return 0;  // V is read in place (MN-major operand): no transposed copy
 }
 
 // qkv bf16 [B,N,3*H*64] -> out bf16 [B,N,H*64]; vt_ws holds the transposed V copy.
 int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int H, cudaStream_t st) {
-  const int Np = (N + 7) / 8 * 8;
-  static const bool v_mn = [] { const char* e = getenv("PIO_ATTN_VT"); return !(e && e[0] == '1'); }();  // PIO_ATTN_VT=1: old V^T path
-  CUtensorMap mqk, mvt;
+  (void)vt_ws;
+  static const int poly = [] { const char* e = getenv("PIO_ATTN_POLY"); return e ? atoi(e) : 3; }();  // 0 = every exponential on the SFU; 3 = one in six on the FMA pipe (measured best)
+  CUtensorMap mqk;
   PIO_TRY(make_map_2d(&mqk, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, BQ, HD));
   static bool attr_set = false;
   if (!attr_set) {
-    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     attr_set = true;
   }
   dim3 grid(cdiv(N, BQ), H, B);
   const float scale_log2e = 0.125f * 1.4426950408889634f;
-  if (v_mn) {
-    launch_pdl(vit_attention_tc_kernel<true>, grid, dim3(ATT_THREADS), ATT_SMEM, st, mqk, mqk, (__nv_bfloat16*)out, N, H, scale_log2e);
-  } else {
-    dim3 tgrid(cdiv(Np, 64), H, B);
-    launch_pdl(transpose_v_kernel, tgrid, dim3(64, 4), 0, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)vt_ws, N, Np, H);
-    PIO_LAUNCHED();
-    PIO_TRY(make_map_2d(&mvt, vt_ws, (long long)B * H * HD, Np, Np, HD, 64));
-    launch_pdl(vit_attention_tc_kernel<false>, grid, dim3(ATT_THREADS), ATT_SMEM, st, mqk, mvt, (__nv_bfloat16*)out, N, H, scale_log2e);
-  }
+  auto* kern = poly == 0 ? vit_attention_tc_kernel<0> : poly == 1 ? vit_attention_tc_kernel<1> : poly == 2 ? vit_attention_tc_kernel<2>
+                                                                                                     : vit_attention_tc_kernel<3>;
+  launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM, st, mqk, (__nv_bfloat16*)out, N, H, scale_log2e);
   PIO_LAUNCHED();
   return PIO_OK;
 }
