@@ -9,6 +9,7 @@
 // (torch float floor-division, inclusive end, Python slice clamping) and is exported as int32
 // bounds so that tests can compare it bit-for-bit.
 #include "tc_ptx.cuh"
+#include <stdlib.h>
 
 namespace pio {
 namespace {
@@ -258,6 +259,97 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_slab_kernel(const float* __
   }
 }
 
+
+// ---------------------------------------------------------------------------------- box pooling (mean / gaussian)
+// Warp-per-box variant for the two closed-form weightings (the dense-captioning hot path: 64 boxes per image).
+// grid = (D/16, B): a CTA stages a [P x 16-channel] slab (64-byte row segments, 88 KB at 518 px) so TWO CTAs share an SM and
+// one CTA's cp.async staging overlaps the other's arithmetic.  Each warp owns whole boxes (no shared-memory atomics, no
+// per-box bookkeeping by the other warps): a warp visits 8 patches of a box row per step, 4 lanes x float4 per patch, so one
+// LDS.128 per lane reads 512 contiguous bytes of the slab per warp (conflict free) and feeds 4 FMAs.  Separable gaussian:
+// the lane-distributed x / y factors are computed once per box and broadcast with shuffles (x-factors hoisted per box).
+constexpr int PB_THREADS = 512;
+template <int SRC>  // 0 mean, 1 gaussian
+__global__ void __launch_bounds__(PB_THREADS, 2) pool_box_kernel(const float* __restrict__ tokens, long long img_stride,
+                                                                long long row_stride, int grid, int D,
+                                                                const int* __restrict__ bounds, int R, float variance,
+                                                                float* __restrict__ out) {
+  extern __shared__ __align__(128) float slab[];  // [P][16]
+  const int P = grid * grid;
+  const int b = blockIdx.y, c0 = blockIdx.x * 16;
+  {
+    const float* src = tokens + (long long)b * img_stride + c0;
+    const uint32_t dst0 = tc::smem_u32(slab);
+    for (int i = threadIdx.x; i < P * 4; i += PB_THREADS) {
+      const int p = i >> 2, q = (i & 3) * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(p * 16 + q) * 4),
+                   "l"(src + (long long)p * row_stride + q)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 2, quad = lane & 3;  // 8 patches per step, each read as 4 x float4 (16 channels = 64 bytes)
+  bool staged = false;
+  for (int j = warp; j < R; j += PB_THREADS / 32) {
+    const int bi = b * R + j;
+    const int4 bd = __ldg(reinterpret_cast<const int4*>(bounds) + bi);  // y0, y1, x0, x1
+    const int hs = bd.y - bd.x, ws = bd.w - bd.z;
+    // lane-distributed separable factors (grid <= 64: two registers per axis)
+    float wxa = 1.f, wxb = 1.f, wya = 1.f, wyb = 1.f, nrm;
+    if (SRC == 1) {
+      wxa = wxb = wya = wyb = 0.f;
+      if (lane < ws) { const float x = linspace_m1_1(lane, ws); wxa = expf(-(x * x) / variance); }
+      if (lane + 32 < ws) { const float x = linspace_m1_1(lane + 32, ws); wxb = expf(-(x * x) / variance); }
+      if (lane < hs) { const float y = linspace_m1_1(lane, hs); wya = expf(-(y * y) / variance); }
+      if (lane + 32 < hs) { const float y = linspace_m1_1(lane + 32, hs); wyb = expf(-(y * y) / variance); }
+      const float sx = warp_sum(wxa + wxb), sy = warp_sum(wya + wyb);
+      nrm = (hs > 0 && ws > 0) ? 1.0f / (sy * sx) : 0.f;  // empty box -> zeros, like the reference
+    } else {
+      nrm = 1.0f / (float)(hs * ws);  // empty box -> inf -> 0 * inf = NaN like tensor.mean()
+    }
+    if (!staged) {  // the box parameters above overlap the tail of the staging copy
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      staged = true;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int steps = (ws + 7) >> 3;
+    // this lane's x-factors for the patches it visits (x = 8 k + grp): hoisted out of the row loop
+    float wxk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int x = 8 * k + grp;
+      float w = (SRC == 1) ? __shfl_sync(0xffffffffu, x < 32 ? wxa : wxb, x & 31) : 1.0f;
+      wxk[k] = (x < ws) ? w : 0.f;
+    }
+    for (int r = 0; r < hs; ++r) {
+      float wy = 1.0f;
+      if (SRC == 1) wy = __shfl_sync(0xffffffffu, r < 32 ? wya : wyb, r & 31);
+      const float4* sp = reinterpret_cast<const float4*>(slab + ((bd.x + r) * grid + bd.z) * 16) + quad;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < steps) {  // warp-uniform
+          const int x = min(8 * k + grp, ws - 1);
+          const float w = wy * wxk[k];
+          const float4 v = sp[x * 4];
+          acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (grp == 0)
+      *reinterpret_cast<float4*>(out + (long long)bi * D + c0 + quad * 4) = make_float4(acc.x * nrm, acc.y * nrm, acc.z * nrm, acc.w * nrm);
+  }
+  if (!staged) {  // more warps than boxes: nobody may leave while copies into this CTA's shared memory are in flight
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------- traces
 // One CTA per trace; Python-double binning of bbox_utils.py:158-168.
 __global__ void __launch_bounds__(256) trace_bins_kernel(const double* __restrict__ pts, const int* __restrict__ offsets, int grid,
@@ -340,6 +432,17 @@ int launch_slab(const float* tokens, long long img_stride, long long row_stride,
   return PIO_OK;
 }
 
+template <int SRC>
+int launch_box(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D, const int* bounds, int R,
+               float variance, float* out, cudaStream_t st) {
+  const size_t smem = (size_t)grid * grid * 16 * sizeof(float);
+  PIO_CUDA(cudaFuncSetAttribute(pool_box_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 g(D / 16, B);
+  pool_box_kernel<SRC><<<g, PB_THREADS, smem, st>>>(tokens, img_stride, row_stride, grid, D, bounds, R, variance, out);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
 }  // namespace
 
 int cls_attention(const void* qkv, int dt, int B, int N, int D, int ng, float* out, float* logits_ws, cudaStream_t st) {
@@ -398,9 +501,15 @@ int pio_pool_boxes(const float* tokens, long long img_stride, long long row_stri
     PIO_LAUNCHED();
     return launch_slab<2>(tokens, img_stride, row_stride, B, grid, D, bounds, R, 0.f, per_box, 1.0f, out, st);
   }
+  // closed-form weights: warp-per-box kernel (two CTAs per SM when the 16-channel slab fits twice); PIO_POOL_SLAB=1 keeps
+  // the 32-channel slab kernel for A/B runs
+  static const bool old_slab = [] { const char* e = getenv("PIO_POOL_SLAB"); return e && e[0] == '1'; }();
+  const bool box_ok = !old_slab && grid <= 64 && (size_t)grid * grid * 16 * sizeof(float) <= 113 * 1024;
   if (mode == PIO_POOL_GAUSS)
-    return launch_slab<1>(tokens, img_stride, row_stride, B, grid, D, bounds, R, variance, nullptr, 1.0f, out, st);
-  return launch_slab<0>(tokens, img_stride, row_stride, B, grid, D, bounds, R, 0.f, nullptr, 1.0f, out, st);
+    return box_ok ? launch_box<1>(tokens, img_stride, row_stride, B, grid, D, bounds, R, variance, out, st)
+                  : launch_slab<1>(tokens, img_stride, row_stride, B, grid, D, bounds, R, variance, nullptr, 1.0f, out, st);
+  return box_ok ? launch_box<0>(tokens, img_stride, row_stride, B, grid, D, bounds, R, 0.f, out, st)
+                : launch_slab<0>(tokens, img_stride, row_stride, B, grid, D, bounds, R, 0.f, nullptr, 1.0f, out, st);
 }
 
 int pio_pool_grid(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D,
