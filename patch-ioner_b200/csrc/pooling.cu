@@ -268,6 +268,35 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_slab_kernel(const float* __
 // LDS.128 per lane reads 512 contiguous bytes of the slab per warp (conflict free) and feeds 4 FMAs.  Separable gaussian:
 // the lane-distributed x / y factors are computed once per box and broadcast with shuffles (x-factors hoisted per box).
 constexpr int PB_THREADS = 512;
+// Rows of one box for a warp: STEPS x 8 patches per row (x = 8 k + grp), float4 = 4 channels per lane.
+template <int SRC, int STEPS>
+__device__ __forceinline__ float4 box_rows(const float4* sp0, int grid, int hs, int ws, int grp, float wxa, float wxb, float wya,
+                                           float wyb) {
+  float wxk[STEPS];
+  int off[STEPS];
+#pragma unroll
+  for (int k = 0; k < STEPS; ++k) {
+    const int x = 8 * k + grp;
+    const float w = (SRC == 1) ? __shfl_sync(0xffffffffu, x < 32 ? wxa : wxb, x & 31) : 1.0f;
+    wxk[k] = (x < ws) ? w : 0.f;
+    off[k] = min(x, ws - 1) * 4;  // float4 units; lanes beyond the row re-read its last patch with weight 0
+  }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc;
+  const float4* sp = sp0;
+  for (int r = 0; r < hs; ++r, sp += grid * 4) {
+    float wy = 1.0f;
+    if (SRC == 1) wy = __shfl_sync(0xffffffffu, r < 32 ? wya : wyb, r & 31);
+#pragma unroll
+    for (int k = 0; k < STEPS; ++k) {
+      const float w = (SRC == 1) ? wy * wxk[k] : wxk[k];
+      const float4 v = sp[off[k]];
+      if (k & 1) { acc2.x = fmaf(w, v.x, acc2.x); acc2.y = fmaf(w, v.y, acc2.y); acc2.z = fmaf(w, v.z, acc2.z); acc2.w = fmaf(w, v.w, acc2.w); }
+      else       { acc.x = fmaf(w, v.x, acc.x);   acc.y = fmaf(w, v.y, acc.y);   acc.z = fmaf(w, v.z, acc.z);   acc.w = fmaf(w, v.w, acc.w); }
+    }
+  }
+  return make_float4(acc.x + acc2.x, acc.y + acc2.y, acc.z + acc2.z, acc.w + acc2.w);
+}
+
 template <int SRC>  // 0 mean, 1 gaussian
 __global__ void __launch_bounds__(PB_THREADS, 2) pool_box_kernel(const float* __restrict__ tokens, long long img_stride,
                                                                 long long row_stride, int grid, int D,
@@ -313,28 +342,17 @@ __global__ void __launch_bounds__(PB_THREADS, 2) pool_box_kernel(const float* __
       staged = true;
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int steps = (ws + 7) >> 3;
-    // this lane's x-factors for the patches it visits (x = 8 k + grp): hoisted out of the row loop
-    float wxk[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int x = 8 * k + grp;
-      float w = (SRC == 1) ? __shfl_sync(0xffffffffu, x < 32 ? wxa : wxb, x & 31) : 1.0f;
-      wxk[k] = (x < ws) ? w : 0.f;
-    }
-    for (int r = 0; r < hs; ++r) {
-      float wy = 1.0f;
-      if (SRC == 1) wy = __shfl_sync(0xffffffffu, r < 32 ? wya : wyb, r & 31);
-      const float4* sp = reinterpret_cast<const float4*>(slab + ((bd.x + r) * grid + bd.z) * 16) + quad;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (k < steps) {  // warp-uniform
-          const int x = min(8 * k + grp, ws - 1);
-          const float w = wy * wxk[k];
-          const float4 v = sp[x * 4];
-          acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-        }
-      }
+    const float4* sp0 = reinterpret_cast<const float4*>(slab + (bd.x * grid + bd.z) * 16) + quad;
+    switch ((ws + 7) >> 3) {  // warp-uniform: a fully unrolled row loop per step count, no predicated-off issue slots
+      case 1: acc = box_rows<SRC, 1>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 2: acc = box_rows<SRC, 2>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 3: acc = box_rows<SRC, 3>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 4: acc = box_rows<SRC, 4>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 5: acc = box_rows<SRC, 5>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 6: acc = box_rows<SRC, 6>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 7: acc = box_rows<SRC, 7>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 8: acc = box_rows<SRC, 8>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      default: break;  // empty box
     }
 #pragma unroll
     for (int o = 4; o < 32; o <<= 1) {
