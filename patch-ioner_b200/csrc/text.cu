@@ -323,8 +323,11 @@ static bool project_exact_requested() {
 }
 
 static int project_chunk_rows(int R) {
-  // keep the S chunk (R x Mc fp32) around 64 MB so that it stays L2 resident between the two GEMMs
-  long long mc = (16ll << 20) / (R > 0 ? R : 1);
+  // S chunk (R x Mc fp32, or P bf16 with twice the columns on the fused path).  Measured at R = 4096, M = 591 753 (B200):
+  // 16 M elements (P = 67 MB, L2 resident) 8.7 ms, 32 M 7.8 ms, 64 M 7.5 ms, 128 M 8.1 ms -- fewer, longer GEMMs beat L2
+  // residency (the P round trip runs at ~3 TB/s, well inside HBM bandwidth).  PIO_PROJECT_CHUNK_M overrides for A/B runs.
+  static const long long elems = [] { const char* e = getenv("PIO_PROJECT_CHUNK_M"); return (long long)(e ? atoi(e) : 64) << 20; }();
+  long long mc = elems / (R > 0 ? R : 1);
   mc = mc / 128 * 128;
   if (mc < 1024) mc = 1024;
   if (mc > 16384) mc = 16384;
