@@ -167,6 +167,12 @@ int pio_pool_grid(const float* tokens, long long img_stride, long long row_strid
 /* (model.py:1052-1053): counts *= attn[t].                                                          */
 int pio_trace_bins(const double* points_xy, const int* offsets, int T, int grid, const float* attn, float* counts,
                    void* stream);
+/* Per-"head" CLS attention maps (process_self_attention(..., ret_self_attn_maps=True), dino_extraction.py:24-34, */
+/* softmaxed over the patches as at model.py:871): the hooked qkv re-cut into heads = 16 groups of D/16 channels,  */
+/* out_maps fp32 [B, heads, P].  Feeds get_attn_heads_capt through pio_pool_grid (model.py:872, 950-960).           */
+int pio_cls_head_attention(const void* qkv, int qkv_dt, int B, int N, int D, int num_global, int heads, float scale,
+                           float* out_maps, void* stream);
+
 /* Gaussian / uniform whole-image weights of compute_region_means (model.py:45-94) -> weights [grid*grid] */
 int pio_region_mean_weights(int grid, float variance, float* weights, void* stream);
 
@@ -189,6 +195,12 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
 int pio_project_rescale(float* O, float* l, const float* m_local, const float* m_global, int R, int D, void* stream);
 /* O / l and optional L2 normalisation (after the SUM all-reduce) */
 int pio_project_finish(float* O, const float* l, int R, int D, int normalize, void* stream);
+/* return_n_best_sims (im2txtprojection.py:382-383): the n largest cosine similarities <q^, bank_j^> per query,   */
+/* descending -> out_sims fp32 [R,n], out_rows int32 [R,n] (bank row of each; may be NULL).  1 <= n <= 32.        */
+/* The bank is walked in the same chunks as pio_project (same workspace size).  A row-sharded bank merges the      */
+/* per-shard lists on the host side (n values per rank).                                                           */
+int pio_best_sims(PioBank* h, const float* q, int R, int n, float* out_sims, int* out_rows, void* workspace,
+                  size_t workspace_bytes, void* stream);
 /* revert_transformation (embedding_utils.py:17-24) is pio_linear with W = A_pinv, bias = -A_pinv b. */
 
 /* ------------------------------------------------------------------------------------------ */

@@ -72,6 +72,7 @@ SIGNATURES = {
     "pio_attention_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "pio_vit_attention": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_size_t, _fp]),
     "pio_cls_attention": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp]),
+    "pio_cls_head_attention": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp]),
     "pio_pool_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "pio_pool_boxes": (C.c_int, [_fp, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_float, _fp, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
@@ -83,6 +84,7 @@ SIGNATURES = {
     "pio_bank_rows": (C.c_longlong, [_fp]),
     "pio_project_workspace_bytes": (C.c_size_t, [_fp, C.c_int]),
     "pio_project": (C.c_int, [_fp, _fp, C.c_int, C.c_float, C.c_int, _fp, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "pio_best_sims": (C.c_int, [_fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
     "pio_project_rescale": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, _fp]),
     "pio_project_finish": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp]),
     "pio_decoder_create": (C.c_int, [C.POINTER(_fp), C.POINTER(PioDecoderWeights), C.c_int, _fp]),

@@ -425,6 +425,27 @@ __global__ void __launch_bounds__(256) cls_logits_kernel(const T* __restrict__ q
   if (lane == 0) logits[warp] = s * (0.125f / 16.0f);
 }
 
+// Per-"head" CLS logits of process_self_attention(ret_self_attn_maps=True) (dino_extraction.py:24-34): the hooked qkv is
+// re-cut into `heads` = 16 groups of D / heads = 48 channels (sic, model.py:336), maps[b,h,j] = 0.125 <q_cls^h, k_j^h>.
+// One warp per (b, patch): lane = (head, half), 24 contiguous channels each.
+template <typename T>
+__global__ void __launch_bounds__(256) cls_head_logits_kernel(const T* __restrict__ qkv, int B, int N, int D, int ng, int heads,
+                                                              float scale, float* __restrict__ maps) {
+  const int P = N - ng;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)B * P) return;
+  const int b = (int)(warp / P), j = (int)(warp % P);
+  const int hd = D / heads, per = hd / 2;  // 48, 24
+  const int head = lane >> 1, c0 = head * hd + (lane & 1) * per;
+  const T* q = qkv + (long long)b * N * 3 * D + c0;
+  const T* k = qkv + ((long long)b * N + ng + j) * 3 * D + D + c0;
+  float s = 0.f;
+  for (int d = 0; d < per; ++d) s = fmaf((float)q[d], (float)k[d], s);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if ((lane & 1) == 0 && head < heads) maps[((long long)b * heads + head) * P + j] = s * scale;
+}
+
 __global__ void __launch_bounds__(256) region_mean_weights_kernel(int grid, float variance, float* __restrict__ w) {
   __shared__ float red[8];
   const int P = grid * grid;
@@ -545,6 +566,23 @@ int pio_trace_bins(const double* points_xy, const int* offsets, int T, int grid,
   trace_bins_kernel<<<T, 256, (size_t)grid * grid * sizeof(int), as_stream(stream)>>>(points_xy, offsets, grid, attn, counts);
   PIO_LAUNCHED();
   return PIO_OK;
+}
+
+int pio_cls_head_attention(const void* qkv, int qkv_dt, int B, int N, int D, int num_global, int heads, float scale,
+                           float* out_maps, void* stream) {
+  using namespace pio;
+  PIO_CHECK(qkv && out_maps, "cls_head_attention: null argument");
+  PIO_CHECK(heads == 16 && D % (2 * heads) == 0, "cls_head_attention: 16 head groups of an even width are supported (model.py:336)");
+  if (B == 0) return PIO_OK;
+  cudaStream_t st = as_stream(stream);
+  const int P = N - num_global;
+  const int blocks = cdiv((long long)B * P * 32, 256);
+  if (qkv_dt == PIO_DT_F32)
+    cls_head_logits_kernel<float><<<blocks, 256, 0, st>>>((const float*)qkv, B, N, D, num_global, heads, scale, out_maps);
+  else
+    cls_head_logits_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)qkv, B, N, D, num_global, heads, scale, out_maps);
+  PIO_LAUNCHED();
+  return softmax_rows(out_maps, out_maps, B * heads, P, 1.0f, st);  // self_attn_maps.softmax(dim=-1), model.py:871
 }
 
 int pio_region_mean_weights(int grid, float variance, float* weights, void* stream) {

@@ -218,6 +218,62 @@ __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) 
   if (i < n) o[i] = a[i] + b[i];
 }
 
+
+// Running top-n of a score row: one CTA per query.  Candidates = the running list (n, from earlier chunks) + this chunk's
+// mc scores; n rounds of a block-wide arg-max (ties: smaller bank row first, like a stable descending sort of equal values).
+constexpr int TOPN_MAX = 32;
+__global__ void __launch_bounds__(256) topn_chunk_kernel(const float* __restrict__ S, int lds, int mc, long long row0, int n,
+                                                         float* __restrict__ best_v, int* __restrict__ best_i) {
+  __shared__ float sv[TOPN_MAX];
+  __shared__ int si[TOPN_MAX];
+  __shared__ float rv[8];
+  __shared__ int ri[8];
+  __shared__ int taken[TOPN_MAX];  // candidate ids already selected this call (>= 0: chunk column, < 0: -(slot + 1) of the old list)
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* row = S + (long long)r * lds;
+  if (tid < n) { sv[tid] = best_v[(long long)r * n + tid]; si[tid] = best_i[(long long)r * n + tid]; }
+  __syncthreads();
+  float outv = 0.f;
+  int outi = 0;
+  for (int k = 0; k < n; ++k) {
+    // candidate id space: [0, mc) chunk columns, [mc, mc + n) the old list
+    float bv = -INFINITY;
+    int bc = 0x7fffffff;
+    for (int c = tid; c < mc + n; c += 256) {
+      bool used = false;
+      for (int t = 0; t < k; ++t) used |= (taken[t] == c);
+      if (used) continue;
+      const float v = c < mc ? row[c] : sv[c - mc];
+      if (v > bv || (v == bv && c < bc)) { bv = v; bc = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+    }
+    if ((tid & 31) == 0) { rv[tid >> 5] = bv; ri[tid >> 5] = bc; }
+    __syncthreads();
+    if (tid == 0) {
+      float v = rv[0];
+      int c = ri[0];
+      for (int w = 1; w < 8; ++w)
+        if (rv[w] > v || (rv[w] == v && ri[w] < c)) { v = rv[w]; c = ri[w]; }
+      taken[k] = c;
+      rv[0] = v;
+      ri[0] = c;
+    }
+    __syncthreads();
+    if (tid == k) {  // thread k keeps the k-th winner until the old list has been fully read
+      const int c = ri[0];
+      outv = rv[0];
+      outi = (c == 0x7fffffff) ? -1 : (c < mc ? (int)(row0 + c) : si[c - mc]);
+    }
+    __syncthreads();
+  }
+  if (tid < n) { best_v[(long long)r * n + tid] = outv; best_i[(long long)r * n + tid] = outi; }
+}
+
 int linear(int mode, const void* A, const void* W, void* C, int M, int N, int K, int lda, int ldw, int ldc, int a_dt, int c_dt,
            const float* bias, const float* residual, int act, cudaStream_t st) {
   PioLinear p;
@@ -443,6 +499,41 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
   }
   finish_rows_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(out, l, R, D, normalize);
   PIO_LAUNCHED();
+  return PIO_OK;
+}
+
+int pio_best_sims(PioBank* h, const float* q, int R, int n, float* out_sims, int* out_rows, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  using namespace pio;
+  PIO_CHECK(h && q && out_sims && workspace, "best_sims: null argument");
+  PIO_CHECK(n >= 1 && n <= TOPN_MAX, "best_sims: n %d outside [1,%d]", n, TOPN_MAX);
+  PIO_CHECK(workspace_bytes >= pio_project_workspace_bytes(h, R), "best_sims: workspace too small");
+  PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "best_sims: workspace must be 1024-byte aligned");
+  if (R == 0) return PIO_OK;
+  cudaStream_t st = as_stream(stream);
+  const int D = h->D, Mc = project_chunk_rows(R), adt = h->act_dt;
+  const size_t e = adt == PIO_DT_F32 ? 4 : 2;
+  char* ws = (char*)workspace;
+  void* qn = ws;            ws += align_up((size_t)R * D * e, 1024);
+  float* qn32 = (float*)ws; ws += align_up((size_t)R * D * 4, 1024);
+  float* S = (float*)ws;    ws += align_up((size_t)R * Mc * 4, 1024);
+  int* rows = (int*)ws;     // the P16 region: R * n ints fit easily (n <= 32 << Mc / 2)
+  PIO_CUDA(cudaMemcpyAsync(qn32, q, (size_t)R * D * 4, cudaMemcpyDeviceToDevice, st));
+  PIO_TRY(l2norm_rows(qn32, R, D, st));
+  if (adt == PIO_DT_F32) qn = qn32; else PIO_TRY(f32_to_bf16(qn32, (__nv_bfloat16*)qn, (long long)R * D, st));
+  int* best_i = out_rows ? out_rows : rows;
+  fill_kernel<<<cdiv((long long)R * n, 256), 256, 0, st>>>(out_sims, -INFINITY, (long long)R * n); PIO_LAUNCHED();
+  PIO_CUDA(cudaMemsetAsync(best_i, 0xff, (size_t)R * n * sizeof(int), st));
+  for (long long c0 = 0; c0 < h->M; c0 += Mc) {
+    const int mc = (int)std::min<long long>(Mc, h->M - c0);
+    PioLinear p;
+    memset(&p, 0, sizeof(p));
+    p.A = qn; p.W = (const char*)h->bank + (size_t)c0 * D * e; p.C = S; p.M = R; p.N = mc; p.K = D;
+    p.lda = D; p.ldw = D; p.ldc = Mc; p.a_dt = adt; p.c_dt = PIO_DT_F32; p.colscale = h->inv_norm + c0; p.alpha = 1.0f;
+    PIO_TRY(h->mode == PIO_FP32 ? linear_simt(p, st) : linear_tc(p, st));
+    topn_chunk_kernel<<<R, 256, 0, st>>>(S, Mc, mc, c0, n, out_sims, best_i);
+    PIO_LAUNCHED();
+  }
   return PIO_OK;
 }
 

@@ -54,15 +54,17 @@ class Patchioner:
                  viecap_config=None, regionclip_config=None, invite_config=None, denseclip_config=None,
                  alphaclip_config=None, clipcap_config=None, hf_repo_id=None,
                  # extensions (no network in this image: weights are given as files / state dicts)
-                 dino_weights=None, memory_bank=None, precision="fp32", **kwargs):
+                 dino_weights=None, memory_bank=None, memory_bank_texts=None, precision="fp32", **kwargs):
         for name, val in (("proxyclip_clipmodel", proxyclip_clipmodel), ("viecap", viecap_config),
                           ("regionclip_config", regionclip_config), ("invite_config", invite_config),
                           ("denseclip_config", denseclip_config), ("alphaclip_config", alphaclip_config),
                           ("clipcap", clipcap_config)):
             if val is not None:
                 raise NotImplementedError(f"'{name}' selects a backbone/captioner outside the B200 hot path (SURVEY.md 8)")
-        if calculate_argmax_text or online_texts is not None:
-            raise NotImplementedError("calculate_argmax_text / online_texts need the bank's texts (out of scope)")
+        if online_texts is not None:
+            raise NotImplementedError("online_texts builds a bank with a CLIP text encoder (im2txtprojection.py:448-560): out of scope")
+        if calculate_argmax_text and (memory_bank_texts is None or support_memory_size <= 0):
+            raise ValueError("calculate_argmax_text needs the bank and its captions (memory_bank_texts)")
         if dino_model is None or "dinov2" not in dino_model or "vitb14" not in dino_model or "reg" not in dino_model:
             raise NotImplementedError(f"dino_model={dino_model!r}: only 'dinov2_vitb14_reg' is built (model.py:342-343)")
         if attention_type != "qkv":
@@ -86,7 +88,10 @@ class Patchioner:
         self.num_tokens = self.num_global_tokens + self.num_patch_tokens
         self.backbone_type = "DINO"
         self.viecap = self.clipcap = None
-        self.calculate_argmax_text = False
+        self.calculate_argmax_text = bool(calculate_argmax_text)
+        # indexed by the row of the zero-row-FILTERED bank, like the reference (text_dataset is not filtered, embs are:
+        # im2txtprojection.py:342-345, :372)
+        self.text_dataset = list(memory_bank_texts) if memory_bank_texts is not None else None
 
         # --- backbone (model.py:342-343 loads it from torch.hub; here: a state dict with the hub's key names)
         if isinstance(dino_weights, str):
@@ -179,6 +184,7 @@ class Patchioner:
             hf_repo_id=config.get("hf_repo_id", None),
             dino_weights=config.get("dino_weights", None),
             memory_bank=config.get("memory_bank", None),
+            memory_bank_texts=config.get("memory_bank_texts", None),
             precision=config.get("precision", "fp32"),
         )
 
@@ -259,8 +265,18 @@ class Patchioner:
 
     def caption_tokens(self, dino_tokens, project=True, return_n_best_sims=None, compute_scores: bool = False):
         """model.py:1392-1423."""
+        if self.calculate_argmax_text:
+            # model.py:1408-1411 -> im2txtprojection.py:371-375: the caption is the text of the most similar bank row
+            feats = dino_tokens.reshape(-1, dino_tokens.shape[-1])
+            sims, rows = self.im_proj.best_sims(feats, int(return_n_best_sims or 1), with_rows=True)
+            texts = [self.text_dataset[i] for i in rows[:, 0].cpu().tolist()]
+            captions = [t.decode() if isinstance(t, (bytes, bytearray)) else t for t in texts]
+            ret = (captions, sims.cpu().tolist()) if return_n_best_sims else captions
+            return (ret, [1.0] * len(captions)) if compute_scores else ret
         if return_n_best_sims:
-            raise NotImplementedError("return_n_best_sims (im2txtprojection.py:382-383) is a 'next' row (SURVEY.md 8f.4)")
+            # the reference only honours it together with calculate_argmax_text (model.py:1408-1411); with the decoder
+            # path its forward() fails while unpacking (model.py:1033)
+            raise ValueError("return_n_best_sims needs calculate_argmax_text=True (as in the reference, model.py:1408-1411)")
         r = self.caption_token_ids(dino_tokens, project, compute_scores)
         if compute_scores:
             return self._ids_to_text(r[0]), r[1].cpu().tolist()
@@ -300,20 +316,39 @@ class Patchioner:
          -> ``mask_capts``; ``return_ids=True`` returns int32 id tensors instead of strings."""
         assert clean_from in ["cls", "avg_self_attn"]
         assert cleaning_type in [None, "orthogonal_projection", "contrastive_mask"]
-        if double_DINO_for_bboxes or cleaning_type is not None or caption_bboxes_type is not None or get_attn_heads_capt:
-            raise NotImplementedError("double_DINO / cleaning_type / caption_bboxes_type / get_attn_heads_capt are "
+        if double_DINO_for_bboxes or cleaning_type is not None or caption_bboxes_type is not None:
+            raise NotImplementedError("double_DINO / cleaning_type / caption_bboxes_type are "
                                       "'next' rows (SURVEY.md 8f.4), not built in this round")
-        if return_n_best_sims is not None:
-            raise NotImplementedError("return_n_best_sims is a 'next' row (SURVEY.md 8f.4)")
+        if self.calculate_argmax_text and return_ids:
+            raise ValueError("return_ids has no meaning with calculate_argmax_text (captions are bank texts)")
         imgs = imgs.to(self.device, non_blocking=True)
         outs: Dict[str, object] = {}
         bs = imgs.shape[0]
-        tokens, self_attn, _ = self.dino.forward(imgs, want_attn=True)
+        tokens, self_attn, qkv_last = self.dino.forward(imgs, want_attn=True, want_qkv=bool(get_attn_heads_capt))
         cls, reg, patch = tokens[:, 0], tokens[:, 1:5], tokens[:, 5:]
         P, D = patch.shape[1], patch.shape[2]
         g = int(P ** 0.5)
 
+        def emit_texts(key, feats, group=None):
+            """calculate_argmax_text (model.py:1408-1411): captions are bank texts; only the box branch asks for sims."""
+            want_sims = return_n_best_sims if key == "bbox_capts" else None
+            ret = self.caption_tokens(feats, return_n_best_sims=want_sims, compute_scores=compute_scores)
+            ret, sc = (ret if compute_scores else (ret, None))
+            capts, sims = (ret if want_sims else (ret, None))
+            cut = (lambda v: [v[i * group:(i + 1) * group] for i in range(bs)]) if group is not None else (lambda v: v)
+            outs[key] = cut(capts)
+            if sims is not None:
+                outs["bbox_sims"] = cut(sims)
+            if compute_scores:
+                skey = {"bbox_capts": "bbox_scores", "patch_tokens_capts": "patch_tokens_scores", "register_capts": "register_scores",
+                        "attn_heads_capts": "attn_heads_scores"}.get(key, key + "_scores")
+                outs[skey] = cut(sc)
+
         def emit(key, feats, group=None):
+            if self.calculate_argmax_text:
+                return emit_texts(key, feats, group)
+            if return_n_best_sims is not None and key == "bbox_capts":
+                self.caption_tokens(feats[:0], return_n_best_sims=return_n_best_sims)  # raises like the reference's decoder path
             r = self.caption_token_ids(feats, compute_scores=compute_scores)
             ids, sc = (r if compute_scores else (r, None))
             vals = ids if return_ids else self._ids_to_text(ids)
@@ -323,7 +358,7 @@ class Patchioner:
             if compute_scores:
                 s = sc.cpu().tolist()
                 skey = {"bbox_capts": "bbox_scores", "patch_tokens_capts": "patch_tokens_scores",
-                        "register_capts": "register_scores"}.get(key, key + "_scores")
+                        "register_capts": "register_scores", "attn_heads_capts": "attn_heads_scores"}.get(key, key + "_scores")
                 outs[skey] = s if group is None else [s[i * group:(i + 1) * group] for i in range(bs)]
 
         if get_cls_capt:
@@ -333,6 +368,9 @@ class Patchioner:
         if get_avg_patch_capt:      # model.py:45-94
             w = ops.region_mean_weights(g, gaussian_img_variance, patch.device)
             emit("avg_patch_capt", ops.pool_grid(patch, w.reshape(1, 1, P).expand(bs, 1, P), 1.0)[:, 0])
+        if get_attn_heads_capt:     # model.py:871-872, 950-960: one embedding per "head" map (16 x 48-channel re-cut, sic)
+            maps = ops.cls_head_attention(qkv_last, self.num_global_tokens, self.num_attn_heads, 0.125)
+            emit("attn_heads_capts", ops.pool_grid(patch, maps, 1.0 / P).reshape(-1, D), group=self.num_attn_heads)
         if get_patch_capts:
             emit("patch_tokens_capts", patch.reshape(-1, D), group=P)
         if get_register_capts:

@@ -223,6 +223,16 @@ def cls_attention(qkv: torch.Tensor, num_global: int = 5) -> torch.Tensor:
     return out
 
 
+def cls_head_attention(qkv: torch.Tensor, num_global: int = 5, heads: int = 16, scale: float = 0.125) -> torch.Tensor:
+    """Per-"head" CLS attention maps, softmaxed over the patches (dino_extraction.py:24-34 + model.py:871): [B, heads, P]."""
+    _need_cuda(qkv)
+    B, N, C3 = qkv.shape
+    out = torch.empty(B, heads, N - num_global, dtype=torch.float32, device=qkv.device)
+    L.check(L.lib().pio_cls_head_attention(qkv.contiguous().data_ptr(), _dt(qkv), B, N, C3 // 3, num_global, heads, float(scale),
+                                           out.data_ptr(), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------ pooling
 def _token_view(patch_tokens: torch.Tensor):
     """patch tokens [B,P,D] (possibly a view into [B,N,D]) -> (ptr, img_stride, row_stride)."""
@@ -344,6 +354,21 @@ class Bank:
         L.check(L.lib().pio_project(self._h, q.data_ptr(), R, float(temperature), int(normalize), out.data_ptr(), _ptr(m),
                                     _ptr(l), ws.data_ptr(), nbytes, _stream()))
         return (m, l, out) if partial else out
+
+
+    def best_sims(self, q: torch.Tensor, n: int, with_rows: bool = False):
+        """The n largest cosine similarities of each query against the bank, descending (``return_n_best_sims``,
+        im2txtprojection.py:382-383) -> [R, n] fp32 (and the bank rows [R, n] int32)."""
+        _need_cuda(q)
+        q = q.float().contiguous()
+        R = q.shape[0]
+        sims = torch.empty(R, n, dtype=torch.float32, device=q.device)
+        rows = torch.empty(R, n, dtype=torch.int32, device=q.device)
+        nbytes = L.lib().pio_project_workspace_bytes(self._h, R)
+        ws = workspace(nbytes, q.device, "project")
+        L.check(L.lib().pio_best_sims(self._h, q.data_ptr(), R, int(n), sims.data_ptr(), rows.data_ptr(), ws.data_ptr(), nbytes,
+                                      _stream()))
+        return (sims, rows) if with_rows else sims
 
 
 def project_rescale_(O, l, m_local, m_global):

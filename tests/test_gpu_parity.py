@@ -525,3 +525,83 @@ def test_forward_bf16_embeddings(dev):
     e = m.region_embeddings(imgs.to(dev), bboxes=boxes, gaussian_avg=True, gaussian_bbox_variance=1.0)
     c = cos_min(e["bbox"].cpu(), ref)
     assert c >= 0.999, c
+
+
+# ----------------------------------------------------------------------------------------- widened forward modes
+def test_cls_head_attention_maps(dev, ops):
+    """Per-"head" CLS maps (16 x 48-channel re-cut) and the disentangled tokens of model.py:871-872 vs the oracle's literal
+    restatement of process_self_attention (itself pinned to the reference's output in tests/golden/self_attention.pt)."""
+    gen = torch.Generator().manual_seed(31)
+    B, g = 2, 16
+    N = 5 + g * g
+    qkv = torch.randn(B, N, 2304, generator=gen)
+    patch = torch.randn(B, g * g, 768, generator=gen)
+    _, maps = o_pool.process_self_attention_literal(qkv)
+    want_maps = maps.softmax(dim=-1)
+    want_tok = (patch.unsqueeze(1) * want_maps.unsqueeze(-1)).mean(dim=2)
+    got_maps = ops.cls_head_attention(qkv.to(dev))
+    torch.testing.assert_close(got_maps.cpu(), want_maps, rtol=1e-4, atol=1e-7)
+    got_tok = ops.pool_grid(patch.to(dev), got_maps, 1.0 / (g * g))
+    torch.testing.assert_close(got_tok.cpu(), want_tok, rtol=1e-4, atol=1e-7)
+    got16 = ops.cls_head_attention(qkv.to(dev).bfloat16())
+    torch.testing.assert_close(got16.cpu(), want_maps, rtol=5e-2, atol=1e-4)
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("bf16", 4e-3)])
+def test_best_sims(dev, ops, mode, tol):
+    """return_n_best_sims (im2txtprojection.py:382-383): the n largest cosines per query, descending, over several chunks."""
+    bank = o_pipe.synth_bank(40000, 768, seed=41, zero_frac=0.001)
+    fb = o_mem.drop_zero_rows(bank)
+    gen = torch.Generator().manual_seed(42)
+    q = torch.randn(50, 768, generator=gen)
+    q[3] = fb[39000] * 2.0 + 0.05 * torch.randn(768, generator=gen)
+    q[4] = fb[5] + fb[20000]
+    sim = (q / q.norm(dim=-1, keepdim=True)) @ (fb / fb.norm(dim=-1, keepdim=True)).T
+    want = sim.sort(dim=-1, descending=True)
+    b = ops.Bank(bank, dev, mode)
+    sims, rows = b.best_sims(q.to(dev), 5, with_rows=True)
+    torch.testing.assert_close(sims.cpu(), want.values[:, :5], rtol=0, atol=tol)
+    assert (sims[:, :-1] >= sims[:, 1:]).all()
+    if mode == "fp32":
+        assert torch.equal(rows.cpu().long(), want.indices[:, :5])
+    else:
+        assert torch.equal(rows[3:5, 0].cpu().long(), want.indices[3:5, 0])
+    one = b.best_sims(q.to(dev), 1)
+    torch.testing.assert_close(one.cpu(), want.values[:, :1], rtol=0, atol=tol)
+
+
+def test_forward_argmax_text_and_attn_heads(dev):
+    """calculate_argmax_text (model.py:1408-1411) with return_n_best_sims, and get_attn_heads_capt (model.py:950-960)."""
+    from patchioner_b200 import Patchioner
+
+    vit_w, dec_w = o_vit.make_weights(seed=1234), o_decap.make_weights(seed=1234)
+    bank = o_pipe.synth_bank(3000, 768, seed=7, zero_frac=0.002)
+    fb = o_mem.drop_zero_rows(bank)
+    texts = [f"caption {i}".encode() for i in range(bank.shape[0])]
+    cfg = {"decap_weights": dec_w, "prefix_size": 768, "support_memory_size": 3000, "dino_model": "dinov2_vitb14_reg",
+           "normalize": True, "resize_dim": 224, "crop_dim": 224, "dino_weights": vit_w, "memory_bank": bank, "precision": "fp32"}
+    imgs = o_pipe.synth_images(2, 224, seed=1)
+    boxes = o_pipe.synth_boxes(2, 3, 224, seed=1, pad="dense")
+    d = o_vit.forward(vit_w, imgs)
+    feats = o_pool.extract_bboxes_feats(d["x_norm_patchtokens"], boxes.clone(), False, 0.5).reshape(-1, 768)
+    sim = (feats / feats.norm(dim=-1, keepdim=True)) @ (fb / fb.norm(dim=-1, keepdim=True)).T
+    want = sim.sort(dim=-1, descending=True)
+
+    m = Patchioner.from_config(dict(cfg, calculate_argmax_text=True, memory_bank_texts=texts), device=dev)
+    out = m(imgs, get_cls_capt=True, bboxes=boxes, return_n_best_sims=3, compute_scores=True)
+    assert set(out) == {"cls_capt", "cls_capt_scores", "bbox_capts", "bbox_scores", "bbox_sims"}
+    flat = [c for per_img in out["bbox_capts"] for c in per_img]
+    assert flat == [f"caption {i}" for i in want.indices[:, 0].tolist()]   # texts are indexed by the FILTERED row, like the reference
+    torch.testing.assert_close(torch.tensor(out["bbox_sims"]).reshape(-1, 3), want.values[:, :3], rtol=0, atol=2e-4)
+    assert out["bbox_scores"] == [[1.0] * 3] * 2 and out["cls_capt_scores"] == [1.0, 1.0]
+
+    m2 = Patchioner.from_config(cfg, device=dev)
+    with pytest.raises(ValueError):
+        m2(imgs, bboxes=boxes, return_n_best_sims=3)      # decoder path: the reference fails too (model.py:1033)
+    o2 = m2(imgs, get_cls_capt=False, get_attn_heads_capt=True, return_ids=True)
+    assert o2["attn_heads_capts"].shape == (2, 16, 30)
+    _, maps = o_pool.process_self_attention_literal(d["qkv"])
+    tok = (d["x_norm_patchtokens"].unsqueeze(1) * maps.softmax(dim=-1).unsqueeze(-1)).mean(dim=2).reshape(-1, 768)
+    ref = o_pipe.OracleModel(vit_w, dec_w, bank).caption_tokens(tok)
+    agree = (o2["attn_heads_capts"].reshape(-1, 30).cpu().long() == ref).all(dim=1).float().mean().item()
+    assert agree >= 0.99, agree
