@@ -202,25 +202,32 @@ def run_ours(args):
     def step_resident(i):
         return model(dev_imgs[i % n_sets], get_cls_capt=False, bboxes=dev_boxes[i % n_sets], return_ids=True, **kw)["bbox_capts"]
 
-    def step_e2e(i):
-        imgs = host_imgs[i % n_sets].to(dev, non_blocking=True)
-        boxes = host_boxes[i % n_sets].to(dev, non_blocking=True)
-        ids = model(imgs, get_cls_capt=False, bboxes=boxes, return_ids=True, **kw)["bbox_capts"]
-        return ids.cpu()  # device -> host read of the step's result
+    def run_e2e(n):
+        """n steps through the public serving API: every step copies its pinned host inputs in (the copy of step i+1 is
+        issued under step i's kernels: Patchioner.forward_pipelined) and reads its ids back to the host."""
+        batches = ({"imgs": host_imgs[i % n_sets], "bboxes": host_boxes[i % n_sets]} for i in range(n))
+        for out in model.forward_pipelined(batches, get_cls_capt=False, return_ids=True, **kw):
+            out["bbox_capts"].cpu()  # device -> host read of the step's result
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
+    def timed(fn, steps, warmup, whole_run=False):
+        if whole_run:
+            fn(warmup)
+        else:
+            for i in range(warmup):
+                fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for i in range(steps):
-            fn(warmup + i)
+        if whole_run:
+            fn(steps)
+        else:
+            for i in range(steps):
+                fn(warmup + i)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
@@ -239,7 +246,7 @@ def run_ours(args):
     # launches counted include the warm-up steps: keep the timed share
     launches = launches * args.steps // (args.steps + args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e = timed(run_e2e, args.steps, max(1, args.warmup // 2), whole_run=True)
 
     regions = B * R * world
     value = regions * args.steps / (ms_total / 1e3)

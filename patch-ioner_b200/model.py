@@ -393,3 +393,51 @@ class Patchioner:
         return outs
 
     __call__ = forward
+
+    def forward_pipelined(self, batches, **flags):
+        """Serving loop over host-resident batches: yields ``forward(**batch, **flags)`` for every batch.
+
+        ``batches`` is an iterable of dicts (``imgs`` plus optional ``bboxes`` / ``masks`` tensors, ``traces`` lists), ideally in
+        pinned memory.  The host->device copy of batch i+1 is issued on a copy stream before batch i is computed, so it
+        overlaps the compute; results come back in order.  Same outputs as calling ``forward`` batch by batch."""
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+            self._stage_bufs, self._stage_free = {}, {}
+        copy = self._copy_stream
+
+        def stage(batch, slot):
+            """copy `batch` into the persistent device buffers of `slot` (allocated once per shape: no allocator traffic,
+            no implicit synchronisation in the loop)"""
+            dev_batch, ev = {}, torch.cuda.Event()
+            with torch.cuda.stream(copy):
+                if slot in self._stage_free:
+                    copy.wait_event(self._stage_free[slot])  # the forward that last read this slot has finished
+                for k, v in batch.items():
+                    if torch.is_tensor(v):
+                        key = (slot, k, tuple(v.shape), v.dtype)
+                        buf = self._stage_bufs.get(key)
+                        if buf is None:
+                            buf = self._stage_bufs[key] = torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                        buf.copy_(v, non_blocking=True)
+                        dev_batch[k] = buf
+                    else:
+                        dev_batch[k] = v
+                ev.record(copy)
+            return dev_batch, ev
+
+        it = iter(batches)
+        i = 0
+        nxt = next(it, None)
+        staged = stage(nxt, 0) if nxt is not None else None
+        while staged is not None:
+            cur, ev = staged
+            nxt = next(it, None)
+            staged = stage(nxt, (i + 1) & 1) if nxt is not None else None  # next batch's copy runs under this batch's kernels
+            main.wait_event(ev)
+            out = self.forward(**cur, **flags)
+            done = torch.cuda.Event()
+            done.record(main)
+            self._stage_free[i & 1] = done
+            i += 1
+            yield out

@@ -605,3 +605,13 @@ def test_forward_argmax_text_and_attn_heads(dev):
     ref = o_pipe.OracleModel(vit_w, dec_w, bank).caption_tokens(tok)
     agree = (o2["attn_heads_capts"].reshape(-1, 30).cpu().long() == ref).all(dim=1).float().mean().item()
     assert agree >= 0.99, agree
+
+
+def test_forward_pipelined_matches_forward(dev):
+    """The serving loop (host->device copy of batch i+1 under batch i's kernels) returns what forward returns, in order."""
+    m = _model(dev, "fp32", True)
+    batches = [{"imgs": o_pipe.synth_images(2, 224, seed=s).pin_memory(), "bboxes": o_pipe.synth_boxes(2, 3, 224, seed=s).pin_memory()}
+               for s in (1, 2, 3)]
+    want = [m(b["imgs"], bboxes=b["bboxes"].clone(), get_cls_capt=False, return_ids=True)["bbox_capts"].cpu() for b in batches]
+    got = [o["bbox_capts"].cpu() for o in m.forward_pipelined(iter(batches), get_cls_capt=False, return_ids=True)]
+    assert len(got) == 3 and all(torch.equal(a, b) for a, b in zip(got, want))
