@@ -40,15 +40,55 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--boxes", type=int, default=64)
+    ap.add_argument("--workload", default="dense", choices=["dense", "traces", "regionset"],
+                    help="dense = BASELINE configs[1] (the headline); traces = configs[2] (1 mouse trace / image, attention weighting, "
+                         "batch 256); regionset = configs[3] (talk2dino_capdec, box sets -> one caption / image)")
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--boxes", type=int, default=None)
     ap.add_argument("--size", type=int, default=518)
     ap.add_argument("--bank-rows", type=int, default=BANK_ROWS)
     ap.add_argument("--pool", default="gauss", choices=["mean", "gauss", "attn"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-images", type=int, default=1)
     ap.add_argument("--cpu-sample-boxes", type=int, default=8)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 256 if a.workload == "traces" else 64
+    if a.boxes is None:
+        a.boxes = {"dense": 64, "traces": 1, "regionset": 8}[a.workload]
+    if a.workload == "regionset":
+        a.bank_rows = 0  # CapDec: no caption memory (configs/mlp_noise.k.yaml: support_memory_size 0)
+    return a
+
+
+def workload_flags(args):
+    """forward() keywords of the workload (the eval drivers' flag mapping)."""
+    if args.workload == "traces":   # eval_trace_captioning.py:309-324 (gaussian flags are passed and ignored by the trace branch)
+        return dict(use_attention_tracing=True, gaussian_avg=True, gaussian_bbox_variance=1.0)
+    if args.workload == "regionset":  # eval_region_set_captioning.py:322-337
+        return dict(get_controllable_capts=True, gaussian_avg=True, gaussian_bbox_variance=1.0)
+    return dict(gaussian_avg=args.pool == "gauss", gaussian_bbox_variance=1.0, use_attn_map_for_bboxes=args.pool == "attn")
+
+
+def workload_batch(args, synth_mod, B, seed):
+    """One synthetic host batch of the workload: dict of forward() inputs."""
+    S = args.size
+    batch = {"imgs": synth_mod.synth_images(B, S, seed=seed)}
+    if args.workload == "traces":
+        batch["traces"] = synth_mod.synth_traces(B, seed=seed)
+    elif args.workload == "regionset":
+        batch["bboxes"] = synth_mod.synth_boxes(B, args.boxes, S, seed=seed, pad="set")
+    else:
+        batch["bboxes"] = synth_mod.synth_boxes(B, args.boxes, S, seed=seed, pad="dense")
+    return batch
+
+
+def out_key(args):
+    return {"dense": "bbox_capts", "traces": "trace_capts", "regionset": "set_controllable_capts"}[args.workload]
+
+
+def captions_per_step(args):
+    return args.batch * args.boxes if args.workload == "dense" else args.batch
 
 
 def peaks():
@@ -113,23 +153,26 @@ def cpu_sample(args, steps: int, warmup: int):
 
     torch.set_num_threads(os.cpu_count() or 1)
     B, R, S = args.cpu_sample_images, args.cpu_sample_boxes, args.size
+    if args.workload != "dense":
+        B, R = max(B, 4), args.boxes
     vit_w, dec_w = o_vit.make_weights(1234), o_decap.make_weights(1234)
-    bank = o_pipe.synth_bank(args.bank_rows, 768, seed=7)
+    bank = o_pipe.synth_bank(args.bank_rows, 768, seed=7) if args.bank_rows > 0 else None
     model = o_pipe.OracleModel(vit_w, dec_w, bank)
-    kw = dict(gaussian_avg=args.pool == "gauss", gaussian_bbox_variance=1.0, use_attn_map_for_bboxes=args.pool == "attn")
+    kw = workload_flags(args)
+    sub = argparse.Namespace(**dict(vars(args), boxes=R))
     times = []
     for i in range(warmup + steps):
-        imgs = o_pipe.synth_images(B, S, seed=100 + i)
-        boxes = o_pipe.synth_boxes(B, R, S, seed=100 + i, pad="dense")
+        batch = workload_batch(sub, o_pipe, B, 100 + i)
         t0 = time.perf_counter()
-        model.forward(imgs, get_cls_capt=False, bboxes=boxes, use_cache=False, **kw)
+        model.forward(batch.pop("imgs"), get_cls_capt=False, use_cache=False, **batch, **kw)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     sec = sum(times) / len(times)
-    sample = (f"{B} x {S}px image(s), {R} boxes each = {B * R} regions/step, bank M={args.bank_rows}, fp32, reference algorithm "
-              f"(no KV cache, 30 steps), {len(times)} timed step(s) after {warmup} warm-up")
-    return B * R / sec, sec, sample
+    n = B * R if args.workload == "dense" else B
+    sample = (f"{args.workload}: {B} x {S}px image(s), {R} box(es)/trace(s) each = {n} captions/step, bank M={args.bank_rows}, fp32, "
+              f"reference algorithm (no KV cache, 30 steps), {len(times)} timed step(s) after {warmup} warm-up")
+    return n / sec, sec, sample
 
 
 def run_reference(args):
@@ -149,9 +192,14 @@ def run_reference(args):
 
 
 def workload_config(args, per_step_note=None):
-    cfg = {"workload": f"talk2dino_decap dense captioning: {args.size}px images, {args.boxes} synthetic bboxes/image, batch {args.batch} per GPU "
-                       f"(BASELINE.json configs[1])",
-           "images_per_gpu": args.batch, "boxes_per_image": args.boxes, "regions_per_gpu_per_step": args.batch * args.boxes,
+    name = {"dense": f"talk2dino_decap dense captioning: {args.size}px images, {args.boxes} synthetic bboxes/image, batch {args.batch} per GPU "
+                     f"(BASELINE.json configs[1])",
+            "traces": f"talk2dino_decap trace captioning with attention weighting: {args.size}px images, 1 synthetic mouse trace/image, "
+                      f"batch {args.batch} per GPU (BASELINE.json configs[2])",
+            "regionset": f"talk2dino_capdec region-set captioning: {args.size}px images, sets of up to {args.boxes} boxes/image -> one "
+                         f"caption per image, batch {args.batch} per GPU (BASELINE.json configs[3])"}[args.workload]
+    cfg = {"workload": name,
+           "images_per_gpu": args.batch, "boxes_per_image": args.boxes, "regions_per_gpu_per_step": captions_per_step(args),
            "image_size": args.size, "bank_rows": args.bank_rows, "pooling": args.pool, "decode_steps": 30,
            "parallelism": f"dp{args.gpus} over images, no collective",
            "cache": "per-step inputs (206 MB of images) and activations (> 1 GB) exceed the 126 MB L2; no explicit flush"}
@@ -184,30 +232,33 @@ def run_ours(args):
 
     B, R, S = args.batch, args.boxes, args.size
     vit_w, dec_w = synth.make_vit_weights(1234), synth.make_decoder_weights(1234)
-    bank = synth.synth_bank(args.bank_rows, 768, seed=7)
+    bank = synth.synth_bank(args.bank_rows, 768, seed=7) if args.bank_rows > 0 else None
     model = Patchioner.from_config({"decap_weights": dec_w, "prefix_size": 768, "support_memory_size": args.bank_rows,
                                     "dino_model": "dinov2_vitb14_reg", "normalize": True, "resize_dim": S, "crop_dim": S,
                                     "dino_weights": vit_w, "memory_bank": bank, "precision": args.precision}, device=dev)
     del bank, vit_w, dec_w
-    kw = dict(gaussian_avg=args.pool == "gauss", gaussian_bbox_variance=1.0, use_attn_map_for_bboxes=args.pool == "attn")
+    kw = workload_flags(args)
+    key = out_key(args)
 
     # distinct synthetic batches per rank (data-parallel shards), pinned on the host for the e2e leg
     n_sets = 2
-    host_imgs = [synth.synth_images(B, S, seed=1000 * rank + i).pin_memory() for i in range(n_sets)]
-    host_boxes = [synth.synth_boxes(B, R, S, seed=1000 * rank + i, pad="dense").pin_memory() for i in range(n_sets)]
-    dev_imgs = [t.to(dev) for t in host_imgs]
-    dev_boxes = [t.to(dev) for t in host_boxes]
+    host = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in workload_batch(args, synth, B, 1000 * rank + i).items()}
+            for i in range(n_sets)]
+    resident = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in b.items()} for b in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values() if torch.is_tensor(v))
+    if args.workload == "traces":  # trace points travel as [n, 2] doubles + offsets
+        h2d_bytes += sum(len(t) for t in host[0]["traces"]) * 16 + (B + 1) * 4
     stream = torch.cuda.current_stream()
 
     def step_resident(i):
-        return model(dev_imgs[i % n_sets], get_cls_capt=False, bboxes=dev_boxes[i % n_sets], return_ids=True, **kw)["bbox_capts"]
+        return model(**resident[i % n_sets], get_cls_capt=False, return_ids=True, **kw)[key]
 
     def run_e2e(n):
         """n steps through the public serving API: every step copies its pinned host inputs in (the copy of step i+1 is
         issued under step i's kernels: Patchioner.forward_pipelined) and reads its ids back to the host."""
-        batches = ({"imgs": host_imgs[i % n_sets], "bboxes": host_boxes[i % n_sets]} for i in range(n))
+        batches = (host[i % n_sets] for i in range(n))
         for out in model.forward_pipelined(batches, get_cls_capt=False, return_ids=True, **kw):
-            out["bbox_capts"].cpu()  # device -> host read of the step's result
+            out[key].cpu()  # device -> host read of the step's result
 
     def barrier():
         if world > 1:
@@ -248,13 +299,13 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(run_e2e, args.steps, max(1, args.warmup // 2), whole_run=True)
 
-    regions = B * R * world
+    regions = captions_per_step(args) * world
     value = regions * args.steps / (ms_total / 1e3)
     e2e_value = regions * args.steps / (ms_e2e / 1e3)
 
     extra = {}
     if rank == 0:
-        extra = stage_breakdown(model, ops, dev_imgs[0], dev_boxes[0], kw, args, stream)
+        extra = stage_breakdown(model, ops, resident[0], kw, args, stream)
     line = None
     if rank == 0:
         pk = peaks()
@@ -268,8 +319,8 @@ def run_ours(args):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                        "h2d_bytes_per_step": int(host_imgs[0].numel() * 4 + host_boxes[0].numel() * 4) * world,
-                        "d2h_bytes_per_step": int(B * R * 30 * 4) * world},
+                        "h2d_bytes_per_step": int(h2d_bytes) * world,
+                        "d2h_bytes_per_step": int(captions_per_step(args) * 30 * 4) * world},
                 "gpu_launches": int(launches), "roofline": roof, "stages": extra,
                 "vit_images_per_s": extra.get("vit_images_per_s")}
         if not args.no_cpu_baseline and world == 1:
@@ -285,7 +336,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def stage_breakdown(model, ops, imgs, boxes, kw, args, stream):
+def stage_breakdown(model, ops, batch, kw, args, stream):
     """One extra instrumented step (not the timed one): CUDA-event time per stage and for the dominant kernel."""
     from patchioner_b200 import _lib as L
 
@@ -298,13 +349,25 @@ def stage_breakdown(model, ops, imgs, boxes, kw, args, stream):
         return torch.cuda.Event(enable_timing=True)
 
     B, R, S = args.batch, args.boxes, args.size
+    imgs = batch["imgs"]
+    P = (S // 14) ** 2
     marks = [ev() for _ in range(5)]
     torch.cuda.synchronize()
     marks[0].record(stream)
     tokens, attn, _ = model.dino.forward(imgs, want_attn=True)
     marks[1].record(stream)
     patch = tokens[:, 5:]
-    feats = ops.pool_boxes(patch, boxes, 14, kw["gaussian_avg"], kw["gaussian_bbox_variance"], attn if kw["use_attn_map_for_bboxes"] else None)
+    if args.workload == "traces":
+        w = ops.trace_bins(batch["traces"], S // 14, patch.device, attn)
+        feats = ops.pool_grid(patch, w.reshape(B, 1, P), 1.0 / P)[:, 0]
+        n_out = 1
+    elif args.workload == "regionset":
+        feats = ops.pool_boxes(patch, batch["bboxes"], 14, True, 1.0, None, get_single_embedding_per_image=True)
+        n_out = 1
+    else:
+        feats = ops.pool_boxes(patch, batch["bboxes"], 14, kw["gaussian_avg"], kw["gaussian_bbox_variance"],
+                               attn if kw["use_attn_map_for_bboxes"] else None)
+        n_out = R
     marks[2].record(stream)
     pre = model.embed_tokens(feats.reshape(-1, 768))
     marks[3].record(stream)
@@ -314,17 +377,16 @@ def stage_breakdown(model, ops, imgs, boxes, kw, args, stream):
     t = [marks[i].elapsed_time(marks[i + 1]) for i in range(4)]
     pk = peaks()
     vit_flops = flops_per_image(S) * B
-    P = (S // 14) ** 2
-    pool_bytes = B * (P * 768 * 4 + R * 768 * 4 + R * 16)
-    proj_flops = 4.0 * model.im_proj.M * 768 * B * R if model.im_proj is not None else 0.0
-    dec_flops = 2 * (4 * 12 * 768 * 768 + 50257 * 768) * 30 * B * R
+    pool_bytes = B * (P * 768 * 4 + n_out * 768 * 4 + R * 16)
+    proj_flops = 4.0 * model.im_proj.M * 768 * B * n_out if model.im_proj is not None else 0.0
+    dec_flops = 2 * (4 * 12 * 768 * 768 + 50257 * 768) * 30 * B * n_out
     out = {"vit_ms": t[0], "pool_ms": t[1], "project_ms": t[2], "decode_ms": t[3],
            "vit_images_per_s": B / (t[0] / 1e3), "vit_tflops": vit_flops / t[0] / 1e9,
            "pool_gbs": pool_bytes / t[1] / 1e6, "pool_frac_of_hbm": pool_bytes / t[1] / 1e6 / pk["hbm_gbs"],
            "project_tflops": proj_flops / t[2] / 1e9 if t[2] > 0 else None, "decode_tflops": dec_flops / t[3] / 1e9}
     # dominant kernel: the dense layers (tcgen05 GEMM in bf16 mode).  Time the ViT fc1 shape alone.
     N = 5 + P
-    M = B * N
+    M = 64 * N  # the BASELINE configs[1] batch, whatever the workload: the committed ncu capture is of this shape
     dt = torch.bfloat16 if args.precision == "bf16" else torch.float32
     A = torch.randn(M, 768, device=imgs.device).to(dt)
     W = torch.randn(3072, 768, device=imgs.device).to(dt) / 28
