@@ -173,6 +173,12 @@ int pio_trace_bins(const double* points_xy, const int* offsets, int T, int grid,
 int pio_cls_head_attention(const void* qkv, int qkv_dt, int B, int N, int D, int num_global, int heads, float scale,
                            float* out_maps, void* stream);
 
+/* ctx_cleaner (model.py:1425-1436): rows fp32 [B,P,D] (strided view allowed) cleaned against one context vector per image */
+/* (ctx fp32 [B,D]) -> out fp32 [B,P,D] contiguous.  mode 0 = orthogonal_projection (alpha), 1 = contrastive_mask (eps).    */
+/* prenorm != 0 L2-normalises rows and context first (clean_after_projection=False, model.py:905-913).                      */
+int pio_ctx_clean(const float* rows, long long img_stride, long long row_stride, const float* ctx, long long ctx_stride, int B, int P,
+                  int D, int mode, float alpha, float eps, int prenorm, float* out, void* stream);
+
 /* Gaussian / uniform whole-image weights of compute_region_means (model.py:45-94) -> weights [grid*grid] */
 int pio_region_mean_weights(int grid, float variance, float* weights, void* stream);
 

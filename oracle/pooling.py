@@ -270,3 +270,16 @@ def process_self_attention_literal(qkv, num_attn_heads=16, scale=0.125, num_glob
 def avg_self_attn_token(self_attn: torch.Tensor, patch_tokens: torch.Tensor) -> torch.Tensor:
     """model.py:869: (self_attn[...,None] * patch).mean(1)."""
     return (self_attn.unsqueeze(-1) * patch_tokens).mean(dim=1)
+
+
+def ctx_cleaner(dirty_embeds: torch.Tensor, ctx_embed: torch.Tensor, cleaning_type: str = "orthogonal_projection",
+                alpha: float = 1.0, epsilon: float = 1e-6) -> torch.Tensor:
+    """Patchioner.ctx_cleaner, src/model.py:1425-1436.  dirty_embeds [B,P,D], ctx_embed [B,D]."""
+    ctx = ctx_embed.unsqueeze(1)
+    if cleaning_type == "orthogonal_projection":
+        projection = (dirty_embeds @ ctx.transpose(-1, -2)) / (torch.norm(ctx, dim=-1, keepdim=True) ** 2)
+        return dirty_embeds - alpha * projection * ctx
+    if cleaning_type == "contrastive_mask":
+        ctx_norm = torch.norm(ctx, p=2, dim=2, keepdim=True) + epsilon
+        return dirty_embeds * (1 - (ctx / ctx_norm))
+    raise ValueError(cleaning_type)

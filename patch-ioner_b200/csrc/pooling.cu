@@ -446,6 +446,33 @@ __global__ void __launch_bounds__(256) cls_head_logits_kernel(const T* __restric
   if ((lane & 1) == 0 && head < heads) maps[((long long)b * heads + head) * P + j] = s * scale;
 }
 
+// ctx_cleaner (model.py:1425-1436): rows [B*P, D] against one context vector per image.  Warp per row.
+//   mode 0 orthogonal_projection: d - alpha * (<d, c> / |c|^2) * c        mode 1 contrastive_mask: d * (1 - c / (|c| + eps))
+//   prenorm != 0: rows and context are L2-normalised first (the clean_after_projection=False branch, model.py:905-913).
+__global__ void __launch_bounds__(256) ctx_clean_kernel(const float* __restrict__ rows, long long img_stride, long long row_stride,
+                                                        const float* __restrict__ ctx, long long ctx_stride, int B, int P, int D,
+                                                        int mode, float alpha, float eps, int prenorm, float* __restrict__ out) {
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= (long long)B * P) return;
+  const int b = (int)(warp / P), p = (int)(warp % P);
+  const float* d = rows + (long long)b * img_stride + (long long)p * row_stride;
+  const float* c = ctx + (long long)b * ctx_stride;
+  float* o = out + warp * D;
+  float dc = 0.f, cc = 0.f, dd = 0.f;
+  for (int i = lane; i < D; i += 32) { const float x = d[i], y = c[i]; dc = fmaf(x, y, dc); cc = fmaf(y, y, cc); dd = fmaf(x, x, dd); }
+  dc = warp_sum(dc); cc = warp_sum(cc); dd = warp_sum(dd);
+  float dn = 1.0f, cn = 1.0f;  // 1 / |d|, 1 / |c| when pre-normalising
+  if (prenorm) { dn = 1.0f / sqrtf(dd); cn = 1.0f / sqrtf(cc); dc *= dn * cn; cc = 1.0f; }
+  if (mode == 0) {
+    const float k = alpha * dc / cc;
+    for (int i = lane; i < D; i += 32) o[i] = d[i] * dn - k * (c[i] * cn);
+  } else {
+    const float inv = 1.0f / (sqrtf(cc) + eps);
+    for (int i = lane; i < D; i += 32) o[i] = (d[i] * dn) * (1.0f - (c[i] * cn) * inv);
+  }
+}
+
 __global__ void __launch_bounds__(256) region_mean_weights_kernel(int grid, float variance, float* __restrict__ w) {
   __shared__ float red[8];
   const int P = grid * grid;
@@ -583,6 +610,18 @@ int pio_cls_head_attention(const void* qkv, int qkv_dt, int B, int N, int D, int
     cls_head_logits_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)qkv, B, N, D, num_global, heads, scale, out_maps);
   PIO_LAUNCHED();
   return softmax_rows(out_maps, out_maps, B * heads, P, 1.0f, st);  // self_attn_maps.softmax(dim=-1), model.py:871
+}
+
+int pio_ctx_clean(const float* rows, long long img_stride, long long row_stride, const float* ctx, long long ctx_stride, int B, int P,
+                  int D, int mode, float alpha, float eps, int prenorm, float* out, void* stream) {
+  using namespace pio;
+  PIO_CHECK(rows && ctx && out, "ctx_clean: null argument");
+  PIO_CHECK(mode == 0 || mode == 1, "ctx_clean: mode %d (0 orthogonal_projection, 1 contrastive_mask)", mode);
+  if (B == 0 || P == 0) return PIO_OK;
+  ctx_clean_kernel<<<cdiv((long long)B * P * 32, 256), 256, 0, as_stream(stream)>>>(rows, img_stride, row_stride, ctx, ctx_stride, B, P, D,
+                                                                                   mode, alpha, eps, prenorm, out);
+  PIO_LAUNCHED();
+  return PIO_OK;
 }
 
 int pio_region_mean_weights(int grid, float variance, float* weights, void* stream) {

@@ -233,6 +233,11 @@ class Patchioner:
             x = ops.linear(a, self._inv_w, self.precision, bias=self._inv_bias)
         return x
 
+    def _project_rows(self, x: torch.Tensor, chunk: int = 8192) -> torch.Tensor:
+        """im_proj.project(x, normalize=True) for many rows (chunked to bound the workspace)."""
+        x = x.reshape(-1, x.shape[-1])
+        return torch.cat([self.im_proj.project(x[s:s + chunk], normalize=True) for s in range(0, x.shape[0], chunk)], 0)
+
     def caption_token_ids(self, dino_tokens: torch.Tensor, project: bool = True, compute_scores: bool = False):
         """ids int32 [R,30] on the device (+ scores).  Chunked only to bound the decoder workspace."""
         feats = dino_tokens.reshape(-1, dino_tokens.shape[-1])
@@ -316,9 +321,10 @@ class Patchioner:
          -> ``mask_capts``; ``return_ids=True`` returns int32 id tensors instead of strings."""
         assert clean_from in ["cls", "avg_self_attn"]
         assert cleaning_type in [None, "orthogonal_projection", "contrastive_mask"]
-        if double_DINO_for_bboxes or cleaning_type is not None or caption_bboxes_type is not None:
-            raise NotImplementedError("double_DINO / cleaning_type / caption_bboxes_type are "
-                                      "'next' rows (SURVEY.md 8f.4), not built in this round")
+        if double_DINO_for_bboxes or caption_bboxes_type is not None:
+            raise NotImplementedError("double_DINO / caption_bboxes_type are 'next' rows (SURVEY.md 8f.4), not built in this round")
+        if cleaning_type is not None and self.im_proj is None:
+            raise ValueError("cleaning_type needs the caption memory (the reference calls im_proj.project, model.py:895-913)")
         if self.calculate_argmax_text and return_ids:
             raise ValueError("return_ids has no meaning with calculate_argmax_text (captions are bank texts)")
         imgs = imgs.to(self.device, non_blocking=True)
@@ -328,6 +334,23 @@ class Patchioner:
         cls, reg, patch = tokens[:, 0], tokens[:, 1:5], tokens[:, 5:]
         P, D = patch.shape[1], patch.shape[2]
         g = int(P ** 0.5)
+
+        avg_self_attn_token = None
+        if get_avg_self_attn_capt or (cleaning_type is not None and clean_from == "avg_self_attn"):
+            avg_self_attn_token = ops.pool_grid(patch, self_attn.reshape(bs, 1, P), 1.0 / P)[:, 0]  # model.py:869, before any cleaning
+        project_regions = True
+        patch_orig = patch  # the per-head tokens are taken before any cleaning (model.py:872)
+        if cleaning_type is not None:
+            # model.py:879-922: the patch tokens are REPLACED by context-cleaned, memory-projected tokens; the patch and box
+            # captions then skip the projection (project = cleaning_type is None, model.py:966, 1014)
+            ctx = cls if clean_from == "cls" else avg_self_attn_token
+            if clean_after_projection:
+                pp = self._project_rows(patch.reshape(-1, D)).reshape(bs, P, D)
+                patch = ops.ctx_clean(pp, self._project_rows(ctx), cleaning_type, alpha)
+            else:
+                cleaned = ops.ctx_clean(patch, ctx.contiguous(), cleaning_type, alpha, prenorm=True)
+                patch = self._project_rows(cleaned.reshape(-1, D)).reshape(bs, P, D)
+            project_regions = False
 
         def emit_texts(key, feats, group=None):
             """calculate_argmax_text (model.py:1408-1411): captions are bank texts; only the box branch asks for sims."""
@@ -344,12 +367,12 @@ class Patchioner:
                         "attn_heads_capts": "attn_heads_scores"}.get(key, key + "_scores")
                 outs[skey] = cut(sc)
 
-        def emit(key, feats, group=None):
+        def emit(key, feats, group=None, project=True):
             if self.calculate_argmax_text:
                 return emit_texts(key, feats, group)
             if return_n_best_sims is not None and key == "bbox_capts":
                 self.caption_tokens(feats[:0], return_n_best_sims=return_n_best_sims)  # raises like the reference's decoder path
-            r = self.caption_token_ids(feats, compute_scores=compute_scores)
+            r = self.caption_token_ids(feats, project=project, compute_scores=compute_scores)
             ids, sc = (r if compute_scores else (r, None))
             vals = ids if return_ids else self._ids_to_text(ids)
             if group is not None:
@@ -364,21 +387,21 @@ class Patchioner:
         if get_cls_capt:
             emit("cls_capt", cls)
         if get_avg_self_attn_capt:  # model.py:869
-            emit("avg_self_attn_capt", ops.pool_grid(patch, self_attn.reshape(bs, 1, P), 1.0 / P)[:, 0])
+            emit("avg_self_attn_capt", avg_self_attn_token)
         if get_avg_patch_capt:      # model.py:45-94
             w = ops.region_mean_weights(g, gaussian_img_variance, patch.device)
             emit("avg_patch_capt", ops.pool_grid(patch, w.reshape(1, 1, P).expand(bs, 1, P), 1.0)[:, 0])
         if get_attn_heads_capt:     # model.py:871-872, 950-960: one embedding per "head" map (16 x 48-channel re-cut, sic)
             maps = ops.cls_head_attention(qkv_last, self.num_global_tokens, self.num_attn_heads, 0.125)
-            emit("attn_heads_capts", ops.pool_grid(patch, maps, 1.0 / P).reshape(-1, D), group=self.num_attn_heads)
+            emit("attn_heads_capts", ops.pool_grid(patch_orig, maps, 1.0 / P).reshape(-1, D), group=self.num_attn_heads)
         if get_patch_capts:
-            emit("patch_tokens_capts", patch.reshape(-1, D), group=P)
+            emit("patch_tokens_capts", patch.reshape(-1, D), group=P, project=project_regions)
         if get_register_capts:
             emit("register_capts", reg.reshape(-1, D), group=4)
         if bboxes is not None and not get_controllable_capts:
             amap = self_attn if use_attn_map_for_bboxes else None
             feats = ops.pool_boxes(patch, bboxes, self.patch_size, gaussian_avg, gaussian_bbox_variance, amap)
-            emit("bbox_capts", feats.reshape(-1, D), group=bboxes.shape[1])
+            emit("bbox_capts", feats.reshape(-1, D), group=bboxes.shape[1], project=project_regions)
         elif bboxes is not None and get_controllable_capts:
             amap = self_attn if use_attn_map_for_bboxes else None
             feats = ops.pool_boxes(patch, bboxes, self.patch_size, gaussian_avg, gaussian_bbox_variance, amap,

@@ -223,6 +223,19 @@ def cls_attention(qkv: torch.Tensor, num_global: int = 5) -> torch.Tensor:
     return out
 
 
+def ctx_clean(rows: torch.Tensor, ctx: torch.Tensor, cleaning_type: str = "orthogonal_projection", alpha: float = 1.0,
+              epsilon: float = 1e-6, prenorm: bool = False) -> torch.Tensor:
+    """ctx_cleaner (model.py:1425-1436) for rows [B,P,D] against ctx [B,D] -> [B,P,D]."""
+    _need_cuda(rows, ctx)
+    assert rows.dtype == torch.float32 and ctx.dtype == torch.float32 and rows.stride(2) == 1 and ctx.stride(1) == 1
+    B, P, D = rows.shape
+    out = torch.empty(B, P, D, dtype=torch.float32, device=rows.device)
+    mode = {"orthogonal_projection": 0, "contrastive_mask": 1}[cleaning_type]
+    L.check(L.lib().pio_ctx_clean(rows.data_ptr(), rows.stride(0), rows.stride(1), ctx.data_ptr(), ctx.stride(0), B, P, D, mode,
+                                  float(alpha), float(epsilon), int(prenorm), out.data_ptr(), _stream()))
+    return out
+
+
 def cls_head_attention(qkv: torch.Tensor, num_global: int = 5, heads: int = 16, scale: float = 0.125) -> torch.Tensor:
     """Per-"head" CLS attention maps, softmaxed over the patches (dino_extraction.py:24-34 + model.py:871): [B, heads, P]."""
     _need_cuda(qkv)

@@ -615,3 +615,41 @@ def test_forward_pipelined_matches_forward(dev):
     want = [m(b["imgs"], bboxes=b["bboxes"].clone(), get_cls_capt=False, return_ids=True)["bbox_capts"].cpu() for b in batches]
     got = [o["bbox_capts"].cpu() for o in m.forward_pipelined(iter(batches), get_cls_capt=False, return_ids=True)]
     assert len(got) == 3 and all(torch.equal(a, b) for a, b in zip(got, want))
+
+
+@pytest.mark.parametrize("kind", ["orthogonal_projection", "contrastive_mask"])
+def test_ctx_clean(dev, ops, kind):
+    gen = torch.Generator().manual_seed(51)
+    tok = torch.randn(3, 5 + 100, 768, generator=gen)
+    d = tok[:, 5:]                      # strided view, like x_norm_patchtokens
+    c = torch.randn(3, 768, generator=gen)
+    want = o_pool.ctx_cleaner(d, c, kind, alpha=0.7)
+    got = ops.ctx_clean(tok.to(dev)[:, 5:], c.to(dev), kind, alpha=0.7)
+    torch.testing.assert_close(got.cpu(), want, rtol=1e-4, atol=1e-5)
+    dn, cn = d / d.norm(dim=-1, keepdim=True), c / c.norm(dim=-1, keepdim=True)
+    got = ops.ctx_clean(tok.to(dev)[:, 5:], c.to(dev), kind, alpha=0.7, prenorm=True)
+    torch.testing.assert_close(got.cpu(), o_pool.ctx_cleaner(dn, cn, kind, alpha=0.7), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("after", [True, False])
+def test_forward_cleaning_type(dev, after):
+    """cleaning_type (model.py:879-922): patch tokens replaced by context-cleaned, projected tokens; box captions skip the projection."""
+    m = _model(dev, "fp32", True)
+    vit_w, dec_w = o_vit.make_weights(seed=1234), o_decap.make_weights(seed=1234)
+    bank = o_mem.drop_zero_rows(o_pipe.synth_bank(3000, 768, seed=7, zero_frac=0.002))
+    imgs = o_pipe.synth_images(2, 224, seed=1)
+    boxes = o_pipe.synth_boxes(2, 3, 224, seed=1, pad="dense")
+    d = o_vit.forward(vit_w, imgs)
+    patch, cls = d["x_norm_patchtokens"], d["x_norm_clstoken"]
+    if after:
+        cleaned = o_pool.ctx_cleaner(o_mem.project(patch, bank, normalize=True), o_mem.project(cls, bank, normalize=True),
+                                     "orthogonal_projection", 0.8)
+    else:
+        cleaned = o_mem.project(o_pool.ctx_cleaner(patch / patch.norm(dim=-1, keepdim=True), cls / cls.norm(dim=-1, keepdim=True),
+                                                   "orthogonal_projection", 0.8), bank, normalize=True)
+    feats = o_pool.extract_bboxes_feats(cleaned, boxes.clone(), False, 0.5).reshape(-1, 768)
+    want = o_pipe.OracleModel(vit_w, dec_w, bank).caption_tokens(feats, project=False)
+    out = m(imgs, get_cls_capt=False, bboxes=boxes, cleaning_type="orthogonal_projection", alpha=0.8, clean_after_projection=after,
+            return_ids=True)
+    got = out["bbox_capts"].reshape(-1, 30).cpu().long()
+    assert (got == want).all(dim=1).float().mean().item() >= 0.99
