@@ -417,6 +417,38 @@ class Patchioner:
 
     __call__ = forward
 
+    # ------------------------------------------------------------------------------------------ user-level surface
+    def preprocess(self, images, keep_img_ratio: bool = True) -> torch.Tensor:
+        """PIL images -> normalised fp32 batch [B,3,crop,crop].  keep_img_ratio=True: resize the short side + centre crop
+        (``image_transforms``, eval_densecap.py:313-316); False: squash to a square (``image_transforms_no_crop``, :339-342).
+        Boxes must be adjusted accordingly by the caller (adjust_bbox_for_transform / ..._no_scale, bbox_utils.py:170-250)."""
+        tf = self.image_transforms if keep_img_ratio else self.image_transforms_no_crop
+        return torch.stack([tf(im) for im in images])
+
+    def caption(self, imgs, caption_from: str = "patches", bboxes=None, traces=None, masks=None, region_sets: bool = False,
+                use_gaussian_weighting: bool = False, gaussian_variance: float = 1.0, use_attention_weighting: bool = False,
+                compute_scores: bool = False, return_ids: bool = False):
+        """The eval drivers' / HF wrapper's vocabulary mapped onto ``forward``:
+
+        caption_from='cls' -> get_cls_capt; 'avg_self_attn' -> get_avg_self_attn_capt; 'patches' -> the region inputs decide:
+        ``bboxes`` (one caption per box, or per box SET with region_sets=True), ``traces``, ``masks``, or -- with no region at
+        all -- the whole-image patch average (get_avg_patch_capt).  use_gaussian_weighting -> gaussian_avg +
+        gaussian_bbox_variance (boxes) / gaussian_img_variance (whole image); use_attention_weighting ->
+        use_attn_map_for_bboxes (boxes) / use_attention_tracing (traces)."""
+        if caption_from not in ("patches", "cls", "avg_self_attn"):
+            raise ValueError(f"caption_from={caption_from!r}: expected 'patches', 'cls' or 'avg_self_attn'")
+        kw = dict(get_cls_capt=caption_from == "cls", get_avg_self_attn_capt=caption_from == "avg_self_attn",
+                  compute_scores=compute_scores, return_ids=return_ids)
+        if caption_from == "patches":
+            if bboxes is None and traces is None and masks is None:
+                kw.update(get_avg_patch_capt=True, gaussian_img_variance=gaussian_variance if use_gaussian_weighting else 100)
+            else:
+                kw.update(bboxes=bboxes, traces=traces, masks=masks, get_controllable_capts=region_sets,
+                          gaussian_avg=use_gaussian_weighting, gaussian_bbox_variance=gaussian_variance,
+                          use_attn_map_for_bboxes=use_attention_weighting and bboxes is not None,
+                          use_attention_tracing=use_attention_weighting and traces is not None)
+        return self.forward(imgs, **kw)
+
     def forward_pipelined(self, batches, **flags):
         """Serving loop over host-resident batches: yields ``forward(**batch, **flags)`` for every batch.
 

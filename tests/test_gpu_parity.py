@@ -653,3 +653,29 @@ def test_forward_cleaning_type(dev, after):
             return_ids=True)
     got = out["bbox_capts"].reshape(-1, 30).cpu().long()
     assert (got == want).all(dim=1).float().mean().item() >= 0.99
+
+
+def test_caption_surface_maps_onto_forward(dev):
+    """caption(caption_from=..., use_gaussian_weighting=..., use_attention_weighting=...) == forward with the mapped flags."""
+    from patchioner_b200 import AutoModel
+
+    vit_w, dec_w = o_vit.make_weights(seed=1234), o_decap.make_weights(seed=1234)
+    m = AutoModel.from_pretrained({"decap_weights": dec_w, "prefix_size": 768, "support_memory_size": 0, "dino_model": "dinov2_vitb14_reg",
+                                   "resize_dim": 224, "crop_dim": 224, "dino_weights": vit_w, "precision": "fp32"}, device=dev)
+    imgs = o_pipe.synth_images(2, 224, seed=3)
+    boxes = o_pipe.synth_boxes(2, 3, 224, seed=3)
+    traces = o_pipe.synth_traces(2, seed=3)
+    a = m.caption(imgs, "patches", bboxes=boxes, use_gaussian_weighting=True, gaussian_variance=1.0, return_ids=True)
+    b = m(imgs, get_cls_capt=False, bboxes=boxes, gaussian_avg=True, gaussian_bbox_variance=1.0, return_ids=True)
+    assert set(a) == {"bbox_capts"} and torch.equal(a["bbox_capts"], b["bbox_capts"])
+    a = m.caption(imgs, "patches", traces=traces, use_attention_weighting=True, return_ids=True)
+    b = m(imgs, get_cls_capt=False, traces=traces, use_attention_tracing=True, return_ids=True)
+    assert torch.equal(a["trace_capts"], b["trace_capts"])
+    a = m.caption(imgs, "patches", bboxes=boxes, region_sets=True, return_ids=True)
+    assert a["set_controllable_capts"].shape == (2, 30)
+    assert set(m.caption(imgs, "cls", return_ids=True)) == {"cls_capt"}
+    assert set(m.caption(imgs, "avg_self_attn", return_ids=True)) == {"avg_self_attn_capt"}
+    assert set(m.caption(imgs, "patches", return_ids=True)) == {"avg_patch_capt"}
+    from PIL import Image
+    pil = [Image.new("RGB", (320, 240), (200, 30, 90)), Image.new("RGB", (100, 300), (5, 5, 5))]
+    assert m.preprocess(pil, keep_img_ratio=True).shape == (2, 3, 224, 224) and m.preprocess(pil, keep_img_ratio=False).shape == (2, 3, 224, 224)
