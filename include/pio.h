@@ -83,7 +83,7 @@ typedef struct {
   /* pio_argmax_finish() reduces them.  Replaces logits -> softmax -> argmax of decap.py:133-141.           */
   float* argmax_val;
   int* argmax_idx;
-  float* argmax_sumexp;
+  float* argmax_sumexp; /* may be NULL: no sum of exponentials (only the log-prob score needs it) */
   int argmax_ld;
   /* fused exponential (PIO_BF16 mode only, C must be bf16): when exp_ref != NULL the epilogue stores           */
   /*   C[m,n] = exp2( alpha*colscale[n]*acc - exp_ref[m] )   and writes, per (row, column-slab) pair s,           */

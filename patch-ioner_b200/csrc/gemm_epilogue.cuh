@@ -275,6 +275,7 @@ __device__ __forceinline__ void epilogue_exp(uint32_t tmem_acc, int quarter, int
 }
 
 // Fused arg-max epilogue: this warp's columns [c_begin, c_end) of its row -> (max, first arg-max, sum exp(v - max)).
+template <bool WITH_SUMEXP>  // the sum of exponentials (log-prob of the arg-max) is only needed for compute_scores
 __device__ __forceinline__ void epilogue_argmax(uint32_t tmem_acc, int quarter, int c_begin, int c_end, int m, int M, int n0, int N,
                                                 int slab, const Epilogue& epi, const float* s_scale, const float* s_bias) {
   float best = -INFINITY, sum = 0.f;
@@ -298,18 +299,20 @@ __device__ __forceinline__ void epilogue_argmax(uint32_t tmem_acc, int quarter, 
 #pragma unroll
       for (int i = 31; i >= 0; --i)
         if (v[i] == cmax) ci = i;
-      sum *= __expf(best - cmax);
+      if (WITH_SUMEXP) sum *= __expf(best - cmax);
       best = cmax;
       bidx = n + ci;
     }
+    if (WITH_SUMEXP) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) sum += __expf(v[i] - best);
+      for (int i = 0; i < 32; ++i) sum += __expf(v[i] - best);
+    }
   }
   if (m < M) {
     const long long o = (long long)m * epi.argmax_ld + slab;
     epi.argmax_val[o] = best;
     epi.argmax_idx[o] = bidx;
-    epi.argmax_sumexp[o] = sum;
+    if (WITH_SUMEXP) epi.argmax_sumexp[o] = sum;
   }
 }
 
@@ -324,7 +327,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tacc, int quarter, int la
   const int cb = half * (BN / 2), ce = cb + BN / 2;
   const bool hr = epi.residual != nullptr;
   if (epi.argmax_val != nullptr) {
-    epilogue_argmax(tacc, quarter, cb, ce, m, M, n0, N, slab, epi, s_scale, s_bias);
+    if (epi.argmax_sumexp != nullptr) epilogue_argmax<true>(tacc, quarter, cb, ce, m, M, n0, N, slab, epi, s_scale, s_bias);
+    else epilogue_argmax<false>(tacc, quarter, cb, ce, m, M, n0, N, slab, epi, s_scale, s_bias);
   } else if (epi.exp_ref != nullptr) {
     epilogue_exp(tacc, quarter, lane, cb, ce, m, M, n0, N, slab, C, ldc, epi, s_scale, to);
   } else

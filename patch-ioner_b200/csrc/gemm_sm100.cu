@@ -206,8 +206,8 @@ int linear_tc(const PioLinear& p, cudaStream_t st) {
   PIO_CHECK((((uintptr_t)p.A) & 15) == 0 && (((uintptr_t)p.W) & 15) == 0, "tcgen05 GEMM: operands must be 16-byte aligned");
   PIO_CHECK(p.K > 0, "tcgen05 GEMM: K must be positive");
   if (p.M == 0 || p.N == 0) return PIO_OK;
-  PIO_CHECK(p.argmax_val == nullptr || (p.argmax_idx && p.argmax_sumexp && p.argmax_ld >= argmax_slabs_tc(p.M, p.N)),
-            "tcgen05 GEMM: fused arg-max needs val/idx/sumexp buffers with ld >= pio_argmax_slabs()");
+  PIO_CHECK(p.argmax_val == nullptr || (p.argmax_idx && p.argmax_ld >= argmax_slabs_tc(p.M, p.N)),
+            "tcgen05 GEMM: fused arg-max needs val/idx (and optionally sumexp) buffers with ld >= pio_argmax_slabs()");
   PIO_CHECK(p.exp_ref == nullptr || (p.exp_psum && p.exp_pmax && p.c_dt == PIO_DT_BF16 && p.exp_ld >= argmax_slabs_tc(p.M, p.N)),
             "tcgen05 GEMM: fused exp needs bf16 C and psum/pmax buffers with ld >= pio_argmax_slabs()");
   static const bool use_2cta = [] { const char* e = getenv("PIO_GEMM_2CTA"); return !(e && e[0] == '0'); }();

@@ -710,7 +710,7 @@ int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int*
       memset(&p, 0, sizeof(p));
       p.A = hb; p.W = h->wte; p.C = nullptr; p.M = R; p.N = gV; p.K = gD; p.lda = gD; p.ldw = gD; p.ldc = gVld;
       p.a_dt = adt; p.c_dt = PIO_DT_F32; p.alpha = 1.0f;
-      p.argmax_val = av; p.argmax_idx = ai; p.argmax_sumexp = as; p.argmax_ld = slabs;
+      p.argmax_val = av; p.argmax_idx = ai; p.argmax_sumexp = out_logprob_sum ? as : nullptr; p.argmax_ld = slabs;  // sum exp only for scores
       PIO_TRY(linear_tc(p, st));
       launch_pdl(argmax_finish_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, av, ai, as, slabs, slabs, R, out_ids, steps, t,
                  out_logprob_sum);
