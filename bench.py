@@ -257,7 +257,8 @@ def run_ours(args):
         """n steps through the public serving API: every step copies its pinned host inputs in (the copy of step i+1 is
         issued under step i's kernels: Patchioner.forward_pipelined) and reads its ids back to the host."""
         batches = (host[i % n_sets] for i in range(n))
-        for out in model.forward_pipelined(batches, get_cls_capt=False, return_ids=True, **kw):
+        overlap = os.environ.get("PIO_E2E_OVERLAP", "1") != "0"  # A/B switch: second compute stream for batch i+1
+        for out in model.forward_pipelined(batches, overlap_compute=overlap, get_cls_capt=False, return_ids=True, **kw):
             out[key].cpu()  # device -> host read of the step's result
 
     def barrier():

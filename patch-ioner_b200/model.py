@@ -449,17 +449,21 @@ class Patchioner:
                           use_attention_tracing=use_attention_weighting and traces is not None)
         return self.forward(imgs, **kw)
 
-    def forward_pipelined(self, batches, **flags):
-        """Serving loop over host-resident batches: yields ``forward(**batch, **flags)`` for every batch.
+    def forward_pipelined(self, batches, overlap_compute: bool = True, **flags):
+        """Serving loop over host-resident batches: yields ``forward(**batch, **flags)`` for every batch, in order.
 
         ``batches`` is an iterable of dicts (``imgs`` plus optional ``bboxes`` / ``masks`` tensors, ``traces`` lists), ideally in
-        pinned memory.  The host->device copy of batch i+1 is issued on a copy stream before batch i is computed, so it
-        overlaps the compute; results come back in order.  Same outputs as calling ``forward`` batch by batch."""
+        pinned memory.  Two things run under the kernels of batch i: the host->device copy of batch i+1 (copy stream, two
+        persistent staging slots) and -- with ``overlap_compute`` -- the forward of batch i+1 itself, issued on a second
+        compute stream with its own scratch buffers, so that its large ViT kernels fill the SMs the small decode kernels of
+        batch i leave idle.  Same outputs as calling ``forward`` batch by batch."""
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(self.device)
+            self._alt_stream = torch.cuda.Stream(self.device)
             self._stage_bufs, self._stage_free = {}, {}
         copy = self._copy_stream
+        streams = (main, self._alt_stream) if overlap_compute else (main, main)
 
         def stage(batch, slot):
             """copy `batch` into the persistent device buffers of `slot` (allocated once per shape: no allocator traffic,
@@ -481,18 +485,37 @@ class Patchioner:
                 ev.record(copy)
             return dev_batch, ev
 
-        it = iter(batches)
-        i = 0
-        nxt = next(it, None)
-        staged = stage(nxt, 0) if nxt is not None else None
-        while staged is not None:
+        def launch(i, staged):
+            """issue the forward of batch i on its compute stream; returns (outputs, completion event)"""
             cur, ev = staged
-            nxt = next(it, None)
-            staged = stage(nxt, (i + 1) & 1) if nxt is not None else None  # next batch's copy runs under this batch's kernels
-            main.wait_event(ev)
-            out = self.forward(**cur, **flags)
-            done = torch.cuda.Event()
-            done.record(main)
+            st = streams[i & 1]
+            with torch.cuda.stream(st):
+                st.wait_event(ev)
+                if i == 1 and first_done:
+                    st.wait_event(first_done[0])  # lazily built device caches (pos-embed ...) of the very first forward are complete
+                out = self.forward(**cur, **flags)
+                done = torch.cuda.Event()
+                done.record(st)
             self._stage_free[i & 1] = done
+            if i == 0:
+                first_done.append(done)
+            return out, done
+
+        it = iter(batches)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        i = 0
+        first_done: list = []
+        inflight = launch(0, stage(nxt, 0))
+        while inflight is not None:
+            nxt = next(it, None)
+            following = launch(i + 1, stage(nxt, (i + 1) & 1)) if nxt is not None else None  # issued before batch i is consumed
+            out, done = inflight
+            main.wait_event(done)  # the caller reads the results on the current stream
+            for v in out.values():
+                if torch.is_tensor(v):
+                    v.record_stream(main)
+            inflight = following
             i += 1
             yield out

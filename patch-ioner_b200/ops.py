@@ -35,12 +35,13 @@ def _dt(t: torch.Tensor) -> int:
     raise L.PioError(f"unsupported dtype {t.dtype}")
 
 
-_ws_cache: Dict[Tuple[int, str], torch.Tensor] = {}
+_ws_cache: Dict[Tuple[int, str, int], torch.Tensor] = {}
 
 
 def workspace(nbytes: int, device, tag: str = "") -> torch.Tensor:
-    """A cached, 1024-byte aligned scratch buffer per (device, tag); grows monotonically."""
-    key = (torch.device(device).index or 0, tag)
+    """A cached, 1024-byte aligned scratch buffer per (device, tag, current stream); grows monotonically.  Keyed by the
+    stream so that two forwards in flight on two streams (Patchioner.forward_pipelined) never share scratch memory."""
+    key = (torch.device(device).index or 0, tag, torch.cuda.current_stream(device).cuda_stream)
     buf = _ws_cache.get(key)
     need = nbytes + 1024
     if buf is None or buf.numel() < need:
