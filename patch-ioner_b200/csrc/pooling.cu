@@ -265,11 +265,40 @@ __global__ void __launch_bounds__(POOL_THREADS) pool_slab_kernel(const float* __
 // grid = (D/16, B): a CTA stages a [P x 16-channel] slab (64-byte row segments, 88 KB at 518 px) so TWO CTAs share an SM and
 // one CTA's cp.async staging overlaps the other's arithmetic.  Each warp owns whole boxes (no shared-memory atomics, no
 // per-box bookkeeping by the other warps): a warp visits 8 patches of a box row per step, 4 lanes x float4 per patch, so one
-// LDS.128 per lane reads 512 contiguous bytes of the slab per warp (conflict free) and feeds 4 FMAs.  Separable gaussian:
-// the lane-distributed x / y factors are computed once per box and broadcast with shuffles (x-factors hoisted per box).
+// LDS.128 per lane reads 512 contiguous bytes of the slab per warp (conflict free) and feeds 4 FMAs.  The separable x / y
+// factors come from box_factors_kernel's table (lane-distributed, broadcast with shuffles, x-factors hoisted per box).
 constexpr int PB_THREADS = 512;
+// Per-box separable factors, computed ONCE per box (the pooling CTAs of an image -- 48 channel slabs -- would otherwise each
+// redo the expf / linspace / normalisation work, which dominated their instruction count): fac[bi] = wx[64] | wy[64] | nrm.
+// mode 0 (mean): wx = wy = 1 inside the box, nrm = 1 / (hs ws) (inf for an empty box: 0 * inf = NaN like tensor.mean());
+// mode 1 (gaussian): exp(-x^2 / var) on linspace(-1, 1, span), nrm = 1 / (sum_y sum_x) (0 for an empty box, like the reference).
+constexpr int FAC_STRIDE = 132;
+__global__ void __launch_bounds__(256) box_factors_kernel(const int* __restrict__ bounds, int n, int mode, float variance,
+                                                          float* __restrict__ fac) {
+  const int bi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (bi >= n) return;
+  const int4 bd = __ldg(reinterpret_cast<const int4*>(bounds) + bi);
+  const int hs = bd.y - bd.x, ws = bd.w - bd.z;
+  float wxa = 0.f, wxb = 0.f, wya = 0.f, wyb = 0.f, nrm;
+  if (mode == 1) {
+    if (lane < ws) { const float x = linspace_m1_1(lane, ws); wxa = expf(-(x * x) / variance); }
+    if (lane + 32 < ws) { const float x = linspace_m1_1(lane + 32, ws); wxb = expf(-(x * x) / variance); }
+    if (lane < hs) { const float y = linspace_m1_1(lane, hs); wya = expf(-(y * y) / variance); }
+    if (lane + 32 < hs) { const float y = linspace_m1_1(lane + 32, hs); wyb = expf(-(y * y) / variance); }
+    const float sx = warp_sum(wxa + wxb), sy = warp_sum(wya + wyb);
+    nrm = (hs > 0 && ws > 0) ? 1.0f / (sy * sx) : 0.f;
+  } else {
+    wxa = lane < ws ? 1.f : 0.f; wxb = lane + 32 < ws ? 1.f : 0.f;
+    wya = lane < hs ? 1.f : 0.f; wyb = lane + 32 < hs ? 1.f : 0.f;
+    nrm = 1.0f / (float)(hs * ws);
+  }
+  float* f = fac + (long long)bi * FAC_STRIDE;
+  f[lane] = wxa; f[lane + 32] = wxb; f[64 + lane] = wya; f[96 + lane] = wyb;
+  if (lane == 0) f[128] = nrm;
+}
+
 // Rows of one box for a warp: STEPS x 8 patches per row (x = 8 k + grp), float4 = 4 channels per lane.
-template <int SRC, int STEPS>
+template <bool GAUSS, int STEPS>
 __device__ __forceinline__ float4 box_rows(const float4* sp0, int grid, int hs, int ws, int grp, float wxa, float wxb, float wya,
                                            float wyb) {
   float wxk[STEPS];
@@ -277,18 +306,17 @@ __device__ __forceinline__ float4 box_rows(const float4* sp0, int grid, int hs, 
 #pragma unroll
   for (int k = 0; k < STEPS; ++k) {
     const int x = 8 * k + grp;
-    const float w = (SRC == 1) ? __shfl_sync(0xffffffffu, x < 32 ? wxa : wxb, x & 31) : 1.0f;
-    wxk[k] = (x < ws) ? w : 0.f;
+    wxk[k] = __shfl_sync(0xffffffffu, x < 32 ? wxa : wxb, x & 31);  // 0 beyond the box
     off[k] = min(x, ws - 1) * 4;  // float4 units; lanes beyond the row re-read its last patch with weight 0
   }
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f), acc2 = acc;
   const float4* sp = sp0;
   for (int r = 0; r < hs; ++r, sp += grid * 4) {
     float wy = 1.0f;
-    if (SRC == 1) wy = __shfl_sync(0xffffffffu, r < 32 ? wya : wyb, r & 31);
+    if (GAUSS) wy = __shfl_sync(0xffffffffu, r < 32 ? wya : wyb, r & 31);
 #pragma unroll
     for (int k = 0; k < STEPS; ++k) {
-      const float w = (SRC == 1) ? wy * wxk[k] : wxk[k];
+      const float w = GAUSS ? wy * wxk[k] : wxk[k];
       const float4 v = sp[off[k]];
       if (k & 1) { acc2.x = fmaf(w, v.x, acc2.x); acc2.y = fmaf(w, v.y, acc2.y); acc2.z = fmaf(w, v.z, acc2.z); acc2.w = fmaf(w, v.w, acc2.w); }
       else       { acc.x = fmaf(w, v.x, acc.x);   acc.y = fmaf(w, v.y, acc.y);   acc.z = fmaf(w, v.z, acc.z);   acc.w = fmaf(w, v.w, acc.w); }
@@ -297,43 +325,47 @@ __device__ __forceinline__ float4 box_rows(const float4* sp0, int grid, int hs, 
   return make_float4(acc.x + acc2.x, acc.y + acc2.y, acc.z + acc2.z, acc.w + acc2.w);
 }
 
-template <int SRC>  // 0 mean, 1 gaussian
+template <bool GAUSS>  // mean mode needs no factor table: wx is the box indicator, nrm = 1 / (hs ws)
 __global__ void __launch_bounds__(PB_THREADS, 2) pool_box_kernel(const float* __restrict__ tokens, long long img_stride,
                                                                 long long row_stride, int grid, int D,
-                                                                const int* __restrict__ bounds, int R, float variance,
+                                                                const int* __restrict__ bounds, const float* __restrict__ fac, int R,
                                                                 float* __restrict__ out) {
   extern __shared__ __align__(128) float slab[];  // [P][16]
   const int P = grid * grid;
   const int b = blockIdx.y, c0 = blockIdx.x * 16;
   {
-    const float* src = tokens + (long long)b * img_stride + c0;
-    const uint32_t dst0 = tc::smem_u32(slab);
-    for (int i = threadIdx.x; i < P * 4; i += PB_THREADS) {
-      const int p = i >> 2, q = (i & 3) * 4;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)(p * 16 + q) * 4),
-                   "l"(src + (long long)p * row_stride + q)
-                   : "memory");
-    }
+    // thread t copies 16-byte piece t & 3 of patches t >> 2, t >> 2 + 128, ...: two pointer bumps per copy
+    const float* src = tokens + (long long)b * img_stride + c0 + (long long)(threadIdx.x >> 2) * row_stride + (threadIdx.x & 3) * 4;
+    uint32_t dst = tc::smem_u32(slab) + threadIdx.x * 16;
+    const long long sstep = (long long)(PB_THREADS / 4) * row_stride;
+    for (int p = threadIdx.x >> 2; p < P; p += PB_THREADS / 4, src += sstep, dst += PB_THREADS * 16)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 2, quad = lane & 3;  // 8 patches per step, each read as 4 x float4 (16 channels = 64 bytes)
   bool staged = false;
-  for (int j = warp; j < R; j += PB_THREADS / 32) {
-    const int bi = b * R + j;
-    const int4 bd = __ldg(reinterpret_cast<const int4*>(bounds) + bi);  // y0, y1, x0, x1
+  constexpr int NW = PB_THREADS / 32;
+  // lane l fetches the bounds of this warp's l-th box up front (one load under the staging copy instead of one dependent
+  // global load per box); they are handed out with shuffles
+  int4 myb = make_int4(0, 0, 0, 0);
+  for (int k = 0; warp + k * NW < R; ++k) {
+    if ((k & 31) == 0) {
+      const int jm = warp + (k + lane) * NW;
+      myb = jm < R ? __ldg(reinterpret_cast<const int4*>(bounds) + b * R + jm) : make_int4(0, 0, 0, 0);
+    }
+    const int bi = b * R + warp + k * NW;
+    int4 bd;  // y0, y1, x0, x1
+    bd.x = __shfl_sync(0xffffffffu, myb.x, k & 31); bd.y = __shfl_sync(0xffffffffu, myb.y, k & 31);
+    bd.z = __shfl_sync(0xffffffffu, myb.z, k & 31); bd.w = __shfl_sync(0xffffffffu, myb.w, k & 31);
     const int hs = bd.y - bd.x, ws = bd.w - bd.z;
-    // lane-distributed separable factors (grid <= 64: two registers per axis)
-    float wxa = 1.f, wxb = 1.f, wya = 1.f, wyb = 1.f, nrm;
-    if (SRC == 1) {
-      wxa = wxb = wya = wyb = 0.f;
-      if (lane < ws) { const float x = linspace_m1_1(lane, ws); wxa = expf(-(x * x) / variance); }
-      if (lane + 32 < ws) { const float x = linspace_m1_1(lane + 32, ws); wxb = expf(-(x * x) / variance); }
-      if (lane < hs) { const float y = linspace_m1_1(lane, hs); wya = expf(-(y * y) / variance); }
-      if (lane + 32 < hs) { const float y = linspace_m1_1(lane + 32, hs); wyb = expf(-(y * y) / variance); }
-      const float sx = warp_sum(wxa + wxb), sy = warp_sum(wya + wyb);
-      nrm = (hs > 0 && ws > 0) ? 1.0f / (sy * sx) : 0.f;  // empty box -> zeros, like the reference
+    float wxa, wxb, wya = 1.f, wyb = 1.f, nrm;
+    if (GAUSS) {
+      const float* f = fac + (long long)bi * FAC_STRIDE;
+      wxa = __ldg(f + lane); wxb = __ldg(f + 32 + lane); wya = __ldg(f + 64 + lane); wyb = __ldg(f + 96 + lane);
+      nrm = __ldg(f + 128);
     } else {
+      wxa = lane < ws ? 1.f : 0.f; wxb = lane + 32 < ws ? 1.f : 0.f;
       nrm = 1.0f / (float)(hs * ws);  // empty box -> inf -> 0 * inf = NaN like tensor.mean()
     }
     if (!staged) {  // the box parameters above overlap the tail of the staging copy
@@ -344,14 +376,14 @@ __global__ void __launch_bounds__(PB_THREADS, 2) pool_box_kernel(const float* __
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4* sp0 = reinterpret_cast<const float4*>(slab + (bd.x * grid + bd.z) * 16) + quad;
     switch ((ws + 7) >> 3) {  // warp-uniform: a fully unrolled row loop per step count, no predicated-off issue slots
-      case 1: acc = box_rows<SRC, 1>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
-      case 2: acc = box_rows<SRC, 2>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
-      case 3: acc = box_rows<SRC, 3>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
-      case 4: acc = box_rows<SRC, 4>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
-      case 5: acc = box_rows<SRC, 5>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
-      case 6: acc = box_rows<SRC, 6>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
-      case 7: acc = box_rows<SRC, 7>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
-      case 8: acc = box_rows<SRC, 8>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 1: acc = box_rows<GAUSS, 1>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 2: acc = box_rows<GAUSS, 2>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 3: acc = box_rows<GAUSS, 3>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 4: acc = box_rows<GAUSS, 4>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 5: acc = box_rows<GAUSS, 5>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 6: acc = box_rows<GAUSS, 6>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 7: acc = box_rows<GAUSS, 7>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
+      case 8: acc = box_rows<GAUSS, 8>(sp0, grid, hs, ws, grp, wxa, wxb, wya, wyb); break;
       default: break;  // empty box
     }
 #pragma unroll
@@ -498,13 +530,23 @@ int launch_slab(const float* tokens, long long img_stride, long long row_stride,
   return PIO_OK;
 }
 
-template <int SRC>
 int launch_box(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D, const int* bounds, int R,
-               float variance, float* out, cudaStream_t st) {
+               int mode, float variance, float* fac, float* out, cudaStream_t st) {
   const size_t smem = (size_t)grid * grid * 16 * sizeof(float);
-  PIO_CUDA(cudaFuncSetAttribute(pool_box_kernel<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;
+  if (!attr_set) {
+    PIO_CUDA(cudaFuncSetAttribute(pool_box_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    PIO_CUDA(cudaFuncSetAttribute(pool_box_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    attr_set = true;
+  }
   dim3 g(D / 16, B);
-  pool_box_kernel<SRC><<<g, PB_THREADS, smem, st>>>(tokens, img_stride, row_stride, grid, D, bounds, R, variance, out);
+  if (mode == 1) {
+    box_factors_kernel<<<cdiv((long long)B * R * 32, 256), 256, 0, st>>>(bounds, B * R, mode, variance, fac);
+    PIO_LAUNCHED();
+    pool_box_kernel<true><<<g, PB_THREADS, smem, st>>>(tokens, img_stride, row_stride, grid, D, bounds, fac, R, out);
+  } else {
+    pool_box_kernel<false><<<g, PB_THREADS, smem, st>>>(tokens, img_stride, row_stride, grid, D, bounds, fac, R, out);
+  }
   PIO_LAUNCHED();
   return PIO_OK;
 }
@@ -530,7 +572,8 @@ extern "C" {
 size_t pio_pool_workspace_bytes(int B, int R, int grid) {
   const size_t P = (size_t)grid * grid;
   return pio::align_up((size_t)B * R * 4 * sizeof(int), 256) + pio::align_up((size_t)B * R * sizeof(int), 256) +
-         pio::align_up((size_t)B * R * P * sizeof(float), 256) + pio::align_up((size_t)B * P * sizeof(float), 256) + 1024;
+         pio::align_up((size_t)B * R * (P > 132 ? P : 132) * sizeof(float), 256) /* per-box weights, or the 132-float factor rows */ +
+         pio::align_up((size_t)B * P * sizeof(float), 256) + 1024;
 }
 
 int pio_pool_boxes(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D, const void* boxes,
@@ -551,7 +594,7 @@ int pio_pool_boxes(const float* tokens, long long img_stride, long long row_stri
   char* ws = (char*)workspace;
   int* bounds = (int*)ws; ws += align_up((size_t)B * R * 4 * sizeof(int), 256);
   int* skip = (int*)ws;   ws += align_up((size_t)B * R * sizeof(int), 256);
-  float* per_box = (float*)ws; ws += align_up((size_t)B * R * P * sizeof(float), 256);
+  float* per_box = (float*)ws; ws += align_up((size_t)B * R * (P > 132 ? P : 132) * sizeof(float), 256);
   float* set_map = (float*)ws;
   box_bounds_kernel<<<cdiv(B * R, 128), 128, 0, st>>>(boxes, boxes_dt, B * R, patch_size, grid, bounds, skip);
   PIO_LAUNCHED();
@@ -571,11 +614,11 @@ int pio_pool_boxes(const float* tokens, long long img_stride, long long row_stri
   // the 32-channel slab kernel for A/B runs
   static const bool old_slab = [] { const char* e = getenv("PIO_POOL_SLAB"); return e && e[0] == '1'; }();
   const bool box_ok = !old_slab && grid <= 64 && (size_t)grid * grid * 16 * sizeof(float) <= 113 * 1024;
+  if (box_ok)  // the factor table lives in the (otherwise unused here) per-box weight region of the workspace
+    return launch_box(tokens, img_stride, row_stride, B, grid, D, bounds, R, mode == PIO_POOL_GAUSS ? 1 : 0, variance, per_box, out, st);
   if (mode == PIO_POOL_GAUSS)
-    return box_ok ? launch_box<1>(tokens, img_stride, row_stride, B, grid, D, bounds, R, variance, out, st)
-                  : launch_slab<1>(tokens, img_stride, row_stride, B, grid, D, bounds, R, variance, nullptr, 1.0f, out, st);
-  return box_ok ? launch_box<0>(tokens, img_stride, row_stride, B, grid, D, bounds, R, 0.f, out, st)
-                : launch_slab<0>(tokens, img_stride, row_stride, B, grid, D, bounds, R, 0.f, nullptr, 1.0f, out, st);
+    return launch_slab<1>(tokens, img_stride, row_stride, B, grid, D, bounds, R, variance, nullptr, 1.0f, out, st);
+  return launch_slab<0>(tokens, img_stride, row_stride, B, grid, D, bounds, R, 0.f, nullptr, 1.0f, out, st);
 }
 
 int pio_pool_grid(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D,
