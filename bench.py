@@ -121,14 +121,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """start of the window whose samples count (the sampler itself is started earlier: nvidia-smi needs ~1 s to come up)"""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        t1 = time.perf_counter()
+        time.sleep(0.15)  # let the sample that covers the end of the window arrive
         self.proc.terminate()
+        t0 = getattr(self, "t0", 0.0)
+        window = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.15]
+        if not window:  # a window shorter than the sampling period: take the samples closest to it
+            window = [ln for (_, ln) in self.lines[-2:]]
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -230,6 +240,9 @@ def run_ours(args):
         dist.barrier()
     from patchioner_b200 import Patchioner, ops, synth
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # early: nvidia-smi takes about a second to deliver its first sample
     B, R, S = args.batch, args.boxes, args.size
     vit_w, dec_w = synth.make_vit_weights(1234), synth.make_decoder_weights(1234)
     bank = synth.synth_bank(args.bank_rows, 768, seed=7) if args.bank_rows > 0 else None
@@ -266,13 +279,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, whole_run=False):
+    def timed(fn, steps, warmup, whole_run=False, mark=None):
         if whole_run:
             fn(warmup)
         else:
             for i in range(warmup):
                 fn(i)
         barrier()
+        if rank == 0:
+            (mark or sampler).mark()  # clock samples count from here (the timed region of this leg)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         if whole_run:
@@ -289,16 +304,17 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ops.reset_launch_count()
     ms_total = timed(step_resident, args.steps, args.warmup)
     launches = ops.launch_count()
     # launches counted include the warm-up steps: keep the timed share
     launches = launches * args.steps // (args.steps + args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(run_e2e, args.steps, max(1, args.warmup // 2), whole_run=True)
+    sampler2 = ClockSampler(local)
+    if rank == 0:
+        sampler2.start()
+    ms_e2e = timed(run_e2e, args.steps, max(2, args.warmup), whole_run=True, mark=sampler2)  # >= 2 warm-up batches: both streams' scratch exists
+    clocks_e2e = sampler2.stop() if rank == 0 else None
 
     regions = captions_per_step(args) * world
     value = regions * args.steps / (ms_total / 1e3)
@@ -319,7 +335,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "clocks": clocks_e2e,
                         "h2d_bytes_per_step": int(h2d_bytes) * world,
                         "d2h_bytes_per_step": int(captions_per_step(args) * 30 * 4) * world},
                 "gpu_launches": int(launches), "roofline": roof, "stages": extra,

@@ -459,7 +459,8 @@ class Patchioner:
         batch i leave idle.  Same outputs as calling ``forward`` batch by batch."""
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(self.device)
+            # high priority: the copies get their own hardware queue and are never stuck behind a forward's ~1300 queued kernels
+            self._copy_stream = torch.cuda.Stream(self.device, priority=-1)
             self._alt_stream = torch.cuda.Stream(self.device)
             self._stage_bufs, self._stage_free = {}, {}
         copy = self._copy_stream
