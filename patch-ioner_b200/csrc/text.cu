@@ -401,6 +401,7 @@ size_t pio_project_workspace_bytes(const PioBank* h, int R) {
 int pio_project(PioBank* h, const float* q, int R, float temperature, int normalize, float* out, float* part_m, float* part_l,
                 void* workspace, size_t workspace_bytes, void* stream) {
   using namespace pio;
+  if (R == 0) return PIO_OK;  // nothing to do (empty tensors have null data pointers)
   PIO_CHECK(h && q && out && workspace, "project: null argument");
   PIO_CHECK(temperature > 0.f, "project: temperature must be positive");
   PIO_CHECK(workspace_bytes >= pio_project_workspace_bytes(h, R), "project: workspace too small");
@@ -505,6 +506,7 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
 int pio_best_sims(PioBank* h, const float* q, int R, int n, float* out_sims, int* out_rows, void* workspace,
                   size_t workspace_bytes, void* stream) {
   using namespace pio;
+  if (R == 0) return PIO_OK;
   PIO_CHECK(h && q && out_sims && workspace, "best_sims: null argument");
   PIO_CHECK(n >= 1 && n <= TOPN_MAX, "best_sims: n %d outside [1,%d]", n, TOPN_MAX);
   PIO_CHECK(workspace_bytes >= pio_project_workspace_bytes(h, R), "best_sims: workspace too small");
@@ -662,6 +664,7 @@ size_t pio_decode_workspace_bytes(const PioDecoder* h, int R, int steps) {
 int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int* out_ids, float* out_logprob_sum,
                       void* workspace, size_t workspace_bytes, void* stream) {
   using namespace pio;
+  if (R == 0) return PIO_OK;
   PIO_CHECK(h && prefix && out_ids && workspace, "decode_greedy: null argument");
   PIO_CHECK(steps >= 1 && steps <= gT, "decode_greedy: steps %d outside [1,%d]", steps, gT);
   PIO_CHECK(workspace_bytes >= pio_decode_workspace_bytes(h, R, steps), "decode_greedy: workspace too small");

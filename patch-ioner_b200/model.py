@@ -368,6 +368,11 @@ class Patchioner:
                 outs[skey] = cut(sc)
 
         def emit(key, feats, group=None, project=True):
+            if feats.shape[0] == 0:  # e.g. bboxes of shape [B, 0, 4]: no region, no caption
+                outs[key] = (torch.empty(bs, 0, 30, dtype=torch.int32, device=self.device) if return_ids else [[] for _ in range(bs)])
+                if compute_scores:
+                    outs[{"bbox_capts": "bbox_scores"}.get(key, key + "_scores")] = [[] for _ in range(bs)]
+                return None
             if self.calculate_argmax_text:
                 return emit_texts(key, feats, group)
             if return_n_best_sims is not None and key == "bbox_capts":

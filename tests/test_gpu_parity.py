@@ -679,3 +679,30 @@ def test_caption_surface_maps_onto_forward(dev):
     from PIL import Image
     pil = [Image.new("RGB", (320, 240), (200, 30, 90)), Image.new("RGB", (100, 300), (5, 5, 5))]
     assert m.preprocess(pil, keep_img_ratio=True).shape == (2, 3, 224, 224) and m.preprocess(pil, keep_img_ratio=False).shape == (2, 3, 224, 224)
+
+
+def test_cabi_rejects_bad_arguments(dev, ops):
+    """Error behaviour of the C ABI: status code + message through PioError, nothing launched, no crash."""
+    from patchioner_b200 import PioError
+
+    x = torch.randn(4, 5 * 5, 768, device=dev)
+    boxes = torch.tensor([[[0.0, 0.0, 28.0, 28.0]]] * 4, device=dev)
+    with pytest.raises(PioError, match="variance 0"):
+        ops.pool_boxes(x, boxes, 14, True, 0.0)                      # python-random centre: not reproduced (DESIGN.md)
+    A = torch.randn(64, 100, device=dev).bfloat16()                   # K = 100: 200-byte rows, not a legal TMA stride
+    W = torch.randn(32, 100, device=dev).bfloat16()
+    with pytest.raises(PioError, match="multiples of 8"):
+        ops.linear(A, W, "bf16")
+    bank = ops.Bank(o_pipe.synth_bank(300, 768, seed=1), dev, "fp32")
+    with pytest.raises(PioError, match="outside"):
+        bank.best_sims(torch.randn(3, 768, device=dev), 33)
+    w = o_decap.make_weights(seed=1234)
+    dec = ops.Decoder(w, dev, "fp32")
+    with pytest.raises(PioError, match="steps"):
+        dec.decode(torch.randn(2, 768, device=dev), 33)
+    # empty inputs are fine and launch nothing
+    m = _model(dev, "fp32", True)
+    o = m(o_pipe.synth_images(2, 224, seed=1), get_cls_capt=False, bboxes=torch.zeros(2, 0, 4))
+    assert o["bbox_capts"] == [[], []]
+    assert ops.pool_boxes(x[:0], boxes[:0], 14).shape == (0, 1, 768)
+    assert bank.project(torch.randn(0, 768, device=dev)).shape == (0, 768)
