@@ -178,6 +178,18 @@ def test_pooling_bounds_bit_exact_random(dev, ops):
     assert torch.equal(bounds_i.cpu(), o_pool.all_box_bounds(boxes.long(), 14, g))
 
 
+def test_pooling_many_boxes_per_image(dev, ops):
+    """R = 600 boxes per image (a warp owns more than 32 boxes: the per-warp bounds prefetch reloads), values vs the oracle."""
+    g, B, R, D = 16, 2, 600, 32
+    gen = torch.Generator().manual_seed(13)
+    tok = torch.randn(B, g * g, D, generator=gen)
+    boxes = o_pipe.synth_boxes(B, R, 224, seed=13, degenerate_frac=0.1)
+    for gauss in (False, True):
+        ref = o_pool.extract_bboxes_feats(tok, boxes.clone(), gauss, 1.0)
+        got = ops.pool_boxes(tok.to(dev), boxes, gaussian_avg=gauss, gaussian_bbox_variance=1.0).cpu()
+        torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-5, equal_nan=True)
+
+
 def test_pooling_edge_cases(dev, ops):
     g, D = 16, 64
     tok = torch.randn(1, g * g, D, generator=torch.Generator().manual_seed(2))
