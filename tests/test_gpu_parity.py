@@ -718,3 +718,25 @@ def test_cabi_rejects_bad_arguments(dev, ops):
     assert o["bbox_capts"] == [[], []]
     assert ops.pool_boxes(x[:0], boxes[:0], 14).shape == (0, 1, 768)
     assert bank.project(torch.randn(0, 768, device=dev)).shape == (0, 768)
+
+
+def test_decode_repeatable(dev, ops):
+    """Repeated decodes of the same prefixes through recycled buffers: identical ids and scores, identical launch counts
+    (no state leaks from one call into the next through the KV cache or the workspace)."""
+    w = o_decap.make_weights(seed=1234)
+    gen = torch.Generator().manual_seed(77)
+    for mode in ("bf16", "fp32"):
+        dec = ops.Decoder(w, dev, mode)
+        pre = torch.randn(37, 768, generator=gen).to(dev)
+        first, counts = None, []
+        for i in range(5):
+            ops.reset_launch_count()
+            r = dec.decode(pre, 30, True)
+            torch.cuda.synchronize()
+            counts.append(ops.launch_count())
+            got = (r[0].clone(), r[1].clone())
+            del r  # the result buffers go back to the allocator, so the next call sees the same pointers
+            if first is None:
+                first = got
+            assert torch.equal(got[0], first[0]) and torch.allclose(got[1], first[1], rtol=1e-5, atol=1e-6)
+        assert len(set(counts)) == 1, counts
