@@ -6,8 +6,8 @@ libpio_sm100.so (hand-written sm_100a CUDA) -- there is no PyTorch compute path 
 
 Scope: DINOv2-reg backbone + DeCap / CapDec text side.  The alternative backbones and
 captioners of the reference (ProxyCLIP, RegionCLIP, INViTE, DenseCLIP, AlphaCLIP, ViECap, MeaCap, ClipCap),
-``double_DINO_for_bboxes``, ``cleaning_type``, ``caption_bboxes_type`` and ``get_attn_heads_capt`` are out of
-scope for this round and raise ``NotImplementedError`` instead of silently doing something else.
+``double_DINO_for_bboxes`` is out of scope for this round and raises ``NotImplementedError`` instead of silently
+doing something else.
 """
 from __future__ import annotations
 
@@ -321,8 +321,10 @@ class Patchioner:
          -> ``mask_capts``; ``return_ids=True`` returns int32 id tensors instead of strings."""
         assert clean_from in ["cls", "avg_self_attn"]
         assert cleaning_type in [None, "orthogonal_projection", "contrastive_mask"]
-        if double_DINO_for_bboxes or caption_bboxes_type is not None:
-            raise NotImplementedError("double_DINO / caption_bboxes_type are 'next' rows (SURVEY.md 8f.4), not built in this round")
+        if caption_bboxes_type is not None:  # model.py:770-771: caption the CROP of every box as a whole image
+            return self.caption_bboxes(imgs, bboxes, caption_bboxes_type, compute_scores=compute_scores)
+        if double_DINO_for_bboxes:
+            raise NotImplementedError("double_DINO re-runs the last block on per-box token subsets: a 'next' row (SURVEY.md 8f.4)")
         if cleaning_type is not None and self.im_proj is None:
             raise ValueError("cleaning_type needs the caption memory (the reference calls im_proj.project, model.py:895-913)")
         if self.calculate_argmax_text and return_ids:
@@ -421,6 +423,25 @@ class Patchioner:
         return outs
 
     __call__ = forward
+
+    def caption_bboxes(self, imgs, bboxes, capt_type: str = "cls_capt", crop_boxes: bool = False, compute_scores: bool = False):
+        """model.py:1356-1390 (the crop-and-recaption baseline): ``imgs`` is a list of PIL images, ``bboxes`` [B,R,4] xywh in their
+        pixels; every box is cropped (PIL), sent through ``image_transforms_no_crop`` (or ``image_transforms`` with crop_boxes),
+        and captioned from its CLS token ('cls_capt') or its attention-weighted patch average ('avg_self_attn_capt').
+        All B*R crops go through one forward (the reference runs R chunks of B; captions do not depend on the chunking)."""
+        if capt_type not in ("cls_capt", "avg_self_attn_capt"):
+            raise ValueError(f"capt_type={capt_type!r}: expected 'cls_capt' or 'avg_self_attn_capt'")
+        bs, n = len(imgs), bboxes.shape[1]
+        tf = self.image_transforms if crop_boxes else self.image_transforms_no_crop
+        crops = torch.stack([tf(img.crop((x, y, x + w, y + h))) for img, bb in zip(imgs, bboxes.tolist()) for (x, y, w, h) in bb])
+        out = self.forward(crops, get_cls_capt=capt_type == "cls_capt", get_avg_self_attn_capt=capt_type == "avg_self_attn_capt",
+                           compute_scores=compute_scores)
+        capts = out[capt_type]
+        ret = {"bbox_capts": [capts[i * n:(i + 1) * n] for i in range(bs)]}
+        if compute_scores:
+            sc = out[capt_type + "_scores"]
+            ret["bbox_scores"] = [sc[i * n:(i + 1) * n] for i in range(bs)]
+        return ret
 
     # ------------------------------------------------------------------------------------------ user-level surface
     def preprocess(self, images, keep_img_ratio: bool = True) -> torch.Tensor:

@@ -740,3 +740,22 @@ def test_decode_repeatable(dev, ops):
                 first = got
             assert torch.equal(got[0], first[0]) and torch.allclose(got[1], first[1], rtol=1e-5, atol=1e-6)
         assert len(set(counts)) == 1, counts
+
+
+def test_caption_bboxes_crops(dev):
+    """caption_bboxes_type (model.py:1356-1390): PIL crop of every box -> transform -> caption of the crop's CLS token."""
+    from PIL import Image
+    import numpy as np
+
+    m = _model(dev, "fp32", False)
+    seen = []
+    m.decoding_method = lambda ids: (seen.append(list(ids)) or "c%d" % len(seen))
+    rng = np.random.RandomState(3)
+    pil = [Image.fromarray(rng.randint(0, 255, (260, 300, 3), dtype=np.uint8)), Image.fromarray(rng.randint(0, 255, (240, 240, 3), dtype=np.uint8))]
+    boxes = torch.tensor([[[10.0, 20.0, 100.0, 80.0], [50.0, 50.0, 120.0, 150.0]], [[0.0, 0.0, 240.0, 240.0], [30.0, 40.0, 60.0, 60.0]]])
+    out = m(pil, bboxes=boxes, caption_bboxes_type="cls_capt")
+    assert set(out) == {"bbox_capts"} and [len(r) for r in out["bbox_capts"]] == [2, 2]
+    got = [list(r) for r in seen]
+    crops = torch.stack([m.image_transforms_no_crop(im.crop((x, y, x + w, y + h))) for im, bb in zip(pil, boxes.tolist()) for (x, y, w, h) in bb])
+    want = m(crops, get_cls_capt=True, return_ids=True)["cls_capt"].cpu().tolist()
+    assert got == want
