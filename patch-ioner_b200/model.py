@@ -5,8 +5,8 @@ names, same output keys), ``caption_tokens`` (:1392-1423).  Underneath, every nu
 libpio_sm100.so (hand-written sm_100a CUDA) -- there is no PyTorch compute path and no CPU fallback.
 
 Scope: DINOv2-reg backbone + DeCap / CapDec text side.  The alternative backbones and
-captioners of the reference (ProxyCLIP, RegionCLIP, INViTE, DenseCLIP, AlphaCLIP, ViECap, MeaCap, ClipCap),
-``double_DINO_for_bboxes`` is out of scope for this round and raises ``NotImplementedError`` instead of silently
+captioners of the reference (ProxyCLIP, RegionCLIP, INViTE, DenseCLIP, AlphaCLIP, ViECap, MeaCap, ClipCap) and
+``double_DINO_for_bboxes`` are out of scope for this round and raise ``NotImplementedError`` instead of silently
 doing something else.
 """
 from __future__ import annotations
