@@ -183,6 +183,19 @@ int pio_ctx_clean(const float* rows, long long img_stride, long long row_stride,
 int pio_region_mean_weights(int grid, float variance, float* weights, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Image preprocessing on the device: replaces the PIL / torchvision transforms of src/model.py:347-357                 */
+/*   Resize(resize_dim, BICUBIC) [+ CenterCrop(crop_dim)] + ToTensor + Normalize                                        */
+/* for B images of one size.  imgs u8 [B,H,W,3]; kx/bx, ky/by: Pillow's fixed-point coefficient tables of the           */
+/* horizontal / vertical pass (k [out, ksize] int32, bounds [out, 2] = first input index, tap count), built on the      */
+/* host (patch-ioner_b200/preprocess.py); only the crop window [crop_top, +crop_h) x [crop_left, +crop_w) of the        */
+/* resized image is computed; [row_first, +rows) are the input rows the vertical pass of that window needs.             */
+/* mean3 / std3 are HOST pointers.  out fp32 [B,3,crop_h,crop_w].  Resized bytes are bit-identical to Pillow's.         */
+size_t pio_preprocess_workspace_bytes(int B, int rows, int crop_w);
+int pio_preprocess(const unsigned char* imgs, int B, int H, int W, const int* kx, const int* bx, int ksize_x, const int* ky,
+                   const int* by, int ksize_y, int crop_left, int crop_top, int crop_w, int crop_h, int row_first, int rows,
+                   const float* mean3, const float* std3, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* DeCap caption-memory projection: replaces Im2TxtProjector.project (im2txtprojection.py:353-385).  */
 typedef struct PioBank PioBank;
 /* bank fp32 [M,D] (zero rows already dropped, :345).  Builds library-owned copies: the bank, its     */

@@ -444,10 +444,16 @@ class Patchioner:
         return ret
 
     # ------------------------------------------------------------------------------------------ user-level surface
-    def preprocess(self, images, keep_img_ratio: bool = True) -> torch.Tensor:
+    def preprocess(self, images, keep_img_ratio: bool = True, on_device: bool = False) -> torch.Tensor:
         """PIL images -> normalised fp32 batch [B,3,crop,crop].  keep_img_ratio=True: resize the short side + centre crop
         (``image_transforms``, eval_densecap.py:313-316); False: squash to a square (``image_transforms_no_crop``, :339-342).
-        Boxes must be adjusted accordingly by the caller (adjust_bbox_for_transform / ..._no_scale, bbox_utils.py:170-250)."""
+        Boxes must be adjusted accordingly by the caller (adjust_bbox_for_transform / ..._no_scale, bbox_utils.py:170-250).
+        on_device=True runs the same pipeline in ``pio_preprocess`` (bit-identical output, result stays on the GPU; images may
+        also be uint8 [H,W,3] arrays / tensors); the default runs torchvision on the host like the reference."""
+        if on_device:
+            from .preprocess import preprocess_images
+
+            return preprocess_images(images, self.device, self.resize_dim, self.crop_dim, keep_img_ratio)
         tf = self.image_transforms if keep_img_ratio else self.image_transforms_no_crop
         return torch.stack([tf(im) for im in images])
 

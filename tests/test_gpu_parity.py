@@ -759,3 +759,24 @@ def test_caption_bboxes_crops(dev):
     crops = torch.stack([m.image_transforms_no_crop(im.crop((x, y, x + w, y + h))) for im, bb in zip(pil, boxes.tolist()) for (x, y, w, h) in bb])
     want = m(crops, get_cls_capt=True, return_ids=True)["cls_capt"].cpu().tolist()
     assert got == want
+
+
+@pytest.mark.parametrize("keep", [True, False])
+def test_preprocess_on_device_matches_torchvision(dev, keep):
+    """pio_preprocess vs the reference's own torchvision pipeline (src/model.py:347-357) on images of mixed sizes: the resized
+    bytes are Pillow's bit for bit, so the normalised floats are identical."""
+    from PIL import Image
+    import numpy as np
+    from oracle import preprocess as o_pre
+    from patchioner_b200 import preprocess as pre
+
+    rng = np.random.RandomState(5)
+    sizes = [(480, 640), (640, 480), (480, 640), (333, 1001), (600, 600), (230, 300)]
+    pil = [Image.fromarray(rng.randint(0, 256, (h, w, 3), dtype=np.uint8)) for (h, w) in sizes]
+    for resize_dim, crop_dim in ((518, 518), (224, 224)):
+        want = o_pre.reference_transform(pil, resize_dim, crop_dim, keep)
+        got = pre.preprocess_images(pil, dev, resize_dim, crop_dim, keep).cpu()
+        assert got.shape == want.shape
+        assert torch.equal(got, want), (got - want).abs().max()
+    m = _model(dev, "fp32", False)
+    assert torch.equal(m.preprocess(pil, keep_img_ratio=keep, on_device=True).cpu(), m.preprocess(pil, keep_img_ratio=keep))
