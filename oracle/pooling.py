@@ -283,3 +283,33 @@ def ctx_cleaner(dirty_embeds: torch.Tensor, ctx_embed: torch.Tensor, cleaning_ty
         ctx_norm = torch.norm(ctx, p=2, dim=2, keepdim=True) + epsilon
         return dirty_embeds * (1 - (ctx / ctx_norm))
     raise ValueError(cleaning_type)
+
+
+def adjust_bbox_for_transform(orig_width: int, orig_height: int, bbox, resize_dim: int, crop_dim: int):
+    """src/bbox_utils.py:170-218: box [x, y, w, h] of the original image -> the resized (short side = resize_dim) and
+    centre-cropped image.  Python doubles, operation for operation."""
+    x1, y1, w, h = bbox
+    if orig_width < orig_height:
+        scale_w = resize_dim / orig_width
+        scale_h = (resize_dim * orig_height) / orig_width / orig_height
+    else:
+        scale_h = resize_dim / orig_height
+        scale_w = (resize_dim * orig_width) / orig_height / orig_width
+    new_width = int(orig_width * scale_w)
+    new_height = int(orig_height * scale_h)
+    x1, y1, w, h = x1 * scale_w, y1 * scale_h, w * scale_w, h * scale_h
+    x1 -= max(0, (new_width - crop_dim) // 2)
+    y1 -= max(0, (new_height - crop_dim) // 2)
+    x1 = max(0, min(x1, crop_dim - 1))
+    y1 = max(0, min(y1, crop_dim - 1))
+    w = max(0, min(w, crop_dim - x1))
+    h = max(0, min(h, crop_dim - y1))
+    return [x1, y1, w, h]
+
+
+def adjust_bbox_for_transform_no_scale(orig_width: int, orig_height: int, bbox, target_width: int, target_height: int):
+    """src/bbox_utils.py:222-250: box of the original image -> the image squashed to target_width x target_height."""
+    x1, y1, w, h = bbox
+    scale_w = target_width / orig_width
+    scale_h = target_height / orig_height
+    return [x1 * scale_w, y1 * scale_h, w * scale_w, h * scale_h]

@@ -457,6 +457,13 @@ class Patchioner:
         tf = self.image_transforms if keep_img_ratio else self.image_transforms_no_crop
         return torch.stack([tf(im) for im in images])
 
+    def adjust_bboxes(self, sizes, bboxes, keep_img_ratio: bool = True) -> torch.Tensor:
+        """Boxes of the ORIGINAL images ((width, height) per image, xywh pixels) -> the coordinates of ``preprocess(...,
+        keep_img_ratio)``: the vectorised adjust_bbox_for_transform / ..._no_scale of the eval drivers (bbox_utils.py:170-250)."""
+        from .boxes import adjust_bboxes
+
+        return adjust_bboxes(sizes, bboxes, self.resize_dim, self.crop_dim, keep_img_ratio)
+
     def caption(self, imgs, caption_from: str = "patches", bboxes=None, traces=None, masks=None, region_sets: bool = False,
                 use_gaussian_weighting: bool = False, gaussian_variance: float = 1.0, use_attention_weighting: bool = False,
                 compute_scores: bool = False, return_ids: bool = False):
