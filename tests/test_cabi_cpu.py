@@ -83,3 +83,32 @@ def test_detokenizer_hook():
     from patchioner_b200.detok import _id_renderer
 
     assert _id_renderer([5, 49407, 7]).split("<|endoftext|>")[0].strip() == "5"
+
+
+def test_clip_bpe_decoder_against_reference_tokenizer():
+    """Decode-only CLIP BPE vs the reference's SimpleTokenizer.decode (src/clip/simple_tokenizer.py:129-131) on random id rows.
+    Needs the vocabulary asset and the reference source next to this container (skipped on the GPU box, which has neither)."""
+    import importlib.util
+    import random
+    import sys
+    import types
+
+    bpe = "/root/reference/Patch-ioner/src/clip/bpe_simple_vocab_16e6.txt.gz"
+    src = "/root/reference/Patch-ioner/src/clip/simple_tokenizer.py"
+    if not (os.path.exists(bpe) and os.path.exists(src)):
+        pytest.skip("CLIP BPE vocabulary / reference tokenizer not available")
+    if "ftfy" not in sys.modules:  # the reference imports ftfy only for encode(); decode() does not use it
+        stub = types.ModuleType("ftfy")
+        stub.fix_text = lambda s: s
+        sys.modules["ftfy"] = stub
+    spec = importlib.util.spec_from_file_location("ref_simple_tokenizer", src)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    tok = ref.SimpleTokenizer(bpe)
+    from patchioner_b200.detok import ClipBpeDecoder
+
+    dec = ClipBpeDecoder(bpe)
+    rnd = random.Random(3)
+    for _ in range(200):
+        ids = [rnd.randrange(0, 49408) for _ in range(30)]
+        assert dec(ids) == tok.decode(ids)
