@@ -43,6 +43,16 @@ def _load_tensor_file(path: str):
     raise ValueError(f"do not know how to read {path}")
 
 
+def _load_h5_texts(path: str):
+    try:
+        import h5py
+    except ImportError:  # pragma: no cover - h5py is absent from this image
+        return None
+    with h5py.File(path, "r") as hf:
+        keys = [k for k in hf.keys() if k.endswith("-text")]
+        return list(hf[keys[0]][:]) if keys else None
+
+
 class Patchioner:
     """See module docstring.  Not an ``nn.Module``: the weights live in library-owned device memory."""
 
@@ -63,8 +73,9 @@ class Patchioner:
                 raise NotImplementedError(f"'{name}' selects a backbone/captioner outside the B200 hot path (SURVEY.md 8)")
         if online_texts is not None:
             raise NotImplementedError("online_texts builds a bank with a CLIP text encoder (im2txtprojection.py:448-560): out of scope")
-        if calculate_argmax_text and (memory_bank_texts is None or support_memory_size <= 0):
-            raise ValueError("calculate_argmax_text needs the bank and its captions (memory_bank_texts)")
+        h5_bank = isinstance(memory_bank, str) and memory_bank.endswith((".h5", ".hdf5"))
+        if calculate_argmax_text and ((memory_bank_texts is None and not h5_bank) or support_memory_size <= 0):
+            raise ValueError("calculate_argmax_text needs the bank and its captions (memory_bank_texts, or an HDF5 bank with a '-text' dataset)")
         if dino_model is None or "dinov2" not in dino_model or "vitb14" not in dino_model or "reg" not in dino_model:
             raise NotImplementedError(f"dino_model={dino_model!r}: only 'dinov2_vitb14_reg' is built (model.py:342-343)")
         if attention_type != "qkv":
@@ -116,11 +127,16 @@ class Patchioner:
             if bank is None and isinstance(projection_type, str) and os.path.exists(projection_type):
                 bank = projection_type
             if isinstance(bank, str):
+                if memory_bank_texts is None and bank.endswith((".h5", ".hdf5")):
+                    memory_bank_texts = _load_h5_texts(bank)  # the '{name}-text' dataset next to the embeddings (:320-323)
+                    self.text_dataset = memory_bank_texts
                 bank = _load_tensor_file(bank)
             if bank is None:
                 raise ValueError("support_memory_size > 0 needs memory_bank (tensor or file); building banks from "
                                  "captions needs CLIP text encoders + network (out of scope)")
             self.im_proj = ops.Bank(bank, self.device, precision)
+        if self.calculate_argmax_text and self.text_dataset is None:
+            raise ValueError("calculate_argmax_text: the memory bank file carries no captions")
 
         # --- Talk2DINO inversion (model.py:618-627)
         self.embed_inversion = False
