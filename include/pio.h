@@ -183,6 +183,18 @@ int pio_ctx_clean(const float* rows, long long img_stride, long long row_stride,
 int pio_region_mean_weights(int grid, float variance, float* weights, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* double-DINO (extract_bboxes_feats_double_dino, src/bbox_utils.py:300-403, called at model.py:983-992): the last      */
+/* block of the backbone is run again on [cls | registers | the patches of one box] for every box.                      */
+/* pio_vit_block_rows runs block `layer` (negative counts from the end) on PACKED sequences: x fp32 [T,768] in/out,      */
+/* rows grouped in buckets of sequences of equal length (HOST arrays bucket_nseq / bucket_len; bucket rows contiguous).  */
+size_t pio_vit_block_workspace_bytes(const PioVit* h, int T);
+int pio_vit_block_rows(PioVit* h, int layer, float* x, int T, const int* bucket_nseq, const int* bucket_len, int nbuckets,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* out[t,:] = src[idx[t],:] (src rows src_ld floats apart); out[s,:] = mean of x rows [seg_start[s], +seg_len[s])        */
+int pio_gather_rows(const float* src, long long src_ld, const int* idx, int T, int D, float* out, void* stream);
+int pio_segment_mean(const float* x, const int* seg_start, const int* seg_len, int nseg, int D, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Image preprocessing on the device: replaces the PIL / torchvision transforms of src/model.py:347-357                 */
 /*   Resize(resize_dim, BICUBIC) [+ CenterCrop(crop_dim)] + ToTensor + Normalize                                        */
 /* for B images of one size.  imgs u8 [B,H,W,3]; kx/bx, ky/by: Pillow's fixed-point coefficient tables of the           */

@@ -313,3 +313,49 @@ def adjust_bbox_for_transform_no_scale(orig_width: int, orig_height: int, bbox, 
     scale_w = target_width / orig_width
     scale_h = target_height / orig_height
     return [x1 * scale_w, y1 * scale_h, w * scale_w, h * scale_h]
+
+
+def extract_bboxes_feats_double_dino(block_fn, patch_embeddings, bboxes, cls_token, registers_tokens, patch_size=14,
+                                     return_type="cls", gaussian_bbox_variance=0.5):
+    """src/bbox_utils.py:300-403.  ``block_fn(x [1,L,D]) -> [1,L,D]`` stands for ``dino_model.blocks[-1]``.
+    Kept as written, including the slice [bb[1] : bb[3] + 1, bb[0] : bb[2] + 1] that uses w, h as END indices (:329)."""
+    N, n_boxes = patch_embeddings.shape[0], bboxes.shape[1]
+    grid = int(patch_embeddings.shape[1] ** 0.5)
+    D = patch_embeddings.shape[-1]
+    bb = bboxes.clone()
+    bb //= patch_size
+    bb = bb.int()
+    pe = patch_embeddings.view(N, grid, grid, D)
+    if cls_token is not None:
+        offset = 5 if registers_tokens is not None else 1
+    else:
+        assert return_type != "cls"
+        offset = 0
+    means = []
+    for i in range(N):
+        image_means = []
+        for j in range(n_boxes):
+            region_xy = pe[i, bb[i, j, 1]:bb[i, j, 3] + 1, bb[i, j, 0]:bb[i, j, 2] + 1, :]
+            region = region_xy.reshape(1, -1, D)
+            if cls_token is not None:
+                parts = [cls_token[i].reshape(1, 1, D)]
+                if registers_tokens is not None:
+                    parts.append(registers_tokens[i].reshape(1, 4, D))
+                inputs = torch.cat(parts + [region], dim=1)
+            else:
+                inputs = region
+            outputs = block_fn(inputs)
+            out_region = outputs[0, offset:]
+            if return_type == "gaussian_avg":
+                h_span, w_span = region_xy.shape[:2]
+                y, x = torch.meshgrid(torch.linspace(-1, 1, h_span), torch.linspace(-1, 1, w_span), indexing="ij")
+                wgt = torch.exp(-(x ** 2 + y ** 2) / gaussian_bbox_variance)
+                wgt = wgt / wgt.sum()
+                region_mean = (region_xy * wgt.unsqueeze(-1)).sum(dim=(0, 1))
+            elif return_type == "avg":
+                region_mean = out_region.mean(dim=0)
+            else:
+                region_mean = outputs[0, 0]
+            image_means.append(region_mean)
+        means.append(torch.stack(image_means))
+    return torch.stack(means)

@@ -72,6 +72,10 @@ SIGNATURES = {
     "pio_attention_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "pio_vit_attention": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_size_t, _fp]),
     "pio_cls_attention": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp]),
+    "pio_vit_block_workspace_bytes": (C.c_size_t, [_fp, C.c_int]),
+    "pio_vit_block_rows": (C.c_int, [_fp, C.c_int, _fp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, _fp, C.c_size_t, _fp]),
+    "pio_gather_rows": (C.c_int, [_fp, C.c_longlong, _fp, C.c_int, C.c_int, _fp, _fp]),
+    "pio_segment_mean": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, _fp, _fp]),
     "pio_preprocess_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "pio_preprocess": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_int, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), _fp, _fp, C.c_size_t, _fp]),

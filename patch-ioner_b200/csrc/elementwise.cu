@@ -63,6 +63,28 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, long long src_ld, const int* __restrict__ idx,
+                                                          int T, int D, float* __restrict__ out) {
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (t >= T) return;
+  const float4* s = reinterpret_cast<const float4*>(src + (long long)idx[t] * src_ld);
+  float4* o = reinterpret_cast<float4*>(out + (long long)t * D);
+  for (int i = lane; i < D / 4; i += 32) o[i] = __ldg(s + i);
+}
+__global__ void __launch_bounds__(64) segment_mean_kernel(const float* __restrict__ x, const int* __restrict__ seg_start,
+                                                          const int* __restrict__ seg_len, int D, float* __restrict__ out) {
+  const int s = blockIdx.x, c4 = blockIdx.y * 64 + threadIdx.x;
+  if (c4 >= D / 4) return;
+  const int r0 = seg_start[s], n = seg_len[s];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < n; ++r) {
+    const float4 v = reinterpret_cast<const float4*>(x + (long long)(r0 + r) * D)[c4];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const float inv = 1.0f / (float)n;  // n == 0 -> inf -> 0 * inf = NaN
+  reinterpret_cast<float4*>(out + (long long)s * D)[c4] = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n4) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -254,6 +276,25 @@ int softmax_rows(const float* in, float* out, int rows, int cols, float scale, c
 }  // namespace pio
 
 extern "C" {
+// out[t, :] = src[idx[t], :]   (rows of D floats, D % 4 == 0)
+int pio_gather_rows(const float* src, long long src_ld, const int* idx, int T, int D, float* out, void* stream) {
+  using namespace pio;
+  if (T == 0) return PIO_OK;
+  PIO_CHECK(src && idx && out && D % 4 == 0 && src_ld % 4 == 0, "gather_rows: bad arguments");
+  gather_rows_kernel<<<cdiv((long long)T * 32, 256), 256, 0, as_stream(stream)>>>(src, src_ld, idx, T, D, out);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+// out[s, :] = mean of rows [seg_start[s], seg_start[s] + seg_len[s]) of x   (an empty segment gives NaN, like tensor.mean())
+int pio_segment_mean(const float* x, const int* seg_start, const int* seg_len, int nseg, int D, float* out, void* stream) {
+  using namespace pio;
+  if (nseg == 0) return PIO_OK;
+  PIO_CHECK(x && seg_start && seg_len && out && D % 4 == 0, "segment_mean: bad arguments");
+  segment_mean_kernel<<<dim3(nseg, cdiv(D / 4, 64)), 64, 0, as_stream(stream)>>>(x, seg_start, seg_len, D, out);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
 const char* pio_last_error(void) { return pio::g_err; }
 int pio_version(void) { return 100; }
 long long pio_launch_count(void) { return pio::g_launches.load(); }

@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restric
       logprob_sum[blockIdx.x] += -logf(tot);  // log softmax(logits)[argmax] = -log sum exp(l - max)
     }
   }
-  if (threadIdx.x == 0) ids[(long long)blockIdx.x * ids_ld + t] = bi;
+  // a row of NaN logits (e.g. the NaN embedding of an empty box) never compares greater: torch.argmax answers 0 there
+  if (threadIdx.x == 0) ids[(long long)blockIdx.x * ids_ld + t] = (bi == 0x7fffffff) ? 0 : bi;
 }
 
 // Reduce the per-slab (max, first index, sum exp) triples of the fused lm-head epilogue: one warp per row.
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(256) argmax_finish_kernel(const float* __restr
     s = warp_sum(s);
     if (lane == 0) logprob_sum[row] += -logf(s);
   }
-  if (lane == 0) ids[(long long)row * ids_ld + t] = bi;
+  if (lane == 0) ids[(long long)row * ids_ld + t] = (bi == 0x7fffffff) ? 0 : bi;  // all-NaN row -> 0, like torch.argmax
 }
 
 // x[r,:] = wte[ids[r,t],:] + wpe[pos,:]
@@ -203,7 +204,7 @@ __global__ void embed_kernel(const float* __restrict__ wte, const float* __restr
   pdl_wait();
   pdl_launch_dependents();
   if (warp >= R) return;
-  const int tok = ids[(long long)warp * ids_ld + t];
+  const int tok = min(max(ids[(long long)warp * ids_ld + t], 0), 50257 - 1);  // never index outside the table
   const float4* a = reinterpret_cast<const float4*>(wte + (long long)tok * D);
   const float4* b = reinterpret_cast<const float4*>(wpe + (long long)pos * D);
   float4* o = reinterpret_cast<float4*>(x + (long long)warp * D);

@@ -213,6 +213,56 @@ int pio_vit_forward(PioVit* h, const float* imgs, int B, int S, const float* pos
   return PIO_OK;
 }
 
+size_t pio_vit_block_workspace_bytes(const PioVit* h, int T) {
+  using namespace pio;
+  const size_t e = h->act_dt == PIO_DT_F32 ? 4 : 2;
+  return align_up((size_t)T * kD * e, 1024) + align_up((size_t)T * 3 * kD * e, 1024) + align_up((size_t)T * kMlp * e, 1024) + 4096;
+}
+
+// One transformer block of the backbone on PACKED token sequences (double-DINO, bbox_utils.py:300-403 runs blocks[-1] on
+// [cls | registers | the patches of a box] for every box): x fp32 [T,768] in/out, rows grouped in buckets of sequences of
+// equal length (bucket b: bucket_nseq[b] sequences of bucket_len[b] rows, contiguous), so that attention runs as a regular
+// batch per bucket while LayerNorm and the dense layers run once over all T rows.
+int pio_vit_block_rows(PioVit* h, int layer, float* x, int T, const int* bucket_nseq, const int* bucket_len, int nbuckets,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace pio;
+  if (T == 0) return PIO_OK;
+  PIO_CHECK(h && x && bucket_nseq && bucket_len && workspace, "vit_block_rows: null argument");
+  PIO_CHECK(layer >= -kDepth && layer < kDepth, "vit_block_rows: layer %d outside [-12, 12)", layer);
+  PIO_CHECK(workspace_bytes >= pio_vit_block_workspace_bytes(h, T), "vit_block_rows: workspace too small");
+  PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "vit_block_rows: workspace must be 1024-byte aligned");
+  long long rows = 0;
+  for (int b = 0; b < nbuckets; ++b) {
+    PIO_CHECK(bucket_nseq[b] >= 0 && bucket_len[b] > 0, "vit_block_rows: bad bucket %d", b);
+    rows += (long long)bucket_nseq[b] * bucket_len[b];
+  }
+  PIO_CHECK(rows == T, "vit_block_rows: buckets cover %lld rows, T = %d", rows, T);
+  cudaStream_t st = as_stream(stream);
+  const PioVit::Blk& w = h->blk[layer < 0 ? layer + kDepth : layer];
+  const int adt = h->act_dt, mode = h->mode;
+  const size_t e = adt == PIO_DT_F32 ? 4 : 2;
+  char* ws = (char*)workspace;
+  char* hb = ws;   ws += align_up((size_t)T * kD * e, 1024);
+  char* qkv = ws;  ws += align_up((size_t)T * 3 * kD * e, 1024);
+  void* f = ws;
+  PIO_TRY(layernorm(x, kD, w.ln1_w, w.ln1_b, hb, adt, kD, T, kD, 1e-6f, st));
+  PIO_TRY(gemm(mode, hb, w.qkv_w, qkv, T, 3 * kD, kD, kD, kD, 3 * kD, adt, adt, w.qkv_b, nullptr, nullptr, PIO_ACT_NONE, st));
+  long long r0 = 0;
+  for (int b = 0; b < nbuckets; ++b) {
+    if (bucket_nseq[b] == 0) continue;
+    const void* q = qkv + (size_t)r0 * 3 * kD * e;
+    void* o = hb + (size_t)r0 * kD * e;
+    if (adt == PIO_DT_BF16) PIO_TRY(vit_attention_tc(q, o, nullptr, bucket_nseq[b], bucket_len[b], kHeads, st));
+    else PIO_TRY(vit_attention(q, o, adt, bucket_nseq[b], bucket_len[b], kHeads, st));
+    r0 += (long long)bucket_nseq[b] * bucket_len[b];
+  }
+  PIO_TRY(gemm(mode, hb, w.proj_w, x, T, kD, kD, kD, kD, kD, adt, PIO_DT_F32, w.proj_b, w.ls1, x, PIO_ACT_NONE, st));
+  PIO_TRY(layernorm(x, kD, w.ln2_w, w.ln2_b, hb, adt, kD, T, kD, 1e-6f, st));
+  PIO_TRY(gemm(mode, hb, w.fc1_w, f, T, kMlp, kD, kD, kD, kMlp, adt, adt, w.fc1_b, nullptr, nullptr, PIO_ACT_GELU_ERF, st));
+  PIO_TRY(gemm(mode, f, w.fc2_w, x, T, kD, kMlp, kMlp, kMlp, kD, adt, PIO_DT_F32, w.fc2_b, w.ls2, x, PIO_ACT_NONE, st));
+  return PIO_OK;
+}
+
 size_t pio_attention_workspace_bytes(int dt, int B, int N, int H) {
   return dt == PIO_DT_BF16 ? pio::align_up(pio::vit_attention_tc_workspace(B, N, H), 1024) : 0;
 }

@@ -5,9 +5,8 @@ names, same output keys), ``caption_tokens`` (:1392-1423).  Underneath, every nu
 libpio_sm100.so (hand-written sm_100a CUDA) -- there is no PyTorch compute path and no CPU fallback.
 
 Scope: DINOv2-reg backbone + DeCap / CapDec text side.  The alternative backbones and
-captioners of the reference (ProxyCLIP, RegionCLIP, INViTE, DenseCLIP, AlphaCLIP, ViECap, MeaCap, ClipCap) and
-``double_DINO_for_bboxes`` are out of scope for this round and raise ``NotImplementedError`` instead of silently
-doing something else.
+captioners of the reference (ProxyCLIP, RegionCLIP, INViTE, DenseCLIP, AlphaCLIP, ViECap, MeaCap, ClipCap) are out of
+scope for this round and raise ``NotImplementedError`` instead of silently doing something else.
 """
 from __future__ import annotations
 
@@ -339,8 +338,8 @@ class Patchioner:
         assert cleaning_type in [None, "orthogonal_projection", "contrastive_mask"]
         if caption_bboxes_type is not None:  # model.py:770-771: caption the CROP of every box as a whole image
             return self.caption_bboxes(imgs, bboxes, caption_bboxes_type, compute_scores=compute_scores)
-        if double_DINO_for_bboxes:
-            raise NotImplementedError("double_DINO re-runs the last block on per-box token subsets: a 'next' row (SURVEY.md 8f.4)")
+        if double_DINO_for_bboxes and (bboxes is None or get_controllable_capts):
+            raise ValueError("double_DINO_for_bboxes applies to the per-box branch (bboxes given, get_controllable_capts=False)")
         if cleaning_type is not None and self.im_proj is None:
             raise ValueError("cleaning_type needs the caption memory (the reference calls im_proj.project, model.py:895-913)")
         if self.calculate_argmax_text and return_ids:
@@ -421,7 +420,12 @@ class Patchioner:
             emit("patch_tokens_capts", patch.reshape(-1, D), group=P, project=project_regions)
         if get_register_capts:
             emit("register_capts", reg.reshape(-1, D), group=4)
-        if bboxes is not None and not get_controllable_capts:
+        if bboxes is not None and not get_controllable_capts and double_DINO_for_bboxes:
+            # model.py:983-992: the hooked output of blocks[-1], normalised, is exactly `tokens`; note that the reference hands over
+            # the (possibly cleaned) patch tokens' source, i.e. the un-cleaned layer output
+            feats = self.double_dino_feats(tokens, bboxes, double_DINO_for_bboxes_return_type, double_DINO_use_cls, gaussian_bbox_variance)
+            emit("bbox_capts", feats.reshape(-1, D), group=bboxes.shape[1], project=project_regions)
+        elif bboxes is not None and not get_controllable_capts:
             amap = self_attn if use_attn_map_for_bboxes else None
             feats = ops.pool_boxes(patch, bboxes, self.patch_size, gaussian_avg, gaussian_bbox_variance, amap)
             emit("bbox_capts", feats.reshape(-1, D), group=bboxes.shape[1], project=project_regions)
@@ -439,6 +443,68 @@ class Patchioner:
         return outs
 
     __call__ = forward
+
+    def double_dino_feats(self, tokens: torch.Tensor, bboxes: torch.Tensor, return_type: str = "avg", use_cls: bool = False,
+                          gaussian_bbox_variance: float = 0.5) -> torch.Tensor:
+        """extract_bboxes_feats_double_dino (bbox_utils.py:300-403): for every box the last block runs again on
+        [cls | 4 registers | the box's patch tokens] (use_cls) or on the patch tokens alone; 'avg' = mean of the patch outputs,
+        'cls' = output of the cls position, 'gaussian_avg' = Gaussian pooling of the block's INPUT patches (sic, :377-389).
+        Quirk kept: the box is floor-divided by the patch size and then sliced as [y : h + 1, x : w + 1] -- width and height are
+        used as END indices (:329) -- with Python slice clamping.  -> [B, R, 768]."""
+        if return_type not in ("avg", "cls", "gaussian_avg"):
+            raise ValueError(f"double_DINO return type {return_type!r}")
+        if return_type == "cls" and not use_cls:
+            raise AssertionError("return_type 'cls' needs double_DINO_use_cls (bbox_utils.py:340)")
+        B, N, D = tokens.shape
+        P = N - self.num_global_tokens
+        g = int(P ** 0.5)
+        bb = bboxes.detach().clone().cpu()
+        bb //= self.patch_size        # torch floor division, like :319-320
+        bb = bb.int().tolist()
+        n_glob = self.num_global_tokens if use_cls else 0
+        seqs = []                      # (length, b, j, token indices)
+        for b in range(B):
+            for j, (x, y, w, h) in enumerate(bb[b]):
+                ys, xs = range(g)[y:h + 1], range(g)[x:w + 1]      # Python slice semantics (negative wrap, clamping)
+                idx = [b * N + t for t in range(n_glob)] + [b * N + self.num_global_tokens + yy * g + xx for yy in ys for xx in xs]
+                seqs.append((len(idx), b, j, idx, (ys[0] if len(ys) else 0, xs[0] if len(xs) else 0, len(ys), len(xs))))
+        R = bboxes.shape[1]
+        if return_type == "gaussian_avg":
+            # Gaussian pooling of the block's INPUT patches over the sliced rectangle (:377-389; the second pass through the block
+            # does not enter the result): the standard box kernel in patch units (patch_size 1 -> span = w + 1)
+            rect = torch.tensor([[[float(r[1]), float(r[0]), float(max(r[3] - 1, 0)), float(max(r[2] - 1, 0))]
+                                  for (_, _, _, _, r) in seqs[b * R:(b + 1) * R]] for b in range(B)])
+            empty = torch.tensor([[r[2] == 0 or r[3] == 0 for (_, _, _, _, r) in seqs[b * R:(b + 1) * R]] for b in range(B)])
+            out = ops.pool_boxes(tokens[:, self.num_global_tokens:], rect, 1, True, gaussian_bbox_variance)
+            if empty.any():  # an empty rectangle sums to zeros in the reference
+                out[empty.to(out.device)] = 0.0
+            return out
+        order = sorted(range(len(seqs)), key=lambda i: seqs[i][0])
+        lens = [seqs[i][0] for i in order]
+        flat_idx, seg_start, seg_len, cls_rows, buckets, pos = [], [], [], [], [], 0
+        for i in order:
+            L_, _, _, idx, _ = seqs[i]
+            if L_ == 0:
+                seg_start.append(pos); seg_len.append(0); cls_rows.append(0)
+                continue
+            if buckets and buckets[-1][1] == L_:
+                buckets[-1][0] += 1
+            else:
+                buckets.append([1, L_])
+            flat_idx += idx
+            seg_start.append(pos + n_glob); seg_len.append(L_ - n_glob); cls_rows.append(pos)
+            pos += L_
+        dev = tokens.device
+        x = ops.gather_rows(tokens.reshape(B * N, D), torch.tensor(flat_idx, dtype=torch.int32, device=dev))
+        if x.shape[0] > 0:
+            self.dino.block_rows(x, [b[0] for b in buckets], [b[1] for b in buckets], layer=-1)
+        if return_type == "cls":
+            res = ops.gather_rows(x, torch.tensor(cls_rows, dtype=torch.int32, device=dev))
+        else:
+            res = ops.segment_mean(x, torch.tensor(seg_start, dtype=torch.int32, device=dev), torch.tensor(seg_len, dtype=torch.int32, device=dev))
+        inv = torch.empty(len(order), dtype=torch.long)
+        inv[torch.tensor(order)] = torch.arange(len(order))
+        return res[inv.to(dev)].reshape(B, R, D)
 
     def caption_bboxes(self, imgs, bboxes, capt_type: str = "cls_capt", crop_boxes: bool = False, compute_scores: bool = False):
         """model.py:1356-1390 (the crop-and-recaption baseline): ``imgs`` is a list of PIL images, ``bboxes`` [B,R,4] xywh in their

@@ -203,6 +203,38 @@ class Vit:
                                         _ptr(attn), _ptr(qkv), ws.data_ptr(), nbytes, _stream()))
         return tokens, attn, qkv
 
+    def block_rows(self, x: torch.Tensor, bucket_nseq: Sequence[int], bucket_len: Sequence[int], layer: int = -1) -> torch.Tensor:
+        """Run block ``layer`` on packed sequences, IN PLACE: ``x`` fp32 [T,768], rows grouped in buckets of equal-length
+        sequences (see pio_vit_block_rows).  Returns ``x`` (the block's output, before any final norm)."""
+        _need_cuda(x)
+        assert x.is_contiguous() and x.dtype == torch.float32 and x.shape[1] == self.D
+        n = len(bucket_nseq)
+        a, b = (C.c_int * n)(*[int(v) for v in bucket_nseq]), (C.c_int * n)(*[int(v) for v in bucket_len])
+        nbytes = L.lib().pio_vit_block_workspace_bytes(self._h, x.shape[0])
+        ws = workspace(nbytes, x.device, "vit_block")
+        L.check(L.lib().pio_vit_block_rows(self._h, int(layer), x.data_ptr(), x.shape[0], a, b, n, ws.data_ptr(), nbytes, _stream()))
+        return x
+
+
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """out[t] = src[idx[t]] for a 2-D fp32 ``src`` (rows may be strided) and int32 ``idx`` on the same device."""
+    _need_cuda(src, idx)
+    assert src.dim() == 2 and src.dtype == torch.float32 and src.stride(1) == 1 and idx.dtype == torch.int32
+    out = torch.empty(idx.numel(), src.shape[1], dtype=torch.float32, device=src.device)
+    L.check(L.lib().pio_gather_rows(src.data_ptr(), src.stride(0), idx.contiguous().data_ptr(), idx.numel(), src.shape[1], out.data_ptr(),
+                                    _stream()))
+    return out
+
+
+def segment_mean(x: torch.Tensor, seg_start: torch.Tensor, seg_len: torch.Tensor) -> torch.Tensor:
+    """Row means of contiguous segments of ``x`` [T,D] (empty segment -> NaN, like tensor.mean())."""
+    _need_cuda(x, seg_start, seg_len)
+    assert x.is_contiguous() and x.dtype == torch.float32 and seg_start.dtype == torch.int32 and seg_len.dtype == torch.int32
+    out = torch.empty(seg_start.numel(), x.shape[1], dtype=torch.float32, device=x.device)
+    L.check(L.lib().pio_segment_mean(x.data_ptr(), seg_start.contiguous().data_ptr(), seg_len.contiguous().data_ptr(), seg_start.numel(),
+                                     x.shape[1], out.data_ptr(), _stream()))
+    return out
+
 
 def vit_attention(qkv: torch.Tensor, heads: int = 12) -> torch.Tensor:
     """One block's multi-head self-attention: qkv [B,N,3*heads*64] (fp32 or bf16) -> [B,N,heads*64]."""

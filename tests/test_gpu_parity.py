@@ -780,3 +780,49 @@ def test_preprocess_on_device_matches_torchvision(dev, keep):
         assert torch.equal(got, want), (got - want).abs().max()
     m = _model(dev, "fp32", False)
     assert torch.equal(m.preprocess(pil, keep_img_ratio=keep, on_device=True).cpu(), m.preprocess(pil, keep_img_ratio=keep))
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-3), ("bf16", 6e-2)])
+def test_double_dino_feats(dev, mode, tol):
+    """double_DINO_for_bboxes (bbox_utils.py:300-403): the last block re-run on [cls | registers | box patches] per box."""
+    m = _model(dev, mode, False)
+    vit_w = o_vit.make_weights(seed=1234)
+    imgs = o_pipe.synth_images(2, 224, seed=6)
+    boxes = o_pipe.synth_boxes(2, 5, 224, seed=6)
+    boxes[0, 0] = torch.tensor([20.0, 30.0, 150.0, 120.0])   # x < w, y < h: a non-empty [y : h + 1, x : w + 1] slice
+    boxes[1, 1] = torch.tensor([0.0, 0.0, 223.0, 223.0])
+    boxes[1, 2] = torch.tensor([200.0, 200.0, 10.0, 10.0])   # end before start: empty region
+    d = o_vit.forward(vit_w, imgs)
+    block = lambda x: o_vit.block_forward(vit_w, 11, x)      # noqa: E731
+    tokens, _, _ = m.dino.forward(imgs.to(dev), want_attn=False)
+    for rt, use_cls in (("avg", True), ("cls", True), ("avg", False), ("gaussian_avg", True)):
+        want = o_pool.extract_bboxes_feats_double_dino(block, d["x_norm_patchtokens"], boxes.clone(),
+                                                       d["x_norm_clstoken"] if use_cls else None,
+                                                       d["x_norm_regtokens"] if use_cls else None, 14, rt, 0.5)
+        got = m.double_dino_feats(tokens, boxes, rt, use_cls, 0.5).cpu()
+        ok = ~torch.isnan(want).any(-1)
+        assert torch.equal(torch.isnan(got).any(-1), ~ok), rt
+        if mode == "fp32":
+            torch.testing.assert_close(got[ok], want[ok], rtol=tol, atol=tol)
+        nz = ok & (want.abs().sum(-1) > 0)  # an empty rectangle pools to exact zeros in 'gaussian_avg'
+        assert (got[ok & ~nz] == 0).all()
+        assert cos_min(got[nz], want[nz]) >= (0.9999 if mode == "fp32" else 0.999), (rt, use_cls)
+    out = m(imgs, get_cls_capt=False, bboxes=boxes, double_DINO_for_bboxes=True, double_DINO_use_cls=True, return_ids=True)
+    assert out["bbox_capts"].shape == (2, 5, 30)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_nan_embedding_decodes_like_torch_argmax(dev, ops, mode):
+    """An empty box pools to NaN (like the reference); its NaN logits must decode to token 0 at every step, as torch.argmax does
+    (first NaN index), instead of indexing the embedding table out of bounds."""
+    dec = ops.Decoder(o_decap.make_weights(seed=1234), dev, mode)
+    pre = torch.randn(5, 768, generator=torch.Generator().manual_seed(3))
+    pre[2] = float("nan")
+    ids = dec.decode(pre.to(dev), 30).cpu()
+    assert (ids[2] == 0).all()
+    clean = dec.decode(pre[[0, 1, 3, 4]].to(dev), 30).cpu()
+    assert torch.equal(ids[[0, 1, 3, 4]], clean)      # the NaN row does not disturb its neighbours
+    m = _model(dev, mode, True)
+    out = m(o_pipe.synth_images(1, 224, seed=1), get_cls_capt=False, bboxes=torch.tensor([[[500.0, 500.0, 10.0, 10.0], [0.0, 0.0, 100.0, 100.0]]]),
+            return_ids=True)
+    assert (out["bbox_capts"][0, 0] == 0).all()
