@@ -826,3 +826,36 @@ def test_nan_embedding_decodes_like_torch_argmax(dev, ops, mode):
     out = m(o_pipe.synth_images(1, 224, seed=1), get_cls_capt=False, bboxes=torch.tensor([[[500.0, 500.0, 10.0, 10.0], [0.0, 0.0, 100.0, 100.0]]]),
             return_ids=True)
     assert (out["bbox_capts"][0, 0] == 0).all()
+
+
+def test_full_size_bf16_against_fp32_mode(dev):
+    """BASELINE configs[1] geometry (518 px, 64 boxes / image; 8 images to keep the fp32 SIMT arm short): the bf16 tensor-core path
+    stays within the north-star tolerance of the fp32 parity mode at every stage -- tokens, region embeddings, projected prefixes."""
+    m32, m16 = _model(dev, "fp32", True), _model(dev, "bf16", True)
+    m32.resize_dim = m32.crop_dim = m16.resize_dim = m16.crop_dim = 518
+    imgs = o_pipe.synth_images(8, 518, seed=21).to(dev)
+    boxes = o_pipe.synth_boxes(8, 64, 518, seed=21, pad="dense")
+    t32, a32, _ = m32.dino.forward(imgs)
+    t16, a16, _ = m16.dino.forward(imgs)
+    assert cos_min(t16.cpu(), t32.cpu()) >= 0.999
+    torch.testing.assert_close(a16.cpu(), a32.cpu(), rtol=5e-2, atol=1e-5)
+    e32 = m32.region_embeddings(imgs, bboxes=boxes, gaussian_avg=True, gaussian_bbox_variance=1.0)["bbox"].reshape(-1, 768)
+    e16 = m16.region_embeddings(imgs, bboxes=boxes, gaussian_avg=True, gaussian_bbox_variance=1.0)["bbox"].reshape(-1, 768)
+    ok = ~torch.isnan(e32).any(-1)
+    assert cos_min(e16[ok].cpu(), e32[ok].cpu()) >= 0.999
+    p32, p16 = m32.embed_tokens(e32[ok]), m16.embed_tokens(e32[ok])    # same queries: isolates the projection
+    assert cos_min(p16.cpu(), p32.cpu()) >= 0.999
+
+
+def test_deterministic_and_batch_invariant(dev):
+    """Same inputs twice -> identical ids (bf16 and fp32); in fp32 mode the caption of an image does not depend on its batch."""
+    imgs = o_pipe.synth_images(4, 224, seed=31)
+    boxes = o_pipe.synth_boxes(4, 3, 224, seed=31, pad="dense")
+    for mode in ("bf16", "fp32"):
+        m = _model(dev, mode, True)
+        a = m(imgs, get_cls_capt=True, bboxes=boxes, return_ids=True)
+        b = m(imgs, get_cls_capt=True, bboxes=boxes, return_ids=True)
+        assert torch.equal(a["bbox_capts"], b["bbox_capts"]) and torch.equal(a["cls_capt"], b["cls_capt"])
+        if mode == "fp32":
+            one = m(imgs[2:3], get_cls_capt=True, bboxes=boxes[2:3], return_ids=True)
+            assert torch.equal(one["bbox_capts"][0], a["bbox_capts"][2]) and torch.equal(one["cls_capt"][0], a["cls_capt"][2])
