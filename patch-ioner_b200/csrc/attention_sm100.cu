@@ -30,17 +30,22 @@ namespace {
 
 constexpr int HD = 64;        // head dim
 constexpr int BQ = 128;       // queries per CTA
-constexpr int BKV = 128;      // keys per tile
 constexpr int KV_STAGES = 2;
 constexpr int Q_BYTES = BQ * HD * 2;            // 16 KB
-constexpr int K_BYTES = BKV * HD * 2;           // 16 KB
-constexpr int V_BYTES = HD * BKV * 2;           // 16 KB (two [64 d x 64 keys] sub-tiles)
-constexpr int KV_BYTES = K_BYTES + V_BYTES;
-constexpr int P_BYTES = BQ * BKV * 2;           // 32 KB (two [128 q x 64 keys] sub-tiles)
 constexpr int NUM_BARS = 1 + 2 * KV_STAGES + 3;
-constexpr int ATT_SMEM = Q_BYTES + KV_STAGES * KV_BYTES + P_BYTES + NUM_BARS * 8 + 16;  // no static smem: base stays 1024-aligned
 constexpr int ATT_THREADS = 192;
-constexpr uint32_t TM_S0 = 0, TM_PV0 = 128, TM_COLS = 256;  // S at cols 0..127, O (sum of P V) at cols 128..191
+// Two tile shapes: 128 keys per step with two CTAs per SM (long sequences: 518 px, N = 1374), and 64 keys per step with three
+// CTAs per SM (short sequences: 224 px, N = 261, where 128-key tiles would pad 261 keys to 384).  Measured: 0.655 vs 0.684 ms
+// at N = 1374 and 0.091 vs 0.075 ms at N = 261 (B = 64).
+template <int BKV> struct AttCfg {
+  static constexpr int K_BYTES = BKV * HD * 2;           // 16 / 8 KB
+  static constexpr int V_BYTES = HD * BKV * 2;           // 16 / 8 KB, [keys x 64 dims] as stored
+  static constexpr int KV_BYTES = K_BYTES + V_BYTES;
+  static constexpr int P_BYTES = BQ * BKV * 2;           // 32 / 16 KB ([128 q x 64 keys] sub-tiles)
+  static constexpr int SMEM = Q_BYTES + KV_STAGES * KV_BYTES + P_BYTES + NUM_BARS * 8 + 16;  // no static smem: base stays 1024-aligned
+  static constexpr uint32_t TM_S0 = 0, TM_PV0 = BKV, TM_COLS = 2 * BKV;  // S at cols [0, BKV), O (sum of P V) at [BKV, BKV + 64)
+  static constexpr int CTAS_PER_SM = BKV == 128 ? 2 : 3;
+};
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -71,7 +76,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // Exact row max of one 128-key tile (only the first tile needs it).  MASK for a partial tile.
-template <bool MASK>
+template <bool MASK, int BKV>
 __device__ __forceinline__ float row_max(uint32_t s_addr, int kbase, int N) {
   float mx0 = -INFINITY, mx1 = -INFINITY;
   uint32_t ra[16], rb[16];
@@ -113,7 +118,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-template <bool MASK, int POLY>
+template <bool MASK, int POLY, int BKV>
 __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, int row, int kbase, int N, float scale_log2e,
                                               float ref, float& tmax) {
   float s0 = 0.f, s1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
@@ -159,9 +164,13 @@ __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, in
   return s0 + s1;
 }
 
-template <int POLY>
-__global__ void __launch_bounds__(ATT_THREADS, 2)
-vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, __nv_bfloat16* __restrict__ out, int N, int H, float scale_log2e) {
+template <int POLY, int BKV>
+__global__ void __launch_bounds__(ATT_THREADS, AttCfg<BKV>::CTAS_PER_SM)
+vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_kv,
+                        __nv_bfloat16* __restrict__ out, int N, int H, float scale_log2e) {
+  using cfg = AttCfg<BKV>;
+  constexpr int K_BYTES = cfg::K_BYTES, KV_BYTES = cfg::KV_BYTES, P_BYTES = cfg::P_BYTES;
+  constexpr uint32_t TM_S0 = cfg::TM_S0, TM_PV0 = cfg::TM_PV0, TM_COLS = cfg::TM_COLS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if ((smem_base & 1023u) != 0) __trap();  // the 128B-swizzle atoms need 1024-byte alignment
@@ -185,6 +194,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, __nv_bfloat1
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     mbar_init(s_ready, 1);
@@ -211,8 +221,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, __nv_bfloat1
         mbar_wait(kv_empty(s), ph ^ 1);
         const uint32_t dst = sKV + s * KV_BYTES;
         mbar_expect_tx(kv_full(s), KV_BYTES);
-        tma_load_2d(dst, &map_qk, kv_full(s), H * HD + h * HD, row_base + j * BKV);           // K_j  [128 keys x 64]
-        tma_load_2d(dst + K_BYTES, &map_qk, kv_full(s), 2 * H * HD + h * HD, row_base + j * BKV);  // V_j  [128 keys x 64], as stored
+        tma_load_2d(dst, &map_kv, kv_full(s), H * HD + h * HD, row_base + j * BKV);           // K_j  [128 keys x 64]
+        tma_load_2d(dst + K_BYTES, &map_kv, kv_full(s), 2 * H * HD + h * HD, row_base + j * BKV);  // V_j  [128 keys x 64], as stored
       }
     }
     __syncwarp();
@@ -291,14 +301,14 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, __nv_bfloat1
       const bool mask = (j + 1) * BKV > N;
       const int kbase = j * BKV;
       if (j == 0) {
-        ref = (mask ? row_max<true>(s_addr, kbase, N) : row_max<false>(s_addr, kbase, N)) * scale_log2e;  // finite: >= 1 valid key
+        ref = (mask ? row_max<true, BKV>(s_addr, kbase, N) : row_max<false, BKV>(s_addr, kbase, N)) * scale_log2e;  // finite: >= 1 valid key
       } else if (__any_sync(0xffffffffu, fmaf(seen, scale_log2e, -ref) > 8.f)) {
         rescale(j, fmaxf(ref, seen * scale_log2e));
       }
       float ls;
       for (;;) {
-        ls = mask ? softmax_pass<true, POLY>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax)
-                  : softmax_pass<false, POLY>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax);
+        ls = mask ? softmax_pass<true, POLY, BKV>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax)
+                  : softmax_pass<false, POLY, BKV>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax);
         // exponent headroom: a row whose tile max sits more than 2^64 above its reference redoes the tile
         if (!__any_sync(0xffffffffu, fmaf(tmax, scale_log2e, -ref) > 64.f)) break;
         rescale(j, fmaxf(ref, tmax * scale_log2e));
@@ -359,21 +369,27 @@ size_t vit_attention_tc_workspace(int B, int N, int H) {
 int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int H, cudaStream_t st) {
   (void)vt_ws;
   static const int poly = [] { const char* e = getenv("PIO_ATTN_POLY"); return e ? atoi(e) : 3; }();  // 0 = every exponential on the SFU; 3 = one in six on the FMA pipe (measured best)
-  CUtensorMap mqk;
+  CUtensorMap mqk, mkv;
   PIO_TRY(make_map_2d(&mqk, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, BQ, HD));
-  static bool attr_set = false;
-  if (!attr_set) {
-    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    attr_set = true;
-  }
+  // tile choice by sequence length: fewer padded keys for short sequences (PIO_ATTN_BKV=64|128 overrides)
+  static const int force_bkv = [] { const char* e = getenv("PIO_ATTN_BKV"); return e ? atoi(e) : 0; }();
+  const int bkv = force_bkv ? force_bkv : (N <= 640 ? 64 : 128);
+  PIO_TRY(make_map_2d(&mkv, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, bkv, HD));
   dim3 grid(cdiv(N, BQ), H, B);
   const float scale_log2e = 0.125f * 1.4426950408889634f;
-  auto* kern = poly == 0 ? vit_attention_tc_kernel<0> : poly == 1 ? vit_attention_tc_kernel<1> : poly == 2 ? vit_attention_tc_kernel<2>
-                                                                                                     : vit_attention_tc_kernel<3>;
-  launch_pdl(kern, grid, dim3(ATT_THREADS), ATT_SMEM, st, mqk, (__nv_bfloat16*)out, N, H, scale_log2e);
+#define PIO_ATT_LAUNCH(POLY, BKVV)                                                                                                \
+  do {                                                                                                                            \
+    static bool set = false;                                                                                                      \
+    if (!set) {                                                                                                                   \
+      PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<POLY, BKVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<BKVV>::SMEM)); \
+      set = true;                                                                                                                 \
+    }                                                                                                                             \
+    launch_pdl(vit_attention_tc_kernel<POLY, BKVV>, grid, dim3(ATT_THREADS), AttCfg<BKVV>::SMEM, st, mqk, mkv, (__nv_bfloat16*)out, N, H, \
+               scale_log2e);                                                                                                      \
+  } while (0)
+  if (bkv == 64) { if (poly == 0) PIO_ATT_LAUNCH(0, 64); else PIO_ATT_LAUNCH(3, 64); }
+  else           { if (poly == 0) PIO_ATT_LAUNCH(0, 128); else if (poly == 2) PIO_ATT_LAUNCH(2, 128); else PIO_ATT_LAUNCH(3, 128); }
+#undef PIO_ATT_LAUNCH
   PIO_LAUNCHED();
   return PIO_OK;
 }
