@@ -323,12 +323,12 @@ int vit_attention(const void* qkv, void* out, int dt, int B, int N, int H, cudaS
   dim3 grid(cdiv(N, BR), H, B);
   const float scale = 0.125f;  // 64^-0.5
   if (dt == PIO_DT_F32) {
-    static bool set = false;
-    if (!set) { PIO_CUDA(cudaFuncSetAttribute(vit_attention_kernel<float, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+    static SmemAttrOnce once;
+    PIO_CUDA(once.ensure(vit_attention_kernel<float, float>, (int)smem));
     vit_attention_kernel<float, float><<<grid, 256, smem, st>>>((const float*)qkv, (float*)out, N, H, scale);
   } else {
-    static bool set = false;
-    if (!set) { PIO_CUDA(cudaFuncSetAttribute(vit_attention_kernel<__nv_bfloat16, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = true; }
+    static SmemAttrOnce once;
+    PIO_CUDA(once.ensure(vit_attention_kernel<__nv_bfloat16, __nv_bfloat16>, (int)smem));
     vit_attention_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)out, N, H, scale);
   }
   PIO_LAUNCHED();

@@ -379,11 +379,8 @@ int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int 
   const float scale_log2e = 0.125f * 1.4426950408889634f;
 #define PIO_ATT_LAUNCH(POLY, BKVV)                                                                                                \
   do {                                                                                                                            \
-    static bool set = false;                                                                                                      \
-    if (!set) {                                                                                                                   \
-      PIO_CUDA(cudaFuncSetAttribute(vit_attention_tc_kernel<POLY, BKVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttCfg<BKVV>::SMEM)); \
-      set = true;                                                                                                                 \
-    }                                                                                                                             \
+    static SmemAttrOnce once;                                                                                                     \
+    PIO_CUDA(once.ensure(vit_attention_tc_kernel<POLY, BKVV>, AttCfg<BKVV>::SMEM));                                                \
     launch_pdl(vit_attention_tc_kernel<POLY, BKVV>, grid, dim3(ATT_THREADS), AttCfg<BKVV>::SMEM, st, mqk, mkv, (__nv_bfloat16*)out, N, H, \
                scale_log2e);                                                                                                      \
   } while (0)

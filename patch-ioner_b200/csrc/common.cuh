@@ -60,6 +60,22 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device setting: remember it per (call site, device), so that a process
+// that drives several GPUs still configures every one of them (one process per GPU is the deployment model, this is the guard).
+struct SmemAttrOnce {
+  bool done[64] = {};
+  template <typename K>
+  cudaError_t ensure(K kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+    return e;
+  }
+};
+
 // ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl() may start while its predecessor in
 // the stream is still draining; it must execute pdl_wait() before it touches anything a predecessor wrote (or before it
 // overwrites anything a predecessor reads).  Everything ahead of pdl_wait() -- barrier init, tensor-memory allocation,

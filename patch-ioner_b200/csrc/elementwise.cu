@@ -171,8 +171,7 @@ __global__ void l2norm_kernel(float* __restrict__ x, int rows, int dim) {
 }
 
 // one CTA per row: out = softmax(in * scale)
-__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ in, float* __restrict__ out, int cols,
-                                                           float scale) {
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const float* in, float* out, int cols, float scale) {  // in == out allowed
   __shared__ float red[8];
   const float* r = in + (long long)blockIdx.x * cols;
   float* o = out + (long long)blockIdx.x * cols;

@@ -220,11 +220,8 @@ int linear_tc2(const PioLinear& p, cudaStream_t st) {
   const int store_mode = tma_store_enabled() ? pick_store_mode(p) : STORE_DIRECT;
   if (store_mode != STORE_DIRECT) PIO_TRY(make_map_out(&mc, p.C, p.M, p.N, p.ldc, p.c_dt));
   else mc = ma;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PIO_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-    attr_set = true;
-  }
+  static SmemAttrOnce once;
+  PIO_CUDA(once.ensure(gemm_tc2_kernel, SMEM2_BYTES));
   const int tiles = cdiv(p.M, 2 * BM2) * cdiv(p.N, BN2);
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
   launch_pdl(gemm_tc2_kernel, dim3(2 * pairs), dim3(NUM_THREADS2), SMEM2_BYTES, st, ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc,

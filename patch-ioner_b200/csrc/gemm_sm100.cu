@@ -183,11 +183,8 @@ int launch(const PioLinear& p, cudaStream_t st) {
   const int store_mode = (cfg::TMA_OUT && box_fits && tma_store_enabled()) ? pick_store_mode(p) : STORE_DIRECT;
   if (store_mode != STORE_DIRECT) PIO_TRY(make_map_out(&mc, p.C, p.M, p.N, p.ldc, p.c_dt));
   else mc = ma;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PIO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static SmemAttrOnce once;
+  PIO_CUDA(once.ensure(gemm_tc_kernel<BN>, cfg::SMEM_BYTES));
   const int tiles = cdiv(p.M, BM) * cdiv(p.N, BN);
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), cfg::SMEM_BYTES, st, ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc,

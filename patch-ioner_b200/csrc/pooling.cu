@@ -533,12 +533,9 @@ int launch_slab(const float* tokens, long long img_stride, long long row_stride,
 int launch_box(const float* tokens, long long img_stride, long long row_stride, int B, int grid, int D, const int* bounds, int R,
                int mode, float variance, float* fac, float* out, cudaStream_t st) {
   const size_t smem = (size_t)grid * grid * 16 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PIO_CUDA(cudaFuncSetAttribute(pool_box_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    PIO_CUDA(cudaFuncSetAttribute(pool_box_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    attr_set = true;
-  }
+  static SmemAttrOnce once_g, once_m;
+  PIO_CUDA(once_g.ensure(pool_box_kernel<true>, 113 * 1024));
+  PIO_CUDA(once_m.ensure(pool_box_kernel<false>, 113 * 1024));
   dim3 g(D / 16, B);
   if (mode == 1) {
     box_factors_kernel<<<cdiv((long long)B * R * 32, 256), 256, 0, st>>>(bounds, B * R, mode, variance, fac);
