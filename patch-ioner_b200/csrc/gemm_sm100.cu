@@ -47,7 +47,8 @@ template <int BN> struct Cfg {
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-               const __grid_constant__ CUtensorMap map_c, int store_mode, void* C, int M, int N, int K, int ldc, int c_dt, Epilogue epi) {
+               const __grid_constant__ CUtensorMap map_c, int store_mode, void* C, int M, int N, int K, int ldc, int c_dt, Epilogue epi,
+               int k_splits) {
   using cfg = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms
@@ -64,8 +65,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
-  const int num_tiles = m_blocks * n_blocks;
+  // split-K (k_splits > 1, accumulate-only epilogue through the copy engine's reduce-add): work item w = split * tiles + tile
+  // covers k-blocks [split * kbs, min(k_blocks, (split + 1) * kbs)); the host guarantees that no split is empty
+  const int out_tiles = m_blocks * n_blocks;
+  const int num_tiles = out_tiles * k_splits;
   const int k_blocks = (K + BK - 1) / BK;
+  const int kbs = (k_blocks + k_splits - 1) / k_splits;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -87,9 +92,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
+        const int tile = w % out_tiles, split = w / out_tiles;
         const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = split * kbs, kb1 = min(k_blocks, kb0 + kbs);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * cfg::STAGE_BYTES, sb = sa + cfg::A_BYTES;
           mbar_expect_tx(full_bar(stage), cfg::STAGE_BYTES);
@@ -106,13 +113,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int w = blockIdx.x; w < num_tiles; w += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tempty_bar(as), aphase ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * BN;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      const int kb0 = (w / out_tiles) * kbs, kb1 = min(k_blocks, kb0 + kbs);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (lane == 0) {
@@ -121,10 +129,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0) || (k != 0));
           }
           umma_commit(empty_bar(stage));                       // ring slot reusable once these MMAs retire
-          if (kb == k_blocks - 1) umma_commit(tfull_bar(as));  // accumulator complete
+          if (kb == kb1 - 1) umma_commit(tfull_bar(as));  // accumulator complete
         }
         __syncwarp();
         if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -137,7 +145,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int et = threadIdx.x - 64;           // 0..255 among the epilogue threads
     const TmaOut to{&map_c, smem_base + cfg::STAGES * cfg::STAGE_BYTES + (warp - 2) * 4096, cfg::TMA_OUT ? store_mode : STORE_DIRECT};
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int w = blockIdx.x; w < num_tiles; w += gridDim.x, ++it) {
+      const int tile = w % out_tiles;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
@@ -186,9 +195,21 @@ int launch(const PioLinear& p, cudaStream_t st) {
   static SmemAttrOnce once;
   PIO_CUDA(once.ensure(gemm_tc_kernel<BN>, cfg::SMEM_BYTES));
   const int tiles = cdiv(p.M, BM) * cdiv(p.N, BN);
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  // split-K: a long-K accumulation (C += A W^T, nothing else in the epilogue) with too few output tiles to fill the machine --
+  // the recombination GEMM of the memory projection for a handful of queries -- is cut along K; the partial tiles meet in C
+  // through the bulk reduce-add.
+  int k_splits = 1;
+  const int k_blocks = cdiv(p.K, BK);
+  if (store_mode == STORE_TMA_ADD && p.bias == nullptr && p.gamma == nullptr && p.colscale == nullptr && p.act == PIO_ACT_NONE &&
+      tiles * 2 <= kNumSMs && k_blocks >= 64) {
+    k_splits = std::min(kNumSMs / tiles, k_blocks / 32);
+    const int kbs = cdiv(k_blocks, k_splits);
+    k_splits = cdiv(k_blocks, kbs);  // no empty split
+  }
+  const int work = tiles * k_splits;
+  const int grid = work < kNumSMs ? work : kNumSMs;
   launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), cfg::SMEM_BYTES, st, ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc,
-             p.c_dt, make_epilogue(p));
+             p.c_dt, make_epilogue(p), k_splits);
   PIO_LAUNCHED();
   return PIO_OK;
 }

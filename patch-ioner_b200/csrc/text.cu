@@ -98,6 +98,13 @@ __global__ void row_inv_norm_kernel(const float* __restrict__ x, float* __restri
   if (lane == 0) inv[warp] = 1.0f / sqrtf(s);
 }
 
+// O[r,:] *= alpha[r]   (the running-output rescale, applied ahead of an accumulate-only, split-K recombination GEMM)
+__global__ void scale_rows_kernel(float* __restrict__ O, const float* __restrict__ alpha, int R, int D) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const float a = alpha[warp];
+  for (int i = lane; i < D; i += 32) O[(long long)warp * D + i] *= a;
+}
 // O[r,:] *= f, l[r] *= f with f = exp(m_local - m_global)
 __global__ void rescale_rows_kernel(float* __restrict__ O, float* __restrict__ l, const float* __restrict__ ml,
                                     const float* __restrict__ mg, int R, int D) {
@@ -383,11 +390,16 @@ static int project_chunk_rows(int R) {
   // S chunk (R x Mc fp32, or P bf16 with twice the columns on the fused path).  Measured at R = 4096, M = 591 753 (B200):
   // 16 M elements (P = 67 MB, L2 resident) 8.7 ms, 32 M 7.8 ms, 64 M 7.5 ms, 128 M 8.1 ms -- fewer, longer GEMMs beat L2
   // residency (the P round trip runs at ~3 TB/s, well inside HBM bandwidth).  PIO_PROJECT_CHUNK_M overrides for A/B runs.
-  static const long long elems = [] { const char* e = getenv("PIO_PROJECT_CHUNK_M"); return (long long)(e ? atoi(e) : 64) << 20; }();
+  // Few queries (R = 32 ... 256: image-level captions, traces, small batches) are launch-bound, not bandwidth-bound: the chunk
+  // may then grow to 131072 rows (3 chunks instead of 19 for the 591 753-row bank).  Both limits are read per call so that
+  // tests can force many small chunks (PIO_PROJECT_MAX_CHUNK).
+  const char* e = getenv("PIO_PROJECT_CHUNK_M");
+  const char* c = getenv("PIO_PROJECT_MAX_CHUNK");
+  const long long elems = (long long)(e ? atoi(e) : 64) << 20, cap = c ? atoi(c) : 131072;
   long long mc = elems / (R > 0 ? R : 1);
   mc = mc / 128 * 128;
+  if (mc > cap) mc = cap / 128 * 128;
   if (mc < 1024) mc = 1024;
-  if (mc > 16384) mc = 16384;
   return (int)mc;
 }
 
@@ -434,6 +446,7 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
     // no separate softmax pass).  m_ref lags by one chunk and never drops below log2e * (1/T - 70), so with
     // |s| <= 1/T the exponent stays <= 70 / ln 2: no overflow for any input; accurate while max cosine >= -0.4.
     const float log2e = 1.4426950408889634f;
+    const bool few_queries = R <= 768;
     // the S region (R x Mc fp32) hosts P (bf16, R x 2Mc columns) on this path: twice the chunk, same bytes
     const int Mf = 2 * Mc;
     __nv_bfloat16* P = (__nv_bfloat16*)S;
@@ -457,7 +470,12 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
       memset(&p, 0, sizeof(p));
       p.A = P; p.W = (const char*)h->bankT + (size_t)c0 * e; p.C = out; p.M = R; p.N = D; p.K = mc_pad;
       p.lda = Mf; p.ldw = (int)h->Mp; p.ldc = D; p.a_dt = adt; p.c_dt = PIO_DT_F32; p.residual = out; p.ldres = D;
-      p.res_rowscale = alpha; p.alpha = 1.0f;
+      p.alpha = 1.0f;
+      if (few_queries) {  // O *= alpha first, then a pure accumulation that the GEMM may split along K (too few output tiles)
+        scale_rows_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(out, alpha, R, D); PIO_LAUNCHED();
+      } else {
+        p.res_rowscale = alpha;
+      }
       PIO_TRY(linear_tc(p, st));
       launch_pdl(project_update_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, psum, pmax, slabs_max, slabs, R, m, m_used, l,
                  alpha);

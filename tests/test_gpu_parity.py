@@ -367,8 +367,9 @@ def test_project_against_golden(dev, ops, golden, mode, cmin):
         torch.testing.assert_close(b.project(qd, normalize=False).cpu(), rec["out_raw"], rtol=1e-3, atol=1e-3)
 
 
-def test_project_multi_chunk_and_sharded(dev, ops):
+def test_project_multi_chunk_and_sharded(dev, ops, monkeypatch):
     """M spans several chunks; the sharded (m, l, O) form merged like the NCCL path equals the monolithic one."""
+    monkeypatch.setenv("PIO_PROJECT_MAX_CHUNK", "16384")
     bank = o_pipe.synth_bank(40000, 768, seed=21, zero_frac=0.001)
     q = torch.randn(300, 768, generator=torch.Generator().manual_seed(22))
     ref = o_mem.project(q, o_mem.drop_zero_rows(bank), normalize=True)
@@ -387,9 +388,10 @@ def test_project_multi_chunk_and_sharded(dev, ops):
     assert cos_min(merged, ref) >= 0.9999
 
 
-def test_project_bf16_fused_multi_chunk_and_sharded(dev, ops):
+def test_project_bf16_fused_multi_chunk_and_sharded(dev, ops, monkeypatch):
     """bf16 fast path (exp fused in the GEMM epilogue, lagging reference max): several chunks, a near-duplicate query
     (logit ~ 1/T = 100 -> the overflow guard), opposite-direction queries, and the sharded (m, l, O) merge."""
+    monkeypatch.setenv("PIO_PROJECT_MAX_CHUNK", "16384")
     bank = o_pipe.synth_bank(70000, 768, seed=23, zero_frac=0.001)
     gen = torch.Generator().manual_seed(24)
     q = torch.randn(200, 768, generator=gen)
@@ -408,6 +410,17 @@ def test_project_bf16_fused_multi_chunk_and_sharded(dev, ops):
         ops.project_rescale_(pO, pl, pm, m)
     merged = ops.project_finish_(sum(p[2] for p in parts), sum(p[1] for p in parts), True).cpu()
     assert cos_min(merged, ref) >= 0.999, cos_min(merged, ref)
+
+
+@pytest.mark.parametrize("mode,cmin", [("fp32", 0.9999), ("bf16", 0.999)])
+def test_project_few_queries_large_chunks(dev, ops, mode, cmin):
+    """Few queries take the large-chunk path (up to 131072 bank rows per GEMM): same result as the oracle."""
+    bank = o_pipe.synth_bank(300000, 768, seed=33, zero_frac=0.001)
+    q = torch.randn(7, 768, generator=torch.Generator().manual_seed(34))
+    q[2] = bank[299000] * 1.7 + 0.02 * torch.randn(768, generator=torch.Generator().manual_seed(35))
+    ref = o_mem.project(q, o_mem.drop_zero_rows(bank), normalize=True)
+    out = ops.Bank(bank, dev, mode).project(q.to(dev), normalize=True).cpu()
+    assert cos_min(out, ref) >= cmin
 
 
 # ----------------------------------------------------------------------------------------- decoder
@@ -560,8 +573,9 @@ def test_cls_head_attention_maps(dev, ops):
 
 
 @pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("bf16", 4e-3)])
-def test_best_sims(dev, ops, mode, tol):
+def test_best_sims(dev, ops, mode, tol, monkeypatch):
     """return_n_best_sims (im2txtprojection.py:382-383): the n largest cosines per query, descending, over several chunks."""
+    monkeypatch.setenv("PIO_PROJECT_MAX_CHUNK", "16384")
     bank = o_pipe.synth_bank(40000, 768, seed=41, zero_frac=0.001)
     fb = o_mem.drop_zero_rows(bank)
     gen = torch.Generator().manual_seed(42)
@@ -859,3 +873,17 @@ def test_deterministic_and_batch_invariant(dev):
         if mode == "fp32":
             one = m(imgs[2:3], get_cls_capt=True, bboxes=boxes[2:3], return_ids=True)
             assert torch.equal(one["bbox_capts"][0], a["bbox_capts"][2]) and torch.equal(one["cls_capt"][0], a["cls_capt"][2])
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 768, 16384), (200, 768, 40000), (128, 192, 8192)])
+def test_linear_split_k_accumulate(dev, ops, M, N, K):
+    """Long-K accumulation with few output tiles: the GEMM splits K over the SMs and the partial tiles meet through the bulk
+    reduce-add; same result as the unsplit product."""
+    g = torch.Generator().manual_seed(K)
+    A = (torch.randn(M, K, generator=g) / 8).bfloat16()
+    W = (torch.randn(N, K, generator=g) / 8).bfloat16()
+    C0 = torch.randn(M, N, generator=g)
+    ref = C0.double() + A.double() @ W.double().T
+    X = C0.clone().to(dev)
+    ops.linear(A.to(dev), W.to(dev), "bf16", residual=X, out=X)
+    torch.testing.assert_close(X.cpu().double(), ref, rtol=2e-3, atol=2e-2)
