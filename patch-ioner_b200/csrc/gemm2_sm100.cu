@@ -111,24 +111,38 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   cluster_sync_all();  // barriers and tensor memory of BOTH CTAs are ready
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_var);
-  pdl_wait();
   pdl_launch_dependents();
+  // pdl_wait() is per role (see gemm_sm100.cu): weight tiles are fetched ahead of it, A tiles and C accesses after it
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs, own halves)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int pre = 0;
+      if (pair < num_tiles) {
+        const int n0 = (pair % n_blocks) * BN2 + (int)rank * BNH;
+        pre = min(STAGES2, k_blocks);
+        for (int i = 0; i < pre; ++i) {
+          const uint32_t lbar = full_bar(i) & PEER_MASK;
+          if (leader) mbar_expect_tx(full_bar(i), 2 * STAGE2_BYTES);
+          tma_load_2d_2sm(smem_base + i * STAGE2_BYTES + A2_BYTES, &map_w, lbar, i * BK2, n0);
+        }
+      }
+      pdl_wait();
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m0 = (tile / n_blocks) * (2 * BM2) + (int)rank * BM2;
         const int n0 = (tile % n_blocks) * BN2 + (int)rank * BNH;
         for (int kb = 0; kb < k_blocks; ++kb) {
+          const bool w_in_flight = (tile == pair) && (kb < pre);
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * STAGE2_BYTES, sb = sa + A2_BYTES;
           const uint32_t lbar = full_bar(stage) & PEER_MASK;  // the LEADER's full barrier
-          if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
+          if (!w_in_flight) {
+            if (leader) mbar_expect_tx(full_bar(stage), 2 * STAGE2_BYTES);
+            tma_load_2d_2sm(sb, &map_w, lbar, kb * BK2, n0);
+          }
           tma_load_2d_2sm(sa, &map_a, lbar, kb * BK2, m0);
-          tma_load_2d_2sm(sb, &map_w, lbar, kb * BK2, n0);
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
@@ -169,6 +183,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;
     const TmaOut to{&map_c, smem_base + STAGES2 * STAGE2_BYTES + (warp - 2) * OUT_STAGE_BYTES, store_mode};
+    pdl_wait();
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int as = it & 1;

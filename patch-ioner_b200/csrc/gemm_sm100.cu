@@ -84,24 +84,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_var);
-  pdl_wait();               // everything above overlapped the previous kernel's tail
   pdl_launch_dependents();  // the next kernel may start its own prologue as soon as this grid's CTAs retire
+  // pdl_wait() is per role: the producer fetches WEIGHT tiles first (W is never written by a kernel of this pipeline that is
+  // still in flight; A and the residual are), the epilogue waits before it touches C, the MMA warp never touches global memory.
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int pre = 0;  // ring slots of the first work item whose W tile is already in flight (issued ahead of pdl_wait)
+      if ((int)blockIdx.x < num_tiles) {
+        const int tile = blockIdx.x % out_tiles, split = blockIdx.x / out_tiles;
+        const int n0 = (tile % n_blocks) * BN, kb0 = split * kbs, kb1 = min(k_blocks, kb0 + kbs);
+        pre = min(cfg::STAGES, kb1 - kb0);
+        for (int i = 0; i < pre; ++i) {
+          mbar_expect_tx(full_bar(i), cfg::STAGE_BYTES);
+          tma_load_2d(smem_base + i * cfg::STAGE_BYTES + cfg::A_BYTES, &map_w, full_bar(i), (kb0 + i) * BK, n0);
+        }
+      }
+      pdl_wait();  // the previous kernel's output (our A operand) is complete and visible
       for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
         const int tile = w % out_tiles, split = w / out_tiles;
         const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
         const int kb0 = split * kbs, kb1 = min(k_blocks, kb0 + kbs);
         for (int kb = kb0; kb < kb1; ++kb) {
+          const bool w_in_flight = (w == (int)blockIdx.x) && (kb - kb0 < pre);
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * cfg::STAGE_BYTES, sb = sa + cfg::A_BYTES;
-          mbar_expect_tx(full_bar(stage), cfg::STAGE_BYTES);
+          if (!w_in_flight) {
+            mbar_expect_tx(full_bar(stage), cfg::STAGE_BYTES);
+            tma_load_2d(sb, &map_w, full_bar(stage), kb * BK, n0);
+          }
           tma_load_2d(sa, &map_a, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sb, &map_w, full_bar(stage), kb * BK, n0);
           if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -144,6 +159,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int half = (warp - 2) >> 2;          // which half of the tile's columns
     const int et = threadIdx.x - 64;           // 0..255 among the epilogue threads
     const TmaOut to{&map_c, smem_base + cfg::STAGES * cfg::STAGE_BYTES + (warp - 2) * 4096, cfg::TMA_OUT ? store_mode : STORE_DIRECT};
+    pdl_wait();  // C / the residual may still be read or written by the previous kernel
     int it = 0;
     for (int w = blockIdx.x; w < num_tiles; w += gridDim.x, ++it) {
       const int tile = w % out_tiles;
