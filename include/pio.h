@@ -259,6 +259,50 @@ size_t pio_decode_workspace_bytes(const PioDecoder* h, int R, int steps);
 int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int* out_ids, float* out_logprob_sum,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* ViECap captioner on the same region embeddings (src/viecap/entrypoint.py:98-162)                         */
+/* GPT-2 with n_layer blocks of 12 heads x 64 (pretrained 'gpt2': 12 layers; viecap/ClipCap.py:157), no prefix            */
+/* projection: the prompt arrives as input embeddings.  KV cache of up to 128 positions.                                 */
+typedef struct {
+  const float* wte; /* [50257,768] (tied lm_head) */
+  const float* wpe; /* [1024,768]                 */
+  const float *lnf_w, *lnf_b;
+  const PioGptBlock* blk; /* n_layer entries       */
+  int n_layer, n_head;
+} PioGpt2Weights;
+int pio_decoder_create_gpt2(PioDecoder** out, const PioGpt2Weights* w, int mode, void* stream);
+size_t pio_decode_prompt_workspace_bytes(const PioDecoder* h, int R, int prompt_len, int steps);
+/* greedy_search (viecap/search.py:108-191): prompt fp32 [R,prompt_len,768] input embeddings (position embeddings are     */
+/* added here), then `steps` arg-max tokens (on the logits, first-index tie-break), out_ids int32 [R,steps].  No early    */
+/* exit (the reference only exits early at batch 1, search.py:173-176); the sentence is cut at '.' on the host.           */
+int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prompt_len, int steps, int* out_ids,
+                             float* out_logprob_sum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Mapping network (viecap/ClipCap.py:122-153): Linear weights in torch layout [out,in]                                  */
+typedef struct {
+  const float *norm1_w, *norm1_b, *q_w /*[768,768]*/, *kv_w /*[1536,768]*/, *proj_w /*[768,768]*/, *proj_b;
+  const float *norm2_w, *norm2_b, *fc1_w /*[hidden,768]*/, *fc1_b, *fc2_w /*[768,hidden]*/, *fc2_b;
+} PioMapperLayer;
+typedef struct {
+  int clip_size, project_len, prefix_len, n_layer, n_head, hidden;
+  const float* linear_w;     /* [project_len*768, clip_size] */
+  const float* linear_b;     /* [project_len*768]            */
+  const float* prefix_const; /* [prefix_len,768]             */
+  const PioMapperLayer* layers;
+} PioMapperWeights;
+typedef struct PioMapper PioMapper;
+int pio_mapper_create(PioMapper** out, const PioMapperWeights* w, int mode, void* stream);
+void pio_mapper_destroy(PioMapper* h);
+size_t pio_mapper_workspace_bytes(const PioMapper* h, int R);
+/* feats fp32 [R,clip_size], L2-normalised by the caller (entrypoint.py:108) -> out fp32 [R,prefix_len,768]              */
+int pio_mapper_forward(PioMapper* h, const float* feats, int R, float* out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+/* Entity retrieval (retrieval_categories.py:87-115): p = softmax(q . E^T / temperature) over n_ent unit-norm entity      */
+/* embeddings [n_ent,D] (q [R,D] unit-norm), then the k largest probabilities in descending order (lowest index first     */
+/* on ties) -> out_prob fp32 [R,k], out_idx int32 [R,k].  fp32 arithmetic in both modes.  k <= 32, n_ent <= 8192.         */
+int pio_entity_topk(const float* q, const float* ent, int R, int n_ent, int D, float temperature, int k, float* out_prob,
+                    int* out_idx, void* stream);
+
 /* L2-normalise rows in place */
 int pio_l2_normalize(float* x, int rows, int dim, void* stream);
 

@@ -55,6 +55,25 @@ class PioDecoderWeights(C.Structure):
                 ("prefix_w", _fp), ("prefix_b", _fp), ("prefix_size", C.c_int)]
 
 
+class PioGpt2Weights(C.Structure):
+    _fields_ = [("wte", _fp), ("wpe", _fp), ("lnf_w", _fp), ("lnf_b", _fp), ("blk", C.POINTER(PioGptBlock)),
+                ("n_layer", C.c_int), ("n_head", C.c_int)]
+
+
+MAPPER_LAYER_FIELDS = ["norm1_w", "norm1_b", "q_w", "kv_w", "proj_w", "proj_b",
+                       "norm2_w", "norm2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b"]
+
+
+class PioMapperLayer(C.Structure):
+    _fields_ = [(n, _fp) for n in MAPPER_LAYER_FIELDS]
+
+
+class PioMapperWeights(C.Structure):
+    _fields_ = [("clip_size", C.c_int), ("project_len", C.c_int), ("prefix_len", C.c_int), ("n_layer", C.c_int),
+                ("n_head", C.c_int), ("hidden", C.c_int), ("linear_w", _fp), ("linear_b", _fp), ("prefix_const", _fp),
+                ("layers", C.POINTER(PioMapperLayer))]
+
+
 # name -> (restype, argtypes); must list every symbol include/pio.h declares (tests check this)
 SIGNATURES = {
     "pio_last_error": (C.c_char_p, []),
@@ -101,6 +120,14 @@ SIGNATURES = {
     "pio_decode_workspace_bytes": (C.c_size_t, [_fp, C.c_int, C.c_int]),
     "pio_decode_greedy": (C.c_int, [_fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
     "pio_l2_normalize": (C.c_int, [_fp, C.c_int, C.c_int, _fp]),
+    "pio_decoder_create_gpt2": (C.c_int, [C.POINTER(_fp), C.POINTER(PioGpt2Weights), C.c_int, _fp]),
+    "pio_decode_prompt_workspace_bytes": (C.c_size_t, [_fp, C.c_int, C.c_int, C.c_int]),
+    "pio_decode_greedy_prompt": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "pio_mapper_create": (C.c_int, [C.POINTER(_fp), C.POINTER(PioMapperWeights), C.c_int, _fp]),
+    "pio_mapper_destroy": (None, [_fp]),
+    "pio_mapper_workspace_bytes": (C.c_size_t, [_fp, C.c_int]),
+    "pio_mapper_forward": (C.c_int, [_fp, _fp, C.c_int, _fp, _fp, C.c_size_t, _fp]),
+    "pio_entity_topk": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp, _fp]),
 }
 
 _lib = None

@@ -335,7 +335,175 @@ int vit_attention(const void* qkv, void* out, int dt, int B, int N, int H, cudaS
   return PIO_OK;
 }
 
+namespace {
+// ---------------------------------------------------------------------------------------------
+// Decoder attention for longer caches (GPT-2 small: head_dim 64, up to 128 positions).  One warp per (region, head).
+// Scores: lane l owns positions l, l+32, l+64, l+96 and walks its key rows whole (a 64-element row is one or two
+// 128-byte lines); output: lane l owns dims 2l, 2l+1 and the warp reads each value row with one coalesced request.
+template <typename T> __device__ __forceinline__ void load8f(const T* p, float (&f)[8]);
+template <> __device__ __forceinline__ void load8f<float>(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8f<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  unpack8(u, f);
+}
+template <typename T> __device__ __forceinline__ float2 load2f(const T* p);
+template <> __device__ __forceinline__ float2 load2f<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 load2f<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+}
+template <typename T> __device__ __forceinline__ void store2f(T* p, float a, float b);
+template <> __device__ __forceinline__ void store2f<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <> __device__ __forceinline__ void store2f<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) decode_attention_long_kernel(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
+                                                                    T* __restrict__ out, int R, int H, int Tmax, int t, float scale) {
+  constexpr int HDIM = 64, MAXC = 4;
+  __shared__ float qs[4][HDIM];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * 4 + wib;
+  if (warp >= R * H) return;
+  const int r = warp / H, h = warp % H;
+  const T* row = qkv + (long long)r * 3 * H * HDIM + h * HDIM;
+  T* kbase = kc + ((long long)(r * H + h) * Tmax) * HDIM;
+  T* vbase = vc + ((long long)(r * H + h) * Tmax) * HDIM;
+  {
+    const float2 q2 = load2f<T>(row + lane * 2), k2 = load2f<T>(row + H * HDIM + lane * 2), v2 = load2f<T>(row + 2 * H * HDIM + lane * 2);
+    qs[wib][lane * 2] = q2.x; qs[wib][lane * 2 + 1] = q2.y;
+    store2f<T>(kbase + (long long)t * HDIM + lane * 2, k2.x, k2.y);   // append this step's key / value
+    store2f<T>(vbase + (long long)t * HDIM + lane * 2, v2.x, v2.y);
+  }
+  __syncwarp();  // the appended row and q are visible to the whole warp
+  float sc[MAXC];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int j = lane + 32 * c;
+    sc[c] = -INFINITY;
+    if (j <= t) {
+      const T* kr = kbase + (long long)j * HDIM;
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < HDIM; d += 8) {
+        float kf[8];
+        load8f<T>(kr + d, kf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a = fmaf(qs[wib][d + e], kf[e], a);
+      }
+      sc[c] = a * scale;
+    }
+    mx = fmaxf(mx, sc[c]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    sc[c] = (lane + 32 * c <= t) ? __expf(sc[c] - mx) : 0.f;
+    sum += sc[c];
+  }
+  const float inv = 1.0f / warp_sum(sum);
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    if (32 * c > t) break;  // warp-uniform
+    const int n = min(32, t + 1 - 32 * c);
+#pragma unroll 4
+    for (int jj = 0; jj < n; ++jj) {
+      const float pj = __shfl_sync(0xffffffffu, sc[c], jj);
+      const float2 v2 = load2f<T>(vbase + (long long)(32 * c + jj) * HDIM + lane * 2);
+      a0 = fmaf(pj, v2.x, a0);
+      a1 = fmaf(pj, v2.y, a1);
+    }
+  }
+  store2f<T>(out + (long long)r * H * HDIM + h * HDIM + lane * 2, a0 * inv, a1 * inv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bidirectional attention over a short sequence (ViECap mapping network: 20 tokens, 8 heads x 96; ClipCap.py:51-68).
+// q [R*n, ldq] (head h at column h*hd), kv [R*n, ldkv] (keys at h*hd, values at H*hd + h*hd), out [R*n, ldo].
+// One CTA per (region, head): q, k, v and the n x n probabilities live in shared memory as fp32.
+template <typename T>
+__global__ void __launch_bounds__(128) small_attention_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ kv,
+                                                              long long ldkv, T* __restrict__ out, long long ldo, int n, int H, int hd,
+                                                              float scale) {
+  extern __shared__ __align__(16) float sm[];
+  const int ld = hd + 1;
+  float* Q = sm;
+  float* K = Q + n * ld;
+  float* V = K + n * ld;
+  float* P = V + n * ld;  // [n][n+1]
+  const int r = blockIdx.x / H, h = blockIdx.x % H, tid = threadIdx.x;
+  for (int idx = tid; idx < n * hd; idx += 128) {
+    const int i = idx / hd, d = idx % hd;
+    const long long row = (long long)r * n + i;
+    Q[i * ld + d] = (float)q[row * ldq + h * hd + d];
+    K[i * ld + d] = (float)kv[row * ldkv + h * hd + d];
+    V[i * ld + d] = (float)kv[row * ldkv + (long long)H * hd + h * hd + d];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * n; idx += 128) {
+    const int i = idx / n, j = idx % n;
+    float a = 0.f;
+    for (int d = 0; d < hd; ++d) a = fmaf(Q[i * ld + d], K[j * ld + d], a);
+    P[i * (n + 1) + j] = a * scale;
+  }
+  __syncthreads();
+  if (tid < n) {
+    float mx = -INFINITY, s = 0.f;
+    for (int j = 0; j < n; ++j) mx = fmaxf(mx, P[tid * (n + 1) + j]);
+    for (int j = 0; j < n; ++j) {
+      const float e = expf(P[tid * (n + 1) + j] - mx);
+      P[tid * (n + 1) + j] = e;
+      s += e;
+    }
+    const float inv = 1.0f / s;
+    for (int j = 0; j < n; ++j) P[tid * (n + 1) + j] *= inv;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n * hd; idx += 128) {
+    const int i = idx / hd, d = idx % hd;
+    float a = 0.f;
+    for (int j = 0; j < n; ++j) a = fmaf(P[i * (n + 1) + j], V[j * ld + d], a);
+    out[((long long)r * n + i) * ldo + h * hd + d] = (T)a;
+  }
+}
+
+}  // namespace
+
+int small_attention(const void* q, long long ldq, const void* kv, long long ldkv, void* out, long long ldo, int dt, int R, int n, int H,
+                    int hd, cudaStream_t st) {
+  PIO_CHECK(n >= 1 && n <= 64 && hd >= 1 && hd <= 128, "small attention: n %d / head_dim %d outside the built range (<=64, <=128)", n, hd);
+  const size_t smem = ((size_t)3 * n * (hd + 1) + (size_t)n * (n + 1)) * sizeof(float);
+  PIO_CHECK(smem <= 48 * 1024, "small attention: %zu bytes of shared memory exceed 48 KB", smem);
+  const float scale = 1.0f / sqrtf((float)hd);
+  if (dt == PIO_DT_F32)
+    small_attention_kernel<float><<<R * H, 128, smem, st>>>((const float*)q, ldq, (const float*)kv, ldkv, (float*)out, ldo, n, H, hd, scale);
+  else
+    small_attention_kernel<__nv_bfloat16><<<R * H, 128, smem, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kv, ldkv,
+                                                                    (__nv_bfloat16*)out, ldo, n, H, hd, scale);
+  PIO_LAUNCHED();
+  return PIO_OK;
+}
+
 int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int R, int H, int T, int t, cudaStream_t st) {
+  if (H == 12) {  // GPT-2 small: 12 heads x 64
+    PIO_CHECK(t < T && T <= 128, "decode attention: position %d outside cache of %d (max 128)", t, T);
+    const int blocks = cdiv((long long)R * H, 4);
+    if (dt == PIO_DT_F32)
+      decode_attention_long_kernel<float><<<blocks, 128, 0, st>>>((const float*)qkv, (float*)kc, (float*)vc, (float*)out, R, H, T, t, 0.125f);
+    else
+      decode_attention_long_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc,
+                                                                          (__nv_bfloat16*)out, R, H, T, t, 0.125f);
+    PIO_LAUNCHED();
+    return PIO_OK;
+  }
+  PIO_CHECK(H == 4, "decode attention: %d heads (built: 4 x 192 and 12 x 64)", H);
+
   PIO_CHECK(t < T && T <= 32, "decode attention: position %d outside cache of %d (max 32)", t, T);
   const float scale = rsqrtf(192.0f);
   const int blocks = cdiv((long long)R * H * 32, 128);

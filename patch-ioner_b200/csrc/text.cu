@@ -221,6 +221,20 @@ __global__ void embed_kernel(const float* __restrict__ wte, const float* __restr
   }
 }
 
+// x[r,:] = prompt[r,p,:] + wpe[p,:]   (inputs_embeds of a prompt position; GPT-2 adds the position embedding)
+__global__ void prompt_embed_kernel(const float* __restrict__ prompt, int P, int p, const float* __restrict__ wpe,
+                                    float* __restrict__ x, int R, int D) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= R) return;
+  const float4* a = reinterpret_cast<const float4*>(prompt + ((long long)warp * P + p) * D);
+  const float4* b = reinterpret_cast<const float4*>(wpe + (long long)p * D);
+  float4* o = reinterpret_cast<float4*>(x + (long long)warp * D);
+  for (int i = lane; i < D / 4; i += 32) {
+    float4 u = __ldg(a + i), v = __ldg(b + i);
+    o[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+}
+
 __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = a[i] + b[i];
@@ -576,17 +590,19 @@ int pio_project_finish(float* O, const float* l, int R, int D, int normalize, vo
 
 // ==========================================================================================
 namespace pio {
-constexpr int gD = 768, gH = 4, gL = 4, gV = 50257, gVld = 50264, gFF = 3072, gT = 32;
+constexpr int gD = 768, gV = 50257, gVld = 50264, gFF = 3072;
 }
+// L blocks x H heads; T = positions the KV cache of one call may hold (DeCap: 4 x 4 x 32; GPT-2 small for ViECap: 12 x 12 x 128)
 struct PioDecoder {
-  int mode, act_dt, prefix_size;
+  int mode, act_dt, prefix_size, L, H, T;
   std::vector<void*> owned;
   const float *wte32, *wpe, *lnf_w, *lnf_b, *prefix_b0;  // prefix_b0 = prefix bias + wpe[0]
   const void *wte, *prefix_w;                             // act dtype
   struct Blk {
     const float *ln1_w, *ln1_b, *attn_b, *proj_b, *ln2_w, *ln2_b, *fc_b, *fc2_b;
     const void *attn_w, *proj_w, *fc_w, *fc2_w;  // act dtype, transposed to [out, in]
-  } blk[4];
+  };
+  std::vector<Blk> blk;
 };
 
 namespace pio {
@@ -625,27 +641,31 @@ int d_mat(PioDecoder* h, const void** dst, const float* src, size_t n, cudaStrea
 
 extern "C" {
 
-int pio_decoder_create(PioDecoder** out, const PioDecoderWeights* w, int mode, void* stream) {
+static int decoder_build(PioDecoder** out, const float* wte, const float* wpe, const float* lnf_w, const float* lnf_b,
+                         const float* prefix_w, const float* prefix_b, int prefix_size, const PioGptBlock* blocks, int n_layer,
+                         int n_head, int max_len, int mode, void* stream) {
   using namespace pio;
-  PIO_CHECK(out && w, "decoder_create: null argument");
-  PIO_CHECK(mode == PIO_FP32 || mode == PIO_BF16, "decoder_create: unknown mode %d", mode);
-  PIO_CHECK(w->prefix_size > 0 && w->prefix_size % 64 == 0, "decoder_create: prefix_size %d must be a multiple of 64", w->prefix_size);
   cudaStream_t st = as_stream(stream);
   PioDecoder* h = new PioDecoder();
-  h->mode = mode; h->act_dt = mode == PIO_FP32 ? PIO_DT_F32 : PIO_DT_BF16; h->prefix_size = w->prefix_size;
+  h->mode = mode; h->act_dt = mode == PIO_FP32 ? PIO_DT_F32 : PIO_DT_BF16; h->prefix_size = prefix_size;
+  h->L = n_layer; h->H = n_head; h->T = max_len;
+  h->blk.resize(n_layer);
+  h->prefix_w = nullptr; h->prefix_b0 = nullptr;
   auto go = [&]() -> int {
-    PIO_TRY(d_f32(h, &h->wte32, w->wte, (size_t)gV * gD, st));
-    if (h->act_dt == PIO_DT_F32) h->wte = h->wte32; else PIO_TRY(d_mat(h, &h->wte, w->wte, (size_t)gV * gD, st));
-    PIO_TRY(d_f32(h, &h->wpe, w->wpe, (size_t)1024 * gD, st));
-    PIO_TRY(d_f32(h, &h->lnf_w, w->lnf_w, gD, st)); PIO_TRY(d_f32(h, &h->lnf_b, w->lnf_b, gD, st));
-    PIO_TRY(d_mat(h, &h->prefix_w, w->prefix_w, (size_t)gD * w->prefix_size, st));
-    void* pb;
-    PIO_TRY(d_own(h, &pb, gD * 4));
-    add_vec_kernel<<<cdiv(gD, 256), 256, 0, st>>>(w->prefix_b, w->wpe, (float*)pb, gD);
-    PIO_LAUNCHED();
-    h->prefix_b0 = (const float*)pb;
-    for (int i = 0; i < gL; ++i) {
-      const PioGptBlock& s = w->blk[i];
+    PIO_TRY(d_f32(h, &h->wte32, wte, (size_t)gV * gD, st));
+    if (h->act_dt == PIO_DT_F32) h->wte = h->wte32; else PIO_TRY(d_mat(h, &h->wte, wte, (size_t)gV * gD, st));
+    PIO_TRY(d_f32(h, &h->wpe, wpe, (size_t)1024 * gD, st));
+    PIO_TRY(d_f32(h, &h->lnf_w, lnf_w, gD, st)); PIO_TRY(d_f32(h, &h->lnf_b, lnf_b, gD, st));
+    if (prefix_w) {
+      PIO_TRY(d_mat(h, &h->prefix_w, prefix_w, (size_t)gD * prefix_size, st));
+      void* pb;
+      PIO_TRY(d_own(h, &pb, gD * 4));
+      add_vec_kernel<<<cdiv(gD, 256), 256, 0, st>>>(prefix_b, wpe, (float*)pb, gD);
+      PIO_LAUNCHED();
+      h->prefix_b0 = (const float*)pb;
+    }
+    for (int i = 0; i < n_layer; ++i) {
+      const PioGptBlock& s = blocks[i];
       PioDecoder::Blk& d = h->blk[i];
       PIO_TRY(d_f32(h, &d.ln1_w, s.ln1_w, gD, st)); PIO_TRY(d_f32(h, &d.ln1_b, s.ln1_b, gD, st));
       PIO_TRY(d_f32(h, &d.attn_b, s.attn_b, 3 * gD, st)); PIO_TRY(d_f32(h, &d.proj_b, s.proj_b, gD, st));
@@ -664,20 +684,103 @@ int pio_decoder_create(PioDecoder** out, const PioDecoderWeights* w, int mode, v
   return PIO_OK;
 }
 
+int pio_decoder_create(PioDecoder** out, const PioDecoderWeights* w, int mode, void* stream) {
+  using namespace pio;
+  PIO_CHECK(out && w, "decoder_create: null argument");
+  PIO_CHECK(mode == PIO_FP32 || mode == PIO_BF16, "decoder_create: unknown mode %d", mode);
+  PIO_CHECK(w->prefix_size > 0 && w->prefix_size % 64 == 0, "decoder_create: prefix_size %d must be a multiple of 64", w->prefix_size);
+  return decoder_build(out, w->wte, w->wpe, w->lnf_w, w->lnf_b, w->prefix_w, w->prefix_b, w->prefix_size, w->blk, 4, 4, 32, mode,
+                       stream);
+}
+
+int pio_decoder_create_gpt2(PioDecoder** out, const PioGpt2Weights* w, int mode, void* stream) {
+  using namespace pio;
+  PIO_CHECK(out && w && w->blk, "decoder_create_gpt2: null argument");
+  PIO_CHECK(mode == PIO_FP32 || mode == PIO_BF16, "decoder_create_gpt2: unknown mode %d", mode);
+  PIO_CHECK(w->n_layer >= 1 && w->n_layer <= 48, "decoder_create_gpt2: n_layer %d outside [1,48]", w->n_layer);
+  PIO_CHECK(w->n_head == 12, "decoder_create_gpt2: n_head %d (only 12 heads x 64 are built)", w->n_head);
+  return decoder_build(out, w->wte, w->wpe, w->lnf_w, w->lnf_b, nullptr, nullptr, 0, w->blk, w->n_layer, w->n_head, 128, mode, stream);
+}
+
 void pio_decoder_destroy(PioDecoder* h) {
   if (!h) return;
   for (void* p : h->owned) cudaFree(p);
   delete h;
 }
 
-size_t pio_decode_workspace_bytes(const PioDecoder* h, int R, int steps) {
+namespace {
+struct DecodeWs {
+  float* x; void* hb; void* qkv; void* f; float* logits; char* kc; char* vc; void* pfx; size_t kv_layer, total;
+};
+// carve the decode workspace for R rows and a KV cache of T positions (same layout for sizing and for use)
+DecodeWs decode_ws(const PioDecoder* h, char* base, int R, int T, size_t tail_elems) {
   using namespace pio;
-  (void)steps;
   const size_t e = h->act_dt == PIO_DT_F32 ? 4 : 2;
-  return align_up((size_t)R * gD * 4, 1024) /*x*/ + align_up((size_t)R * gD * e, 1024) /*h*/ +
-         align_up((size_t)R * 3 * gD * e, 1024) /*qkv*/ + align_up((size_t)R * gFF * e, 1024) /*f*/ +
-         align_up((size_t)R * gVld * 4, 1024) /*logits*/ + 2 * align_up((size_t)gL * R * gH * gT * (gD / gH) * e, 1024) /*kv*/ +
-         align_up((size_t)R * h->prefix_size * e, 1024) + 4096;
+  DecodeWs w;
+  char* ws = base;
+  w.kv_layer = (size_t)R * T * gD * e;
+  w.x = (float*)ws;      ws += align_up((size_t)R * gD * 4, 1024);
+  w.hb = ws;             ws += align_up((size_t)R * gD * e, 1024);
+  w.qkv = ws;            ws += align_up((size_t)R * 3 * gD * e, 1024);
+  w.f = ws;              ws += align_up((size_t)R * gFF * e, 1024);
+  w.logits = (float*)ws; ws += align_up((size_t)R * gVld * 4, 1024);
+  w.kc = ws;             ws += align_up(h->L * w.kv_layer, 1024);
+  w.vc = ws;             ws += align_up(h->L * w.kv_layer, 1024);
+  w.pfx = ws;            ws += align_up(tail_elems * e, 1024);
+  w.total = (size_t)(ws - base) + 4096;
+  return w;
+}
+
+// all transformer blocks for the single new position t (KV cache of T positions per head)
+int decode_blocks(PioDecoder* h, const DecodeWs& w, int R, int T, int t, cudaStream_t st) {
+  using namespace pio;
+  const int adt = h->act_dt, mode = h->mode;
+  float* x = w.x;
+  for (int i = 0; i < h->L; ++i) {
+    const PioDecoder::Blk& b = h->blk[i];
+    PIO_TRY(layernorm(x, gD, b.ln1_w, b.ln1_b, w.hb, adt, gD, R, gD, 1e-5f, st));
+    PIO_TRY(linear(mode, w.hb, b.attn_w, w.qkv, R, 3 * gD, gD, gD, gD, 3 * gD, adt, adt, b.attn_b, nullptr, PIO_ACT_NONE, st));
+    PIO_TRY(decode_attention(w.qkv, w.kc + i * w.kv_layer, w.vc + i * w.kv_layer, w.hb, adt, R, h->H, T, t, st));
+    PIO_TRY(linear(mode, w.hb, b.proj_w, x, R, gD, gD, gD, gD, gD, adt, PIO_DT_F32, b.proj_b, x, PIO_ACT_NONE, st));
+    PIO_TRY(layernorm(x, gD, b.ln2_w, b.ln2_b, w.hb, adt, gD, R, gD, 1e-5f, st));
+    PIO_TRY(linear(mode, w.hb, b.fc_w, w.f, R, gFF, gD, gD, gD, gFF, adt, adt, b.fc_b, nullptr, PIO_ACT_GELU_NEW, st));
+    PIO_TRY(linear(mode, w.f, b.fc2_w, x, R, gD, gFF, gFF, gFF, gD, adt, PIO_DT_F32, b.fc2_b, x, PIO_ACT_NONE, st));
+  }
+  return PIO_OK;
+}
+
+// ln_f + tied lm-head + greedy arg-max -> out_ids[:, col]
+int decode_pick(PioDecoder* h, const DecodeWs& w, int R, int* out_ids, int ids_ld, int col, float* out_logprob_sum, cudaStream_t st) {
+  using namespace pio;
+  const int adt = h->act_dt, mode = h->mode;
+  PIO_TRY(layernorm(w.x, gD, h->lnf_w, h->lnf_b, w.hb, adt, gD, R, gD, 1e-5f, st));
+  if (mode == PIO_BF16) {
+    // lm_head with the arg-max fused in the epilogue: the R x 50257 logits are never materialised
+    const int slabs = argmax_slabs_tc(R, gV);
+    float* av = w.logits;
+    int* ai = (int*)(w.logits + (size_t)R * slabs);
+    float* as = w.logits + 2 * (size_t)R * slabs;
+    PioLinear p;
+    memset(&p, 0, sizeof(p));
+    p.A = w.hb; p.W = h->wte; p.C = nullptr; p.M = R; p.N = gV; p.K = gD; p.lda = gD; p.ldw = gD; p.ldc = gVld;
+    p.a_dt = adt; p.c_dt = PIO_DT_F32; p.alpha = 1.0f;
+    p.argmax_val = av; p.argmax_idx = ai; p.argmax_sumexp = out_logprob_sum ? as : nullptr; p.argmax_ld = slabs;  // sum exp only for scores
+    PIO_TRY(linear_tc(p, st));
+    launch_pdl(argmax_finish_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, av, ai, as, slabs, slabs, R, out_ids, ids_ld, col,
+               out_logprob_sum);
+    PIO_LAUNCHED();
+  } else {
+    PIO_TRY(linear(mode, w.hb, h->wte, w.logits, R, gV, gD, gD, gD, gVld, adt, PIO_DT_F32, nullptr, nullptr, PIO_ACT_NONE, st));
+    argmax_rows_kernel<<<R, 256, 0, st>>>(w.logits, gVld, gV, out_ids, ids_ld, col, out_logprob_sum);
+    PIO_LAUNCHED();
+  }
+  return PIO_OK;
+}
+}  // namespace
+
+size_t pio_decode_workspace_bytes(const PioDecoder* h, int R, int steps) {
+  (void)steps;
+  return decode_ws(h, nullptr, R, h->T, (size_t)R * h->prefix_size).total;
 }
 
 int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int* out_ids, float* out_logprob_sum,
@@ -685,71 +788,235 @@ int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int*
   using namespace pio;
   if (R == 0) return PIO_OK;
   PIO_CHECK(h && prefix && out_ids && workspace, "decode_greedy: null argument");
-  PIO_CHECK(steps >= 1 && steps <= gT, "decode_greedy: steps %d outside [1,%d]", steps, gT);
+  PIO_CHECK(h->prefix_w, "decode_greedy: this decoder has no prefix projection (use pio_decode_greedy_prompt)");
+  PIO_CHECK(steps >= 1 && steps <= h->T, "decode_greedy: steps %d outside [1,%d]", steps, h->T);
   PIO_CHECK(workspace_bytes >= pio_decode_workspace_bytes(h, R, steps), "decode_greedy: workspace too small");
   PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "decode_greedy: workspace must be 1024-byte aligned");
-  if (R == 0) return PIO_OK;
   cudaStream_t st = as_stream(stream);
-  const int adt = h->act_dt, mode = h->mode;
-  const size_t e = adt == PIO_DT_F32 ? 4 : 2;
-  const size_t kv_layer = (size_t)R * gH * gT * (gD / gH) * e;
-  char* ws = (char*)workspace;
-  float* x = (float*)ws;      ws += align_up((size_t)R * gD * 4, 1024);
-  void* hb = ws;              ws += align_up((size_t)R * gD * e, 1024);
-  void* qkv = ws;             ws += align_up((size_t)R * 3 * gD * e, 1024);
-  void* f = ws;               ws += align_up((size_t)R * gFF * e, 1024);
-  float* logits = (float*)ws; ws += align_up((size_t)R * gVld * 4, 1024);
-  char* kc = ws;              ws += align_up(gL * kv_layer, 1024);
-  char* vc = ws;              ws += align_up(gL * kv_layer, 1024);
-  void* pfx = ws;
+  const int adt = h->act_dt, mode = h->mode, T = h->T;
+  const DecodeWs w = decode_ws(h, (char*)workspace, R, T, (size_t)R * h->prefix_size);
 
   // prefix embedding at position 0: clip_project(feats) + wpe[0]   (decap.py:124; GPT-2 adds wpe)
   const void* pA = prefix;
-  if (adt != PIO_DT_F32) { PIO_TRY(f32_to_bf16(prefix, (__nv_bfloat16*)pfx, (long long)R * h->prefix_size, st)); pA = pfx; }
-  PIO_TRY(linear(mode, pA, h->prefix_w, x, R, gD, h->prefix_size, h->prefix_size, h->prefix_size, gD, adt, PIO_DT_F32,
+  if (adt != PIO_DT_F32) { PIO_TRY(f32_to_bf16(prefix, (__nv_bfloat16*)w.pfx, (long long)R * h->prefix_size, st)); pA = w.pfx; }
+  PIO_TRY(linear(mode, pA, h->prefix_w, w.x, R, gD, h->prefix_size, h->prefix_size, h->prefix_size, gD, adt, PIO_DT_F32,
                  h->prefix_b0, nullptr, PIO_ACT_NONE, st));
   if (out_logprob_sum) PIO_CUDA(cudaMemsetAsync(out_logprob_sum, 0, (size_t)R * 4, st));
 
   for (int t = 0; t < steps; ++t) {
-    for (int i = 0; i < gL; ++i) {
-      const PioDecoder::Blk& w = h->blk[i];
-      PIO_TRY(layernorm(x, gD, w.ln1_w, w.ln1_b, hb, adt, gD, R, gD, 1e-5f, st));
-      PIO_TRY(linear(mode, hb, w.attn_w, qkv, R, 3 * gD, gD, gD, gD, 3 * gD, adt, adt, w.attn_b, nullptr, PIO_ACT_NONE, st));
-      PIO_TRY(decode_attention(qkv, kc + i * kv_layer, vc + i * kv_layer, hb, adt, R, gH, gT, t, st));
-      PIO_TRY(linear(mode, hb, w.proj_w, x, R, gD, gD, gD, gD, gD, adt, PIO_DT_F32, w.proj_b, x, PIO_ACT_NONE, st));
-      PIO_TRY(layernorm(x, gD, w.ln2_w, w.ln2_b, hb, adt, gD, R, gD, 1e-5f, st));
-      PIO_TRY(linear(mode, hb, w.fc_w, f, R, gFF, gD, gD, gD, gFF, adt, adt, w.fc_b, nullptr, PIO_ACT_GELU_NEW, st));
-      PIO_TRY(linear(mode, f, w.fc2_w, x, R, gD, gFF, gFF, gFF, gD, adt, PIO_DT_F32, w.fc2_b, x, PIO_ACT_NONE, st));
-    }
-    PIO_TRY(layernorm(x, gD, h->lnf_w, h->lnf_b, hb, adt, gD, R, gD, 1e-5f, st));
-    if (mode == PIO_BF16) {
-      // lm_head with the arg-max fused in the epilogue: the R x 50257 logits are never materialised
-      const int slabs = argmax_slabs_tc(R, gV);
-      float* av = logits;
-      int* ai = (int*)(logits + (size_t)R * slabs);
-      float* as = logits + 2 * (size_t)R * slabs;
-      PioLinear p;
-      memset(&p, 0, sizeof(p));
-      p.A = hb; p.W = h->wte; p.C = nullptr; p.M = R; p.N = gV; p.K = gD; p.lda = gD; p.ldw = gD; p.ldc = gVld;
-      p.a_dt = adt; p.c_dt = PIO_DT_F32; p.alpha = 1.0f;
-      p.argmax_val = av; p.argmax_idx = ai; p.argmax_sumexp = out_logprob_sum ? as : nullptr; p.argmax_ld = slabs;  // sum exp only for scores
-      PIO_TRY(linear_tc(p, st));
-      launch_pdl(argmax_finish_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, av, ai, as, slabs, slabs, R, out_ids, steps, t,
-                 out_logprob_sum);
-      PIO_LAUNCHED();
-    } else {
-      PIO_TRY(linear(mode, hb, h->wte, logits, R, gV, gD, gD, gD, gVld, adt, PIO_DT_F32, nullptr, nullptr, PIO_ACT_NONE, st));
-      argmax_rows_kernel<<<R, 256, 0, st>>>(logits, gVld, gV, out_ids, steps, t, out_logprob_sum);
-      PIO_LAUNCHED();
-    }
+    PIO_TRY(decode_blocks(h, w, R, T, t, st));
+    PIO_TRY(decode_pick(h, w, R, out_ids, steps, t, out_logprob_sum, st));
     if (t + 1 < steps) {
-      launch_pdl(embed_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, h->wte32, h->wpe, out_ids, steps, t, t + 1, x, R, gD);
+      launch_pdl(embed_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, h->wte32, h->wpe, (const int*)out_ids, steps, t, t + 1,
+                 w.x, R, gD);
       PIO_LAUNCHED();
     }
   }
   return PIO_OK;
 }
 
+size_t pio_decode_prompt_workspace_bytes(const PioDecoder* h, int R, int prompt_len, int steps) {
+  return decode_ws(h, nullptr, R, prompt_len + steps - 1, 0).total;
+}
+
+// Greedy continuation of a prompt of P input embeddings per row (ViECap: soft + hard prompt; viecap/search.py:108-191).
+// The prompt is consumed one position at a time through the same single-position blocks as the generation steps.
+int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prompt_len, int steps, int* out_ids,
+                             float* out_logprob_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace pio;
+  if (R == 0) return PIO_OK;
+  PIO_CHECK(h && prompt && out_ids && workspace, "decode_greedy_prompt: null argument");
+  const int T = prompt_len + steps - 1;
+  PIO_CHECK(prompt_len >= 1 && steps >= 1 && T <= h->T, "decode_greedy_prompt: %d prompt + %d new positions exceed the cache of %d",
+            prompt_len, steps, h->T);
+  PIO_CHECK(workspace_bytes >= pio_decode_prompt_workspace_bytes(h, R, prompt_len, steps), "decode_greedy_prompt: workspace too small");
+  PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "decode_greedy_prompt: workspace must be 1024-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const DecodeWs w = decode_ws(h, (char*)workspace, R, T, 0);
+  if (out_logprob_sum) PIO_CUDA(cudaMemsetAsync(out_logprob_sum, 0, (size_t)R * 4, st));
+  for (int p = 0; p < prompt_len; ++p) {
+    prompt_embed_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(prompt, prompt_len, p, h->wpe, w.x, R, gD);
+    PIO_LAUNCHED();
+    PIO_TRY(decode_blocks(h, w, R, T, p, st));
+  }
+  for (int s = 0; s < steps; ++s) {
+    PIO_TRY(decode_pick(h, w, R, out_ids, steps, s, out_logprob_sum, st));
+    if (s + 1 < steps) {
+      launch_pdl(embed_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, h->wte32, h->wpe, (const int*)out_ids, steps, s,
+                 prompt_len + s, w.x, R, gD);
+      PIO_LAUNCHED();
+      PIO_TRY(decode_blocks(h, w, R, T, prompt_len + s, st));
+    }
+  }
+  return PIO_OK;
+}
+
+}  // extern "C"
+
+// ==========================================================================================
+// ViECap mapping network (viecap/ClipCap.py:122-153): Linear(clip -> project_len x 768) tokens + prefix_len learnt tokens
+// -> n_layer pre-LN transformer layers (q / kv projections without bias, ReLU MLP) -> the prefix_len last tokens.
+struct PioMapper {
+  int mode, act_dt, clip, plen, clen, L, H, hidden, n;  // n = plen + clen tokens per region
+  std::vector<void*> owned;
+  const void* lin_w; const float *lin_b, *prefix_const;
+  struct Layer {
+    const float *n1_w, *n1_b, *proj_b, *n2_w, *n2_b, *fc1_b, *fc2_b;
+    const void *qkv_w /*[3*768,768]: q | k | v*/, *proj_w, *fc1_w, *fc2_w;
+  };
+  std::vector<Layer> layers;
+};
+
+namespace pio {
+namespace {
+int m_f32(PioMapper* h, const float** dst, const float* src, size_t n, cudaStream_t st) {
+  void* p;
+  PIO_CUDA(cudaMalloc(&p, n * 4));
+  h->owned.push_back(p);
+  PIO_CUDA(cudaMemcpyAsync(p, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  *dst = (const float*)p;
+  return PIO_OK;
+}
+// [rows, cols] fp32 -> act dtype at dst (+ row offset), dst allocated by the caller
+int m_conv(PioMapper* h, void* dst, size_t elem_off, const float* src, size_t n, cudaStream_t st) {
+  if (h->act_dt == PIO_DT_F32) PIO_CUDA(cudaMemcpyAsync((float*)dst + elem_off, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  else PIO_TRY(f32_to_bf16(src, (__nv_bfloat16*)dst + elem_off, (long long)n, st));
+  return PIO_OK;
+}
+int m_mat(PioMapper* h, const void** dst, const float* src, size_t n, cudaStream_t st) {
+  void* p;
+  PIO_CUDA(cudaMalloc(&p, n * (h->act_dt == PIO_DT_F32 ? 4 : 2)));
+  h->owned.push_back(p);
+  PIO_TRY(m_conv(h, p, 0, src, n, st));
+  *dst = p;
+  return PIO_OK;
+}
+
+// x[r, clen + i, :] = prefix_const[i, :]
+__global__ void mapper_prefix_kernel(const float* __restrict__ pc, float* __restrict__ x, int R, int n, int clen, int plen, int D) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, per = (long long)plen * D / 4;
+  if (i >= (long long)R * per) return;
+  const long long r = i / per, o = i % per;
+  reinterpret_cast<float4*>(x + (r * n + clen) * D)[o] = __ldg(reinterpret_cast<const float4*>(pc) + o);
+}
+template <typename T>
+__global__ void relu_kernel(T* __restrict__ x, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = (float)x[i] > 0.f ? x[i] : (T)0.f;
+}
+}  // namespace
+}  // namespace pio
+
+extern "C" {
+void pio_mapper_destroy(PioMapper* h) {
+  if (!h) return;
+  for (void* p : h->owned) cudaFree(p);
+  delete h;
+}
+
+int pio_mapper_create(PioMapper** out, const PioMapperWeights* w, int mode, void* stream) {
+  using namespace pio;
+  PIO_CHECK(out && w && w->layers, "mapper_create: null argument");
+  PIO_CHECK(mode == PIO_FP32 || mode == PIO_BF16, "mapper_create: unknown mode %d", mode);
+  PIO_CHECK(w->clip_size > 0 && w->clip_size % 64 == 0, "mapper_create: clip_size %d must be a multiple of 64", w->clip_size);
+  PIO_CHECK(w->n_head > 0 && gD % w->n_head == 0 && gD / w->n_head <= 128, "mapper_create: %d heads do not divide 768", w->n_head);
+  PIO_CHECK(w->project_len >= 1 && w->prefix_len >= 1 && w->project_len + w->prefix_len <= 64, "mapper_create: %d + %d tokens (max 64)",
+            w->project_len, w->prefix_len);
+  PIO_CHECK(w->hidden > 0 && w->hidden % 64 == 0, "mapper_create: mlp hidden size %d must be a multiple of 64", w->hidden);
+  cudaStream_t st = as_stream(stream);
+  PioMapper* h = new PioMapper();
+  h->mode = mode; h->act_dt = mode == PIO_FP32 ? PIO_DT_F32 : PIO_DT_BF16;
+  h->clip = w->clip_size; h->clen = w->project_len; h->plen = w->prefix_len; h->L = w->n_layer; h->H = w->n_head; h->hidden = w->hidden;
+  h->n = h->clen + h->plen;
+  h->layers.resize(h->L);
+  const size_t e = h->act_dt == PIO_DT_F32 ? 4 : 2;
+  auto go = [&]() -> int {
+    PIO_TRY(m_mat(h, &h->lin_w, w->linear_w, (size_t)h->clen * gD * h->clip, st));
+    PIO_TRY(m_f32(h, &h->lin_b, w->linear_b, (size_t)h->clen * gD, st));
+    PIO_TRY(m_f32(h, &h->prefix_const, w->prefix_const, (size_t)h->plen * gD, st));
+    for (int i = 0; i < h->L; ++i) {
+      const PioMapperLayer& s = w->layers[i];
+      PioMapper::Layer& d = h->layers[i];
+      PIO_TRY(m_f32(h, &d.n1_w, s.norm1_w, gD, st)); PIO_TRY(m_f32(h, &d.n1_b, s.norm1_b, gD, st));
+      PIO_TRY(m_f32(h, &d.n2_w, s.norm2_w, gD, st)); PIO_TRY(m_f32(h, &d.n2_b, s.norm2_b, gD, st));
+      PIO_TRY(m_f32(h, &d.proj_b, s.proj_b, gD, st));
+      PIO_TRY(m_f32(h, &d.fc1_b, s.fc1_b, h->hidden, st)); PIO_TRY(m_f32(h, &d.fc2_b, s.fc2_b, gD, st));
+      void* qkv;
+      PIO_CUDA(cudaMalloc(&qkv, (size_t)3 * gD * gD * e));
+      h->owned.push_back(qkv);
+      PIO_TRY(m_conv(h, qkv, 0, s.q_w, (size_t)gD * gD, st));                       // to_queries      [768,768]
+      PIO_TRY(m_conv(h, qkv, (size_t)gD * gD, s.kv_w, (size_t)2 * gD * gD, st));     // to_keys_values [1536,768]: keys | values
+      d.qkv_w = qkv;
+      PIO_TRY(m_mat(h, &d.proj_w, s.proj_w, (size_t)gD * gD, st));
+      PIO_TRY(m_mat(h, &d.fc1_w, s.fc1_w, (size_t)h->hidden * gD, st));
+      PIO_TRY(m_mat(h, &d.fc2_w, s.fc2_w, (size_t)gD * h->hidden, st));
+    }
+    return PIO_OK;
+  };
+  int rc = go();
+  if (rc != PIO_OK) { pio_mapper_destroy(h); return rc; }
+  *out = h;
+  return PIO_OK;
+}
+
+size_t pio_mapper_workspace_bytes(const PioMapper* h, int R) {
+  using namespace pio;
+  const size_t e = h->act_dt == PIO_DT_F32 ? 4 : 2, rows = (size_t)R * h->n;
+  return align_up(rows * gD * 4, 1024) /*x*/ + align_up(rows * gD * e, 1024) /*h*/ + align_up(rows * 3 * gD * e, 1024) /*qkv*/ +
+         align_up(rows * h->hidden * e, 1024) /*f*/ + align_up((size_t)R * h->clip * e, 1024) + 4096;
+}
+
+// feats fp32 [R, clip_size] (already L2-normalised by the caller, entrypoint.py:108) -> out fp32 [R, prefix_len, 768]
+int pio_mapper_forward(PioMapper* h, const float* feats, int R, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace pio;
+  if (R == 0) return PIO_OK;
+  PIO_CHECK(h && feats && out && workspace, "mapper_forward: null argument");
+  PIO_CHECK(workspace_bytes >= pio_mapper_workspace_bytes(h, R), "mapper_forward: workspace too small");
+  PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "mapper_forward: workspace must be 1024-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int adt = h->act_dt, mode = h->mode, n = h->n, rows = R * n, hd = gD / h->H;
+  const size_t e = adt == PIO_DT_F32 ? 4 : 2;
+  char* ws = (char*)workspace;
+  float* x = (float*)ws; ws += align_up((size_t)rows * gD * 4, 1024);
+  void* hb = ws;         ws += align_up((size_t)rows * gD * e, 1024);
+  char* qkv = ws;        ws += align_up((size_t)rows * 3 * gD * e, 1024);
+  void* f = ws;          ws += align_up((size_t)rows * h->hidden * e, 1024);
+  void* fin = ws;
+
+  const void* pA = feats;
+  if (adt != PIO_DT_F32) { PIO_TRY(f32_to_bf16(feats, (__nv_bfloat16*)fin, (long long)R * h->clip, st)); pA = fin; }
+  // tokens 0..clen-1 of every region: one GEMM whose output rows are n*768 floats apart
+  PIO_TRY(linear(mode, pA, h->lin_w, x, R, h->clen * gD, h->clip, h->clip, h->clip, n * gD, adt, PIO_DT_F32, h->lin_b, nullptr,
+                 PIO_ACT_NONE, st));
+  {
+    const long long tot = (long long)R * h->plen * gD / 4;
+    mapper_prefix_kernel<<<cdiv(tot, 256), 256, 0, st>>>(h->prefix_const, x, R, n, h->clen, h->plen, gD);
+    PIO_LAUNCHED();
+  }
+  for (int i = 0; i < h->L; ++i) {
+    const PioMapper::Layer& w = h->layers[i];
+    PIO_TRY(layernorm(x, gD, w.n1_w, w.n1_b, hb, adt, gD, rows, gD, 1e-5f, st));
+    PIO_TRY(linear(mode, hb, w.qkv_w, qkv, rows, 3 * gD, gD, gD, gD, 3 * gD, adt, adt, nullptr, nullptr, PIO_ACT_NONE, st));
+    PIO_TRY(small_attention(qkv, 3 * gD, qkv + (size_t)gD * e, 3 * gD, hb, gD, adt, R, n, h->H, hd, st));
+    PIO_TRY(linear(mode, hb, w.proj_w, x, rows, gD, gD, gD, gD, gD, adt, PIO_DT_F32, w.proj_b, x, PIO_ACT_NONE, st));
+    PIO_TRY(layernorm(x, gD, w.n2_w, w.n2_b, hb, adt, gD, rows, gD, 1e-5f, st));
+    PIO_TRY(linear(mode, hb, w.fc1_w, f, rows, h->hidden, gD, gD, gD, h->hidden, adt, adt, w.fc1_b, nullptr, PIO_ACT_NONE, st));
+    {
+      const long long tot = (long long)rows * h->hidden;
+      if (adt == PIO_DT_F32) relu_kernel<float><<<cdiv(tot, 256), 256, 0, st>>>((float*)f, tot);
+      else relu_kernel<__nv_bfloat16><<<cdiv(tot, 256), 256, 0, st>>>((__nv_bfloat16*)f, tot);
+      PIO_LAUNCHED();
+    }
+    PIO_TRY(linear(mode, f, w.fc2_w, x, rows, gD, h->hidden, h->hidden, h->hidden, gD, adt, PIO_DT_F32, w.fc2_b, x, PIO_ACT_NONE, st));
+  }
+  // keep the last prefix_len tokens of every region (ClipCap.py:151)
+  PIO_CUDA(cudaMemcpy2DAsync(out, (size_t)h->plen * gD * 4, x + (size_t)h->clen * gD, (size_t)n * gD * 4, (size_t)h->plen * gD * 4, R,
+                             cudaMemcpyDeviceToDevice, st));
+  return PIO_OK;
+}
+}  // extern "C"
+
+extern "C" {
 int pio_argmax_slabs(int M, int N) { return pio::argmax_slabs_tc(M, N); }
 
 int pio_argmax_finish(const float* val, const int* idx, const float* sumexp, int ld, int slabs, int M, int* ids, int ids_ld,
@@ -762,4 +1029,74 @@ int pio_argmax_finish(const float* val, const int* idx, const float* sumexp, int
   PIO_LAUNCHED();
   return PIO_OK;
 }
+}
+
+namespace pio {
+namespace {
+// one CTA per query row: sims -> shared memory, then warp 0 does the softmax and k rounds of arg-max
+__global__ void __launch_bounds__(256) entity_topk_kernel(const float* __restrict__ q, const float* __restrict__ ent, int E, int D,
+                                                          float inv_temp, int k, float* __restrict__ out_prob, int* __restrict__ out_idx) {
+  extern __shared__ float sm_e[];
+  float* qs = sm_e;       // [D]
+  float* sims = qs + D;   // [E]
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int d = tid; d < D; d += 256) qs[d] = q[(long long)r * D + d];
+  __syncthreads();
+  for (int e = warp; e < E; e += 8) {
+    const float* er = ent + (long long)e * D;
+    float a = 0.f;
+    for (int d = lane; d < D; d += 32) a = fmaf(qs[d], __ldg(er + d), a);
+    a = warp_sum(a);
+    if (lane == 0) sims[e] = a * inv_temp;
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  float mx = -INFINITY;
+  for (int e = lane; e < E; e += 32) mx = fmaxf(mx, sims[e]);
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int e = lane; e < E; e += 32) {
+    const float p = expf(sims[e] - mx);
+    sims[e] = p;
+    s += p;
+  }
+  s = warp_sum(s);
+  __syncwarp();
+  const float inv = 1.0f / s;
+  for (int j = 0; j < k; ++j) {
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+    for (int e = lane; e < E; e += 32) {
+      const float p = sims[e];
+      if (p > bv) { bv = p; bi = e; }  // ascending e per lane: first index wins
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
+      out_prob[(long long)r * k + j] = bi < E ? bv * inv : 0.f;
+      out_idx[(long long)r * k + j] = bi < E ? bi : 0;
+      if (bi < E) sims[bi] = -1.f;
+    }
+    __syncwarp();
+  }
+}
+}  // namespace
+}  // namespace pio
+
+extern "C" int pio_entity_topk(const float* q, const float* ent, int R, int n_ent, int D, float temperature, int k, float* out_prob,
+                               int* out_idx, void* stream) {
+  using namespace pio;
+  if (R == 0) return PIO_OK;
+  PIO_CHECK(q && ent && out_prob && out_idx, "entity_topk: null argument");
+  PIO_CHECK(n_ent >= 1 && n_ent <= 8192 && D >= 1 && D <= 2048, "entity_topk: %d entities x %d dims outside (<=8192, <=2048)", n_ent, D);
+  PIO_CHECK(k >= 1 && k <= 32 && k <= n_ent, "entity_topk: k %d outside [1, min(32, n_ent)]", k);
+  PIO_CHECK(temperature > 0.f, "entity_topk: temperature must be positive");
+  const size_t smem = (size_t)(D + n_ent) * sizeof(float);
+  entity_topk_kernel<<<R, 256, smem, as_stream(stream)>>>(q, ent, n_ent, D, 1.0f / temperature, k, out_prob, out_idx);
+  PIO_LAUNCHED();
+  return PIO_OK;
 }

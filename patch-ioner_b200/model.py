@@ -64,7 +64,9 @@ class Patchioner:
                  alphaclip_config=None, clipcap_config=None, hf_repo_id=None,
                  # extensions (no network in this image: weights are given as files / state dicts)
                  dino_weights=None, memory_bank=None, memory_bank_texts=None, precision="fp32", **kwargs):
-        for name, val in (("proxyclip_clipmodel", proxyclip_clipmodel), ("viecap", viecap_config),
+        if viecap_config is not None and viecap_config.get("meacap", False):
+            raise NotImplementedError("viecap.meacap selects MeaCap (model.py:108-110): outside the B200 hot path")
+        for name, val in (("proxyclip_clipmodel", proxyclip_clipmodel),
                           ("regionclip_config", regionclip_config), ("invite_config", invite_config),
                           ("denseclip_config", denseclip_config), ("alphaclip_config", alphaclip_config),
                           ("clipcap", clipcap_config)):
@@ -113,11 +115,17 @@ class Patchioner:
         # --- decoder (model.py:165-166 -> decap.py:188-222)
         if isinstance(decoder_weights, str):
             decoder_weights = torch.load(decoder_weights, map_location="cpu", weights_only=False)
-        if decoder_weights is None:
+        if viecap_config is not None:
+            # model.py:107-113: the ViECap captioner replaces the DeCap decode in caption_tokens (model.py:1394-1398)
+            from .viecap import VieCap
+            self.viecap = VieCap(viecap_config, self.device, clip_model_name, precision=precision)
+        self.decoder = None
+        if decoder_weights is None and self.viecap is None:
             raise ValueError("decap_weights is required")
-        self.decoder = ops.Decoder(decoder_weights, self.device, precision)
-        if self.decoder.prefix_size != prefix_size:
-            raise ValueError(f"prefix_size {prefix_size} != clip_project input {self.decoder.prefix_size}")
+        if decoder_weights is not None:
+            self.decoder = ops.Decoder(decoder_weights, self.device, precision)
+            if self.decoder.prefix_size != prefix_size:
+                raise ValueError(f"prefix_size {prefix_size} != clip_project input {self.decoder.prefix_size}")
 
         # --- caption memory (model.py:144-186).  support_memory_size == 0 -> CapDec, no bank.
         self.im_proj = None
@@ -285,6 +293,10 @@ class Patchioner:
 
     def caption_tokens(self, dino_tokens, project=True, return_n_best_sims=None, compute_scores: bool = False):
         """model.py:1392-1423."""
+        if self.viecap is not None:  # model.py:1394-1398
+            if return_n_best_sims:
+                raise Exception("return_n_best_sims is not supported with viecap")
+            return self.viecap.forward(dino_tokens.reshape(-1, dino_tokens.shape[-1]), compute_scores=compute_scores)
         if self.calculate_argmax_text:
             # model.py:1408-1411 -> im2txtprojection.py:371-375: the caption is the text of the most similar bank row
             feats = dino_tokens.reshape(-1, dino_tokens.shape[-1])
@@ -390,7 +402,7 @@ class Patchioner:
                 if compute_scores:
                     outs[{"bbox_capts": "bbox_scores"}.get(key, key + "_scores")] = [[] for _ in range(bs)]
                 return None
-            if self.calculate_argmax_text:
+            if self.calculate_argmax_text or self.viecap is not None:
                 return emit_texts(key, feats, group)
             if return_n_best_sims is not None and key == "bbox_capts":
                 self.caption_tokens(feats[:0], return_n_best_sims=return_n_best_sims)  # raises like the reference's decoder path

@@ -477,3 +477,126 @@ class Decoder:
         L.check(L.lib().pio_decode_greedy(self._h, prefix.data_ptr(), R, steps, ids.data_ptr(), _ptr(lp), ws.data_ptr(),
                                           nbytes, _stream()))
         return (ids, lp) if compute_scores else ids
+
+
+_GPT_NAMES = {"ln1_w": "ln_1.weight", "ln1_b": "ln_1.bias", "attn_w": "attn.c_attn.weight", "attn_b": "attn.c_attn.bias",
+              "proj_w": "attn.c_proj.weight", "proj_b": "attn.c_proj.bias", "ln2_w": "ln_2.weight", "ln2_b": "ln_2.bias",
+              "fc_w": "mlp.c_fc.weight", "fc_b": "mlp.c_fc.bias", "fc2_w": "mlp.c_proj.weight", "fc2_b": "mlp.c_proj.bias"}
+
+
+class Gpt2Decoder:
+    """GPT-2 (12 heads x 64, any depth) that continues a prompt of input embeddings greedily: the language model of the
+    ViECap captioner (viecap/ClipCap.py:157, search.py:108-191).  Weights by `GPT2LMHeadModel` state-dict key names
+    under `prefix` (ViECap checkpoints: 'gpt.transformer.')."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, mode: str = "fp32", prefix: str = "gpt.transformer."):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.PioError("the decoder needs a CUDA device (there is no CPU fallback)")
+        self.mode = mode
+        T = prefix
+        sd = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items() if k.startswith(T)}
+        n_layer = 1 + max(int(k[len(T) + 2:].split(".")[0]) for k in sd if k.startswith(T + "h."))
+        blocks = (L.PioGptBlock * n_layer)()
+        for i in range(n_layer):
+            for f, n in _GPT_NAMES.items():
+                setattr(blocks[i], f, sd[f"{T}h.{i}.{n}"].data_ptr())
+        w = L.PioGpt2Weights()
+        w.wte, w.wpe = sd[T + "wte.weight"].data_ptr(), sd[T + "wpe.weight"].data_ptr()
+        w.lnf_w, w.lnf_b = sd[T + "ln_f.weight"].data_ptr(), sd[T + "ln_f.bias"].data_ptr()
+        w.blk, w.n_layer, w.n_head = blocks, n_layer, 12
+        self.wte = sd[T + "wte.weight"]  # fp32 [50257,768]: the hard-prompt tokens are embedded with it (word_embed)
+        self.n_layer = n_layer
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().pio_decoder_create_gpt2(C.byref(h), C.byref(w), MODES[mode], _stream()))
+            torch.cuda.current_stream().synchronize()
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.pio_decoder_destroy(h)
+            self._h = None
+
+    def decode(self, prompt: torch.Tensor, steps: int = 64, compute_scores: bool = False):
+        """prompt fp32 [R,P,768] input embeddings -> int32 ids [R,steps] (+ sum of log-probs [R])."""
+        _need_cuda(prompt)
+        prompt = prompt.float().contiguous()
+        R, P, D = prompt.shape
+        assert D == 768
+        ids = torch.empty(R, steps, dtype=torch.int32, device=prompt.device)
+        lp = torch.empty(R, dtype=torch.float32, device=prompt.device) if compute_scores else None
+        nbytes = L.lib().pio_decode_prompt_workspace_bytes(self._h, R, P, steps)
+        ws = workspace(nbytes, prompt.device, "decode_prompt")
+        L.check(L.lib().pio_decode_greedy_prompt(self._h, prompt.data_ptr(), R, P, steps, ids.data_ptr(), _ptr(lp),
+                                                 ws.data_ptr(), nbytes, _stream()))
+        return (ids, lp) if compute_scores else ids
+
+
+class Mapper:
+    """ViECap mapping network (viecap/ClipCap.py:122-153); weights by the reference's key names under `prefix`."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, mode: str = "fp32", prefix: str = "mapping_network.",
+                 n_head: int = 8):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise L.PioError("the mapping network needs a CUDA device (there is no CPU fallback)")
+        T = prefix
+        sd = {k: v.detach().to(self.device, torch.float32).contiguous() for k, v in state_dict.items() if k.startswith(T)}
+        LT = T + "transformer.layers."
+        n_layer = 1 + max(int(k[len(LT):].split(".")[0]) for k in sd if k.startswith(LT))
+        names = {"norm1_w": "norm1.weight", "norm1_b": "norm1.bias", "q_w": "attn.to_queries.weight",
+                 "kv_w": "attn.to_keys_values.weight", "proj_w": "attn.project.weight", "proj_b": "attn.project.bias",
+                 "norm2_w": "norm2.weight", "norm2_b": "norm2.bias", "fc1_w": "mlp.fc1.weight", "fc1_b": "mlp.fc1.bias",
+                 "fc2_w": "mlp.fc2.weight", "fc2_b": "mlp.fc2.bias"}
+        for i in range(n_layer):
+            if f"{LT}{i}.attn.to_queries.bias" in sd:
+                raise NotImplementedError("mapping network with biased q / kv projections (the reference builds bias=False)")
+        layers = (L.PioMapperLayer * n_layer)()
+        for i in range(n_layer):
+            for f, n in names.items():
+                setattr(layers[i], f, sd[f"{LT}{i}.{n}"].data_ptr())
+        w = L.PioMapperWeights()
+        lin_w, pc = sd[T + "linear.weight"], sd[T + "prefix_const"]
+        assert pc.shape[1] == 768 and lin_w.shape[0] % 768 == 0
+        self.clip_size = w.clip_size = lin_w.shape[1]
+        w.project_len = lin_w.shape[0] // 768
+        self.prefix_len = w.prefix_len = pc.shape[0]
+        w.n_layer, w.n_head, w.hidden = n_layer, n_head, sd[f"{LT}0.mlp.fc1.weight"].shape[0]
+        w.linear_w, w.linear_b, w.prefix_const, w.layers = lin_w.data_ptr(), sd[T + "linear.bias"].data_ptr(), pc.data_ptr(), layers
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().pio_mapper_create(C.byref(h), C.byref(w), MODES[mode], _stream()))
+            torch.cuda.current_stream().synchronize()
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h and L is not None and getattr(L, "_lib", None) is not None:
+            L._lib.pio_mapper_destroy(h)
+            self._h = None
+
+    def forward(self, feats: torch.Tensor) -> torch.Tensor:
+        """feats fp32 [R,clip_size] (unit rows) -> fp32 [R,prefix_len,768]."""
+        _need_cuda(feats)
+        feats = feats.float().contiguous()
+        R = feats.shape[0]
+        assert feats.shape[1] == self.clip_size
+        out = torch.empty(R, self.prefix_len, 768, dtype=torch.float32, device=feats.device)
+        nbytes = L.lib().pio_mapper_workspace_bytes(self._h, R)
+        ws = workspace(nbytes, feats.device, "mapper")
+        L.check(L.lib().pio_mapper_forward(self._h, feats.data_ptr(), R, out.data_ptr(), ws.data_ptr(), nbytes, _stream()))
+        return out
+
+
+def entity_topk(q: torch.Tensor, entities: torch.Tensor, temperature: float, k: int):
+    """softmax(q . E^T / temperature) and its k best entries per row (retrieval_categories.py:87-115); q, E unit rows."""
+    _need_cuda(q, entities)
+    q, entities = q.float().contiguous(), entities.float().contiguous()
+    R, D = q.shape
+    prob = torch.empty(R, k, dtype=torch.float32, device=q.device)
+    idx = torch.empty(R, k, dtype=torch.int32, device=q.device)
+    L.check(L.lib().pio_entity_topk(q.data_ptr(), entities.data_ptr(), R, entities.shape[0], D, float(temperature), k,
+                                    prob.data_ptr(), idx.data_ptr(), _stream()))
+    return prob, idx

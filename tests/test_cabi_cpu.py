@@ -63,7 +63,10 @@ def test_unsupported_backbones_raise(built):
 
     with pytest.raises(NotImplementedError):
         Patchioner.from_config({"prefix_size": 768, "support_memory_size": 0, "dino_model": "dinov2_vitb14_reg",
-                                "viecap": {"x": 1}}, device="cuda")
+                                "viecap": {"meacap": True}}, device="cuda")
+    with pytest.raises(NotImplementedError):
+        Patchioner.from_config({"prefix_size": 768, "support_memory_size": 0, "dino_model": "dinov2_vitb14_reg",
+                                "clipcap": {"x": 1}}, device="cuda")
     with pytest.raises(NotImplementedError):
         Patchioner.from_config({"prefix_size": 768, "support_memory_size": 0, "dino_model": "dinov2_vitl14"}, device="cuda")
 

@@ -1,0 +1,196 @@
+"""GPU (-m gpu): the ViECap captioner (mapping network, entity retrieval, prompt-continuing GPT-2 greedy decode) through
+the C ABI, against oracle/viecap.py and the reference outputs in tests/golden/viecap.pt."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import viecap as ov
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from patchioner_b200 import ops as _ops
+
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return ov.make_weights()
+
+
+def _unit(x):
+    return x / x.norm(dim=-1, keepdim=True)
+
+
+def test_mapper_against_oracle(dev, ops, weights):
+    g = torch.Generator().manual_seed(3)
+    feats = _unit(torch.randn(37, 768, generator=g))
+    ref = ov.mapping_network(weights, feats)
+    got = ops.Mapper(weights, dev, "fp32").forward(feats.to(dev)).cpu()
+    torch.testing.assert_close(got, ref, rtol=2e-4, atol=2e-4)
+    got16 = ops.Mapper(weights, dev, "bf16").forward(feats.to(dev)).cpu()
+    cos = torch.nn.functional.cosine_similarity(got16.reshape(-1, 768), ref.reshape(-1, 768), dim=-1)
+    assert cos.min() > 0.995, cos.min()
+    assert ops.Mapper(weights, dev, "fp32").forward(feats[:0].to(dev)).shape == (0, 10, 768)
+
+
+def test_entity_topk_against_oracle(dev, ops):
+    g = torch.Generator().manual_seed(5)
+    for E, R, k in ((12, 40, 3), (80, 300, 3), (1000, 64, 5), (3, 10, 3)):
+        ent = _unit(torch.randn(E, 768, generator=g))
+        q = _unit(torch.randn(R, 768, generator=g) + 3 * ent[torch.randint(0, E, (R,), generator=g)])
+        probs = ov.entity_probs(q, ent, 0.01)
+        rp, ri = torch.topk(probs, k, dim=-1)
+        p, i = ops.entity_topk(q.to(dev), ent.to(dev), 0.01, k)
+        torch.testing.assert_close(p.cpu(), rp, rtol=2e-3, atol=1e-5)
+        clear = (rp[:, :-1] - rp[:, 1:]).min(dim=1).values > 1e-4   # rows whose order is not a near-tie
+        assert torch.equal(i.cpu().long()[clear], ri[clear])
+    with pytest.raises(Exception, match="k 4"):
+        ops.entity_topk(q.to(dev), ent.to(dev), 0.01, 4)
+
+
+def _agree(ids, ref, margin, tol):
+    """rows equal up to the first step whose top-2 logit gap is below tol (a legitimate flip point)"""
+    ok = 0
+    for r in range(ref.shape[0]):
+        same = True
+        for t in range(ref.shape[1]):
+            if margin[r, t] < tol:
+                break
+            if ids[r, t] != ref[r, t]:
+                same = False
+                break
+        ok += same
+    return ok / ref.shape[0]
+
+
+@pytest.mark.parametrize("P,steps", [(1, 5), (14, 12), (33, 40)])
+def test_prompt_decode_fp32_against_oracle(dev, ops, weights, P, steps):
+    g = torch.Generator().manual_seed(P)
+    R = 7
+    prompt = torch.randn(R, P, 768, generator=g) * 0.3
+    ref, margin = ov.greedy_ids(weights, prompt, steps, return_margin=True)
+    dec = ops.Gpt2Decoder(weights, dev, "fp32")
+    ids = dec.decode(prompt.to(dev), steps).cpu().long()
+    assert _agree(ids, ref, margin, 1e-4) == 1.0
+    assert (ids == ref).all(dim=1).float().mean() >= 0.85
+    again = dec.decode(prompt.to(dev), steps).cpu().long()
+    assert torch.equal(ids, again)
+
+
+def test_prompt_decode_bf16_runs_and_mostly_agrees(dev, ops, weights):
+    g = torch.Generator().manual_seed(11)
+    R, P, steps = 64, 18, 16
+    prompt = torch.randn(R, P, 768, generator=g) * 0.3
+    ref, margin = ov.greedy_ids(weights, prompt, steps, return_margin=True)
+    ids = ops.Gpt2Decoder(weights, dev, "bf16").decode(prompt.to(dev), steps).cpu().long()
+    assert ids.min() >= 0 and ids.max() < 50257
+    assert (ids[:, 0] == ref[:, 0]).float().mean() >= 0.8   # bf16 flips near-ties; reported, not a parity claim
+
+
+def test_gpt2_small_depth_and_long_cache(dev, ops):
+    """12 layers (GPT-2 small), prompt + 64 tokens = 91 cache positions: runs, deterministic, fp32 == oracle on row 0."""
+    w = ov.make_weights(seed=77, n_layer_gpt=12, n_layer_map=1)
+    g = torch.Generator().manual_seed(1)
+    prompt = torch.randn(3, 28, 768, generator=g) * 0.3
+    dec = ops.Gpt2Decoder(w, dev, "fp32")
+    assert dec.n_layer == 12
+    ids = dec.decode(prompt.to(dev), 64).cpu().long()
+    ref, margin = ov.greedy_ids(w, prompt[:1], 64, return_margin=True)
+    assert _agree(ids[:1], ref, margin, 1e-4) == 1.0
+    ids16 = ops.Gpt2Decoder(w, dev, "bf16").decode(prompt.to(dev), 64).cpu().long()
+    assert ids16.shape == (3, 64) and ids16.min() >= 0 and ids16.max() < 50257
+
+
+def test_viecap_forward_against_reference_golden(dev, golden, weights):
+    """VieCap.forward through the library, fp32, against the sentences the reference's greedy_search produced."""
+    from patchioner_b200.viecap import VieCap
+
+    g = golden("viecap")
+    tok = ov.ToyTokenizer()
+    cfg = {"state_dict": weights, "entities_text": g["entities"], "texts_embeddings": g["ent_emb"], "tokenizer": tok,
+           "clip_hidden_size": 768, "temperature": 0.01, "top_k": 3, "threshold": 0.4, "using_hard_prompt": True,
+           "soft_prompt_first": True, "using_greedy_search": True}
+    vc = VieCap(cfg, dev, "ViT-B/16", precision="fp32")
+    feats = g["feats"].clone().to(dev)
+    assert [[g["entities"][i] for i in r] for r in vc.detect_entities(_unit(g["feats"]).to(dev))] == g["detected"]
+    assert torch.equal(vc.hard_prompt_tokens(_unit(g["feats"]).to(dev)).cpu().long(), g["hard"])
+    emb = vc.prompt_embeddings(feats.clone())
+    torch.testing.assert_close(emb[:, :10].cpu(), g["cont"], rtol=2e-4, atol=2e-4)
+    ids = vc.forward_ids(feats.clone()).cpu().tolist()
+    assert [vc.cut(r) for r in ids] == g["sentence_ids"]
+    assert vc.forward(feats.clone()) == g["sentences"]
+    # the reference normalises its argument in place (entrypoint.py:108)
+    f = g["feats"].clone().to(dev)
+    vc.forward(f)
+    torch.testing.assert_close(f.norm(dim=-1).cpu(), torch.ones(f.shape[0]), rtol=1e-5, atol=1e-5)
+    # hard prompt first / soft prompt only
+    for extra in ({"soft_prompt_first": False}, {"using_hard_prompt": False}, {"only_hard_prompt": True}):
+        v2 = VieCap({**cfg, **extra}, dev, "ViT-B/16", precision="fp32")
+        want = ov.viecap_forward(weights, g["feats"].clone(), g["entities"], g["ent_emb"], ov.ToyTokenizer(),
+                                 using_hard_prompt=extra.get("using_hard_prompt", True),
+                                 soft_prompt_first=extra.get("soft_prompt_first", True),
+                                 only_hard_prompt=extra.get("only_hard_prompt", False), steps=10)
+        got = v2.gpt.decode(v2.prompt_embeddings(g["feats"].clone().to(dev)), 10).cpu().long()
+        assert (got == want[1]).all(dim=1).float().mean() >= 0.8
+    with pytest.raises(NotImplementedError):
+        VieCap({**cfg, "using_greedy_search": False}, dev, "ViT-B/16")
+
+
+def test_patchioner_with_viecap_region_sets(dev, golden, weights):
+    """BASELINE config 4: region-set embeddings (one per image) captioned by ViECap behind Patchioner.forward."""
+    from oracle import dinov2 as o_vit
+    from oracle import pipeline as o_pipe
+    from patchioner_b200 import Patchioner
+
+    g = golden("viecap")
+    tok = ov.ToyTokenizer()
+    vcfg = {"state_dict": weights, "entities_text": g["entities"], "texts_embeddings": g["ent_emb"], "tokenizer": tok,
+            "clip_hidden_size": 768, "project_length": 10, "temperature": 0.01, "top_k": 3, "threshold": 0.4,
+            "using_hard_prompt": True, "soft_prompt_first": True, "using_greedy_search": True}
+    m = Patchioner.from_config({"prefix_size": 768, "support_memory_size": 0, "dino_model": "dinov2_vitb14_reg", "normalize": False,
+                                "resize_dim": 224, "crop_dim": 224, "dino_weights": o_vit.make_weights(seed=1234),
+                                "clip_model_name": "ViT-B/16", "viecap": vcfg, "precision": "fp32"}, device=dev)
+    B, S, R = 2, 224, 4
+    imgs = o_pipe.synth_images(B, S, seed=1)
+    boxes = o_pipe.synth_boxes(B, R, S, seed=2, pad="set")
+    out = m(imgs, get_cls_capt=False, bboxes=boxes.clone(), get_controllable_capts=True)
+    assert len(out["set_controllable_capts"]) == B and all(isinstance(s, str) for s in out["set_controllable_capts"])
+    emb = m.region_embeddings(imgs.to(dev), bboxes=boxes.clone(), get_controllable_capts=True)["set"]
+    want = ov.viecap_forward(weights, emb.cpu().clone(), g["entities"], g["ent_emb"], tok)[0]
+    assert out["set_controllable_capts"] == want
+    dense = m(imgs, get_cls_capt=True, bboxes=o_pipe.synth_boxes(B, R, S, seed=1, pad="dense"))
+    assert len(dense["bbox_capts"]) == B and len(dense["bbox_capts"][0]) == R and isinstance(dense["cls_capt"][0], str)
+    with pytest.raises(Exception, match="not supported with viecap"):
+        m(imgs, get_cls_capt=False, bboxes=boxes.clone(), return_n_best_sims=2)
+
+
+def test_cabi_errors(dev, ops, weights):
+    from patchioner_b200 import _lib as L
+
+    dec = ops.Gpt2Decoder(weights, dev, "fp32")
+    with pytest.raises(L.PioError, match="exceed the cache"):
+        dec.decode(torch.zeros(2, 70, 768, device=dev), 64)
+    lib = L.lib()
+    ids = torch.zeros(2, 4, dtype=torch.int32, device=dev)
+    assert lib.pio_decode_greedy_prompt(dec._h, None, 2, 3, 4, ids.data_ptr(), None, None, 0, None) != 0
+    assert b"null argument" in lib.pio_last_error()
+    # the DeCap entry point refuses a decoder without prefix projection instead of dereferencing a null weight
+    ws = torch.zeros(lib.pio_decode_prompt_workspace_bytes(dec._h, 2, 3, 4) + (64 << 20), dtype=torch.uint8, device=dev)
+    rc = lib.pio_decode_greedy(dec._h, torch.zeros(2, 768, device=dev).data_ptr(), 2, 4, ids.data_ptr(), None, ws.data_ptr(), ws.numel(), None)
+    assert rc != 0 and b"no prefix projection" in lib.pio_last_error()
+    bad = dict(weights)
+    bad["mapping_network.transformer.layers.0.attn.to_queries.bias"] = torch.zeros(768)
+    with pytest.raises(NotImplementedError):
+        ops.Mapper(bad, dev, "fp32")

@@ -1,0 +1,51 @@
+"""CPU: the ViECap oracle (oracle/viecap.py) against the outputs of the reference's own classes (tests/golden/viecap.pt,
+made by tests/golden/make_golden_viecap.py), plus the host logic of patch-ioner_b200/viecap.py that needs no GPU."""
+import torch
+
+from oracle import viecap as ov
+
+
+def _run(golden):
+    g = golden("viecap")
+    w = ov.make_weights()
+    tok = ov.ToyTokenizer()
+    feats = g["feats"].clone()
+    sentences, ids, emb, hard = ov.viecap_forward(w, feats, g["entities"], g["ent_emb"], tok)
+    return g, w, tok, feats, sentences, ids, emb, hard
+
+
+def test_oracle_matches_reference_outputs(golden):
+    g, w, tok, feats, sentences, ids, emb, hard = _run(golden)
+    # mapping network: same arithmetic as the reference module -> tight
+    torch.testing.assert_close(emb[:, :10], g["cont"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(ov.entity_probs(feats, g["ent_emb"], 0.01), g["probs"], rtol=1e-5, atol=1e-6)
+    assert ov.pick_entities(g["entities"], g["probs"], 3, 0.4) == g["detected"]
+    assert [] in g["detected"] and any(len(d) >= 2 for d in g["detected"])  # 'something' and a multi-entity prompt are covered
+    assert torch.equal(hard, g["hard"])
+    eos = [tok.encode(e)[-1] for e in (".", " .")]
+    assert [ov.cut_sentence(r, eos) for r in ids.tolist()] == g["sentence_ids"]   # greedy_search of the reference
+    assert sentences == g["sentences"]
+
+
+def test_prompt_composition_and_cut():
+    assert ov.compose_prompt([]) == "There are something in image."
+    assert ov.compose_prompt(["dog"]) == "There are dog in image."
+    assert ov.compose_prompt(["person", "traffic light", "kite"]) == "There are person, traffic light, kite in image."
+    assert ov.cut_sentence([5, 6, 7, 6], [7]) == [5, 6, 7]
+    assert ov.cut_sentence([5, 6], [7]) == [5, 6]
+    from patchioner_b200.viecap import compose_discrete_prompt
+    for e in ([], ["dog"], ["a b", "c"]):
+        assert compose_discrete_prompt(e) == ov.compose_prompt(e)
+
+
+def test_piecewise_tokenisation_equals_whole_prompt():
+    """The product tokenises every entity once and concatenates; that must equal tokenising the whole prompt."""
+    tok = ov.ToyTokenizer()
+    ents = ["person", "traffic light", "tv", "hot dog"]
+    head, tail, comma = tok.encode("There are"), tok.encode(" in image."), tok.encode(",")
+    per = [tok.encode(" " + e) for e in ents]
+    for rows in ([0], [1, 3], [2, 0, 1]):
+        pieces = list(head)
+        for j, r in enumerate(rows):
+            pieces += (comma if j else []) + per[r]
+        assert pieces + tail == tok.encode(ov.compose_prompt([ents[r] for r in rows]))
