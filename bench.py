@@ -40,9 +40,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--workload", default="dense", choices=["dense", "traces", "regionset"],
+    ap.add_argument("--workload", default="dense", choices=["dense", "traces", "regionset", "regionset-viecap"],
                     help="dense = BASELINE configs[1] (the headline); traces = configs[2] (1 mouse trace / image, attention weighting, "
-                         "batch 256); regionset = configs[3] (talk2dino_capdec, box sets -> one caption / image)")
+                         "batch 256); regionset = configs[3] (talk2dino_capdec, box sets -> one caption / image); regionset-viecap = configs[3] with "
+                         "the ViECap captioner (mapping network + entity prompt + GPT-2 small, 64 tokens)")
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--boxes", type=int, default=None)
     ap.add_argument("--size", type=int, default=518)
@@ -55,8 +56,8 @@ def parse():
     if a.batch is None:
         a.batch = 256 if a.workload == "traces" else 64
     if a.boxes is None:
-        a.boxes = {"dense": 64, "traces": 1, "regionset": 8}[a.workload]
-    if a.workload == "regionset":
+        a.boxes = {"dense": 64, "traces": 1, "regionset": 8, "regionset-viecap": 8}[a.workload]
+    if a.workload.startswith("regionset"):
         a.bank_rows = 0  # CapDec: no caption memory (configs/mlp_noise.k.yaml: support_memory_size 0)
     return a
 
@@ -65,7 +66,7 @@ def workload_flags(args):
     """forward() keywords of the workload (the eval drivers' flag mapping)."""
     if args.workload == "traces":   # eval_trace_captioning.py:309-324 (gaussian flags are passed and ignored by the trace branch)
         return dict(use_attention_tracing=True, gaussian_avg=True, gaussian_bbox_variance=1.0)
-    if args.workload == "regionset":  # eval_region_set_captioning.py:322-337
+    if args.workload.startswith("regionset"):  # eval_region_set_captioning.py:322-337
         return dict(get_controllable_capts=True, gaussian_avg=True, gaussian_bbox_variance=1.0)
     return dict(gaussian_avg=args.pool == "gauss", gaussian_bbox_variance=1.0, use_attn_map_for_bboxes=args.pool == "attn")
 
@@ -76,7 +77,7 @@ def workload_batch(args, synth_mod, B, seed):
     batch = {"imgs": synth_mod.synth_images(B, S, seed=seed)}
     if args.workload == "traces":
         batch["traces"] = synth_mod.synth_traces(B, seed=seed)
-    elif args.workload == "regionset":
+    elif args.workload.startswith("regionset"):
         batch["bboxes"] = synth_mod.synth_boxes(B, args.boxes, S, seed=seed, pad="set")
     else:
         batch["bboxes"] = synth_mod.synth_boxes(B, args.boxes, S, seed=seed, pad="dense")
@@ -84,7 +85,12 @@ def workload_batch(args, synth_mod, B, seed):
 
 
 def out_key(args):
-    return {"dense": "bbox_capts", "traces": "trace_capts", "regionset": "set_controllable_capts"}[args.workload]
+    return {"dense": "bbox_capts", "traces": "trace_capts", "regionset": "set_controllable_capts",
+            "regionset-viecap": "set_controllable_capts"}[args.workload]
+
+
+def decode_steps(args):
+    return 64 if args.workload == "regionset-viecap" else 30
 
 
 def captions_per_step(args):
@@ -162,6 +168,8 @@ def cpu_sample(args, steps: int, warmup: int):
     from oracle import pipeline as o_pipe
 
     torch.set_num_threads(os.cpu_count() or 1)
+    if args.workload == "regionset-viecap":
+        return cpu_sample_viecap(args, steps, warmup)
     B, R, S = args.cpu_sample_images, args.cpu_sample_boxes, args.size
     if args.workload != "dense":
         B, R = max(B, 4), args.boxes
@@ -183,6 +191,39 @@ def cpu_sample(args, steps: int, warmup: int):
     sample = (f"{args.workload}: {B} x {S}px image(s), {R} box(es)/trace(s) each = {n} captions/step, bank M={args.bank_rows}, fp32, "
               f"reference algorithm (no KV cache, 30 steps), {len(times)} timed step(s) after {warmup} warm-up")
     return n / sec, sec, sample
+
+
+def cpu_sample_viecap(args, steps: int, warmup: int):
+    """configs[3] with the ViECap captioner on the host cores: oracle ViT + box-set pooling + oracle/viecap.py with the KV
+    cache the reference's greedy_search uses, GPT-2 small, 64 tokens."""
+    from oracle import dinov2 as o_vit
+    from oracle import pipeline as o_pipe
+    from oracle import pooling as o_pool
+    from oracle import viecap as ov
+    from patchioner_b200 import synth
+
+    B, R, S = 2, args.boxes, args.size
+    vit_w = o_vit.make_weights(1234)
+    w = ov.make_weights(seed=4321, n_layer_gpt=12, n_layer_map=8)
+    ents, ent_emb = synth.synth_entities(80)
+    tok = ov.ToyTokenizer()
+    kw = workload_flags(args)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            batch = workload_batch(args, o_pipe, B, 100 + i)
+            t0 = time.perf_counter()
+            d = o_vit.forward(vit_w, batch["imgs"])
+            feats = o_pool.extract_bboxes_feats(d["x_norm_patchtokens"], batch["bboxes"], kw["gaussian_avg"], kw["gaussian_bbox_variance"],
+                                                get_single_embedding_per_image=True, patch_size=14)
+            ov.viecap_forward(w, feats.clone(), ents, ent_emb, tok, use_cache=True)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    sec = sum(times) / len(times)
+    sample = (f"regionset-viecap: {B} x {S}px images, sets of {R} boxes = {B} captions/step, fp32, reference algorithm (KV-cached "
+              f"greedy search, 64 tokens, 12-layer GPT-2), {len(times)} timed step(s) after {warmup} warm-up")
+    return B / sec, sec, sample
 
 
 def run_reference(args):
@@ -207,10 +248,13 @@ def workload_config(args, per_step_note=None):
             "traces": f"talk2dino_decap trace captioning with attention weighting: {args.size}px images, 1 synthetic mouse trace/image, "
                       f"batch {args.batch} per GPU (BASELINE.json configs[2])",
             "regionset": f"talk2dino_capdec region-set captioning: {args.size}px images, sets of up to {args.boxes} boxes/image -> one "
-                         f"caption per image, batch {args.batch} per GPU (BASELINE.json configs[3])"}[args.workload]
+                         f"caption per image, batch {args.batch} per GPU (BASELINE.json configs[3])",
+            "regionset-viecap": f"viecap region-set captioning: {args.size}px images, sets of up to {args.boxes} boxes/image -> one caption per "
+                                f"image by the ViECap captioner (8-layer mapping network, 80 synthetic entities, GPT-2 small, 64 greedy "
+                                f"tokens), batch {args.batch} per GPU (BASELINE.json configs[3])"}[args.workload]
     cfg = {"workload": name,
            "images_per_gpu": args.batch, "boxes_per_image": args.boxes, "regions_per_gpu_per_step": captions_per_step(args),
-           "image_size": args.size, "bank_rows": args.bank_rows, "pooling": args.pool, "decode_steps": 30,
+           "image_size": args.size, "bank_rows": args.bank_rows, "pooling": args.pool, "decode_steps": decode_steps(args),
            "parallelism": f"dp{args.gpus} over images, no collective",
            "cache": "per-step inputs (206 MB of images) and activations (> 1 GB) exceed the 126 MB L2; no explicit flush"}
     if per_step_note:
@@ -246,9 +290,18 @@ def run_ours(args):
     B, R, S = args.batch, args.boxes, args.size
     vit_w, dec_w = synth.make_vit_weights(1234), synth.make_decoder_weights(1234)
     bank = synth.synth_bank(args.bank_rows, 768, seed=7) if args.bank_rows > 0 else None
-    model = Patchioner.from_config({"decap_weights": dec_w, "prefix_size": 768, "support_memory_size": args.bank_rows,
-                                    "dino_model": "dinov2_vitb14_reg", "normalize": True, "resize_dim": S, "crop_dim": S,
-                                    "dino_weights": vit_w, "memory_bank": bank, "precision": args.precision}, device=dev)
+    cfg = {"decap_weights": dec_w, "prefix_size": 768, "support_memory_size": args.bank_rows,
+           "dino_model": "dinov2_vitb14_reg", "normalize": True, "resize_dim": S, "crop_dim": S,
+           "dino_weights": vit_w, "memory_bank": bank, "precision": args.precision}
+    if args.workload == "regionset-viecap":  # configs/mlp.viecap.k.yaml
+        ents, ent_emb = synth.synth_entities(80)
+        cfg.update({"decap_weights": None, "normalize": False, "clip_model_name": "ViT-B/16",
+                    "viecap": {"state_dict": synth.make_viecap_weights(), "entities_text": ents, "texts_embeddings": ent_emb,
+                               "tokenizer": synth.WordTokenizer(), "clip_hidden_size": 768, "project_length": 10, "temperature": 0.01,
+                               "top_k": 3, "threshold": 0.4, "using_hard_prompt": True, "soft_prompt_first": True,
+                               "using_greedy_search": True}})
+    model = Patchioner.from_config(cfg, device=dev)
+    del cfg
     del bank, vit_w, dec_w
     kw = workload_flags(args)
     key = out_key(args)
@@ -337,7 +390,7 @@ def run_ours(args):
                 "dtype": args.precision, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "clocks": clocks_e2e,
                         "h2d_bytes_per_step": int(h2d_bytes) * world,
-                        "d2h_bytes_per_step": int(captions_per_step(args) * 30 * 4) * world},
+                        "d2h_bytes_per_step": int(captions_per_step(args) * decode_steps(args) * 4) * world},
                 "gpu_launches": int(launches), "roofline": roof, "stages": extra,
                 "vit_images_per_s": extra.get("vit_images_per_s")}
         if not args.no_cpu_baseline and world == 1:
@@ -378,7 +431,7 @@ def stage_breakdown(model, ops, batch, kw, args, stream):
         w = ops.trace_bins(batch["traces"], S // 14, patch.device, attn)
         feats = ops.pool_grid(patch, w.reshape(B, 1, P), 1.0 / P)[:, 0]
         n_out = 1
-    elif args.workload == "regionset":
+    elif args.workload.startswith("regionset"):
         feats = ops.pool_boxes(patch, batch["bboxes"], 14, True, 1.0, None, get_single_embedding_per_image=True)
         n_out = 1
     else:
@@ -386,9 +439,14 @@ def stage_breakdown(model, ops, batch, kw, args, stream):
                                attn if kw["use_attn_map_for_bboxes"] else None)
         n_out = R
     marks[2].record(stream)
-    pre = model.embed_tokens(feats.reshape(-1, 768))
-    marks[3].record(stream)
-    model.decoder.decode(pre, 30)
+    if model.viecap is not None:
+        pre = model.viecap.prompt_embeddings(feats.reshape(-1, 768).clone())  # mapping network + entity prompt ("project" stage)
+        marks[3].record(stream)
+        model.viecap.gpt.decode(pre, 64)
+    else:
+        pre = model.embed_tokens(feats.reshape(-1, 768))
+        marks[3].record(stream)
+        model.decoder.decode(pre, 30)
     marks[4].record(stream)
     torch.cuda.synchronize()
     t = [marks[i].elapsed_time(marks[i + 1]) for i in range(4)]
@@ -397,6 +455,9 @@ def stage_breakdown(model, ops, batch, kw, args, stream):
     pool_bytes = B * (P * 768 * 4 + n_out * 768 * 4 + R * 16)
     proj_flops = 4.0 * model.im_proj.M * 768 * B * n_out if model.im_proj is not None else 0.0
     dec_flops = 2 * (4 * 12 * 768 * 768 + 50257 * 768) * 30 * B * n_out
+    if model.viecap is not None:  # GPT-2 small over prompt + 63 positions, lm-head on 64 of them; mapping network counted in "project"
+        proj_flops = (2 * 20 * 8 * 8 * 768 * 768 + 2 * 768 * 7680) * B * n_out
+        dec_flops = (2 * 12 * 12 * 768 * 768 * (pre.shape[1] + 63) + 2 * 50257 * 768 * 64) * B * n_out
     out = {"vit_ms": t[0], "pool_ms": t[1], "project_ms": t[2], "decode_ms": t[3],
            "vit_images_per_s": B / (t[0] / 1e3), "vit_tflops": vit_flops / t[0] / 1e9,
            "pool_gbs": pool_bytes / t[1] / 1e6, "pool_frac_of_hbm": pool_bytes / t[1] / 1e6 / pk["hbm_gbs"],

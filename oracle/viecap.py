@@ -161,18 +161,23 @@ def compose_prompt(entities: Sequence[str]) -> str:
     return "There are" + ",".join(" " + e for e in entities) + " in image."
 
 
-def gpt2_hidden(w, emb: torch.Tensor, n_head: int = 12) -> torch.Tensor:
-    """GPT2Model on inputs_embeds [R,T,768] at positions 0..T-1 (full causal recompute) -> ln_f(hidden)."""
+def gpt2_hidden(w, emb: torch.Tensor, n_head: int = 12, kv: Optional[list] = None, pos0: int = 0) -> torch.Tensor:
+    """GPT2Model on inputs_embeds [R,T,768] at positions pos0..pos0+T-1 -> ln_f(hidden).  ``kv`` (a list with one
+    entry per layer, extended in place) is the KV cache the reference's greedy_search uses (search.py:150-163)."""
     Tp = "gpt.transformer."
     R, T, D = emb.shape
     hd = D // n_head
-    x = emb + w[Tp + "wpe.weight"][:T]
-    mask = torch.ones(T, T, dtype=torch.bool).triu(1)
+    x = emb + w[Tp + "wpe.weight"][pos0:pos0 + T]
+    mask = torch.arange(pos0 + T)[None, :] > torch.arange(pos0, pos0 + T)[:, None]  # key position > query position
     for i in range(_layers(w, Tp + "h.")):
         p = f"{Tp}h.{i}."
         h = F.layer_norm(x, (D,), w[p + "ln_1.weight"], w[p + "ln_1.bias"], eps=1e-5)
         qkv = h @ w[p + "attn.c_attn.weight"] + w[p + "attn.c_attn.bias"]
         q, k, v = (t.reshape(R, T, n_head, hd).transpose(1, 2) for t in qkv.split(D, dim=-1))
+        if kv is not None:
+            if kv[i] is not None:
+                k, v = torch.cat([kv[i][0], k], dim=2), torch.cat([kv[i][1], v], dim=2)
+            kv[i] = (k, v)
         att = ((q @ k.transpose(-2, -1)) * hd ** -0.5).masked_fill(mask, float("-inf")).softmax(dim=-1)
         o = (att @ v).transpose(1, 2).reshape(R, T, D)
         x = x + (o @ w[p + "attn.c_proj.weight"] + w[p + "attn.c_proj.bias"])
@@ -184,15 +189,20 @@ def gpt2_hidden(w, emb: torch.Tensor, n_head: int = 12) -> torch.Tensor:
 
 
 @torch.no_grad()
-def greedy_ids(w, prompt: torch.Tensor, steps: int = MAX_LEN, return_margin: bool = False):
+def greedy_ids(w, prompt: torch.Tensor, steps: int = MAX_LEN, return_margin: bool = False, use_cache: bool = False):
     """search.py:146-171 up to the token ids: [R,steps] int64.  (The reference's step loop runs the model once more
     after the last token; that run has no effect on the tokens.)  ``return_margin`` also gives, per step, the gap
     between the best and second-best logit -- tests use it to tell a real mismatch from a near-tie."""
     wte = w["gpt.transformer.wte.weight"]
     seq = prompt.float()
     toks, margins = [], []
-    for _ in range(steps):
-        logits = gpt2_hidden(w, seq)[:, -1] @ wte.T
+    kv = [None] * _layers(w, "gpt.transformer.h.") if use_cache else None
+    for t in range(steps):
+        if use_cache:  # prefill once, then one position per step like the reference (search.py:150-163)
+            new = seq if t == 0 else seq[:, -1:]
+            logits = gpt2_hidden(w, new, kv=kv, pos0=seq.shape[1] - new.shape[1])[:, -1] @ wte.T
+        else:
+            logits = gpt2_hidden(w, seq)[:, -1] @ wte.T
         top2 = logits.topk(2, dim=-1).values
         margins.append(top2[:, 0] - top2[:, 1])
         nxt = torch.argmax(logits, dim=-1)
@@ -214,7 +224,8 @@ def cut_sentence(ids: Sequence[int], eos: Sequence[int]) -> List[int]:
 @torch.no_grad()
 def viecap_forward(w, feats: torch.Tensor, entities_text: Sequence[str], texts_embeddings: torch.Tensor, tokenizer,
                    temperature: float = 0.01, top_k: int = 3, threshold: float = 0.4, using_hard_prompt: bool = True,
-                   soft_prompt_first: bool = True, only_hard_prompt: bool = False, steps: int = MAX_LEN):
+                   soft_prompt_first: bool = True, only_hard_prompt: bool = False, steps: int = MAX_LEN,
+                   use_cache: bool = False):
     """entrypoint.py:98-147 with greedy search.  Returns (sentences, ids [R,steps], prompt embeddings [R,P,768],
     hard-prompt tokens [R,Lmax] or None).  ``feats`` is normalised IN PLACE like the reference (:108)."""
     pad_id = tokenizer.pad_token_id if tokenizer.pad_token_id is not None else 0
@@ -229,7 +240,7 @@ def viecap_forward(w, feats: torch.Tensor, entities_text: Sequence[str], texts_e
         emb = disc if only_hard_prompt else (torch.cat([cont, disc], 1) if soft_prompt_first else torch.cat([disc, cont], 1))
     else:
         emb = cont
-    ids = greedy_ids(w, emb, steps)
+    ids = greedy_ids(w, emb, steps, use_cache=use_cache)
     eos = [tokenizer.encode(e)[-1] for e in (".", " .")]
     sentences = [tokenizer.decode(cut_sentence(r, eos)) for r in ids.tolist()]
     return sentences, ids, emb, hard

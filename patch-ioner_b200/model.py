@@ -402,6 +402,12 @@ class Patchioner:
                 if compute_scores:
                     outs[{"bbox_capts": "bbox_scores"}.get(key, key + "_scores")] = [[] for _ in range(bs)]
                 return None
+            if self.viecap is not None and return_ids:  # extension: the 64 generated ids per region, before the sentence cut
+                if return_n_best_sims is not None and key == "bbox_capts":
+                    raise Exception("return_n_best_sims is not supported with viecap")
+                ids = self.viecap.forward_ids(feats)
+                outs[key] = ids.reshape(bs, group, -1) if group is not None else ids
+                return None
             if self.calculate_argmax_text or self.viecap is not None:
                 return emit_texts(key, feats, group)
             if return_n_best_sims is not None and key == "bbox_capts":

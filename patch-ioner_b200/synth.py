@@ -138,3 +138,83 @@ def synth_bank(M: int, D: int = 768, seed: int = 7, zero_frac: float = 0.001) ->
         idx = torch.randperm(M, generator=g)[:nz]
         bank[idx] = 0.0
     return bank
+
+
+# ------------------------------------------------------------------------------------------ ViECap (BASELINE configs[3])
+def make_viecap_weights(seed: int = 4321, n_layer_gpt: int = 12, n_layer_map: int = 8, clip_size: int = 768, project_len: int = 10,
+                        prefix_len: int = 10, std: float = 0.02) -> Dict[str, torch.Tensor]:
+    """Random-init ViECap checkpoint with the reference's key names (`mapping_network.*`, `gpt.transformer.*`): 8-layer
+    mapping network, GPT-2 small.  Same generator order as oracle/viecap.py::make_weights."""
+    g = torch.Generator().manual_seed(seed)
+    rn = lambda *s, std=std: torch.randn(*s, generator=g) * std  # noqa: E731
+    D = N_EMBD
+    w: Dict[str, torch.Tensor] = {}
+    M = "mapping_network."
+    w[M + "linear.weight"] = rn(project_len * D, clip_size, std=0.05)
+    w[M + "linear.bias"] = rn(project_len * D, std=0.02)
+    w[M + "prefix_const"] = rn(prefix_len, D, std=0.5)
+    for i in range(n_layer_map):
+        p = f"{M}transformer.layers.{i}."
+        w[p + "norm1.weight"] = torch.ones(D) + rn(D, std=0.05)
+        w[p + "norm1.bias"] = rn(D)
+        w[p + "attn.to_queries.weight"] = rn(D, D, std=0.04)
+        w[p + "attn.to_keys_values.weight"] = rn(2 * D, D, std=0.04)
+        w[p + "attn.project.weight"] = rn(D, D, std=0.03)
+        w[p + "attn.project.bias"] = rn(D)
+        w[p + "norm2.weight"] = torch.ones(D) + rn(D, std=0.05)
+        w[p + "norm2.bias"] = rn(D)
+        w[p + "mlp.fc1.weight"] = rn(2 * D, D, std=0.03)
+        w[p + "mlp.fc1.bias"] = rn(2 * D)
+        w[p + "mlp.fc2.weight"] = rn(D, 2 * D, std=0.03)
+        w[p + "mlp.fc2.bias"] = rn(D)
+    T = "gpt.transformer."
+    w[T + "wte.weight"] = rn(VOCAB, D)
+    w[T + "wpe.weight"] = rn(N_POS, D)
+    for i in range(n_layer_gpt):
+        p = f"{T}h.{i}."
+        w[p + "ln_1.weight"] = torch.ones(D) + rn(D, std=0.05)
+        w[p + "ln_1.bias"] = rn(D)
+        w[p + "attn.c_attn.weight"] = rn(D, 3 * D)
+        w[p + "attn.c_attn.bias"] = rn(3 * D, std=0.01)
+        w[p + "attn.c_proj.weight"] = rn(D, D, std=std / math.sqrt(2 * n_layer_gpt))
+        w[p + "attn.c_proj.bias"] = rn(D, std=0.01)
+        w[p + "ln_2.weight"] = torch.ones(D) + rn(D, std=0.05)
+        w[p + "ln_2.bias"] = rn(D)
+        w[p + "mlp.c_fc.weight"] = rn(D, 4 * D)
+        w[p + "mlp.c_fc.bias"] = rn(4 * D, std=0.01)
+        w[p + "mlp.c_proj.weight"] = rn(4 * D, D, std=std / math.sqrt(2 * n_layer_gpt))
+        w[p + "mlp.c_proj.bias"] = rn(D, std=0.01)
+    w[T + "ln_f.weight"] = torch.ones(D) + rn(D, std=0.05)
+    w[T + "ln_f.bias"] = rn(D)
+    w["gpt.lm_head.weight"] = w[T + "wte.weight"]
+    return w
+
+
+class WordTokenizer:
+    """Offline stand-in for the GPT-2 BPE tokenizer (its vocabulary files need the network): GPT-2's word / punctuation
+    pre-tokenisation, one id per piece.  Only for synthetic runs (bench.py); real use passes a real tokenizer."""
+    pad_token_id = None
+
+    def __init__(self):
+        import re
+        self._pat = re.compile(r" ?[A-Za-z]+| ?[0-9]+| ?[^\sA-Za-z0-9]+|\s+")
+        self.names: Dict[int, str] = {}
+
+    def encode(self, text: str) -> List[int]:
+        import zlib
+        out = []
+        for piece in self._pat.findall(text):
+            i = zlib.crc32(piece.encode()) % 50000
+            self.names.setdefault(i, piece)
+            out.append(i)
+        return out
+
+    def decode(self, ids) -> str:
+        return "".join(self.names.get(int(i), f"<{int(i)}>") for i in ids)
+
+
+def synth_entities(n: int = 80, D: int = 768, seed: int = 5):
+    """n entity names (the COCO vocabulary has 80) and random unit embeddings."""
+    g = torch.Generator().manual_seed(seed)
+    e = torch.randn(n, D, generator=g)
+    return sorted(f"thing{i:02d}" for i in range(n)), e / e.norm(dim=-1, keepdim=True)

@@ -17,3 +17,15 @@ def test_generators_match_oracle():
     assert torch.equal(synth.synth_boxes(3, 7, 224, 2, pad="set"), o_pipe.synth_boxes(3, 7, 224, 2, pad="set"))
     assert synth.synth_traces(3, 2) == o_pipe.synth_traces(3, 2)
     assert torch.equal(synth.synth_bank(500, 64, 1), o_pipe.synth_bank(500, 64, 1))
+
+
+def test_viecap_synth_weights_equal_oracle_generator():
+    from oracle import viecap as ov
+    from patchioner_b200 import synth
+
+    a = synth.make_viecap_weights(seed=4321, n_layer_gpt=2, n_layer_map=2)
+    b = ov.make_weights(seed=4321, n_layer_gpt=2, n_layer_map=2)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    t1, t2 = synth.WordTokenizer(), ov.ToyTokenizer()
+    s = "There are person, traffic light in image."
+    assert t1.encode(s) == t2.encode(s) and t1.decode(t1.encode(s)) == s

@@ -49,3 +49,11 @@ def test_piecewise_tokenisation_equals_whole_prompt():
         for j, r in enumerate(rows):
             pieces += (comma if j else []) + per[r]
         assert pieces + tail == tok.encode(ov.compose_prompt([ents[r] for r in rows]))
+
+
+def test_cached_greedy_equals_full_recompute():
+    w = ov.make_weights(seed=9, n_layer_gpt=2, n_layer_map=1)
+    prompt = torch.randn(3, 7, 768, generator=torch.Generator().manual_seed(2)) * 0.3
+    a, margin = ov.greedy_ids(w, prompt, 6, return_margin=True)
+    b = ov.greedy_ids(w, prompt, 6, use_cache=True)
+    assert margin.min() > 1e-4 and torch.equal(a, b)
