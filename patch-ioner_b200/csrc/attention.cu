@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(128) decode_attention_long_kernel(const T* __r
 template <typename T>
 __global__ void __launch_bounds__(128) small_attention_kernel(const T* __restrict__ q, long long ldq, const T* __restrict__ kv,
                                                               long long ldkv, T* __restrict__ out, long long ldo, int n, int H, int hd,
-                                                              float scale) {
+                                                              float scale, int causal, T* __restrict__ kc, T* __restrict__ vc, int Tmax) {
   extern __shared__ __align__(16) float sm[];
   const int ld = hd + 1;
   float* Q = sm;
@@ -441,16 +441,22 @@ __global__ void __launch_bounds__(128) small_attention_kernel(const T* __restric
   for (int idx = tid; idx < n * hd; idx += 128) {
     const int i = idx / hd, d = idx % hd;
     const long long row = (long long)r * n + i;
+    const T kk = kv[row * ldkv + h * hd + d], vv = kv[row * ldkv + (long long)H * hd + h * hd + d];
     Q[i * ld + d] = (float)q[row * ldq + h * hd + d];
-    K[i * ld + d] = (float)kv[row * ldkv + h * hd + d];
-    V[i * ld + d] = (float)kv[row * ldkv + (long long)H * hd + h * hd + d];
+    K[i * ld + d] = (float)kk;
+    V[i * ld + d] = (float)vv;
+    if (kc) {  // prompt prefill of a decoder: positions 0..n-1 of this head's KV cache [R][H][Tmax][hd]
+      const long long c = (((long long)r * H + h) * Tmax + i) * hd + d;
+      kc[c] = kk;
+      vc[c] = vv;
+    }
   }
   __syncthreads();
   for (int idx = tid; idx < n * n; idx += 128) {
     const int i = idx / n, j = idx % n;
     float a = 0.f;
     for (int d = 0; d < hd; ++d) a = fmaf(Q[i * ld + d], K[j * ld + d], a);
-    P[i * (n + 1) + j] = a * scale;
+    P[i * (n + 1) + j] = (causal && j > i) ? -INFINITY : a * scale;
   }
   __syncthreads();
   if (tid < n) {
@@ -475,17 +481,21 @@ __global__ void __launch_bounds__(128) small_attention_kernel(const T* __restric
 
 }  // namespace
 
+size_t small_attention_smem(int n, int hd) { return ((size_t)3 * n * (hd + 1) + (size_t)n * (n + 1)) * sizeof(float); }
+
 int small_attention(const void* q, long long ldq, const void* kv, long long ldkv, void* out, long long ldo, int dt, int R, int n, int H,
-                    int hd, cudaStream_t st) {
+                    int hd, bool causal, void* kc, void* vc, int Tmax, cudaStream_t st) {
   PIO_CHECK(n >= 1 && n <= 64 && hd >= 1 && hd <= 128, "small attention: n %d / head_dim %d outside the built range (<=64, <=128)", n, hd);
-  const size_t smem = ((size_t)3 * n * (hd + 1) + (size_t)n * (n + 1)) * sizeof(float);
+  const size_t smem = small_attention_smem(n, hd);
   PIO_CHECK(smem <= 48 * 1024, "small attention: %zu bytes of shared memory exceed 48 KB", smem);
   const float scale = 1.0f / sqrtf((float)hd);
   if (dt == PIO_DT_F32)
-    small_attention_kernel<float><<<R * H, 128, smem, st>>>((const float*)q, ldq, (const float*)kv, ldkv, (float*)out, ldo, n, H, hd, scale);
+    small_attention_kernel<float><<<R * H, 128, smem, st>>>((const float*)q, ldq, (const float*)kv, ldkv, (float*)out, ldo, n, H, hd, scale,
+                                                             causal ? 1 : 0, (float*)kc, (float*)vc, Tmax);
   else
     small_attention_kernel<__nv_bfloat16><<<R * H, 128, smem, st>>>((const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)kv, ldkv,
-                                                                    (__nv_bfloat16*)out, ldo, n, H, hd, scale);
+                                                                    (__nv_bfloat16*)out, ldo, n, H, hd, scale, causal ? 1 : 0,
+                                                                    (__nv_bfloat16*)kc, (__nv_bfloat16*)vc, Tmax);
   PIO_LAUNCHED();
   return PIO_OK;
 }

@@ -235,6 +235,20 @@ __global__ void prompt_embed_kernel(const float* __restrict__ prompt, int P, int
   }
 }
 
+// x[r*P + p, :] = prompt[r, p, :] + wpe[p, :] for every prompt position (batched prefill)
+__global__ void prompt_embed_all_kernel(const float* __restrict__ prompt, int P, const float* __restrict__ wpe, float* __restrict__ x,
+                                        int rows, int D) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float4* a = reinterpret_cast<const float4*>(prompt + (long long)warp * D);
+  const float4* b = reinterpret_cast<const float4*>(wpe + (long long)(warp % P) * D);
+  float4* o = reinterpret_cast<float4*>(x + (long long)warp * D);
+  for (int i = lane; i < D / 4; i += 32) {
+    float4 u = __ldg(a + i), v = __ldg(b + i);
+    o[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+}
+
 __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = a[i] + b[i];
@@ -713,16 +727,18 @@ struct DecodeWs {
   float* x; void* hb; void* qkv; void* f; float* logits; char* kc; char* vc; void* pfx; size_t kv_layer, total;
 };
 // carve the decode workspace for R rows and a KV cache of T positions (same layout for sizing and for use)
-DecodeWs decode_ws(const PioDecoder* h, char* base, int R, int T, size_t tail_elems) {
+// `rows` >= R: rows of the token buffers (R for single-position steps, R * prompt_len for a batched prompt prefill)
+DecodeWs decode_ws(const PioDecoder* h, char* base, int R, int T, size_t tail_elems, size_t rows = 0) {
   using namespace pio;
   const size_t e = h->act_dt == PIO_DT_F32 ? 4 : 2;
   DecodeWs w;
   char* ws = base;
+  if (rows < (size_t)R) rows = R;
   w.kv_layer = (size_t)R * T * gD * e;
-  w.x = (float*)ws;      ws += align_up((size_t)R * gD * 4, 1024);
-  w.hb = ws;             ws += align_up((size_t)R * gD * e, 1024);
-  w.qkv = ws;            ws += align_up((size_t)R * 3 * gD * e, 1024);
-  w.f = ws;              ws += align_up((size_t)R * gFF * e, 1024);
+  w.x = (float*)ws;      ws += align_up(rows * gD * 4, 1024);
+  w.hb = ws;             ws += align_up(rows * gD * e, 1024);
+  w.qkv = ws;            ws += align_up(rows * 3 * gD * e, 1024);
+  w.f = ws;              ws += align_up(rows * gFF * e, 1024);
   w.logits = (float*)ws; ws += align_up((size_t)R * gVld * 4, 1024);
   w.kc = ws;             ws += align_up(h->L * w.kv_layer, 1024);
   w.vc = ws;             ws += align_up(h->L * w.kv_layer, 1024);
@@ -815,8 +831,18 @@ int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int*
   return PIO_OK;
 }
 
+namespace {
+// the prompt is prefilled in one batched pass when its causal attention fits the small-attention kernel
+bool prompt_prefill_batched(const PioDecoder* h, int prompt_len) {
+  static const bool off = [] { const char* e = getenv("PIO_PROMPT_PREFILL"); return e && e[0] == '0'; }();
+  return !off && prompt_len >= 2 && pio::small_attention_smem(prompt_len, pio::gD / h->H) <= 48 * 1024;
+}
+}  // namespace
+
 size_t pio_decode_prompt_workspace_bytes(const PioDecoder* h, int R, int prompt_len, int steps) {
-  return decode_ws(h, nullptr, R, prompt_len + steps - 1, 0).total;
+  const bool batched = prompt_prefill_batched(h, prompt_len);
+  // tail: fp32 [R,768] staging row for the last prompt position (prefill) 
+  return decode_ws(h, nullptr, R, prompt_len + steps - 1, batched ? (size_t)R * pio::gD * 2 : 0, batched ? (size_t)R * prompt_len : 0).total;
 }
 
 // Greedy continuation of a prompt of P input embeddings per row (ViECap: soft + hard prompt; viecap/search.py:108-191).
@@ -832,12 +858,37 @@ int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prom
   PIO_CHECK(workspace_bytes >= pio_decode_prompt_workspace_bytes(h, R, prompt_len, steps), "decode_greedy_prompt: workspace too small");
   PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "decode_greedy_prompt: workspace must be 1024-byte aligned");
   cudaStream_t st = as_stream(stream);
-  const DecodeWs w = decode_ws(h, (char*)workspace, R, T, 0);
+  const bool batched = prompt_prefill_batched(h, prompt_len);
+  const DecodeWs w = decode_ws(h, (char*)workspace, R, T, batched ? (size_t)R * gD * 2 : 0, batched ? (size_t)R * prompt_len : 0);
   if (out_logprob_sum) PIO_CUDA(cudaMemsetAsync(out_logprob_sum, 0, (size_t)R * 4, st));
-  for (int p = 0; p < prompt_len; ++p) {
-    prompt_embed_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(prompt, prompt_len, p, h->wpe, w.x, R, gD);
+  if (batched) {
+    // prefill (search.py:150-153): all prompt positions of all rows in one pass, M = R * prompt_len rows per GEMM
+    const int adt = h->act_dt, mode = h->mode, P = prompt_len, rows = R * P;
+    const size_t e = adt == PIO_DT_F32 ? 4 : 2;
+    prompt_embed_all_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(prompt, P, h->wpe, w.x, rows, gD);
     PIO_LAUNCHED();
-    PIO_TRY(decode_blocks(h, w, R, T, p, st));
+    for (int i = 0; i < h->L; ++i) {
+      const PioDecoder::Blk& b = h->blk[i];
+      PIO_TRY(layernorm(w.x, gD, b.ln1_w, b.ln1_b, w.hb, adt, gD, rows, gD, 1e-5f, st));
+      PIO_TRY(linear(mode, w.hb, b.attn_w, w.qkv, rows, 3 * gD, gD, gD, gD, 3 * gD, adt, adt, b.attn_b, nullptr, PIO_ACT_NONE, st));
+      PIO_TRY(small_attention(w.qkv, 3 * gD, (char*)w.qkv + (size_t)gD * e, 3 * gD, w.hb, gD, adt, R, P, h->H, gD / h->H, true,
+                              w.kc + i * w.kv_layer, w.vc + i * w.kv_layer, T, st));
+      PIO_TRY(linear(mode, w.hb, b.proj_w, w.x, rows, gD, gD, gD, gD, gD, adt, PIO_DT_F32, b.proj_b, w.x, PIO_ACT_NONE, st));
+      PIO_TRY(layernorm(w.x, gD, b.ln2_w, b.ln2_b, w.hb, adt, gD, rows, gD, 1e-5f, st));
+      PIO_TRY(linear(mode, w.hb, b.fc_w, w.f, rows, gFF, gD, gD, gD, gFF, adt, adt, b.fc_b, nullptr, PIO_ACT_GELU_NEW, st));
+      PIO_TRY(linear(mode, w.f, b.fc2_w, w.x, rows, gD, gFF, gFF, gFF, gD, adt, PIO_DT_F32, b.fc2_b, w.x, PIO_ACT_NONE, st));
+    }
+    // the residual stream of the LAST prompt position becomes the single-position state (rows 0..R-1 of x)
+    float* last = (float*)w.pfx;
+    PIO_CUDA(cudaMemcpy2DAsync(last, (size_t)gD * 4, w.x + (size_t)(P - 1) * gD, (size_t)P * gD * 4, (size_t)gD * 4, R,
+                               cudaMemcpyDeviceToDevice, st));
+    PIO_CUDA(cudaMemcpyAsync(w.x, last, (size_t)R * gD * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    for (int p = 0; p < prompt_len; ++p) {
+      prompt_embed_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(prompt, prompt_len, p, h->wpe, w.x, R, gD);
+      PIO_LAUNCHED();
+      PIO_TRY(decode_blocks(h, w, R, T, p, st));
+    }
   }
   for (int s = 0; s < steps; ++s) {
     PIO_TRY(decode_pick(h, w, R, out_ids, steps, s, out_logprob_sum, st));
@@ -997,7 +1048,7 @@ int pio_mapper_forward(PioMapper* h, const float* feats, int R, float* out, void
     const PioMapper::Layer& w = h->layers[i];
     PIO_TRY(layernorm(x, gD, w.n1_w, w.n1_b, hb, adt, gD, rows, gD, 1e-5f, st));
     PIO_TRY(linear(mode, hb, w.qkv_w, qkv, rows, 3 * gD, gD, gD, gD, 3 * gD, adt, adt, nullptr, nullptr, PIO_ACT_NONE, st));
-    PIO_TRY(small_attention(qkv, 3 * gD, qkv + (size_t)gD * e, 3 * gD, hb, gD, adt, R, n, h->H, hd, st));
+    PIO_TRY(small_attention(qkv, 3 * gD, qkv + (size_t)gD * e, 3 * gD, hb, gD, adt, R, n, h->H, hd, false, nullptr, nullptr, 0, st));
     PIO_TRY(linear(mode, hb, w.proj_w, x, rows, gD, gD, gD, gD, gD, adt, PIO_DT_F32, w.proj_b, x, PIO_ACT_NONE, st));
     PIO_TRY(layernorm(x, gD, w.n2_w, w.n2_b, hb, adt, gD, rows, gD, 1e-5f, st));
     PIO_TRY(linear(mode, hb, w.fc1_w, f, rows, h->hidden, gD, gD, gD, h->hidden, adt, adt, w.fc1_b, nullptr, PIO_ACT_NONE, st));

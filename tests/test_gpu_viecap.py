@@ -75,7 +75,7 @@ def _agree(ids, ref, margin, tol):
     return ok / ref.shape[0]
 
 
-@pytest.mark.parametrize("P,steps", [(1, 5), (14, 12), (33, 40)])
+@pytest.mark.parametrize("P,steps", [(1, 5), (2, 3), (14, 12), (33, 40), (49, 6), (55, 8)])  # 2..49: batched prefill; else one position at a time
 def test_prompt_decode_fp32_against_oracle(dev, ops, weights, P, steps):
     g = torch.Generator().manual_seed(P)
     R = 7
