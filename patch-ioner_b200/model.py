@@ -113,6 +113,8 @@ class Patchioner:
         self.dino = ops.Vit(dino_weights, self.device, precision)
 
         # --- decoder (model.py:165-166 -> decap.py:188-222)
+        if isinstance(decoder_weights, str) and viecap_config is not None and not os.path.exists(decoder_weights):
+            decoder_weights = None  # the ViECap configs still name a DeCap checkpoint, which caption_tokens never uses
         if isinstance(decoder_weights, str):
             decoder_weights = torch.load(decoder_weights, map_location="cpu", weights_only=False)
         if viecap_config is not None:
