@@ -319,6 +319,8 @@ def run_ours(args):
     def step_resident(i):
         return model(**resident[i % n_sets], get_cls_capt=False, return_ids=True, **kw)[key]
 
+    e2e_marks = []
+
     def run_e2e(n):
         """n steps through the public serving API: every step copies its pinned host inputs in (the copy of step i+1 is
         issued under step i's kernels: Patchioner.forward_pipelined) and reads its ids back to the host."""
@@ -326,6 +328,7 @@ def run_ours(args):
         overlap = os.environ.get("PIO_E2E_OVERLAP", "1") != "0"  # A/B switch: second compute stream for batch i+1
         for out in model.forward_pipelined(batches, overlap_compute=overlap, get_cls_capt=False, return_ids=True, **kw):
             out[key].cpu()  # device -> host read of the step's result
+            e2e_marks.append(time.perf_counter())  # host time at which each step's ids are on the host (diagnostic only)
 
     def barrier():
         if world > 1:
@@ -368,6 +371,8 @@ def run_ours(args):
         sampler2.start()
     ms_e2e = timed(run_e2e, args.steps, max(2, args.warmup), whole_run=True, mark=sampler2)  # >= 2 warm-up batches: both streams' scratch exists
     clocks_e2e = sampler2.stop() if rank == 0 else None
+    last = e2e_marks[-args.steps:]
+    e2e_gaps = [round((b - a) * 1e3, 2) for a, b in zip(last[:-1], last[1:])]  # host-side gaps between consecutive results
 
     regions = captions_per_step(args) * world
     value = regions * args.steps / (ms_total / 1e3)
@@ -389,6 +394,7 @@ def run_ours(args):
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "clocks": clocks_e2e,
+                        "host_gaps_ms": e2e_gaps,
                         "h2d_bytes_per_step": int(h2d_bytes) * world,
                         "d2h_bytes_per_step": int(captions_per_step(args) * decode_steps(args) * 4) * world},
                 "gpu_launches": int(launches), "roofline": roof, "stages": extra,
