@@ -133,16 +133,18 @@ class ClockSampler:
         """start of the window whose samples count (the sampler itself is started earlier: nvidia-smi needs ~1 s to come up)"""
         self.t0 = time.perf_counter()
 
-    def stop(self):
+    def report(self):
+        """clock statistics of the window [mark(), now]; the sampler keeps running (starting a second nvidia-smi next to a
+        timed region stalls the driver for tens of ms while it initialises)"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         t1 = time.perf_counter()
         time.sleep(0.15)  # let the sample that covers the end of the window arrive
-        self.proc.terminate()
         t0 = getattr(self, "t0", 0.0)
-        window = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.15]
+        lines = list(self.lines)
+        window = [ln for (t, ln) in lines if t0 <= t <= t1 + 0.15]
         if not window:  # a window shorter than the sampling period: take the samples closest to it
-            window = [ln for (_, ln) in self.lines[-2:]]
+            window = [ln for (_, ln) in lines[-2:]]
         sm, mx, reasons, power = [], [], set(), []
         for ln in window:
             f = [x.strip() for x in ln.split(",")]
@@ -157,6 +159,12 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self):
+        out = self.report()
+        if self.proc is not None:
+            self.proc.terminate()
+        return out
 
 
 # ------------------------------------------------------------------------------------------------ reference arm (CPU)
@@ -365,12 +373,9 @@ def run_ours(args):
     launches = ops.launch_count()
     # launches counted include the warm-up steps: keep the timed share
     launches = launches * args.steps // (args.steps + args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
-    sampler2 = ClockSampler(local)
-    if rank == 0:
-        sampler2.start()
-    ms_e2e = timed(run_e2e, args.steps, max(2, args.warmup), whole_run=True, mark=sampler2)  # >= 2 warm-up batches: both streams' scratch exists
-    clocks_e2e = sampler2.stop() if rank == 0 else None
+    clocks = sampler.report() if rank == 0 else None
+    ms_e2e = timed(run_e2e, args.steps, max(2, args.warmup), whole_run=True)  # >= 2 warm-up batches: both streams' scratch exists
+    clocks_e2e = sampler.stop() if rank == 0 else None
     last = e2e_marks[-args.steps:]
     e2e_gaps = [round((b - a) * 1e3, 2) for a, b in zip(last[:-1], last[1:])]  # host-side gaps between consecutive results
 
