@@ -170,6 +170,10 @@ def test_patchioner_with_viecap_region_sets(dev, golden, weights):
     emb = m.region_embeddings(imgs.to(dev), bboxes=boxes.clone(), get_controllable_capts=True)["set"]
     want = ov.viecap_forward(weights, emb.cpu().clone(), g["entities"], g["ent_emb"], tok)[0]
     assert out["set_controllable_capts"] == want
+    piped = list(m.forward_pipelined([{"imgs": imgs, "bboxes": boxes.clone()}] * 3, get_cls_capt=False, get_controllable_capts=True))
+    assert len(piped) == 3 and all(p["set_controllable_capts"] == want for p in piped)
+    ids = m(imgs, get_cls_capt=False, bboxes=boxes.clone(), get_controllable_capts=True, return_ids=True)["set_controllable_capts"]
+    assert ids.shape == (B, 64) and [tok.decode(m.viecap.cut(r)) for r in ids.cpu().tolist()] == want
     dense = m(imgs, get_cls_capt=True, bboxes=o_pipe.synth_boxes(B, R, S, seed=1, pad="dense"))
     assert len(dense["bbox_capts"]) == B and len(dense["bbox_capts"][0]) == R and isinstance(dense["cls_capt"][0], str)
     with pytest.raises(Exception, match="not supported with viecap"):
