@@ -49,6 +49,8 @@ extern "C" {
 #define PIO_ACT_NONE 0
 #define PIO_ACT_GELU_ERF 1 /* DINOv2 mlp (exact erf GELU)                 */
 #define PIO_ACT_GELU_NEW 2 /* GPT-2 'gelu_new' (tanh form)                */
+#define PIO_ACT_TANH 3     /* Talk2DINO projection MLP (talk2dino.py:73-83); fp32 mode only */
+#define PIO_ACT_RELU 4     /* fp32 mode only                              */
 
 const char* pio_last_error(void);
 int pio_version(void);

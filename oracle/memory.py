@@ -79,3 +79,27 @@ def get_pseudo_inverse(A: torch.Tensor) -> torch.Tensor:
 def revert_transformation(features: torch.Tensor, A_pinv: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """embedding_utils.py:24: (x - b) @ A_pinv^T   (768 -> 512 for Talk2DINO ViT-B)."""
     return (features - b) @ A_pinv.t()
+
+
+def talk2dino_project_clip_txt(w, textual_embedding: torch.Tensor, act: str = "tanh") -> torch.Tensor:
+    """``ProjectionLayer.project_clip_txt`` (Patch-ioner/src/talk2dino/talk2dino.py:73-83), applied to the CLIP text
+    features when a caption memory is built (im2txtprojection.py:519-523): Linear, then (act, Linear) per hidden layer."""
+    f = {"tanh": torch.tanh, "relu": torch.relu, None: None}[act]
+    x = torch.nn.functional.linear(textual_embedding.float(), w["linear_layer.weight"], w["linear_layer.bias"])
+    i = 0
+    while f"hidden_layers.{i}.weight" in w:
+        if f is not None:
+            x = f(x)
+        x = torch.nn.functional.linear(x, w[f"hidden_layers.{i}.weight"], w[f"hidden_layers.{i}.bias"])
+        i += 1
+    return x
+
+
+def make_talk2dino_weights(seed: int = 77, clip_dim: int = 512, dino_dim: int = 768, hidden_layers: int = 1):
+    g = torch.Generator().manual_seed(seed)
+    w = {"linear_layer.weight": torch.randn(dino_dim, clip_dim, generator=g) * clip_dim ** -0.5,
+         "linear_layer.bias": torch.randn(dino_dim, generator=g) * 0.1}
+    for i in range(hidden_layers):
+        w[f"hidden_layers.{i}.weight"] = torch.randn(dino_dim, dino_dim, generator=g) * dino_dim ** -0.5
+        w[f"hidden_layers.{i}.bias"] = torch.randn(dino_dim, generator=g) * 0.1
+    return w

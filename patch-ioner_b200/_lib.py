@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libpio_sm100.so")
 PIO_FP32, PIO_BF16 = 0, 1
 DT_F32, DT_BF16, DT_I32 = 0, 1, 2
 POOL_MEAN, POOL_GAUSS, POOL_ATTN = 0, 1, 2
-ACT_NONE, ACT_GELU_ERF, ACT_GELU_NEW = 0, 1, 2
+ACT_NONE, ACT_GELU_ERF, ACT_GELU_NEW, ACT_TANH, ACT_RELU = 0, 1, 2, 3, 4
 
 _fp = C.c_void_p  # device pointers travel as integers
 

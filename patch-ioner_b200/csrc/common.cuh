@@ -117,6 +117,8 @@ __device__ __forceinline__ float gelu_new(float x) {
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == PIO_ACT_GELU_ERF) return gelu_erf(v);
   if (act == PIO_ACT_GELU_NEW) return gelu_new(v);
+  if (act == PIO_ACT_TANH) return tanhf(v);
+  if (act == PIO_ACT_RELU) return fmaxf(v, 0.f);
   return v;
 }
 

@@ -239,6 +239,7 @@ int linear_tc(const PioLinear& p, cudaStream_t st) {
   PIO_CHECK(p.lda % 8 == 0 && p.ldw % 8 == 0, "tcgen05 GEMM: lda/ldw must be multiples of 8 (16-byte TMA strides)");
   PIO_CHECK((((uintptr_t)p.A) & 15) == 0 && (((uintptr_t)p.W) & 15) == 0, "tcgen05 GEMM: operands must be 16-byte aligned");
   PIO_CHECK(p.K > 0, "tcgen05 GEMM: K must be positive");
+  PIO_CHECK(p.act >= PIO_ACT_NONE && p.act <= PIO_ACT_GELU_NEW, "tcgen05 GEMM: activation %d is built for the fp32 mode only", p.act);
   if (p.M == 0 || p.N == 0) return PIO_OK;
   PIO_CHECK(p.argmax_val == nullptr || (p.argmax_idx && p.argmax_ld >= argmax_slabs_tc(p.M, p.N)),
             "tcgen05 GEMM: fused arg-max needs val/idx (and optionally sumexp) buffers with ld >= pio_argmax_slabs()");

@@ -74,7 +74,7 @@ class Patchioner:
                 raise NotImplementedError(f"'{name}' selects a backbone/captioner outside the B200 hot path (SURVEY.md 8)")
         if online_texts is not None:
             raise NotImplementedError("online_texts builds a bank with a CLIP text encoder (im2txtprojection.py:448-560): out of scope")
-        h5_bank = isinstance(memory_bank, str) and memory_bank.endswith((".h5", ".hdf5"))
+        h5_bank = isinstance(memory_bank, str) and memory_bank.endswith((".h5", ".hdf5", ".h5.pt"))
         if calculate_argmax_text and ((memory_bank_texts is None and not h5_bank) or support_memory_size <= 0):
             raise ValueError("calculate_argmax_text needs the bank and its captions (memory_bank_texts, or an HDF5 bank with a '-text' dataset)")
         if dino_model is None or "dinov2" not in dino_model or "vitb14" not in dino_model or "reg" not in dino_model:
@@ -140,6 +140,11 @@ class Patchioner:
                     memory_bank_texts = _load_h5_texts(bank)  # the '{name}-text' dataset next to the embeddings (:320-323)
                     self.text_dataset = memory_bank_texts
                 bank = _load_tensor_file(bank)
+                if isinstance(bank, dict):  # bank_builder.write_bank's torch flavour: '{name}-embeddings' (+ '{name}-text')
+                    tk = [k for k in bank if k.endswith("-text")]
+                    if memory_bank_texts is None and tk:
+                        self.text_dataset = memory_bank_texts = list(bank[tk[0]])
+                    bank = bank[[k for k in bank if k.endswith("-embeddings")][0]]
             if bank is None:
                 raise ValueError("support_memory_size > 0 needs memory_bank (tensor or file); building banks from "
                                  "captions needs CLIP text encoders + network (out of scope)")

@@ -198,3 +198,48 @@ def test_cabi_errors(dev, ops, weights):
     bad["mapping_network.transformer.layers.0.attn.to_queries.bias"] = torch.zeros(768)
     with pytest.raises(NotImplementedError):
         ops.Mapper(bad, dev, "fp32")
+
+
+def test_bank_builder_talk2dino_mlp_against_reference_golden(dev, golden, tmp_path):
+    """Caption-memory builder: the Talk2DINO text projection on the device vs the reference class's outputs, then
+    a bank built from it is loaded by Patchioner-side code and projects like the oracle."""
+    from oracle import memory as om
+    from patchioner_b200 import bank_builder as bb
+    from patchioner_b200 import ops
+
+    g = golden("talk2dino")
+    for key, want in g["out"].items():
+        hidden, act = int(key[1]), key.split("_")[1]
+        w = om.make_talk2dino_weights(seed=77 + hidden, hidden_layers=hidden)
+        got = bb.talk2dino_project(g["feats"], w, act, device=dev, rows_per_call=10)
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+    with pytest.raises(ValueError):
+        bb.talk2dino_project(g["feats"], w, "sigmoid", device=dev)
+    # old checkpoints name the hidden layer linear_layer2 (talk2dino.py:85-91)
+    w1 = om.make_talk2dino_weights(seed=78, hidden_layers=1)
+    old = {"linear_layer.weight": w1["linear_layer.weight"], "linear_layer.bias": w1["linear_layer.bias"],
+           "linear_layer2.weight": w1["hidden_layers.0.weight"], "linear_layer2.bias": w1["hidden_layers.0.bias"]}
+    torch.testing.assert_close(bb.talk2dino_project(g["feats"], old, "tanh", device=dev), g["out"]["h1_tanh"], rtol=1e-4, atol=1e-4)
+    # build -> write -> read -> project
+    feats = torch.randn(500, 512, generator=torch.Generator().manual_seed(8))
+    texts = [f"t{i}" for i in range(500)]
+    emb, path = bb.build_bank(feats, texts, w1, "tanh", out_path=str(tmp_path / bb.bank_filename("synthetic", "ViT-B/16", 500)), device=dev)
+    bank, t2 = bb.read_bank(path)
+    assert t2 == texts and torch.equal(bank, emb)
+    q = torch.randn(9, 768, generator=torch.Generator().manual_seed(9))
+    want = om.project(q.clone(), om.drop_zero_rows(bank), normalize=True)
+    got = ops.Bank(bank, dev, "fp32").project(q.to(dev), normalize=True).cpu()
+    assert torch.nn.functional.cosine_similarity(got, want, dim=-1).min() > 0.9999
+    from oracle import dinov2 as o_vit
+    from oracle import decap as o_decap
+    from oracle import pipeline as o_pipe
+    from patchioner_b200 import Patchioner
+    m = Patchioner.from_config({"decap_weights": o_decap.make_weights(seed=1234), "prefix_size": 768, "support_memory_size": 500,
+                                "dino_model": "dinov2_vitb14_reg", "normalize": True, "resize_dim": 224, "crop_dim": 224,
+                                "dino_weights": o_vit.make_weights(seed=1234), "memory_bank": path, "calculate_argmax_text": True,
+                                "precision": "fp32"}, device=dev)
+    caps = m(o_pipe.synth_images(2, 224, seed=1), get_cls_capt=True)["cls_capt"]
+    assert len(caps) == 2 and all(c in texts for c in caps)
+    from patchioner_b200 import _lib as L
+    with pytest.raises(L.PioError, match="fp32 mode only"):
+        ops.linear(torch.randn(128, 64, device=dev).bfloat16(), torch.randn(64, 64, device=dev).bfloat16(), "bf16", act=L.ACT_TANH)
