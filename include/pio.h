@@ -279,6 +279,12 @@ size_t pio_decode_prompt_workspace_bytes(const PioDecoder* h, int R, int prompt_
 /* exit (the reference only exits early at batch 1, search.py:173-176); the sentence is cut at '.' on the host.           */
 int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prompt_len, int steps, int* out_ids,
                              float* out_logprob_sum, void* workspace, size_t workspace_bytes, void* stream);
+/* compute_scores of the ViECap path (entrypoint.py:164-177): mean negative log-likelihood of every right-padded token row  */
+/* ids int32 [R,n] (lens int32 [R] tokens each) under the language model = GPT2LMHeadModel(input_ids, labels=input_ids).loss  */
+/* of that sentence; the perplexity is exp() of it.  NaN for rows with fewer than two tokens.  n <= 128.                     */
+size_t pio_gpt2_score_workspace_bytes(const PioDecoder* h, int R, int n);
+int pio_gpt2_score_tokens(PioDecoder* h, const int* ids, const int* lens, int R, int n, float* out_nll_mean, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* Mapping network (viecap/ClipCap.py:122-153): Linear weights in torch layout [out,in]                                  */
 typedef struct {

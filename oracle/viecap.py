@@ -212,6 +212,18 @@ def greedy_ids(w, prompt: torch.Tensor, steps: int = MAX_LEN, return_margin: boo
     return (ids, torch.stack(margins, dim=1)) if return_margin else ids
 
 
+@torch.no_grad()
+def perplexity(w, token_ids: Sequence[int]) -> float:
+    """entrypoint.py:164-177 for one sentence: exp of the causal-LM loss of ``GPT2LMHeadModel(input_ids, labels=input_ids)``
+    (mean cross-entropy of token i+1 given tokens 0..i; NaN for fewer than two tokens)."""
+    ids = torch.tensor([int(i) for i in token_ids], dtype=torch.long)
+    wte = w["gpt.transformer.wte.weight"]
+    logits = gpt2_hidden(w, wte[ids][None])[0] @ wte.T
+    if ids.numel() < 2:
+        return float("nan")
+    return float(torch.exp(F.cross_entropy(logits[:-1], ids[1:])))
+
+
 def cut_sentence(ids: Sequence[int], eos: Sequence[int]) -> List[int]:
     """search.py:184-190: keep tokens up to and including the first end-of-sentence token (all of them if none)."""
     ids = [int(i) for i in ids]

@@ -485,9 +485,14 @@ size_t small_attention_smem(int n, int hd) { return ((size_t)3 * n * (hd + 1) + 
 
 int small_attention(const void* q, long long ldq, const void* kv, long long ldkv, void* out, long long ldo, int dt, int R, int n, int H,
                     int hd, bool causal, void* kc, void* vc, int Tmax, cudaStream_t st) {
-  PIO_CHECK(n >= 1 && n <= 64 && hd >= 1 && hd <= 128, "small attention: n %d / head_dim %d outside the built range (<=64, <=128)", n, hd);
+  PIO_CHECK(n >= 1 && n <= 128 && hd >= 1 && hd <= 128, "small attention: n %d / head_dim %d outside the built range (<=128, <=128)", n, hd);
   const size_t smem = small_attention_smem(n, hd);
-  PIO_CHECK(smem <= 48 * 1024, "small attention: %zu bytes of shared memory exceed 48 KB", smem);
+  PIO_CHECK(smem <= 200 * 1024, "small attention: %zu bytes of shared memory exceed 200 KB", smem);
+  if (smem > 48 * 1024) {  // opt in to the large carve-out once per kernel
+    static SmemAttrOnce once_f, once_b;
+    if (dt == PIO_DT_F32) PIO_CUDA(once_f.ensure(small_attention_kernel<float>, 200 * 1024));
+    else PIO_CUDA(once_b.ensure(small_attention_kernel<__nv_bfloat16>, 200 * 1024));
+  }
   const float scale = 1.0f / sqrtf((float)hd);
   if (dt == PIO_DT_F32)
     small_attention_kernel<float><<<R * H, 128, smem, st>>>((const float*)q, ldq, (const float*)kv, ldkv, (float*)out, ldo, n, H, hd, scale,

@@ -249,6 +249,65 @@ __global__ void prompt_embed_all_kernel(const float* __restrict__ prompt, int P,
   }
 }
 
+// x[r*n + i, :] = wte[ids[r,i], :] + wpe[i, :]   (token embeddings of whole sentences)
+__global__ void embed_all_kernel(const float* __restrict__ wte, const float* __restrict__ wpe, const int* __restrict__ ids, int n,
+                                 float* __restrict__ x, int rows, int D) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int tok = min(max(ids[warp], 0), 50257 - 1);
+  const float4* a = reinterpret_cast<const float4*>(wte + (long long)tok * D);
+  const float4* b = reinterpret_cast<const float4*>(wpe + (long long)(warp % n) * D);
+  float4* o = reinterpret_cast<float4*>(x + (long long)warp * D);
+  for (int i = lane; i < D / 4; i += 32) {
+    float4 u = __ldg(a + i), v = __ldg(b + i);
+    o[i] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+  }
+}
+
+// nll[row] = logsumexp(logits[row - row0, :V]) - logits[row - row0, ids[row + 1]] for the positions that have a next token
+// (row = r*n + i with i + 1 < lens[r]); 0 elsewhere.  One CTA per logits row.
+__global__ void __launch_bounds__(256) token_nll_kernel(const float* __restrict__ logits, int ld, int V, const int* __restrict__ ids,
+                                                        const int* __restrict__ lens, int n, int row0, float* __restrict__ nll) {
+  __shared__ float red[8];
+  const int row = row0 + blockIdx.x, r = row / n, i = row % n, tid = threadIdx.x;
+  if (i + 1 >= lens[r]) {
+    if (tid == 0) nll[row] = 0.f;
+    return;
+  }
+  const float* lr = logits + (long long)blockIdx.x * ld;
+  float mx = -INFINITY;
+  for (int v = tid; v < V; v += 256) mx = fmaxf(mx, lr[v]);
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) red[tid >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int v = tid; v < V; v += 256) s += expf(lr[v] - mx);
+  s = warp_sum(s);
+  if ((tid & 31) == 0) red[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const int target = min(max(ids[row + 1], 0), V - 1);
+    nll[row] = mx + logf(t) - lr[target];
+  }
+}
+
+// out[r] = mean of nll[r, 0 .. lens[r]-2]  (HF causal-LM loss of one sentence; NaN for fewer than two tokens)
+__global__ void nll_mean_kernel(const float* __restrict__ nll, const int* __restrict__ lens, int n, int R, float* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int m = lens[r] - 1;
+  float s = 0.f;
+  for (int i = 0; i < m; ++i) s += nll[(long long)r * n + i];
+  out[r] = m > 0 ? s / (float)m : NAN;
+}
+
 __global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) o[i] = a[i] + b[i];
@@ -899,6 +958,52 @@ int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prom
       PIO_TRY(decode_blocks(h, w, R, T, prompt_len + s, st));
     }
   }
+  return PIO_OK;
+}
+
+size_t pio_gpt2_score_workspace_bytes(const PioDecoder* h, int R, int n) {
+  return decode_ws(h, nullptr, R, 1, (size_t)R * n * 2, (size_t)R * n).total;
+}
+
+// Mean negative log-likelihood of each right-padded token row under the language model (ViECap compute_scores:
+// entrypoint.py:164-177 -- GPT2LMHeadModel(input_ids, labels=input_ids).loss per sentence; perplexity = exp of it).
+int pio_gpt2_score_tokens(PioDecoder* h, const int* ids, const int* lens, int R, int n, float* out_nll_mean, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  using namespace pio;
+  if (R == 0) return PIO_OK;
+  PIO_CHECK(h && ids && lens && out_nll_mean && workspace, "gpt2_score_tokens: null argument");
+  PIO_CHECK(n >= 1 && n <= 128, "gpt2_score_tokens: %d tokens per row outside [1,128]", n);
+  PIO_CHECK(workspace_bytes >= pio_gpt2_score_workspace_bytes(h, R, n), "gpt2_score_tokens: workspace too small");
+  PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "gpt2_score_tokens: workspace must be 1024-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int adt = h->act_dt, mode = h->mode, rows = R * n;
+  const size_t e = adt == PIO_DT_F32 ? 4 : 2;
+  const DecodeWs w = decode_ws(h, (char*)workspace, R, 1, (size_t)rows * 2, (size_t)rows);
+  float* nll = (float*)w.pfx;
+  embed_all_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(h->wte32, h->wpe, ids, n, w.x, rows, gD);
+  PIO_LAUNCHED();
+  for (int i = 0; i < h->L; ++i) {
+    const PioDecoder::Blk& b = h->blk[i];
+    PIO_TRY(layernorm(w.x, gD, b.ln1_w, b.ln1_b, w.hb, adt, gD, rows, gD, 1e-5f, st));
+    PIO_TRY(linear(mode, w.hb, b.attn_w, w.qkv, rows, 3 * gD, gD, gD, gD, 3 * gD, adt, adt, b.attn_b, nullptr, PIO_ACT_NONE, st));
+    PIO_TRY(small_attention(w.qkv, 3 * gD, (char*)w.qkv + (size_t)gD * e, 3 * gD, w.hb, gD, adt, R, n, h->H, gD / h->H, true, nullptr,
+                            nullptr, 0, st));
+    PIO_TRY(linear(mode, w.hb, b.proj_w, w.x, rows, gD, gD, gD, gD, gD, adt, PIO_DT_F32, b.proj_b, w.x, PIO_ACT_NONE, st));
+    PIO_TRY(layernorm(w.x, gD, b.ln2_w, b.ln2_b, w.hb, adt, gD, rows, gD, 1e-5f, st));
+    PIO_TRY(linear(mode, w.hb, b.fc_w, w.f, rows, gFF, gD, gD, gD, gFF, adt, adt, b.fc_b, nullptr, PIO_ACT_GELU_NEW, st));
+    PIO_TRY(linear(mode, w.f, b.fc2_w, w.x, rows, gD, gFF, gFF, gFF, gD, adt, PIO_DT_F32, b.fc2_b, w.x, PIO_ACT_NONE, st));
+  }
+  PIO_TRY(layernorm(w.x, gD, h->lnf_w, h->lnf_b, w.hb, adt, gD, rows, gD, 1e-5f, st));
+  // lm-head in slices of R rows (the logits buffer of the decode workspace holds R x 50264 floats)
+  for (int row0 = 0; row0 < rows; row0 += R) {
+    const int m = std::min(R, rows - row0);
+    PIO_TRY(linear(mode, (const char*)w.hb + (size_t)row0 * gD * e, h->wte, w.logits, m, gV, gD, gD, gD, gVld, adt, PIO_DT_F32, nullptr,
+                   nullptr, PIO_ACT_NONE, st));
+    token_nll_kernel<<<m, 256, 0, st>>>(w.logits, gVld, gV, ids, lens, n, row0, nll);
+    PIO_LAUNCHED();
+  }
+  nll_mean_kernel<<<cdiv(R, 128), 128, 0, st>>>(nll, lens, n, R, out_nll_mean);
+  PIO_LAUNCHED();
   return PIO_OK;
 }
 

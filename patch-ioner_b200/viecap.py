@@ -207,9 +207,30 @@ class VieCap:
     def forward(self, image_features: torch.Tensor, compute_scores: bool = False):
         """entrypoint.py:98-162: list of sentences.  Note: a batch of ONE region stops at the first '.', which gives the
         same sentence as cutting afterwards (search.py:173-176 vs :184-190)."""
-        if compute_scores:
-            raise NotImplementedError("ViECap compute_scores (per-sentence GPT-2 perplexity, entrypoint.py:164-177) is not built")
         ids = self.forward_ids(image_features).cpu().tolist()
-        return [self.tokenizer.decode(self.cut(r)) for r in ids]
+        sentences = [self.tokenizer.decode(self.cut(r)) for r in ids]
+        if compute_scores:
+            return sentences, self.compute_perplexity(sentences)
+        return sentences
+
+    @torch.no_grad()
+    def compute_perplexity(self, sentences: Sequence[str], chunk: int = 1024) -> List[float]:
+        """entrypoint.py:164-177: exp of the language model's causal loss of every (re-tokenised) sentence.  The reference
+        runs one sentence at a time in a Python loop; here all sentences go through one batched pass (right padded: with
+        causal attention the padding cannot influence the scored positions)."""
+        toks = [self.tokenizer.encode(s) for s in sentences]
+        out: List[float] = []
+        for s in range(0, len(toks), chunk):
+            part = toks[s:s + chunk]
+            n = max(1, max(len(t) for t in part))
+            if n > 128:
+                raise ValueError(f"a sentence of {n} tokens exceeds the 128 positions the scorer is built for")
+            ids = torch.zeros(len(part), n, dtype=torch.int32)
+            for i, t in enumerate(part):
+                ids[i, :len(t)] = torch.tensor(t, dtype=torch.int32)
+            lens = torch.tensor([len(t) for t in part], dtype=torch.int32)
+            nll = self.gpt.score_tokens(ids.to(self.device), lens.to(self.device))
+            out += torch.exp(nll).cpu().tolist()
+        return out
 
     __call__ = forward

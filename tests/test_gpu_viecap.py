@@ -243,3 +243,26 @@ def test_bank_builder_talk2dino_mlp_against_reference_golden(dev, golden, tmp_pa
     from patchioner_b200 import _lib as L
     with pytest.raises(L.PioError, match="fp32 mode only"):
         ops.linear(torch.randn(128, 64, device=dev).bfloat16(), torch.randn(64, 64, device=dev).bfloat16(), "bf16", act=L.ACT_TANH)
+
+
+def test_viecap_compute_scores_against_reference_golden(dev, golden, weights):
+    """compute_scores = per-sentence perplexity (entrypoint.py:164-177) vs the reference's own numbers."""
+    from patchioner_b200.viecap import VieCap
+
+    g = golden("viecap")
+    tok = ov.ToyTokenizer()
+    cfg = {"state_dict": weights, "entities_text": g["entities"], "texts_embeddings": g["ent_emb"], "tokenizer": tok,
+           "clip_hidden_size": 768, "temperature": 0.01, "top_k": 3, "threshold": 0.4, "using_hard_prompt": True,
+           "soft_prompt_first": True, "using_greedy_search": True}
+    vc = VieCap(cfg, dev, "ViT-B/16", precision="fp32")
+    got = vc.compute_perplexity(g["score_sentences"])
+    torch.testing.assert_close(torch.tensor(got), torch.tensor(g["perplexities"]), rtol=2e-3, atol=0)
+    one = vc.compute_perplexity(["bench"])
+    assert len(one) == 1 and one[0] != one[0]   # a single token has no next-token loss: NaN, like the reference
+    sentences, scores = vc.forward(g["feats"].clone().to(dev), compute_scores=True)
+    assert sentences == g["sentences"] and len(scores) == len(sentences)
+    want = [ov.perplexity(weights, tok.encode(s)) for s in sentences]     # 64 unseen ids re-tokenise to longer rows (> 49: large smem path)
+    torch.testing.assert_close(torch.tensor(scores), torch.tensor(want), rtol=2e-3, atol=0)
+    vc16 = VieCap(cfg, dev, "ViT-B/16", precision="bf16")
+    got16 = vc16.compute_perplexity(g["score_sentences"])
+    torch.testing.assert_close(torch.tensor(got16), torch.tensor(g["perplexities"]), rtol=0.1, atol=0)

@@ -57,3 +57,11 @@ def test_cached_greedy_equals_full_recompute():
     a, margin = ov.greedy_ids(w, prompt, 6, return_margin=True)
     b = ov.greedy_ids(w, prompt, 6, use_cache=True)
     assert margin.min() > 1e-4 and torch.equal(a, b)
+
+
+def test_oracle_perplexity_matches_reference(golden):
+    g = golden("viecap")
+    w = ov.make_weights()
+    got = [ov.perplexity(w, i) for i in g["score_ids"]]
+    torch.testing.assert_close(torch.tensor(got), torch.tensor(g["perplexities"]), rtol=1e-4, atol=0)
+    assert ov.perplexity(w, [5]) != ov.perplexity(w, [5])  # NaN for a single token, like the reference's empty loss
