@@ -259,10 +259,32 @@ def test_viecap_compute_scores_against_reference_golden(dev, golden, weights):
     torch.testing.assert_close(torch.tensor(got), torch.tensor(g["perplexities"]), rtol=2e-3, atol=0)
     one = vc.compute_perplexity(["bench"])
     assert len(one) == 1 and one[0] != one[0]   # a single token has no next-token loss: NaN, like the reference
-    sentences, scores = vc.forward(g["feats"].clone().to(dev), compute_scores=True)
-    assert sentences == g["sentences"] and len(scores) == len(sentences)
-    want = [ov.perplexity(weights, tok.encode(s)) for s in sentences]     # 64 unseen ids re-tokenise to longer rows (> 49: large smem path)
+
+    class RoundTrip(ov.ToyTokenizer):
+        """ids the random model invents decode to a word that encodes back to the same id (a real BPE vocabulary does that)"""
+
+        def decode(self, ids):
+            return "".join(self.names.get(int(i), " q" + "".join(chr(97 + int(c)) for c in str(int(i)))) for i in ids)
+
+        def encode(self, text):
+            out = []
+            for piece in self._pat.findall(text):
+                w_ = piece.strip()
+                if w_.startswith("q") and len(w_) > 1 and all("a" <= c <= "j" for c in w_[1:]):
+                    out.append(int("".join(str(ord(c) - 97) for c in w_[1:])))
+                else:
+                    out += super().encode(piece)
+            return out
+
+    rt = RoundTrip()
+    v2 = VieCap({**cfg, "tokenizer": rt}, dev, "ViT-B/16", precision="fp32")
+    sentences, scores = v2.forward(g["feats"].clone().to(dev), compute_scores=True)
+    assert len(scores) == len(sentences) == g["feats"].shape[0]
+    assert [rt.encode(s_) for s_ in sentences] == g["sentence_ids"]      # 64-token rows: the > 48 KB shared-memory path of the scorer
+    want = [ov.perplexity(weights, i) for i in g["sentence_ids"]]
     torch.testing.assert_close(torch.tensor(scores), torch.tensor(want), rtol=2e-3, atol=0)
+    with pytest.raises(ValueError, match="128 positions"):
+        vc.compute_perplexity([" ".join(["dog"] * 130)])
     vc16 = VieCap(cfg, dev, "ViT-B/16", precision="bf16")
     got16 = vc16.compute_perplexity(g["score_sentences"])
     torch.testing.assert_close(torch.tensor(got16), torch.tensor(g["perplexities"]), rtol=0.1, atol=0)
