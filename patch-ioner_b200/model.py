@@ -298,12 +298,14 @@ class Patchioner:
             outs.append(s)
         return outs
 
-    def caption_tokens(self, dino_tokens, project=True, return_n_best_sims=None, compute_scores: bool = False):
-        """model.py:1392-1423."""
+    def caption_tokens(self, dino_tokens, project=True, return_n_best_sims=None, compute_scores: bool = False, rows_per_call=None):
+        """model.py:1392-1423.  ``rows_per_call`` (extension): the rows are the concatenation of reference calls of that many
+        rows each -- only ViECap's output depends on it (hard prompts are padded per call)."""
         if self.viecap is not None:  # model.py:1394-1398
             if return_n_best_sims:
                 raise Exception("return_n_best_sims is not supported with viecap")
-            return self.viecap.forward(dino_tokens.reshape(-1, dino_tokens.shape[-1]), compute_scores=compute_scores)
+            return self.viecap.forward(dino_tokens.reshape(-1, dino_tokens.shape[-1]), compute_scores=compute_scores,
+                                       pad_group=rows_per_call)
         if self.calculate_argmax_text:
             # model.py:1408-1411 -> im2txtprojection.py:371-375: the caption is the text of the most similar bank row
             feats = dino_tokens.reshape(-1, dino_tokens.shape[-1])
@@ -391,7 +393,9 @@ class Patchioner:
         def emit_texts(key, feats, group=None):
             """calculate_argmax_text (model.py:1408-1411): captions are bank texts; only the box branch asks for sims."""
             want_sims = return_n_best_sims if key == "bbox_capts" else None
-            ret = self.caption_tokens(feats, return_n_best_sims=want_sims, compute_scores=compute_scores)
+            # the reference captions boxes in calls of bs * bs_factor regions (model.py:981-1013), everything else in one call
+            per_call = bs * bs_factor if key == "bbox_capts" else None
+            ret = self.caption_tokens(feats, return_n_best_sims=want_sims, compute_scores=compute_scores, rows_per_call=per_call)
             ret, sc = (ret if compute_scores else (ret, None))
             capts, sims = (ret if want_sims else (ret, None))
             cut = (lambda v: [v[i * group:(i + 1) * group] for i in range(bs)]) if group is not None else (lambda v: v)
@@ -412,7 +416,7 @@ class Patchioner:
             if self.viecap is not None and return_ids:  # extension: the 64 generated ids per region, before the sentence cut
                 if return_n_best_sims is not None and key == "bbox_capts":
                     raise Exception("return_n_best_sims is not supported with viecap")
-                ids = self.viecap.forward_ids(feats)
+                ids = self.viecap.forward_ids(feats, pad_group=bs * bs_factor if key == "bbox_capts" else None)
                 outs[key] = ids.reshape(bs, group, -1) if group is not None else ids
                 return None
             if self.calculate_argmax_text or self.viecap is not None:

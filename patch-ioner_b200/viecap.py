@@ -158,29 +158,33 @@ class VieCap:
             out.append(cur)
         return out
 
-    def hard_prompt_tokens(self, feats: torch.Tensor) -> torch.Tensor:
-        """int32 [R,Lmax] on the device, right padded with pad_id (entrypoint.py:117-126)."""
+    def hard_prompt_token_lists(self, feats: torch.Tensor) -> List[List[int]]:
+        """Token ids of every region's hard prompt, unpadded (entrypoint.py:117-121).  ``feats`` must be unit rows."""
         rows = self.detect_entities(feats)
         if self._entity_tokens is not None:
-            toks = [self._compose_tokens(r) for r in rows]
-        else:
-            toks = [self.tokenizer.encode(compose_discrete_prompt([self.entities_text[i] for i in r])) for r in rows]
-        lmax = max(len(t) for t in toks)
+            return [self._compose_tokens(r) for r in rows]
+        return [self.tokenizer.encode(compose_discrete_prompt([self.entities_text[i] for i in r])) for r in rows]
+
+    def _pad(self, toks: Sequence[Sequence[int]], length: Optional[int] = None) -> torch.Tensor:
+        lmax = length if length is not None else max(len(t) for t in toks)
         flat = torch.full((len(toks), lmax), self.pad_id, dtype=torch.int32)
         for i, t in enumerate(toks):
             flat[i, :len(t)] = torch.tensor(t, dtype=torch.int32)
         return flat.to(self.device, non_blocking=True)
 
-    @torch.no_grad()
-    def prompt_embeddings(self, image_features: torch.Tensor) -> torch.Tensor:
-        """[R,P,768] fp32 input embeddings of the language model (entrypoint.py:108-136).  Normalises IN PLACE (:108)."""
+    def hard_prompt_tokens(self, feats: torch.Tensor) -> torch.Tensor:
+        """int32 [R,Lmax] on the device, right padded with pad_id over the whole call (entrypoint.py:117-126)."""
+        return self._pad(self.hard_prompt_token_lists(feats))
+
+    def _normalised(self, image_features: torch.Tensor) -> torch.Tensor:
+        """fp32 unit rows on the device; normalises IN PLACE when the argument already is such a tensor (entrypoint.py:108)."""
         if image_features.device != self.device or image_features.dtype != torch.float32 or not image_features.is_contiguous():
             image_features = image_features.to(self.device, torch.float32).contiguous()
-        ops.l2_normalize_(image_features)
-        cont = self.mapper.forward(image_features)
-        if not self.args["using_hard_prompt"]:
+        return ops.l2_normalize_(image_features)
+
+    def _join(self, cont: torch.Tensor, hard: Optional[torch.Tensor]) -> torch.Tensor:
+        if hard is None:
             return cont
-        hard = self.hard_prompt_tokens(image_features)
         R, Lh = hard.shape
         disc = ops.gather_rows(self.gpt.wte, hard.reshape(-1)).reshape(R, Lh, 768)       # word_embed (ClipCap.py:196-201)
         if self.args["only_hard_prompt"]:
@@ -188,13 +192,50 @@ class VieCap:
         return torch.cat((cont, disc), 1) if self.args["soft_prompt_first"] else torch.cat((disc, cont), 1)
 
     @torch.no_grad()
-    def forward_ids(self, image_features: torch.Tensor, chunk: int = 4096) -> torch.Tensor:
-        """int32 [R,64] generated ids on the device (before the sentence cut)."""
+    def prompt_embeddings(self, image_features: torch.Tensor) -> torch.Tensor:
+        """[R,P,768] fp32 input embeddings of the language model for ONE call of the reference (entrypoint.py:108-136)."""
+        feats = self._normalised(image_features)
+        cont = self.mapper.forward(feats)
+        return self._join(cont, self.hard_prompt_tokens(feats) if self.args["using_hard_prompt"] else None)
+
+    @torch.no_grad()
+    def forward_ids(self, image_features: torch.Tensor, chunk: int = 4096, pad_group: Optional[int] = None) -> torch.Tensor:
+        """int32 [R,64] generated ids on the device (before the sentence cut).
+
+        The reference right-pads the hard prompts of ONE ``forward`` call to their longest and attends to the padding
+        (entrypoint.py:126, no attention mask), so a caption depends on which regions share its call.  ``pad_group`` = rows
+        per reference call (``Patchioner.forward`` captions boxes in calls of ``bs * bs_factor`` regions, model.py:981-1013;
+        None = one call for everything).  Regions are decoded together across calls whenever their calls pad to the same
+        length, in chunks of ``chunk`` rows that only bound the workspace (3.5 MB of KV cache per region, bf16)."""
         feats = image_features.reshape(-1, image_features.shape[-1])
-        out = []
-        for s in range(0, feats.shape[0], chunk):  # bounds the KV cache (3.5 MB per region at 12 layers x 92 positions, bf16)
-            out.append(self.gpt.decode(self.prompt_embeddings(feats[s:s + chunk]), MAX_LEN))
-        return torch.cat(out, 0) if out else torch.empty(0, MAX_LEN, dtype=torch.int32, device=self.device)
+        R = feats.shape[0]
+        out = torch.empty(R, MAX_LEN, dtype=torch.int32, device=self.device)
+        if R == 0:
+            return out
+        feats = self._normalised(feats)
+        cont = torch.cat([self.mapper.forward(feats[s:s + chunk]) for s in range(0, R, chunk)], 0)
+        if not self.args["using_hard_prompt"]:
+            for s in range(0, R, chunk):
+                out[s:s + chunk] = self.gpt.decode(cont[s:s + chunk], MAX_LEN)
+            return out
+        toks = self.hard_prompt_token_lists(feats)
+        G = R if not pad_group else int(pad_group)
+        buckets: Dict[int, List[int]] = {}
+        for g0 in range(0, R, G):
+            rows = range(g0, min(g0 + G, R))
+            buckets.setdefault(max(len(toks[i]) for i in rows), []).extend(rows)
+        for length, rows in sorted(buckets.items()):
+            for s in range(0, len(rows), chunk):
+                part = rows[s:s + chunk]
+                hard = self._pad([toks[i] for i in part], length)
+                whole = len(part) == R
+                idx = None if whole else torch.tensor(part, dtype=torch.long, device=self.device)
+                ids = self.gpt.decode(self._join(cont if whole else cont[idx], hard), MAX_LEN)
+                if whole:
+                    out = ids
+                else:
+                    out[idx] = ids
+        return out
 
     def cut(self, ids: Sequence[int]) -> List[int]:
         """search.py:184-190: keep up to and including the first end-of-sentence token."""
@@ -204,10 +245,10 @@ class VieCap:
         return list(ids)
 
     @torch.no_grad()
-    def forward(self, image_features: torch.Tensor, compute_scores: bool = False):
+    def forward(self, image_features: torch.Tensor, compute_scores: bool = False, pad_group: Optional[int] = None):
         """entrypoint.py:98-162: list of sentences.  Note: a batch of ONE region stops at the first '.', which gives the
-        same sentence as cutting afterwards (search.py:173-176 vs :184-190)."""
-        ids = self.forward_ids(image_features).cpu().tolist()
+        same sentence as cutting afterwards (search.py:173-176 vs :184-190).  ``pad_group``: see ``forward_ids``."""
+        ids = self.forward_ids(image_features, pad_group=pad_group).cpu().tolist()
         sentences = [self.tokenizer.decode(self.cut(r)) for r in ids]
         if compute_scores:
             return sentences, self.compute_perplexity(sentences)

@@ -288,3 +288,45 @@ def test_viecap_compute_scores_against_reference_golden(dev, golden, weights):
     vc16 = VieCap(cfg, dev, "ViT-B/16", precision="bf16")
     got16 = vc16.compute_perplexity(g["score_sentences"])
     torch.testing.assert_close(torch.tensor(got16), torch.tensor(g["perplexities"]), rtol=0.1, atol=0)
+
+
+def test_viecap_padding_follows_the_reference_calls(dev, golden, weights):
+    """Hard prompts are padded per reference call and the padding is attended (entrypoint.py:126): captioning rows in calls of
+    G rows must equal the oracle run call by call, also when rows of different calls are decoded together."""
+    from oracle import dinov2 as o_vit
+    from oracle import pipeline as o_pipe
+    from oracle import pooling as o_pool
+    from patchioner_b200 import Patchioner
+    from patchioner_b200.viecap import VieCap
+
+    g = golden("viecap")
+    tok = ov.ToyTokenizer()
+    cfg = {"state_dict": weights, "entities_text": g["entities"], "texts_embeddings": g["ent_emb"], "tokenizer": tok,
+           "clip_hidden_size": 768, "temperature": 0.01, "top_k": 3, "threshold": 0.4, "using_hard_prompt": True,
+           "soft_prompt_first": True, "using_greedy_search": True}
+    vc = VieCap(cfg, dev, "ViT-B/16", precision="fp32")
+    lens = [len(t) for t in vc.hard_prompt_token_lists(_unit(g["feats"]).to(dev))]
+    assert len(set(lens)) > 1                                   # the fixture has prompts of different lengths
+    for G in (2, 4, 5):
+        want = []
+        for s in range(0, 6, G):
+            want += ov.viecap_forward(weights, g["feats"][s:s + G].clone(), g["entities"], g["ent_emb"], tok, steps=24)[1].tolist()
+        got = vc.forward_ids(g["feats"].clone().to(dev), pad_group=G)[:, :24].cpu().tolist()
+        assert got == want, G
+    assert vc.forward_ids(g["feats"].clone().to(dev), chunk=2).cpu().tolist() == vc.forward_ids(g["feats"].clone().to(dev)).cpu().tolist()
+
+    # through Patchioner.forward: boxes are captioned in calls of bs * bs_factor regions (model.py:981-1013)
+    m = Patchioner.from_config({"prefix_size": 768, "support_memory_size": 0, "dino_model": "dinov2_vitb14_reg", "normalize": False,
+                                "resize_dim": 224, "crop_dim": 224, "dino_weights": o_vit.make_weights(seed=1234),
+                                "clip_model_name": "ViT-B/16", "viecap": cfg, "precision": "fp32"}, device=dev)
+    B, S, R = 2, 224, 5
+    imgs = o_pipe.synth_images(B, S, seed=3)
+    boxes = o_pipe.synth_boxes(B, R, S, seed=3, pad="dense")
+    emb = m.region_embeddings(imgs.to(dev), bboxes=boxes.clone())["bbox"].reshape(-1, 768).cpu()
+    for bs_factor in (1, 2, 4):
+        per_call = B * bs_factor
+        want = []
+        for s in range(0, B * R, per_call):
+            want += ov.viecap_forward(weights, emb[s:s + per_call].clone(), g["entities"], g["ent_emb"], tok)[0]
+        out = m(imgs, get_cls_capt=False, bboxes=boxes.clone(), bs_factor=bs_factor)["bbox_capts"]
+        assert [c for row in out for c in row] == want, bs_factor
