@@ -367,6 +367,8 @@ __global__ void __launch_bounds__(128) decode_attention_long_kernel(const T* __r
   __shared__ float qs[4][HDIM];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warp = blockIdx.x * 4 + wib;
+  pdl_wait();               // qkv comes from the GEMM just before
+  pdl_launch_dependents();  // the projection GEMM may start its prologue (it waits before touching our output)
   if (warp >= R * H) return;
   const int r = warp / H, h = warp % H;
   const T* row = qkv + (long long)r * 3 * H * HDIM + h * HDIM;
@@ -510,10 +512,11 @@ int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int
     PIO_CHECK(t < T && T <= 128, "decode attention: position %d outside cache of %d (max 128)", t, T);
     const int blocks = cdiv((long long)R * H, 4);
     if (dt == PIO_DT_F32)
-      decode_attention_long_kernel<float><<<blocks, 128, 0, st>>>((const float*)qkv, (float*)kc, (float*)vc, (float*)out, R, H, T, t, 0.125f);
+      launch_pdl(decode_attention_long_kernel<float>, dim3(blocks), dim3(128), 0, st, (const float*)qkv, (float*)kc, (float*)vc, (float*)out,
+                 R, H, T, t, 0.125f);
     else
-      decode_attention_long_kernel<__nv_bfloat16><<<blocks, 128, 0, st>>>((const __nv_bfloat16*)qkv, (__nv_bfloat16*)kc, (__nv_bfloat16*)vc,
-                                                                          (__nv_bfloat16*)out, R, H, T, t, 0.125f);
+      launch_pdl(decode_attention_long_kernel<__nv_bfloat16>, dim3(blocks), dim3(128), 0, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)kc,
+                 (__nv_bfloat16*)vc, (__nv_bfloat16*)out, R, H, T, t, 0.125f);
     PIO_LAUNCHED();
     return PIO_OK;
   }
