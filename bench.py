@@ -503,6 +503,29 @@ def stage_breakdown(model, ops, batch, kw, args, stream):
     out["_gemm"] = {"kernel": "gemm_tc2_kernel: 2-CTA tcgen05 GEMM, 256x256 pair tiles (ViT fc1 + GELU)" if args.precision == "bf16"
                     else "sgemm_tn_kernel (ViT fc1 + GELU)",
                     "shape": [M, 3072, 768], "ms": ms, "flops": flops, "tflops": flops / ms / 1e9, "traffic": traffic}
+    if model.viecap is not None and args.precision == "bf16":
+        # the kernel with the largest share of this workload's launches: the decode-step GEMM at M = regions rows (qkv shape).
+        # Weight-streaming bound at this size: its algorithmic bytes are the bf16 weight panel + the activations.
+        Md = B * n_out
+        A2 = torch.randn(Md, 768, device=imgs.device).to(dt)
+        W2 = torch.randn(2304, 768, device=imgs.device).to(dt) / 28
+        b2 = torch.zeros(2304, device=imgs.device)
+        C2 = torch.empty(Md, 2304, device=imgs.device, dtype=dt)
+        for _ in range(3):
+            ops.linear(A2, W2, args.precision, bias=b2, out=C2)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record(stream)
+        for _ in range(50):
+            ops.linear(A2, W2, args.precision, bias=b2, out=C2)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms2 = e0.elapsed_time(e1) / 50
+        bytes2 = (2304 * 768 + Md * 768 + Md * 2304) * 2
+        out["decode_gemm"] = {"kernel": "gemm_tc_kernel<64> (decode-step qkv GEMM)", "shape": [Md, 2304, 768], "avg_launch_ms": ms2,
+                              "bound": "hbm", "achieved": bytes2 / ms2 / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                              "frac": bytes2 / ms2 / 1e6 / pk["hbm_gbs"], "tflops": 2.0 * Md * 2304 * 768 / ms2 / 1e9,
+                              "note": "back-to-back launches of one shape (weights L2-resident); launch-latency-bound at this M"}
     return out
 
 
