@@ -141,6 +141,8 @@ struct Epilogue {
   float* exp_psum;
   float* exp_pmax;
   int exp_ld;
+  float* split_ws;  // deterministic split-K: partial tiles [work item][128][BN] fp32 (gemm_sm100.cu)
+  int* split_cnt;   //                        arrival counters per output tile, zero between launches
   __device__ __forceinline__ long long out_row(int m) const {
     if (rows_per_group == 0) return m;
     return (long long)(m / rows_per_group) * group_stride + group_offset + (m % rows_per_group);
@@ -182,6 +184,8 @@ inline Epilogue make_epilogue(const PioLinear& p) {
   e.exp_psum = p.exp_psum;
   e.exp_pmax = p.exp_pmax;
   e.exp_ld = p.exp_ld;
+  e.split_ws = nullptr;
+  e.split_cnt = nullptr;
   return e;
 }
 

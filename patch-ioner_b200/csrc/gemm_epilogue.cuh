@@ -51,7 +51,7 @@ struct TmaOut {
   uint32_t smem;           // this warp's staging box
   int mode;                // 0 = direct stores, 1 = TMA store, 2 = TMA reduce-add (C += value)
 };
-enum { STORE_DIRECT = 0, STORE_TMA = 1, STORE_TMA_ADD = 2 };
+enum { STORE_DIRECT = 0, STORE_TMA = 1, STORE_TMA_ADD = 2, STORE_SPLIT_FIXUP = 3 };
 
 __device__ __forceinline__ void stage_wait_free(int lane) {
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

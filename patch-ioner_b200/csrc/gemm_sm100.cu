@@ -16,6 +16,9 @@
 // No CUTLASS: descriptors are built by hand (field layout checked against cute/arch/mma_sm100_desc.hpp).
 #include "tc_ptx.cuh"
 #include "gemm_epilogue.cuh"
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include <algorithm>
 #include <mutex>
@@ -56,6 +59,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __shared__ __align__(8) uint64_t bars[2 * cfg::STAGES + 4];
   __shared__ uint32_t tmem_slot_var;
   __shared__ __align__(16) float s_scale[BN], s_bias[BN], s_gamma[BN];  // per-tile column vectors of the epilogue
+  __shared__ int s_ticket;
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (cfg::STAGES + s); };
@@ -180,6 +184,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
       const uint32_t tacc = tmem_base + as * BN;
+      if (store_mode == STORE_SPLIT_FIXUP) {
+        // Deterministic split-K: every split leaves its raw fp32 partial tile in the workspace; the split that arrives last at
+        // the tile's counter sums all partials in split order (so the result does not depend on the arrival order) and runs
+        // the epilogue.  Only for GEMMs with too few output tiles to occupy the machine (decode steps at small batch).
+        float* part = epi.split_ws + (size_t)w * (BM * BN);
+#pragma unroll 1
+        for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+          uint32_t r[32];
+          tmem_ld32(tacc + ((uint32_t)(quarter * 32) << 16) + c, r);
+          tmem_ld_wait();
+          float4* dst = reinterpret_cast<float4*>(part + (size_t)(quarter * 32 + lane) * BN + c);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                 __uint_as_float(r[4 * i + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+        __threadfence();  // this thread's partial values are visible device-wide before the ticket is taken
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (et == 0) s_ticket = atomicAdd(epi.split_cnt + tile, 1);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (s_ticket == k_splits - 1) {
+          __threadfence();
+          for (int idx = et; idx < BM * (BN / 4); idx += NUM_EPI_WARPS * 32) {
+            const int row = idx / (BN / 4), c4 = (idx % (BN / 4)) * 4;
+            const int mm = m0 + row;
+            if (mm >= M) break;  // rows ascend with idx
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sp = 0; sp < k_splits; ++sp) {  // fixed order; .cg: the partials were written by other SMs
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(epi.split_ws + ((size_t)(sp * out_tiles + tile) * BM + row) * BN + c4));
+              acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            }
+            const long long orow = epi.out_row(mm);
+            const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = n0 + c4 + j;
+              if (n >= N) continue;
+              const float v = epi.apply(av[j], mm, orow, n);
+              if (c_dt == PIO_DT_F32) reinterpret_cast<float*>(C)[orow * ldc + n] = v;
+              else reinterpret_cast<__nv_bfloat16*>(C)[orow * ldc + n] = __float2bfloat16(v);
+            }
+          }
+          if (et == 0) epi.split_cnt[tile] = 0;  // ready for the next launch
+        }
+        continue;
+      }
       epilogue_tile<BN>(tacc, quarter, lane, half, m, M, n0, N, (tile % n_blocks) * 2 + half, C, ldc, c_dt, epi, s_scale, s_bias, s_gamma, to);
       tc_fence_before();
       __syncwarp();
@@ -197,6 +250,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------ host side
+// Workspace of the deterministic split-K: one per (device, stream), allocated on first use (work items never exceed the SM count,
+// a partial tile is at most 128 x 192 floats) and kept for the life of the process.
+struct SplitScratch { float* ws; int* cnt; };
+inline bool split_fixup_enabled() {
+  static const bool on = [] { const char* e = getenv("PIO_GEMM_SPLITK"); return !(e && e[0] == '0'); }();
+  return on;
+}
+inline int split_scratch(cudaStream_t st, SplitScratch* out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SplitScratch> cache;
+  int dev = 0;
+  PIO_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({dev, st});
+  if (it == cache.end()) {
+    SplitScratch sc;
+    PIO_CUDA(cudaMalloc(&sc.ws, (size_t)kNumSMs * BM * 192 * sizeof(float)));
+    PIO_CUDA(cudaMalloc(&sc.cnt, kNumSMs * sizeof(int)));
+    PIO_CUDA(cudaMemset(sc.cnt, 0, kNumSMs * sizeof(int)));
+    it = cache.emplace(std::make_pair(dev, st), sc).first;
+  }
+  *out = it->second;
+  return PIO_OK;
+}
+
 template <int BN>
 int launch(const PioLinear& p, cudaStream_t st) {
   using cfg = Cfg<BN>;
@@ -215,17 +293,33 @@ int launch(const PioLinear& p, cudaStream_t st) {
   // the recombination GEMM of the memory projection for a handful of queries -- is cut along K; the partial tiles meet in C
   // through the bulk reduce-add.
   int k_splits = 1;
+  int mode = store_mode;
   const int k_blocks = cdiv(p.K, BK);
+  Epilogue epi = make_epilogue(p);
   if (store_mode == STORE_TMA_ADD && p.bias == nullptr && p.gamma == nullptr && p.colscale == nullptr && p.act == PIO_ACT_NONE &&
       tiles * 2 <= kNumSMs && k_blocks >= 64) {
     k_splits = std::min(kNumSMs / tiles, k_blocks / 32);
     const int kbs = cdiv(k_blocks, k_splits);
     k_splits = cdiv(k_blocks, kbs);  // no empty split
+  } else if (split_fixup_enabled() && BN <= 192 && tiles * 2 <= kNumSMs && k_blocks >= 24 && p.act == PIO_ACT_NONE &&
+             p.argmax_val == nullptr && p.exp_ref == nullptr) {
+    // Deterministic split-K for long-K GEMMs with a handful of output tiles (decode steps at small batch: each CTA would
+    // stream all of K through one SM's L2 port).  Partials meet in a workspace and are summed in split order.
+    SplitScratch sc;
+    PIO_TRY(split_scratch(st, &sc));
+    k_splits = std::min(kNumSMs / tiles, k_blocks / 6);
+    const int kbs = cdiv(k_blocks, k_splits);
+    k_splits = cdiv(k_blocks, kbs);
+    if (k_splits > 1) {
+      mode = STORE_SPLIT_FIXUP;
+      epi.split_ws = sc.ws;
+      epi.split_cnt = sc.cnt;
+    }
   }
   const int work = tiles * k_splits;
   const int grid = work < kNumSMs ? work : kNumSMs;
-  launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), cfg::SMEM_BYTES, st, ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc,
-             p.c_dt, make_epilogue(p), k_splits);
+  launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), cfg::SMEM_BYTES, st, ma, mw, mc, mode, p.C, p.M, p.N, p.K, p.ldc,
+             p.c_dt, epi, k_splits);
   PIO_LAUNCHED();
   return PIO_OK;
 }

@@ -887,3 +887,37 @@ def test_linear_split_k_accumulate(dev, ops, M, N, K):
     X = C0.clone().to(dev)
     ops.linear(A.to(dev), W.to(dev), "bf16", residual=X, out=X)
     torch.testing.assert_close(X.cpu().double(), ref, rtol=2e-3, atol=2e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 768, 3072), (256, 768, 3072), (130, 1000, 2048), (1, 768, 1536), (300, 2304, 1536)])
+def test_linear_bf16_deterministic_split_k(dev, ops, M, N, K):
+    """Long-K GEMMs with few output tiles are cut along K; the partial tiles are summed in split order by the last-arriving
+    CTA, so the result is exact to accumulation order AND bit-identical from run to run (greedy decoding must be repeatable)."""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).bfloat16()
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    ref = A.float() @ W.float().T
+    Ad, Wd = A.to(dev), W.to(dev)
+    out = ops.linear(Ad, Wd, "bf16")
+    torch.testing.assert_close(out.cpu(), ref, rtol=2e-3, atol=2e-3)
+    for _ in range(3):
+        assert torch.equal(ops.linear(Ad, Wd, "bf16"), out)
+    # the decode step's fc2: x += A W^T + b in place, fp32 residual stream
+    X = res.clone().to(dev)
+    ops.linear(Ad, Wd, "bf16", bias=bias.to(dev), residual=X, out=X)
+    torch.testing.assert_close(X.cpu(), res + ref + bias, rtol=2e-3, atol=2e-3)
+    X2 = res.clone().to(dev)
+    ops.linear(Ad, Wd, "bf16", bias=bias.to(dev), residual=X2, out=X2)
+    assert torch.equal(X, X2)
+    # bf16 output with a column scale, and on a second stream (its own workspace)
+    gamma = torch.rand(N, generator=g)
+    o16 = ops.linear(Ad, Wd, "bf16", bias=bias.to(dev), gamma=gamma.to(dev), out_dtype=torch.bfloat16)
+    torch.testing.assert_close(o16.float().cpu(), gamma * (ref + bias), rtol=2e-2, atol=2e-2)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        o2 = ops.linear(Ad, Wd, "bf16")
+    s.synchronize()
+    assert torch.equal(o2, out)
