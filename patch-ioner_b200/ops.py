@@ -533,21 +533,18 @@ class Gpt2Decoder:
                                                  ws.data_ptr(), nbytes, _stream()))
         return (ids, lp) if compute_scores else ids
 
-
-def _gpt2_score(self, ids: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
-    """Mean negative log-likelihood per right-padded token row (int32 ids [R,n], int32 lens [R]) -> fp32 [R]."""
-    _need_cuda(ids, lens)
-    assert ids.dtype == torch.int32 and lens.dtype == torch.int32 and ids.dim() == 2
-    ids, lens = ids.contiguous(), lens.contiguous()
-    R, n = ids.shape
-    out = torch.empty(R, dtype=torch.float32, device=ids.device)
-    nbytes = L.lib().pio_gpt2_score_workspace_bytes(self._h, R, n)
-    ws = workspace(nbytes, ids.device, "gpt2_score")
-    L.check(L.lib().pio_gpt2_score_tokens(self._h, ids.data_ptr(), lens.data_ptr(), R, n, out.data_ptr(), ws.data_ptr(), nbytes, _stream()))
-    return out
-
-
-Gpt2Decoder.score_tokens = _gpt2_score
+    def score_tokens(self, ids: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
+        """Mean negative log-likelihood per right-padded token row (int32 ids [R,n], int32 lens [R]) -> fp32 [R]."""
+        _need_cuda(ids, lens)
+        assert ids.dtype == torch.int32 and lens.dtype == torch.int32 and ids.dim() == 2
+        ids, lens = ids.contiguous(), lens.contiguous()
+        R, n = ids.shape
+        out = torch.empty(R, dtype=torch.float32, device=ids.device)
+        nbytes = L.lib().pio_gpt2_score_workspace_bytes(self._h, R, n)
+        ws = workspace(nbytes, ids.device, "gpt2_score")
+        L.check(L.lib().pio_gpt2_score_tokens(self._h, ids.data_ptr(), lens.data_ptr(), R, n, out.data_ptr(), ws.data_ptr(), nbytes,
+                                              _stream()))
+        return out
 
 
 class Mapper:
