@@ -1,5 +1,6 @@
 """CPU: the ViECap oracle (oracle/viecap.py) against the outputs of the reference's own classes (tests/golden/viecap.pt,
 made by tests/golden/make_golden_viecap.py), plus the host logic of patch-ioner_b200/viecap.py that needs no GPU."""
+import pytest
 import torch
 
 from oracle import viecap as ov
@@ -65,3 +66,26 @@ def test_oracle_perplexity_matches_reference(golden):
     got = [ov.perplexity(w, i) for i in g["score_ids"]]
     torch.testing.assert_close(torch.tensor(got), torch.tensor(g["perplexities"]), rtol=1e-4, atol=0)
     assert ov.perplexity(w, [5]) != ov.perplexity(w, [5])  # NaN for a single token, like the reference's empty loss
+
+
+def test_entity_files_are_read_like_the_reference(tmp_path):
+    """entrypoint.py:178-221 + load_annotations.py:91-103: vocabulary JSON lower-cased, stripped, SORTED; embeddings pickle named
+    by the suffix with '/' removed and '_with_ensemble' when prompt_ensemble is set."""
+    import json
+    import pickle
+
+    from patchioner_b200.viecap import DEFAULTS, VieCap
+
+    d = tmp_path / "annotations" / "vocabulary"
+    d.mkdir(parents=True)
+    (d / "coco_categories.json").write_text(json.dumps(["Person ", "traffic light", "Dog", "cat"]))
+    emb = torch.randn(4, 8)
+    with open(d / "coco_embeddings_ViT-B16_t2d__with_ensemble.pickle", "wb") as f:
+        pickle.dump(emb, f)
+    cfg = dict(DEFAULTS, name_of_entities_text="coco_entities", files_path=str(tmp_path), prompt_ensemble=True)
+    ents, e = VieCap._load_entities(cfg, "ViT-B/16_t2d_")
+    assert ents == ["cat", "dog", "person", "traffic light"] and torch.equal(e, emb)
+    cfg["disable_all_entities"] = True          # single-word entities only
+    assert VieCap._load_entities(cfg, "ViT-B/16_t2d_")[0] == ["cat", "dog", "person"]
+    with pytest.raises(NotImplementedError):
+        VieCap._load_entities(dict(cfg, name_of_entities_text="open_image_entities"), "x")
