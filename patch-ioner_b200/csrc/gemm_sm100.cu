@@ -257,6 +257,10 @@ inline bool split_fixup_enabled() {
   static const bool on = [] { const char* e = getenv("PIO_GEMM_SPLITK"); return !(e && e[0] == '0'); }();
   return on;
 }
+inline int split_min_kblocks() {
+  static const int v = [] { const char* e = getenv("PIO_GEMM_SPLITK_MIN_KB"); return e ? atoi(e) : 24; }();
+  return v;
+}
 inline int split_scratch(cudaStream_t st, SplitScratch* out) {
   static std::mutex mu;
   static std::map<std::pair<int, cudaStream_t>, SplitScratch> cache;
@@ -301,7 +305,7 @@ int launch(const PioLinear& p, cudaStream_t st) {
     k_splits = std::min(kNumSMs / tiles, k_blocks / 32);
     const int kbs = cdiv(k_blocks, k_splits);
     k_splits = cdiv(k_blocks, kbs);  // no empty split
-  } else if (split_fixup_enabled() && BN <= 192 && tiles * 2 <= kNumSMs && k_blocks >= 24 && p.act == PIO_ACT_NONE &&
+  } else if (split_fixup_enabled() && BN <= 192 && tiles * 2 <= kNumSMs && k_blocks >= split_min_kblocks() && p.act == PIO_ACT_NONE &&
              p.argmax_val == nullptr && p.exp_ref == nullptr) {
     // Deterministic split-K for long-K GEMMs with a handful of output tiles (decode steps at small batch: each CTA would
     // stream all of K through one SM's L2 port).  Partials meet in a workspace and are summed in split order.

@@ -889,7 +889,7 @@ def test_linear_split_k_accumulate(dev, ops, M, N, K):
     torch.testing.assert_close(X.cpu().double(), ref, rtol=2e-3, atol=2e-2)
 
 
-@pytest.mark.parametrize("M,N,K", [(64, 768, 3072), (256, 768, 3072), (130, 1000, 2048), (1, 768, 1536), (300, 2304, 1536)])
+@pytest.mark.parametrize("M,N,K", [(64, 768, 3072), (256, 768, 3072), (130, 1000, 2048), (1, 768, 1536), (300, 2304, 1536), (64, 2304, 768)])
 def test_linear_bf16_deterministic_split_k(dev, ops, M, N, K):
     """Long-K GEMMs with few output tiles are cut along K; the partial tiles are summed in split order by the last-arriving
     CTA, so the result is exact to accumulation order AND bit-identical from run to run (greedy decoding must be repeatable)."""
