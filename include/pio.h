@@ -57,6 +57,9 @@ int pio_version(void);
 /* number of kernels this library launched since the last pio_reset_launch_count() (bench evidence) */
 long long pio_launch_count(void);
 void pio_reset_launch_count(void);
+/* frees the library's lazily allocated per-(device, stream) scratch (deterministic split-K partials and counters); */
+/* call with those streams idle, e.g. at interpreter exit.  The scratch is re-created on demand.                    */
+void pio_release_scratch(void);
 
 /* ------------------------------------------------------------------------------------------ */
 /* generic dense layer:  C[map(m), n] = res + gamma[n] * act( alpha * colscale[n] * (A W^T)[m,n] + bias[n] ) */
@@ -95,6 +98,10 @@ typedef struct {
   float* exp_psum;
   float* exp_pmax;
   int exp_ld;
+  /* w_static != 0: W is not written by any kernel still in flight on the stream (weights, caption bank, wte); the  */
+  /* tcgen05 kernels then fetch their first W tiles AHEAD of the programmatic-dependent-launch wait.  Leave it 0   */
+  /* when W may be the output of the previous call on the same stream (then every load waits for that kernel).     */
+  int w_static;
 } PioLinear;
 int pio_argmax_slabs(int M, int N);
 /* ids[row*ids_ld + t] = arg-max over the slabs (first index wins ties); logprob_sum[row] += log softmax at it (or NULL) */
@@ -313,6 +320,20 @@ int pio_entity_topk(const float* q, const float* ent, int R, int n_ent, int D, f
 
 /* L2-normalise rows in place */
 int pio_l2_normalize(float* x, int rows, int dim, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Batched detokenisation (HOST buffers, no kernel): replaces the per-row loop at the end of decoding_batched            */
+/* (src/decap/decap.py:162-181) and SimpleTokenizer.decode (src/clip/simple_tokenizer.py:129-131).                        */
+/* ids int32 [R, ld] (T used columns); table = concatenated byte strings of the vocabulary, token i = table[offsets[i] :  */
+/* offsets[i+1]] (offsets has vocab + 1 entries).  Row r's bytes = concatenation of its tokens up to (excluding) the first */
+/* eot_id -> out[row_offsets[r] : row_offsets[r+1]]; row_status[r] = 0 whole row, 2 cut at eot_id, 1 an id outside the     */
+/* table (row left empty: the reference raises KeyError there and returns None for the whole call, decap.py:180-181).      */
+/* strip_trailing_sep: drop one trailing byte of rows that were not cut (tables whose entries end in a separator);         */
+/* replace_eow: substitute the bytes "</w>" by " " (simple_tokenizer.py:130).  UTF-8 decoding is left to the caller;       */
+/* *all_ascii (may be NULL) = 1 when every output byte is < 128 (the caller may then decode the buffer in one piece).      */
+int pio_detok_rows(const int* ids, int R, int T, int ld, const unsigned char* table, const long long* offsets, int vocab,
+                   int eot_id, int strip_trailing_sep, int replace_eow, unsigned char* out, long long out_cap,
+                   long long* row_offsets, int* row_status, int* all_ascii);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ class PioLinear(C.Structure):
                 ("ldres", C.c_int), ("alpha", C.c_float), ("act", C.c_int),
                 ("rows_per_group", C.c_int), ("group_stride", C.c_int), ("group_offset", C.c_int),
                 ("argmax_val", _fp), ("argmax_idx", _fp), ("argmax_sumexp", _fp), ("argmax_ld", C.c_int),
-                ("exp_ref", _fp), ("exp_psum", _fp), ("exp_pmax", _fp), ("exp_ld", C.c_int)]
+                ("exp_ref", _fp), ("exp_psum", _fp), ("exp_pmax", _fp), ("exp_ld", C.c_int), ("w_static", C.c_int)]
 
 
 VIT_BLOCK_FIELDS = ["ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ls1",
@@ -80,6 +80,7 @@ SIGNATURES = {
     "pio_version": (C.c_int, []),
     "pio_launch_count": (C.c_longlong, []),
     "pio_reset_launch_count": (None, []),
+    "pio_release_scratch": (None, []),
     "pio_linear": (C.c_int, [C.POINTER(PioLinear), C.c_int, _fp]),
     "pio_argmax_slabs": (C.c_int, [C.c_int, C.c_int]),
     "pio_argmax_finish": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp, _fp]),
@@ -129,6 +130,8 @@ SIGNATURES = {
     "pio_mapper_destroy": (None, [_fp]),
     "pio_mapper_workspace_bytes": (C.c_size_t, [_fp, C.c_int]),
     "pio_mapper_forward": (C.c_int, [_fp, _fp, C.c_int, _fp, _fp, C.c_size_t, _fp]),
+    "pio_detok_rows": (C.c_int, [_fp, C.c_int, C.c_int, C.c_int, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_longlong,
+                                 _fp, _fp, _fp]),
     "pio_entity_topk": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _fp, _fp, _fp]),
 }
 

@@ -193,6 +193,7 @@ inline Epilogue make_epilogue(const PioLinear& p) {
 int linear_simt(const PioLinear& p, cudaStream_t st);    // gemm_simt.cu  (fp32 FFMA)
 int linear_tc(const PioLinear& p, cudaStream_t st);      // gemm_sm100.cu (tcgen05 / TMA / TMEM)
 int argmax_slabs_tc(int M, int N);
+void release_split_scratch();                             // gemm_sm100.cu
 bool linear_tc2_eligible(const PioLinear& p);           // gemm2_sm100.cu: 2-CTA (cta_group::2) 256 x 256 pair tiles
 int linear_tc2(const PioLinear& p, cudaStream_t st);                       // column slabs a fused arg-max call writes per row
 int f32_to_bf16(const float* in, __nv_bfloat16* out, long long n, cudaStream_t st);

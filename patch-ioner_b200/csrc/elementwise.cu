@@ -298,6 +298,7 @@ const char* pio_last_error(void) { return pio::g_err; }
 int pio_version(void) { return 100; }
 long long pio_launch_count(void) { return pio::g_launches.load(); }
 void pio_reset_launch_count(void) { pio::g_launches.store(0); }
+void pio_release_scratch(void) { pio::release_split_scratch(); }
 
 int pio_layernorm(const float* x, int ldx, const float* w, const float* b, void* out, int out_dt, int ldo, int rows,
                   int dim, float eps, void* stream) {

@@ -78,7 +78,8 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS2, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                const __grid_constant__ CUtensorMap map_c, int store_mode, void* C, int M, int N, int K, int ldc, int c_dt, Epilogue epi) {
+                const __grid_constant__ CUtensorMap map_c, int store_mode, void* C, int M, int N, int K, int ldc, int c_dt, Epilogue epi,
+                int prefetch_w) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[2 * STAGES2 + 4];
@@ -120,7 +121,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int pre = 0;
-      if (pair < num_tiles) {
+      if (prefetch_w && pair < num_tiles) {  // PioLinear.w_static, see gemm_sm100.cu
         const int n0 = (pair % n_blocks) * BN2 + (int)rank * BNH;
         pre = min(STAGES2, k_blocks);
         for (int i = 0; i < pre; ++i) {
@@ -240,7 +241,7 @@ int linear_tc2(const PioLinear& p, cudaStream_t st) {
   const int tiles = cdiv(p.M, 2 * BM2) * cdiv(p.N, BN2);
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
   launch_pdl(gemm_tc2_kernel, dim3(2 * pairs), dim3(NUM_THREADS2), SMEM2_BYTES, st, ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc,
-             p.c_dt, make_epilogue(p));
+             p.c_dt, make_epilogue(p), p.w_static ? 1 : 0);
   PIO_LAUNCHED();
   return PIO_OK;
 }

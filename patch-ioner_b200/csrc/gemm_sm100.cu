@@ -51,7 +51,7 @@ template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
                const __grid_constant__ CUtensorMap map_c, int store_mode, void* C, int M, int N, int K, int ldc, int c_dt, Epilogue epi,
-               int k_splits) {
+               int k_splits, int prefetch_w) {
   using cfg = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzle atoms
@@ -89,8 +89,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_var);
   pdl_launch_dependents();  // the next kernel may start its own prologue as soon as this grid's CTAs retire
-  // pdl_wait() is per role: the producer fetches WEIGHT tiles first (W is never written by a kernel of this pipeline that is
-  // still in flight; A and the residual are), the epilogue waits before it touches C, the MMA warp never touches global memory.
+  // pdl_wait() is per role: with prefetch_w (PioLinear.w_static: W is not written by a kernel still in flight -- weights,
+  // bank, wte) the producer fetches WEIGHT tiles first; A and the residual always wait; the epilogue waits before it touches
+  // C, the MMA warp never touches global memory.
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -98,7 +99,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int pre = 0;  // ring slots of the first work item whose W tile is already in flight (issued ahead of pdl_wait)
-      if ((int)blockIdx.x < num_tiles) {
+      if (prefetch_w && (int)blockIdx.x < num_tiles) {  // only when the caller vouches that W is static (PioLinear.w_static)
         const int tile = blockIdx.x % out_tiles, split = blockIdx.x / out_tiles;
         const int n0 = (tile % n_blocks) * BN, kb0 = split * kbs, kb1 = min(k_blocks, kb0 + kbs);
         pre = min(cfg::STAGES, kb1 - kb0);
@@ -258,24 +259,33 @@ inline bool split_fixup_enabled() {
   return on;
 }
 inline int split_min_kblocks() {
-  static const int v = [] { const char* e = getenv("PIO_GEMM_SPLITK_MIN_KB"); return e ? atoi(e) : 24; }();
+  // below 12 k-blocks a split could come out empty (k_blocks / 6 == 0 would divide by zero further down) and never pays
+  static const int v = [] { const char* e = getenv("PIO_GEMM_SPLITK_MIN_KB"); return std::max(12, e ? atoi(e) : 24); }();
   return v;
 }
-inline int split_scratch(cudaStream_t st, SplitScratch* out) {
-  static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, SplitScratch> cache;
+std::mutex g_split_mu;
+std::map<std::pair<int, cudaStream_t>, SplitScratch> g_split_cache;
+// found = false (and no allocation) while `st` is being captured into a CUDA graph and no scratch exists yet: the caller then
+// runs the GEMM without the split (cudaMalloc is not allowed during a capture).
+inline int split_scratch(cudaStream_t st, SplitScratch* out, bool* found) {
   int dev = 0;
   PIO_CUDA(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lock(mu);
-  auto it = cache.find({dev, st});
-  if (it == cache.end()) {
+  std::lock_guard<std::mutex> lock(g_split_mu);
+  auto it = g_split_cache.find({dev, st});
+  if (it == g_split_cache.end()) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    PIO_CUDA(cudaStreamIsCapturing(st, &cap));
+    if (cap != cudaStreamCaptureStatusNone) { *found = false; return PIO_OK; }
     SplitScratch sc;
     PIO_CUDA(cudaMalloc(&sc.ws, (size_t)kNumSMs * BM * 192 * sizeof(float)));
     PIO_CUDA(cudaMalloc(&sc.cnt, kNumSMs * sizeof(int)));
-    PIO_CUDA(cudaMemset(sc.cnt, 0, kNumSMs * sizeof(int)));
-    it = cache.emplace(std::make_pair(dev, st), sc).first;
+    // zeroed ON THE LAUNCH STREAM: torch side streams are non-blocking, nothing would order a legacy-stream memset before
+    // the first kernel's tickets.  The kernels leave the counters at zero again.
+    PIO_CUDA(cudaMemsetAsync(sc.cnt, 0, kNumSMs * sizeof(int), st));
+    it = g_split_cache.emplace(std::make_pair(dev, st), sc).first;
   }
   *out = it->second;
+  *found = true;
   return PIO_OK;
 }
 
@@ -310,8 +320,9 @@ int launch(const PioLinear& p, cudaStream_t st) {
     // Deterministic split-K for long-K GEMMs with a handful of output tiles (decode steps at small batch: each CTA would
     // stream all of K through one SM's L2 port).  Partials meet in a workspace and are summed in split order.
     SplitScratch sc;
-    PIO_TRY(split_scratch(st, &sc));
-    k_splits = std::min(kNumSMs / tiles, k_blocks / 6);
+    bool have = false;
+    PIO_TRY(split_scratch(st, &sc, &have));
+    k_splits = have ? std::max(1, std::min(kNumSMs / tiles, k_blocks / 6)) : 1;
     const int kbs = cdiv(k_blocks, k_splits);
     k_splits = cdiv(k_blocks, kbs);
     if (k_splits > 1) {
@@ -323,7 +334,7 @@ int launch(const PioLinear& p, cudaStream_t st) {
   const int work = tiles * k_splits;
   const int grid = work < kNumSMs ? work : kNumSMs;
   launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), cfg::SMEM_BYTES, st, ma, mw, mc, mode, p.C, p.M, p.N, p.K, p.ldc,
-             p.c_dt, epi, k_splits);
+             p.c_dt, epi, k_splits, p.w_static ? 1 : 0);
   PIO_LAUNCHED();
   return PIO_OK;
 }
@@ -331,6 +342,20 @@ int launch(const PioLinear& p, cudaStream_t st) {
 }  // namespace
 
 int argmax_slabs_tc(int M, int N) { (void)M; return 2 * cdiv(N, 256); }
+
+// frees the split-K scratch of every (device, stream) this process used; the streams must be idle (pio_release_scratch)
+void release_split_scratch() {
+  std::lock_guard<std::mutex> lock(g_split_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : g_split_cache) {
+    cudaSetDevice(kv.first.first);
+    cudaFree(kv.second.ws);
+    cudaFree(kv.second.cnt);
+  }
+  g_split_cache.clear();
+  cudaSetDevice(cur);
+}
 
 int linear_tc(const PioLinear& p, cudaStream_t st) {
   PIO_CHECK(p.a_dt == PIO_DT_BF16, "tcgen05 GEMM needs bf16 operands");

@@ -375,6 +375,7 @@ int linear(int mode, const void* A, const void* W, void* C, int M, int N, int K,
   memset(&p, 0, sizeof(p));
   p.A = A; p.W = W; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw; p.ldc = ldc; p.a_dt = a_dt; p.c_dt = c_dt;
   p.bias = bias; p.residual = residual; p.ldres = ldc; p.alpha = 1.0f; p.act = act;
+  p.w_static = 1;  // every caller of this helper passes model weights
   return mode == PIO_FP32 ? linear_simt(p, st) : linear_tc(p, st);
 }
 
@@ -552,12 +553,12 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
       p.A = qn; p.W = (const char*)h->bank + (size_t)c0 * D * e; p.C = P; p.M = R; p.N = mc; p.K = D;
       p.lda = D; p.ldw = D; p.ldc = Mf; p.a_dt = adt; p.c_dt = PIO_DT_BF16; p.colscale = h->inv_norm + c0;
       p.alpha = log2e / temperature;
-      p.exp_ref = m; p.exp_psum = psum; p.exp_pmax = pmax; p.exp_ld = slabs_max;
+      p.exp_ref = m; p.exp_psum = psum; p.exp_pmax = pmax; p.exp_ld = slabs_max; p.w_static = 1;
       PIO_TRY(linear_tc(p, st));
       memset(&p, 0, sizeof(p));
       p.A = P; p.W = (const char*)h->bankT + (size_t)c0 * e; p.C = out; p.M = R; p.N = D; p.K = mc_pad;
       p.lda = Mf; p.ldw = (int)h->Mp; p.ldc = D; p.a_dt = adt; p.c_dt = PIO_DT_F32; p.residual = out; p.ldres = D;
-      p.alpha = 1.0f;
+      p.alpha = 1.0f; p.w_static = 1;
       if (few_queries) {  // O *= alpha first, then a pure accumulation that the GEMM may split along K (too few output tiles)
         scale_rows_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(out, alpha, R, D); PIO_LAUNCHED();
       } else {
@@ -587,7 +588,7 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
     // S = (q^ . bank_j) * inv_norm_j / T                       (:367,370,376)
     p.A = qn; p.W = (const char*)h->bank + (size_t)c0 * D * e; p.C = S; p.M = R; p.N = mc; p.K = D;
     p.lda = D; p.ldw = D; p.ldc = Mc; p.a_dt = adt; p.c_dt = PIO_DT_F32; p.colscale = h->inv_norm + c0;
-    p.alpha = 1.0f / temperature;
+    p.alpha = 1.0f / temperature; p.w_static = 1;
     PIO_TRY(h->mode == PIO_FP32 ? linear_simt(p, st) : linear_tc(p, st));
     softmax_chunk_kernel<<<R, 256, 0, st>>>(S, Mc, adt == PIO_DT_F32 ? nullptr : P16, Mc, mc, mc_pad, m, l, alpha);
     PIO_LAUNCHED();
@@ -596,7 +597,7 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
     p.A = adt == PIO_DT_F32 ? (const void*)S : (const void*)P16;
     p.W = (const char*)h->bankT + (size_t)c0 * e; p.C = out; p.M = R; p.N = D; p.K = mc_pad;
     p.lda = Mc; p.ldw = (int)h->Mp; p.ldc = D; p.a_dt = adt; p.c_dt = PIO_DT_F32; p.residual = out; p.ldres = D;
-    p.res_rowscale = alpha; p.alpha = 1.0f;
+    p.res_rowscale = alpha; p.alpha = 1.0f; p.w_static = 1;
     PIO_TRY(h->mode == PIO_FP32 ? linear_simt(p, st) : linear_tc(p, st));
   }
   if (part_m) {
@@ -638,6 +639,7 @@ int pio_best_sims(PioBank* h, const float* q, int R, int n, float* out_sims, int
     memset(&p, 0, sizeof(p));
     p.A = qn; p.W = (const char*)h->bank + (size_t)c0 * D * e; p.C = S; p.M = R; p.N = mc; p.K = D;
     p.lda = D; p.ldw = D; p.ldc = Mc; p.a_dt = adt; p.c_dt = PIO_DT_F32; p.colscale = h->inv_norm + c0; p.alpha = 1.0f;
+    p.w_static = 1;
     PIO_TRY(h->mode == PIO_FP32 ? linear_simt(p, st) : linear_tc(p, st));
     topn_chunk_kernel<<<R, 256, 0, st>>>(S, Mc, mc, c0, n, out_sims, best_i);
     PIO_LAUNCHED();
@@ -838,7 +840,7 @@ int decode_pick(PioDecoder* h, const DecodeWs& w, int R, int* out_ids, int ids_l
     PioLinear p;
     memset(&p, 0, sizeof(p));
     p.A = w.hb; p.W = h->wte; p.C = nullptr; p.M = R; p.N = gV; p.K = gD; p.lda = gD; p.ldw = gD; p.ldc = gVld;
-    p.a_dt = adt; p.c_dt = PIO_DT_F32; p.alpha = 1.0f;
+    p.a_dt = adt; p.c_dt = PIO_DT_F32; p.alpha = 1.0f; p.w_static = 1;
     p.argmax_val = av; p.argmax_idx = ai; p.argmax_sumexp = out_logprob_sum ? as : nullptr; p.argmax_ld = slabs;  // sum exp only for scores
     PIO_TRY(linear_tc(p, st));
     launch_pdl(argmax_finish_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, av, ai, as, slabs, slabs, R, out_ids, ids_ld, col,

@@ -92,6 +92,7 @@ int gemm(int mode, const void* A, const void* W, void* C, int M, int N, int K, i
   p.A = A; p.W = W; p.C = C; p.M = M; p.N = N; p.K = K; p.lda = lda; p.ldw = ldw; p.ldc = ldc;
   p.a_dt = a_dt; p.c_dt = c_dt; p.bias = bias; p.gamma = gamma; p.residual = residual; p.ldres = ldc;
   p.alpha = 1.0f; p.act = act; p.rows_per_group = rpg; p.group_stride = gs; p.group_offset = go;
+  p.w_static = 1;  // model weights
   return mode == PIO_FP32 ? linear_simt(p, st) : linear_tc(p, st);
 }
 

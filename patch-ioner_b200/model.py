@@ -18,7 +18,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .detok import default_detokenizer
+from .detok import default_batch_detokenizer
 
 EOT = "<|endoftext|>"
 SOT = "<|startoftext|>"
@@ -288,15 +288,13 @@ class Patchioner:
         return (ids, torch.cat(scores, 0)) if compute_scores else ids
 
     def _ids_to_text(self, ids: torch.Tensor) -> List[str]:
-        """decap.py:162-181: detokenise (``decoding_method`` hook or CLIP-BPE), cut at <|endoftext|>."""
-        rows = ids.cpu().tolist()  # the one device->host read of a caption batch
-        fn = self.decoding_method or default_detokenizer()
-        outs = []
-        for r in rows:
-            s = fn(r)
-            s = s.split(EOT)[0].replace(SOT, "")
-            outs.append(s)
-        return outs
+        """decap.py:162-181: detokenise, cut at <|endoftext|>.  Default: ONE batched call (detok.BatchDetokenizer ->
+        pio_detok_rows) for the whole id matrix; a user ``decoding_method`` hook (model.py:105) is called row by row
+        like the reference does."""
+        host = ids.cpu()  # the one device->host read of a caption batch
+        if self.decoding_method is None:
+            return default_batch_detokenizer()(host)
+        return [self.decoding_method(r).split(EOT)[0].replace(SOT, "") for r in host.tolist()]
 
     def caption_tokens(self, dino_tokens, project=True, return_n_best_sims=None, compute_scores: bool = False, rows_per_call=None):
         """model.py:1392-1423.  ``rows_per_call`` (extension): the rows are the concatenation of reference calls of that many

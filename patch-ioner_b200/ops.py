@@ -62,8 +62,11 @@ def reset_launch_count() -> None:
 # ------------------------------------------------------------------------------------------ dense layer
 def linear(A: torch.Tensor, W: torch.Tensor, mode: str = "fp32", bias=None, act: int = L.ACT_NONE, gamma=None,
            residual=None, out: Optional[torch.Tensor] = None, out_dtype=None, alpha: float = 1.0, colscale=None,
-           res_rowscale=None) -> torch.Tensor:
-    """out = residual * res_rowscale[:,None] + gamma * act(alpha * colscale * (A @ W.T) + bias)."""
+           res_rowscale=None, w_static: bool = False) -> torch.Tensor:
+    """out = residual * res_rowscale[:,None] + gamma * act(alpha * colscale * (A @ W.T) + bias).
+
+    ``w_static=True`` promises that ``W`` is not being written by a kernel still in flight on the stream (model
+    weights): the tcgen05 kernels then fetch their first weight tiles ahead of the dependent-launch wait."""
     _need_cuda(A, W)
     assert A.dim() == 2 and W.dim() == 2 and A.shape[1] == W.shape[1]
     assert A.stride(1) == 1 and W.stride(1) == 1
@@ -80,6 +83,7 @@ def linear(A: torch.Tensor, W: torch.Tensor, mode: str = "fp32", bias=None, act:
     p.residual, p.res_rowscale = _ptr(residual), _ptr(res_rowscale)
     p.ldres = residual.stride(0) if residual is not None else 0
     p.alpha, p.act = alpha, act
+    p.w_static = 1 if w_static else 0
     L.check(L.lib().pio_linear(C.byref(p), MODES[mode], _stream()))
     return out
 

@@ -115,3 +115,35 @@ def test_clip_bpe_decoder_against_reference_tokenizer():
     for _ in range(200):
         ids = [rnd.randrange(0, 49408) for _ in range(30)]
         assert dec(ids) == tok.decode(ids)
+
+    # the batched form (pio_detok_rows) == SimpleTokenizer.decode + the cut of decap.py:173-176, row for row
+    from patchioner_b200.detok import EOT, SOT, BatchDetokenizer, _id_renderer
+
+    bd = BatchDetokenizer(bpe)
+    rows = [[rnd.randrange(0, 49408) for _ in range(30)] for _ in range(1500)]
+    ascii_ids = [i for i, t in enumerate(dec.token_bytes()) if i < 49406 and all(c < 128 for c in t)]
+    rows += [[rnd.choice(ascii_ids) for _ in range(30)] for _ in range(600)]         # realistic (ASCII) captions
+    rows[5][7] = 49407; rows[6][0] = 49407; rows[7][3] = 49406; rows[8][4] = 50000; rows[9][29] = 49407   # noqa: E702
+    lt, sl, wg = (dec_id for dec_id in (tok.encoder["<"], tok.encoder["/"], tok.encoder["w"]))               # "</w" + ">": the
+    rows[10][3:7] = [lt, sl, wg, tok.encoder[">"]]                                      # substitution straddling tokens
+    got = bd(torch.tensor(rows, dtype=torch.int32))
+    for r, row in enumerate(rows):
+        try:
+            want = tok.decode(row).split(EOT)[0].replace(SOT, "")
+        except KeyError:  # the reference gives up on the whole call here (decap.py:180-181); we degrade this row only
+            want = _id_renderer(row).split(EOT)[0].replace(SOT, "")
+        assert got[r] == want, (r, got[r], want)
+    assert bd(torch.tensor(rows[1500:], dtype=torch.int32)) == got[1500:]   # all-ASCII batch: the one-decode fast path
+
+
+def test_batch_detokenizer_id_rendering_matches_row_renderer():
+    """Without the CLIP vocabulary asset (the GPU box): '<id> <id> ...' rows, cut at <|endoftext|>, identical to the row-at-a-time
+    renderer of round 1 -- including its trailing-space and <|startoftext|> quirks."""
+    from patchioner_b200.detok import EOT, SOT, BatchDetokenizer, _id_renderer
+
+    ids = torch.randint(0, 50257, (777, 30), generator=torch.Generator().manual_seed(4), dtype=torch.int32)
+    ids[3, 4] = 49407; ids[9, 29] = 49406; ids[10, 0] = 49406; ids[11, 0] = 49407; ids[12, 29] = 49407; ids[13, 5] = -1   # noqa: E702
+    ids[14, :] = 49406
+    got = BatchDetokenizer(None)(ids)
+    assert got == [_id_renderer(r).split(EOT)[0].replace(SOT, "") for r in ids.tolist()]
+    assert BatchDetokenizer(None)(ids[:0]) == []

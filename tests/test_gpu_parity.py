@@ -921,3 +921,92 @@ def test_linear_bf16_deterministic_split_k(dev, ops, M, N, K):
         o2 = ops.linear(Ad, Wd, "bf16")
     s.synchronize()
     assert torch.equal(o2, out)
+
+
+# ----------------------------------------------------------------------------------------- round-2 evidence
+def _golden_script(name):
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".py")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("mode,rtol,atol,cmin", [("fp32", 2e-4, 2e-4, 0.99999), ("bf16", 3e-2, 3e-2, 0.999)])
+def test_embed_inversion_against_reference_golden(dev, golden, mode, rtol, atol, cmin):
+    """Patchioner(talk2dino_weights=...).embed_tokens == revert_transformation (embedding_utils.py:17-24)
+    of the unmodified reference (tests/golden/make_golden_revert.py)."""
+    from patchioner_b200 import Patchioner
+
+    rec = golden("revert")
+    A, b, x = _golden_script("make_golden_revert").inputs()
+    assert [float(t.double().sum()) for t in (A, b, x)] == rec["in_sums"]
+    m = Patchioner.from_config({"decap_weights": o_decap.make_weights(seed=1234), "prefix_size": 768, "support_memory_size": 0,
+                                "dino_model": "dinov2_vitb14_reg", "normalize": True, "resize_dim": 224, "crop_dim": 224,
+                                "dino_weights": o_vit.make_weights(seed=1234), "precision": mode,
+                                "talk2dino_weights": {"linear_layer.weight": A, "linear_layer.bias": b}}, device=dev)
+    assert m.embed_inversion
+    torch.testing.assert_close(m.talk2dino_A_pinv[:8].cpu(), rec["A_pinv_head"], rtol=1e-4, atol=1e-6)
+    got = m.embed_tokens(x.to(dev)).float().cpu()
+    assert got.shape == (24, 512)
+    assert cos_min(got, rec["revert"]) >= cmin
+    torch.testing.assert_close(got, rec["revert"], rtol=rtol, atol=atol)
+
+
+def test_patch_and_register_captions_against_oracle(dev):
+    """SURVEY 8f.4 / src/model.py:957-979: get_patch_capts (every patch token, grouped per image) and get_register_capts
+    (the 4 register tokens) go through caption_tokens like the reference; ids vs the CPU oracle, fp32 mode."""
+    m = _model(dev, "fp32", True)
+    vit_w, dec_w = o_vit.make_weights(seed=1234), o_decap.make_weights(seed=1234)
+    bank = o_pipe.synth_bank(3000, 768, seed=7, zero_frac=0.002)
+    imgs = o_pipe.synth_images(2, 224, seed=5)
+    out = m(imgs, get_cls_capt=False, get_patch_capts=True, get_register_capts=True, return_ids=True, compute_scores=True)
+    assert set(out) == {"patch_tokens_capts", "patch_tokens_scores", "register_capts", "register_scores"}
+    assert out["patch_tokens_capts"].shape == (2, 256, 30) and out["register_capts"].shape == (2, 4, 30)
+    d = o_vit.forward(vit_w, imgs)
+    om = o_pipe.OracleModel(vit_w, dec_w, bank)
+    # all 8 register rows, and a spread of 96 patch rows (the oracle decodes on the CPU)
+    ref_reg, ref_reg_sc = om.caption_tokens(d["x_norm_regtokens"].reshape(-1, 768), compute_scores=True)
+    got_reg = out["register_capts"].reshape(-1, 30).cpu().long()
+    assert (got_reg == ref_reg).all(dim=1).float().mean().item() >= 0.99
+    torch.testing.assert_close(torch.as_tensor(out["register_scores"], dtype=torch.float32).reshape(-1),
+                               torch.as_tensor(ref_reg_sc, dtype=torch.float32).reshape(-1), rtol=2e-3, atol=1e-30)
+    sel = torch.arange(0, 512, 16).tolist() + torch.arange(5, 512, 8).tolist()
+    ref_patch = om.caption_tokens(d["x_norm_patchtokens"].reshape(-1, 768)[sel])
+    got_patch = out["patch_tokens_capts"].reshape(-1, 30).cpu().long()[sel]
+    agree = (got_patch == ref_patch).all(dim=1).float().mean().item()
+    assert agree >= 0.99, agree
+    # strings: grouped [B][P] / [B][4] lists like the reference
+    s = m(imgs[:1], get_cls_capt=False, get_patch_capts=True, get_register_capts=True)
+    assert len(s["patch_tokens_capts"]) == 1 and len(s["patch_tokens_capts"][0]) == 256 and len(s["register_capts"][0]) == 4
+
+
+def test_vit_bf16_against_oracle_518(dev, ops, vit_w):
+    """bf16 tensor-core ViT at the BASELINE geometry (518 px: N = 1374, the 128-key attention tiles) against the CPU ORACLE, B = 1."""
+    imgs = o_pipe.synth_images(1, 518, seed=3)
+    ref = o_vit.forward(vit_w, imgs)
+    vit = ops.Vit(vit_w, dev, "bf16")
+    tokens, attn, _ = vit.forward(imgs.to(dev), want_attn=True)
+    ref_tok = torch.cat([ref["x_norm_clstoken"][:, None], ref["x_norm_regtokens"], ref["x_norm_patchtokens"]], 1)
+    c = cos_min(tokens.cpu(), ref_tok)
+    assert c >= 0.999, c
+    torch.testing.assert_close(attn.cpu(), o_pool.cls_attention_map(ref["qkv"]), rtol=8e-2, atol=2e-5)
+
+
+def test_linear_chained_dynamic_weight(dev, ops):
+    """W produced by the previous call on the same stream (w_static = 0, the default) must be waited for --
+    the weight-tile prefetch ahead of the dependent-launch wait is only taken when the caller vouches for a static W."""
+    g = torch.Generator().manual_seed(77)
+    a = torch.randn(512, 768, generator=g).to(dev).to(torch.bfloat16)
+    w1 = (torch.randn(768, 768, generator=g) / 28).to(dev).to(torch.bfloat16)
+    x = torch.randn(300, 768, generator=g).to(dev).to(torch.bfloat16)
+    for _ in range(5):
+        y = ops.linear(a, w1, "bf16", out_dtype=torch.bfloat16)             # [512, 768], then used as W
+        z = ops.linear(x, y, "bf16")                                        # [300, 512]
+        ref = x.float() @ (a.float() @ w1.float().T).to(torch.bfloat16).float().T
+        torch.testing.assert_close(z, ref, rtol=2e-2, atol=2e-1)
+        z2 = ops.linear(x, y, "bf16", w_static=True)                        # y is complete by now: same numbers
+        assert torch.equal(z, z2)

@@ -1,6 +1,7 @@
 """CPU: the oracle restatement against fixtures produced by the unmodified reference
 (tests/golden/make_golden.py).  Integer results bit-exact, fp32 results to fp32 round-off."""
 import math
+import os
 
 import pytest
 import torch
@@ -14,6 +15,17 @@ from oracle import pooling as o_pool
 
 def csum(t):
     return float(t.double().sum())
+
+
+def _golden_script(name):
+    """import tests/golden/<name>.py (the generator scripts also define the seeded inputs of their fixtures)"""
+    import importlib.util
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".py")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 def _pool_inputs(g, B, R, D):
@@ -137,6 +149,38 @@ def test_memory_projection_matches_reference(golden):
     parts = [o_mem.project_partial(q, s) for s in fb.chunk(4)]
     merged = o_mem.merge_partials([p[0] for p in parts], [p[1] for p in parts], [p[2] for p in parts])
     torch.testing.assert_close(merged, rec["out_norm"], rtol=1e-4, atol=1e-6)
+
+
+def test_revert_transformation_matches_reference(golden):
+    """SURVEY 8 row a11 (embedding_utils.py:3-24): seeded synthetic first layer (travels to the GPU box) ..."""
+    inputs = _golden_script("make_golden_revert").inputs
+    rec = golden("revert")
+    A, b, x = inputs()
+    assert [csum(t) for t in (A, b, x)] == rec["in_sums"]
+    A_pinv = o_mem.get_pseudo_inverse(A)
+    torch.testing.assert_close(A_pinv[:8], rec["A_pinv_head"], rtol=1e-4, atol=1e-6)
+    assert abs(csum(A_pinv) - rec["A_pinv_sum"]) < 1e-2 and abs(csum(A_pinv.abs()) / rec["A_pinv_abs_sum"] - 1) < 1e-5
+    got = o_mem.revert_transformation(x, A_pinv, b)
+    torch.testing.assert_close(got, rec["revert"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(got, rec["revert_via_layer"], rtol=1e-4, atol=1e-5)
+    # the product's init-time host maths is the same SVD
+    from patchioner_b200.talk2dino import pseudo_inverse
+
+    torch.testing.assert_close(pseudo_inverse(A), A_pinv, rtol=0, atol=0)
+
+
+_T2D = "/root/reference/Patch-ioner/src/viecap/training/talk2dino/weights/vitb_mlp_infonce.pth"
+
+
+@pytest.mark.skipif(not os.path.exists(_T2D), reason="the real Talk2DINO weights live in the build container's /root/reference only")
+def test_revert_transformation_real_weights_golden(golden):
+    """... and memory.pt['revert']: the reference's own output with the in-tree vitb_mlp_infonce.pth first layer (build box only)."""
+    rec = golden("memory")
+    sd = torch.load(_T2D, map_location="cpu")
+    A, b = sd["linear_layer.weight"].float(), sd["linear_layer.bias"].float()
+    A_pinv = o_mem.get_pseudo_inverse(A)
+    assert abs(csum(A_pinv) - rec["A_pinv_sum"]) <= 1e-3 * max(1.0, abs(rec["A_pinv_sum"]))
+    torch.testing.assert_close(o_mem.revert_transformation(rec["out_norm"], A_pinv, b), rec["revert"], rtol=1e-4, atol=1e-5)
 
 
 def test_decoder_matches_reference(golden):
