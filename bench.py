@@ -51,12 +51,18 @@ def parse():
     ap.add_argument("--pool", default="gauss", choices=["mean", "gauss", "attn"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-images", type=int, default=1)
-    ap.add_argument("--cpu-sample-boxes", type=int, default=8)
+    ap.add_argument("--cpu-sample-boxes", type=int, default=None, help="default: the workload's own boxes/image (same mix as the GPU arm)")
+    ap.add_argument("--e2e-ids", action="store_true", help="e2e leg returns id tensors (return_ids=True) instead of the reference's strings")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the eager-PyTorch-on-GPU baseline (tools/gpu_eager.py)")
+    ap.add_argument("--no-parity-sample", action="store_true", help="skip ids_vs_fp32_mode (bf16 captions vs the fp32 parity mode)")
+    ap.add_argument("--no-sharded-bank", action="store_true", help="skip the config[4] sub-record at WORLD_SIZE > 1")
     a = ap.parse_args()
     if a.batch is None:
         a.batch = 256 if a.workload == "traces" else 64
     if a.boxes is None:
         a.boxes = {"dense": 64, "traces": 1, "regionset": 8, "regionset-viecap": 8}[a.workload]
+    if a.cpu_sample_boxes is None:
+        a.cpu_sample_boxes = a.boxes
     if a.workload.startswith("regionset"):
         a.bank_rows = 0  # CapDec: no caption memory (configs/mlp_noise.k.yaml: support_memory_size 0)
     return a
@@ -243,14 +249,15 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, per_step_note="each step is a bounded sample of the workload (see cpu_baseline.sample)"),
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": sample + "; each step of this arm is that bounded sample of the workload"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, per_step_note=None):
+def workload_config(args):
     name = {"dense": f"talk2dino_decap dense captioning: {args.size}px images, {args.boxes} synthetic bboxes/image, batch {args.batch} per GPU "
                      f"(BASELINE.json configs[1])",
             "traces": f"talk2dino_decap trace captioning with attention weighting: {args.size}px images, 1 synthetic mouse trace/image, "
@@ -264,9 +271,9 @@ def workload_config(args, per_step_note=None):
            "images_per_gpu": args.batch, "boxes_per_image": args.boxes, "regions_per_gpu_per_step": captions_per_step(args),
            "image_size": args.size, "bank_rows": args.bank_rows, "pooling": args.pool, "decode_steps": decode_steps(args),
            "parallelism": f"dp{args.gpus} over images, no collective",
-           "cache": "per-step inputs (206 MB of images) and activations (> 1 GB) exceed the 126 MB L2; no explicit flush"}
-    if per_step_note:
-        cfg["note"] = per_step_note
+           "cache": f"per-step inputs ({args.batch * 3 * args.size * args.size * 4 / 1e6:.0f} MB of images) and activations "
+                    f"({args.batch * ((args.size // 14) ** 2 + 5) * 768 * 4 * 5 / 1e6:.0f} MB per ViT layer) exceed the 126 MB L2 between "
+                    "steps; no explicit flush"}
     return cfg
 
 
@@ -329,14 +336,23 @@ def run_ours(args):
 
     e2e_marks = []
 
-    def run_e2e(n):
+    def run_e2e(n, ids=False):
         """n steps through the public serving API: every step copies its pinned host inputs in (the copy of step i+1 is
-        issued under step i's kernels: Patchioner.forward_pipelined) and reads its ids back to the host."""
+        issued under step i's kernels: Patchioner.forward_pipelined) and hands the caller what the reference's forward
+        returns -- caption STRINGS (ids -> pinned host buffer -> batched detokenisation, inside the timed region); with
+        ids=True the extension return_ids=True (int32 ids read back to the host) is timed instead."""
         batches = (host[i % n_sets] for i in range(n))
         overlap = os.environ.get("PIO_E2E_OVERLAP", "1") != "0"  # A/B switch: second compute stream for batch i+1
-        for out in model.forward_pipelined(batches, overlap_compute=overlap, get_cls_capt=False, return_ids=True, **kw):
-            out[key].cpu()  # device -> host read of the step's result
-            e2e_marks.append(time.perf_counter())  # host time at which each step's ids are on the host (diagnostic only)
+        flags = dict(get_cls_capt=False, **kw)
+        if ids:
+            flags["return_ids"] = True
+        for out in model.forward_pipelined(batches, overlap_compute=overlap, **flags):
+            r = out[key]
+            if ids:
+                r.cpu()  # device -> host read of the step's result
+            else:
+                assert isinstance(r, list) and len(r) == B  # [B][R] strings (dense) or [B] strings
+            e2e_marks.append(time.perf_counter())  # host time at which each step's result is on the host (diagnostic only)
 
     def barrier():
         if world > 1:
@@ -374,7 +390,13 @@ def run_ours(args):
     # launches counted include the warm-up steps: keep the timed share
     launches = launches * args.steps // (args.steps + args.warmup)
     clocks = sampler.report() if rank == 0 else None
-    ms_e2e = timed(run_e2e, args.steps, max(2, args.warmup), whole_run=True)  # >= 2 warm-up batches: both streams' scratch exists
+    wu = max(2, args.warmup)  # >= 2 warm-up batches: both streams' scratch exists
+    ms_e2e_ids = timed(lambda n: run_e2e(n, ids=True), args.steps, wu, whole_run=True)
+    if args.e2e_ids:
+        ms_e2e, e2e_returns = ms_e2e_ids, "int32 ids (return_ids=True)"
+    else:
+        del e2e_marks[:]
+        ms_e2e, e2e_returns = timed(run_e2e, args.steps, wu, whole_run=True), "caption strings (the reference's return type)"
     clocks_e2e = sampler.stop() if rank == 0 else None
     last = e2e_marks[-args.steps:]
     e2e_gaps = [round((b - a) * 1e3, 2) for a, b in zip(last[:-1], last[1:])]  # host-side gaps between consecutive results
@@ -386,23 +408,41 @@ def run_ours(args):
     extra = {}
     if rank == 0:
         extra = stage_breakdown(model, ops, resident[0], kw, args, stream)
+    parity = None
+    if rank == 0 and args.precision == "bf16" and not args.no_parity_sample and model.viecap is None:
+        try:
+            parity = ids_vs_fp32_mode(model, args, kw, key, resident[0], synth, dev)
+        except Exception as e:  # reported next to the number, never required for it
+            parity = {"error": f"{type(e).__name__}: {e}"}
     line = None
     if rank == 0:
         pk = peaks()
         gm = extra.pop("_gemm")
+        roofs = extra.pop("_rooflines")
         roof = {"kernel": gm["kernel"], "bound": "tensor", "achieved": gm["tflops"], "peak": pk["bf16_tflops"] if args.precision == "bf16" else None,
                 "unit": "TFLOP/s", "frac": (gm["tflops"] / pk["bf16_tflops"]) if args.precision == "bf16" else None,
                 "traffic": gm.get("traffic"), "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture of this shape: profiles/dominant_kernel.json)",
                 "peak_source": pk["source"] + " (burst figure: kernel timed alone, back to back)",
                 "shape": gm["shape"], "avg_launch_ms": gm["ms"], "algorithmic_flops_per_launch": gm["flops"]}
+        # the whole step against the sustained tensor peak: algorithmic FLOPs of ViT + projection + decode / step time
+        step_flops = extra.get("_step_flops", 0.0)
+        extra.pop("_step_flops", None)
+        step_tflops = step_flops / (ms_total / args.steps) / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic", "config": workload_config(args), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "clocks": clocks_e2e,
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "returns": e2e_returns, "clocks": clocks_e2e,
                         "host_gaps_ms": e2e_gaps,
                         "h2d_bytes_per_step": int(h2d_bytes) * world,
                         "d2h_bytes_per_step": int(captions_per_step(args) * decode_steps(args) * 4) * world},
-                "gpu_launches": int(launches), "roofline": roof, "stages": extra,
+                "e2e_ids": {"value": regions * args.steps / (ms_e2e_ids / 1e3), "unit": UNIT, "ms_per_step": ms_e2e_ids / args.steps,
+                            "returns": "int32 ids (return_ids=True)"},
+                "gpu_launches": int(launches), "roofline": roof, "rooflines": roofs,
+                "step_frac": {"achieved_tflops": step_tflops, "peak": pk["bf16_tflops_sustained"],
+                              "frac": step_tflops / pk["bf16_tflops_sustained"] if args.precision == "bf16" else None,
+                              "what": "algorithmic FLOPs of one step (ViT + projection + KV-cached decode) / ms_per_step, against the "
+                                      "sustained bf16 peak (" + pk["source"] + ")"},
+                "ids_vs_fp32_mode": parity, "stages": extra,
                 "vit_images_per_s": extra.get("vit_images_per_s")}
         if not args.no_cpu_baseline and world == 1:
             try:
@@ -411,6 +451,32 @@ def run_ours(args):
                                         "seconds_per_sample_step": sec}
             except Exception as e:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": f"failed: {e}"}
+        if not args.no_gpu_eager and world == 1 and args.workload == "dense":
+            try:
+                model = None
+                torch.cuda.empty_cache()
+                line["gpu_eager_baseline"] = gpu_eager_baseline(args, synth, dev, host[0])
+                best = max(v for k, v in line["gpu_eager_baseline"]["captions_per_s"].items() if v)
+                line["vs_gpu_eager"] = {"vs_best_eager_variant": value / best,
+                                        "vs_reference_algorithm_fp32": value / line["gpu_eager_baseline"]["captions_per_s"]["fp32_reference_algorithm"]}
+            except Exception as e:
+                line["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"}
+    if world > 1 and not args.no_sharded_bank:
+        # BASELINE configs[4]: the one path with a collective (bank rows sharded over the ranks, max / sum-exp all-reduce),
+        # after the timed legs so that it cannot disturb them; rank 0 attaches the record to the line
+        try:
+            model = None
+            resident = None
+            torch.cuda.empty_cache()
+            from tools.sharded_bank_nccl import run_sharded_bank
+
+            rec = run_sharded_bank(dev, rank, world, 1_000_000, 4096, 5)
+            if rank == 0:
+                line["sharded_bank"] = rec
+        except Exception as e:
+            if rank == 0:
+                line["sharded_bank"] = {"error": f"{type(e).__name__}: {e}"}
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -503,6 +569,50 @@ def stage_breakdown(model, ops, batch, kw, args, stream):
     out["_gemm"] = {"kernel": "gemm_tc2_kernel: 2-CTA tcgen05 GEMM, 256x256 pair tiles (ViT fc1 + GELU)" if args.precision == "bf16"
                     else "sgemm_tn_kernel (ViT fc1 + GELU)",
                     "shape": [M, 3072, 768], "ms": ms, "flops": flops, "tflops": flops / ms / 1e9, "traffic": traffic}
+    # ---- the other kernels the north star names, each against its own roofline (SURVEY.md 8d work-per-unit figures)
+    roofs = [{"kernel": out["_gemm"]["kernel"], "bound": "tensor", "achieved": out["_gemm"]["tflops"], "peak": pk["bf16_tflops"],
+              "unit": "TFLOP/s", "frac": out["_gemm"]["tflops"] / pk["bf16_tflops"], "timed": "alone, 10 launches back to back"}]
+    if args.precision == "bf16":
+        qkv = torch.randn(B, N, 2304, device=imgs.device).to(dt)
+        for _ in range(2):
+            ops.vit_attention(qkv)
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record(stream)
+        for _ in range(5):
+            ops.vit_attention(qkv)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_a = e0.elapsed_time(e1) / 5
+        fl_a = 4.0 * N * N * 64 * 12 * B
+        roofs.append({"kernel": "vit_attention_tc_kernel (one ViT layer, all heads)", "bound": "tensor", "achieved": fl_a / ms_a / 1e9,
+                      "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": fl_a / ms_a / 1e9 / pk["bf16_tflops"], "avg_launch_ms": ms_a,
+                      "shape": [B, N, 12, 64], "timed": "alone, 5 launches back to back"})
+        del qkv
+    if proj_flops > 0 and t[2] > 0:
+        roofs.append({"kernel": "caption-memory projection (similarity GEMM with exp epilogue + recombination GEMM per bank chunk)",
+                      "bound": "tensor", "achieved": proj_flops / t[2] / 1e9, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                      "frac": proj_flops / t[2] / 1e9 / pk["bf16_tflops"], "ms": t[2], "timed": "stage of one instrumented step"})
+    # decode: per step max(weights + KV over HBM, R * F over the tensor pipe)  
+    Rr = B * n_out
+    steps_d = 64 if model.viecap is not None else 30
+    n_layer = 12 if model.viecap is not None else 4
+    w_bytes = (n_layer * 12 * 768 * 768 + 50257 * 768) * 2
+    kv_bytes = sum(2 * n_layer * 768 * 2 * tt for tt in range(1, steps_d + 1)) / steps_d * Rr  # mean over the steps
+    f_tok = 2.0 * (n_layer * 12 * 768 * 768 + 50257 * 768)
+    hbm_ms = (w_bytes + kv_bytes) / (pk["hbm_gbs"] * 1e6)
+    tc_ms = Rr * f_tok / (pk["bf16_tflops_sustained"] * 1e9)
+    floor_ms = max(hbm_ms, tc_ms) * steps_d
+    roofs.append({"kernel": "greedy decode (all kernels of the %d steps)" % steps_d, "bound": "hbm" if hbm_ms >= tc_ms else "tensor",
+                  "achieved": (w_bytes + kv_bytes) * steps_d / t[3] / 1e6 if hbm_ms >= tc_ms else dec_flops / t[3] / 1e9,
+                  "peak": pk["hbm_gbs"] if hbm_ms >= tc_ms else pk["bf16_tflops_sustained"], "unit": "GB/s" if hbm_ms >= tc_ms else "TFLOP/s",
+                  "frac": floor_ms / t[3], "ms": t[3], "floor_ms": floor_ms, "regions": Rr,
+                  "what": "per step max(weight + KV bytes / HBM peak, regions x FLOPs per token / sustained tensor peak)",
+                  "timed": "stage of one instrumented step"})
+    roofs.append({"kernel": "region pooling (pool_box_kernel / pool_slab_kernel)", "bound": "hbm", "achieved": out["pool_gbs"],
+                  "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": out["pool_frac_of_hbm"], "ms": t[1], "timed": "stage of one instrumented step"})
+    out["_rooflines"] = roofs
+    out["_step_flops"] = vit_flops + proj_flops + dec_flops
     if model.viecap is not None and args.precision == "bf16":
         # the kernel with the largest share of this workload's launches: the decode-step GEMM at M = regions rows (qkv shape).
         # Weight-streaming bound at this size: its algorithmic bytes are the bf16 weight panel + the activations.
@@ -527,6 +637,69 @@ def stage_breakdown(model, ops, batch, kw, args, stream):
                               "frac": bytes2 / ms2 / 1e6 / pk["hbm_gbs"], "tflops": 2.0 * Md * 2304 * 768 / ms2 / 1e9,
                               "note": "back-to-back launches of one shape (weights L2-resident); launch-latency-bound at this M"}
     return out
+
+
+def ids_vs_fp32_mode(model16, args, kw, key, batch, synth, dev):
+    """The bf16 number always travels with its id agreement: captions of the first >= 256 regions of the bench batch from the
+    bf16 tensor-core mode vs the fp32 parity mode (the mode whose ids match the reference's on >= 99 % of regions)."""
+    from patchioner_b200 import Patchioner
+
+    per_img = args.boxes if args.workload == "dense" else 1
+    n_img = min(args.batch, max(4, -(-256 // per_img)), 64)
+    sub = {k: (v[:n_img] if torch.is_tensor(v) else v[:n_img]) for k, v in batch.items()}
+    bank = synth.synth_bank(args.bank_rows, 768, seed=7) if args.bank_rows > 0 else None
+    cfg = {"decap_weights": synth.make_decoder_weights(1234), "prefix_size": 768, "support_memory_size": args.bank_rows,
+           "dino_model": "dinov2_vitb14_reg", "normalize": True, "resize_dim": args.size, "crop_dim": args.size,
+           "dino_weights": synth.make_vit_weights(1234), "memory_bank": bank, "precision": "fp32"}
+    m32 = Patchioner.from_config(cfg, device=dev)
+    del cfg, bank
+    a = model16(**sub, get_cls_capt=False, return_ids=True, **kw)[key]
+    b = m32(**sub, get_cls_capt=False, return_ids=True, **kw)[key]
+    a, b = a.reshape(-1, a.shape[-1]).cpu(), b.reshape(-1, b.shape[-1]).cpu()
+    same = (a == b)
+    prefix = same.long().cumprod(dim=1).sum(dim=1).float()
+    del m32
+    torch.cuda.empty_cache()
+    return {"regions": int(a.shape[0]), "identical_caption_rate": float(same.all(dim=1).float().mean()),
+            "mean_common_prefix": float(prefix.mean()), "steps": int(a.shape[1]),
+            "first_token_agreement": float(same[:, 0].float().mean()),
+            "what": "bf16 tensor-core mode vs fp32 parity mode (SIMT fp32), same inputs and random-init weights"}
+
+
+def gpu_eager_baseline(args, synth, dev, host_batch):
+    """SURVEY 8d / BASELINE.md 4 'also timed': the same step in eager PyTorch on this GPU (cuBLAS + SDPA, tools/gpu_eager.py),
+    fp32 and bf16 autocast, with the reference's decode algorithm (no KV cache) and with a KV cache."""
+    from tools.gpu_eager import EagerPipeline
+
+    vit_w, dec_w = synth.make_vit_weights(1234), synth.make_decoder_weights(1234)
+    bank = synth.synth_bank(args.bank_rows, 768, seed=7) if args.bank_rows > 0 else None
+    imgs, boxes = host_batch["imgs"].to(dev), host_batch["bboxes"].to(dev)
+    res, n = {}, imgs.shape[0] * boxes.shape[1]
+    for name, bf16 in (("fp32", False), ("bf16_autocast", True)):
+        ep = EagerPipeline(vit_w, dec_w, bank, dev, autocast_bf16=bf16)
+        for algo, cache in (("reference_algorithm", False), ("kv_cache", True)):
+            ep.dense_step(imgs[:8], boxes[:8], use_cache=cache)  # warm-up (cuBLAS handles, autotuning)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 1 if (not bf16 and not cache) else 2
+            e0.record()
+            for _ in range(reps):
+                ep.dense_step(imgs, boxes, gaussian=kw_gauss(args), use_cache=cache)
+            e1.record()
+            torch.cuda.synchronize()
+            res[f"{name}_{algo}"] = n * reps / (e0.elapsed_time(e1) / 1e3)
+        del ep
+        torch.cuda.empty_cache()
+    return {"captions_per_s": res, "unit": UNIT,
+            "sample": f"the full step: {imgs.shape[0]} x {args.size}px images, {boxes.shape[1]} boxes each = {n} captions, bank M={args.bank_rows}, "
+                      "inputs resident, CUDA events, 1 small warm-up + 1-2 timed steps per variant",
+            "what": "eager PyTorch (cuBLAS GEMMs, SDPA attention, stock elementwise kernels); boxes pooled by one bmm instead of the "
+                    "reference's per-box Python loop; 'reference_algorithm' re-runs the growing sequence every decode step "
+                    "(decap.py:130-155), 'kv_cache' is the same model with a cache"}
+
+
+def kw_gauss(args):
+    return args.pool == "gauss"
 
 
 def main():

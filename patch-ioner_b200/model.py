@@ -4,9 +4,10 @@ Mirrors Patch-ioner/src/model.py: ``Patchioner.from_config`` (:666-715), ``forwa
 names, same output keys), ``caption_tokens`` (:1392-1423).  Underneath, every numeric step runs in
 libpio_sm100.so (hand-written sm_100a CUDA) -- there is no PyTorch compute path and no CPU fallback.
 
-Scope: DINOv2-reg backbone + DeCap / CapDec text side.  The alternative backbones and
-captioners of the reference (ProxyCLIP, RegionCLIP, INViTE, DenseCLIP, AlphaCLIP, ViECap, MeaCap, ClipCap) are out of
-scope for this round and raise ``NotImplementedError`` instead of silently doing something else.
+Scope: DINOv2-reg backbone + DeCap / CapDec text side, plus the ViECap captioner on the same
+embeddings (``viecap:`` config key -> ``viecap.py``).  The alternative backbones and captioners of the
+reference (ProxyCLIP, RegionCLIP, INViTE, DenseCLIP, AlphaCLIP, MeaCap, ClipCap) are out of scope and raise
+``NotImplementedError`` instead of silently doing something else.
 """
 from __future__ import annotations
 
@@ -288,10 +289,12 @@ class Patchioner:
         return (ids, torch.cat(scores, 0)) if compute_scores else ids
 
     def _ids_to_text(self, ids: torch.Tensor) -> List[str]:
-        """decap.py:162-181: detokenise, cut at <|endoftext|>.  Default: ONE batched call (detok.BatchDetokenizer ->
-        pio_detok_rows) for the whole id matrix; a user ``decoding_method`` hook (model.py:105) is called row by row
-        like the reference does."""
-        host = ids.cpu()  # the one device->host read of a caption batch
+        """decap.py:162-181: detokenise, cut at <|endoftext|>."""
+        return self._host_ids_to_text(ids.cpu())  # the one device->host read of a caption batch
+
+    def _host_ids_to_text(self, host: torch.Tensor) -> List[str]:
+        """Default: ONE batched call (detok.BatchDetokenizer -> pio_detok_rows) for the whole id matrix; a user
+        ``decoding_method`` hook (model.py:105) is called row by row like the reference does."""
         if self.decoding_method is None:
             return default_batch_detokenizer()(host)
         return [self.decoding_method(r).split(EOT)[0].replace(SOT, "") for r in host.tolist()]
@@ -634,21 +637,53 @@ class Patchioner:
                 ev.record(copy)
             return dev_batch, ev
 
+        # Strings without a stall: a plain forward() ends in ids.cpu() + detokenisation, which would hold the host until batch i
+        # is finished and leave the GPU idle while batch i+1 is being launched.  Here the forward runs with return_ids=True,
+        # the id matrices are copied to pinned host buffers on the batch's own stream, and the (batched) detokenisation of
+        # batch i happens at consumption time -- under the kernels of batch i+1.
+        defer_text = (not flags.get("return_ids", False) and self.viecap is None and not self.calculate_argmax_text
+                      and flags.get("caption_bboxes_type") is None)
+        run_flags = dict(flags, return_ids=True) if defer_text else flags
+        if getattr(self, "_ids_host", None) is None:
+            self._ids_host = {}
+
         def launch(i, staged):
-            """issue the forward of batch i on its compute stream; returns (outputs, completion event)"""
+            """issue the forward of batch i on its compute stream; returns (outputs, completion event, pinned id copies)"""
             cur, ev = staged
             st = streams[i & 1]
+            host_ids = {}
             with torch.cuda.stream(st):
                 st.wait_event(ev)
                 if i == 1 and first_done:
                     st.wait_event(first_done[0])  # lazily built device caches (pos-embed ...) of the very first forward are complete
-                out = self.forward(**cur, **flags)
+                out = self.forward(**cur, **run_flags)
+                if defer_text:
+                    for k, v in out.items():
+                        if torch.is_tensor(v) and v.dtype == torch.int32:
+                            key = (i & 1, k, tuple(v.shape))
+                            hb = self._ids_host.get(key)
+                            if hb is None:
+                                hb = self._ids_host[key] = torch.empty(v.shape, dtype=torch.int32, pin_memory=True)
+                            hb.copy_(v, non_blocking=True)
+                            host_ids[k] = hb
                 done = torch.cuda.Event()
                 done.record(st)
             self._stage_free[i & 1] = done
             if i == 0:
                 first_done.append(done)
-            return out, done
+            return out, done, host_ids
+
+        def texts(out, host_ids):
+            """the ids of a finished batch -> the reference's string outputs ([B][R] lists / [B] lists)"""
+            res = dict(out)
+            for k, hb in host_ids.items():
+                flat = self._host_ids_to_text(hb.reshape(-1, hb.shape[-1])) if hb.numel() else []
+                if hb.dim() == 3:
+                    g = hb.shape[1]
+                    res[k] = [flat[b * g:(b + 1) * g] for b in range(hb.shape[0])]
+                else:
+                    res[k] = flat
+            return res
 
         it = iter(batches)
         nxt = next(it, None)
@@ -660,11 +695,14 @@ class Patchioner:
         while inflight is not None:
             nxt = next(it, None)
             following = launch(i + 1, stage(nxt, (i + 1) & 1)) if nxt is not None else None  # issued before batch i is consumed
-            out, done = inflight
+            out, done, host_ids = inflight
             main.wait_event(done)  # the caller reads the results on the current stream
             for v in out.values():
                 if torch.is_tensor(v):
                     v.record_stream(main)
+            if defer_text:
+                done.synchronize()  # the pinned id copies of batch i are complete (batch i+1 is already queued)
+                out = texts(out, host_ids)
             inflight = following
             i += 1
             yield out

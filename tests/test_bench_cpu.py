@@ -33,3 +33,35 @@ def test_reference_arm_prints_the_contract_line(workload):
 
 def test_reference_arm_other_ranks_exit_silently():
     assert _run(["--gpus", "2"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_gpu_eager_baseline_pipeline_matches_oracle():
+    """tools/gpu_eager.py (bench.py's eager-PyTorch-on-GPU baseline) computes what the oracle computes: checked here on
+    the CPU (the module is device-agnostic) stage by stage, token ids included, with and without the KV cache."""
+    import torch
+
+    from oracle import decap as od
+    from oracle import dinov2 as ov
+    from oracle import memory as om
+    from oracle import pipeline as op
+    from oracle import pooling as opool
+    from tools.gpu_eager import EagerPipeline
+
+    vw, dw = ov.make_weights(1234), od.make_weights(1234)
+    bank = op.synth_bank(3000, 768, seed=7, zero_frac=0.002)
+    ep = EagerPipeline(vw, dw, bank, "cpu")
+    imgs = op.synth_images(2, 224, seed=1)
+    boxes = op.synth_boxes(2, 5, 224, seed=1, pad="dense")
+    xn, attn = ep.vit(imgs)
+    ref = ov.forward(vw, imgs)
+    torch.testing.assert_close(xn[:, 5:], ref["x_norm_patchtokens"], rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(attn, opool.cls_attention_map(ref["qkv"]), rtol=1e-3, atol=1e-7)
+    for gauss in (True, False):
+        feats = ep.pool(xn[:, 5:], ep.box_weights(boxes, 16, gauss, 1.0))
+        rf = opool.extract_bboxes_feats(ref["x_norm_patchtokens"], boxes.clone(), gauss, 1.0)
+        torch.testing.assert_close(feats, rf, rtol=1e-4, atol=1e-4)
+    pr = ep.project(feats.reshape(-1, 768))
+    rp = om.project(rf.reshape(-1, 768), om.drop_zero_rows(bank), normalize=True)
+    torch.testing.assert_close(pr, rp, rtol=1e-4, atol=1e-5)
+    assert torch.equal(ep.decode(pr[:4], use_cache=True), od.decode_greedy(dw, rp[:4], use_cache=True))
+    assert torch.equal(ep.dense_step(imgs, boxes, gaussian=False, use_cache=True)[:3], od.decode_greedy(dw, rp[:3], use_cache=True))

@@ -1010,3 +1010,20 @@ def test_linear_chained_dynamic_weight(dev, ops):
         torch.testing.assert_close(z, ref, rtol=2e-2, atol=2e-1)
         z2 = ops.linear(x, y, "bf16", w_static=True)                        # y is complete by now: same numbers
         assert torch.equal(z, z2)
+
+
+def test_forward_pipelined_strings_match_forward(dev):
+    """The string-returning serving loop (ids -> pinned host copy on the batch's stream -> batched detokenisation at
+    consumption time) returns exactly what forward() returns, grouped [B][R] / [B] like the reference."""
+    m = _model(dev, "bf16", True)
+    batches = [{"imgs": o_pipe.synth_images(2, 224, seed=s).pin_memory(), "bboxes": o_pipe.synth_boxes(2, 3, 224, seed=s).pin_memory()}
+               for s in (1, 2, 3, 4)]
+    want = [m(b["imgs"], bboxes=b["bboxes"].clone(), get_cls_capt=True) for b in batches]
+    got = list(m.forward_pipelined(iter(batches), get_cls_capt=True))
+    assert len(got) == 4
+    for a, b in zip(got, want):
+        assert a["bbox_capts"] == b["bbox_capts"] and a["cls_capt"] == b["cls_capt"]
+        assert len(a["bbox_capts"]) == 2 and len(a["bbox_capts"][0]) == 3 and isinstance(a["bbox_capts"][0][0], str)
+    m.decoding_method = lambda ids: "|".join(str(i) for i in ids[:2])      # the reference's hook (model.py:105), row by row
+    hooked = list(m.forward_pipelined(iter(batches[:2]), get_cls_capt=False))
+    assert all(len(s.split("|")) == 2 for s in hooked[0]["bbox_capts"][0])
