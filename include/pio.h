@@ -262,6 +262,10 @@ typedef struct PioDecoder PioDecoder;
 int pio_decoder_create(PioDecoder** out, const PioDecoderWeights* w, int mode, void* stream);
 void pio_decoder_destroy(PioDecoder* h);
 size_t pio_decode_workspace_bytes(const PioDecoder* h, int R, int steps);
+/* test / debug aid: byte offsets of the decode workspace regions for R rows (pio_decode_greedy layout):                */
+/* [0] x fp32 [R,768], [1] LayerNorm rows, [2] qkv rows, [3] gelu rows, [4] attention rows (fused decode), [5] key      */
+/* cache, [6] value cache, [7] per-CTA arg-max partials (fused decode)                                                  */
+int pio_decode_debug_layout(const PioDecoder* h, int R, long long* offsets, int n);
 /* prefix fp32 [R,prefix_size]; out_ids int32 [R,steps]; out_logprob_sum fp32 [R] or NULL            */
 /* (compute_scores: sum_t log softmax(logits_t)[tok_t], decap.py:157-160).  Fixed `steps` (30) greedy  */
 /* steps with a KV cache, argmax first-index tie-break, no EOS early exit.                            */

@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_build")
 LIB = os.path.join(HERE, "libpio_sm100.so")
-SOURCES = ["elementwise.cu", "gemm_simt.cu", "gemm_sm100.cu", "gemm2_sm100.cu", "attention.cu", "attention_sm100.cu", "pooling.cu", "preprocess.cu", "vit.cu", "text.cu", "detok.cu"]
+SOURCES = ["elementwise.cu", "gemm_simt.cu", "gemm_sm100.cu", "gemm2_sm100.cu", "attention.cu", "attention_sm100.cu", "pooling.cu", "preprocess.cu", "vit.cu", "text.cu", "detok.cu", "decode_fused_sm100.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-diag-suppress", "177"]
 

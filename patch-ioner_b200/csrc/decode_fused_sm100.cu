@@ -1,0 +1,795 @@
+// decode_fused_sm100.cu -- the whole KV-cached greedy decode at small batch (R <= 256 rows) as ONE persistent, cooperative
+// kernel: the north star's "kernels fused per decode step".  Replaces the ~32 dependent launches per position of text.cu
+// (decoding_batched, src/decap/decap.py:130-155; greedy_search, src/viecap/search.py:108-191) whose fixed cost -- launch,
+// TMEM allocation, barrier init, tensor-map fetch, first TMA round trip, grid completion -- was ~8 us each (8 % of the HBM
+// roofline at 32 rows).
+//
+// One CTA per SM (cooperative launch: the grid-wide phase counters below need co-residency).  A decode step is a sequence of
+// PHASES; a phase is done when every CTA that has work in it has added 1 to the phase's counter in global memory (release),
+// and whoever needs its results polls that counter (acquire):
+//     per block:  LN1 | QKV | ATTN | PROJ(+res) | LN2 | FC(gelu_new) | FC2(+res, split-K 4 with an in-phase fix-up)
+//     then:       LN_f | LM-HEAD (per-CTA arg-max partials) | PICK (final arg-max, ids, next embedding)
+// Dense layers run on the tensor cores with the operands SWAPPED with respect to gemm_sm100.cu: a work unit is 128 OUTPUT
+// FEATURES (the UMMA M dimension, rows of the [out, in] weight matrix) x 12 k-blocks of 64, against all R rows (the UMMA N
+// dimension, R padded to a multiple of 16): D^T[128, R] = W_tile[128, 768] . X[R, 768]^T accumulated in TMEM.  Every unit of
+// every layer is 196 KB of weights; unit u of phase g belongs to CTA (u + 41 g) mod G, so consecutive phases land on
+// different SMs and -- because weights never change -- warp 0 of every CTA streams the weight tiles of its FUTURE units
+// into a shared-memory ring as fast as slots free up, across phase and step boundaries.  The HBM/L2 weight stream is
+// therefore never interrupted by the phase latencies; only the (small, L2-resident) activation tiles wait for a phase.
+//   warp 0        weight producer   : cp.async.bulk.tensor of 128 x 64 weight tiles (128B swizzle), runs ahead
+//   warp 1        activation producer: waits for the previous phase, then TMA-loads R_pad x 64 activation tiles
+//   warp 2        MMA issuer        : tcgen05.mma (UMMA 128 x R_pad x 16), accumulator double-buffered in TMEM
+//   warps 4..11   compute warps     : epilogues (tcgen05.ld: lane = output feature, column = row), LayerNorm, KV-cache
+//                                     attention, arg-max; they also post the CTA's phase arrivals
+// Cross-CTA data (x, h, qkv, attention rows, gelu rows, KV cache, partials) is written with ordinary stores + fences and read
+// either by TMA or with ld.global.cg (never the non-coherent path: the data changes inside the launch).
+// Every wait is bounded (~2 s): on expiry the kernel raises `abort` in global memory and all roles drain, so a logic error
+// ends as PIO_ECUDA on the host instead of a hung GPU.
+#include "tc_ptx.cuh"
+#include "decoder.cuh"
+#include "gemm_epilogue.cuh"
+
+#include <algorithm>
+#include <stdlib.h>
+
+namespace pio {
+using namespace tc;
+
+size_t fused_counter_ints(int L, int steps) { return (size_t)steps * (7 * L + 3) + (size_t)steps * L * 6 + 64; }
+
+namespace {
+
+constexpr int FT_THREADS = 384;          // 12 warps
+constexpr int FT_COMPUTE_WARPS = 8;      // warps 4..11
+constexpr int W_TILE_BYTES = 128 * 64 * 2;
+constexpr int KB_PER_UNIT = 12;          // 768 / 64
+constexpr int MAX_STAGES = 12;
+
+enum PhaseType { P_LN1 = 0, P_QKV, P_ATTN, P_PROJ, P_LN2, P_FC, P_FC2, P_LNF, P_LMHEAD, P_PICK };
+
+struct FusedParams {
+  const CUtensorMap* wmaps;   // [4 L + 1]
+  const FusedLayer* layers;   // [L]
+  const float *lnf_w, *lnf_b, *wte32, *wpe;
+  float* x;                   // [R, 768] residual stream
+  __nv_bfloat16 *h, *qkv, *att, *f;
+  __nv_bfloat16 *kc, *vc;     // [L][R][H][T][hd]
+  long long kv_layer;         // elements per layer
+  float* part;                // [6 * splits][R_pad][128]
+  float* pm_val;              // [G][R_pad]
+  int* pm_idx;
+  int* phase_cnt;             // [steps * PPS]
+  int* tile_cnt;              // [steps * L * 6]
+  int* abort;
+  int* out_ids;
+  int ids_ld;
+  int L, H, hd, T, R, R_pad, steps, pos_base, first_gp, G, nsw, nsa, stop_gp;
+};
+
+// ------------------------------------------------------------------------------------------ small PTX helpers
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ uint4 ld_cg16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_cg_f(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_cg_i(const int* p) {
+  int v;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const void* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------ schedule (same arithmetic in every role)
+struct Sched {
+  int L, G, R, H, cta, PPS;
+  __device__ __forceinline__ int ptype(int p) const { return p < 7 * L ? p % 7 : P_LNF + (p - 7 * L); }
+  __device__ __forceinline__ int units(int pt) const {
+    switch (pt) {
+      case P_QKV: return 18;
+      case P_PROJ: return 6;
+      case P_FC: return 24;
+      case P_FC2: return 6 * kFusedFc2Splits;
+      case P_LMHEAD: return (gV + 127) / 128;
+      case P_ATTN: return R * H;
+      default: return R;  // LN1, LN2, LNF, PICK: one warp per row
+    }
+  }
+  __device__ __forceinline__ bool is_gemm(int pt) const { return pt == P_QKV || pt == P_PROJ || pt == P_FC || pt == P_FC2 || pt == P_LMHEAD; }
+  __device__ __forceinline__ int rot(int gp) const { return (int)(((long long)gp * 41) % G); }  // 41: coprime with 148
+  // first unit of phase gp owned by this CTA; its further units follow at stride G
+  __device__ __forceinline__ int first_unit(int gp) const { return (cta - rot(gp) + G) % G; }
+  __device__ __forceinline__ int participants(int pt) const { return min(G, units(pt)); }
+};
+
+struct Waiter {
+  int* abort;
+  bool dead;
+  __device__ __forceinline__ void fail() {
+    dead = true;
+    atomicExch(abort, 1);
+  }
+  // bounded mbarrier wait
+  __device__ __forceinline__ void mbar(uint32_t bar, uint32_t parity) {
+    if (dead) return;
+    uint32_t done = 0;
+    unsigned long long t0 = 0;
+    for (unsigned it = 0;; ++it) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+      if (done) return;
+      if ((it & 255) == 255) {
+        const unsigned long long now = gtime_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 2000000000ull || ld_acquire(abort) != 0) { fail(); return; }
+      }
+    }
+  }
+  // bounded wait for a phase counter
+  __device__ __forceinline__ void phase(const int* cnt, int target) {
+    if (dead) return;
+    unsigned long long t0 = 0;
+    for (unsigned it = 0;; ++it) {
+      if (ld_acquire(cnt) >= target) return;
+      if ((it & 63) == 63) {
+        const unsigned long long now = gtime_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 2000000000ull || ld_acquire(abort) != 0) { fail(); return; }
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------ row-wise pieces (one warp per row / unit)
+// LayerNorm of x[r] (fp32, 768) -> h[r] (bf16); eps 1e-5 (GPT-2)
+__device__ __forceinline__ void ln_row(const float* __restrict__ xrow, const float* __restrict__ w, const float* __restrict__ b,
+                                       __nv_bfloat16* __restrict__ out, int lane) {
+  float4 v[6];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    v[i] = ld_cg_f4(xrow + 4 * (lane + 32 * i));
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / 768.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+    q += a * a + c * c + d * d + e * e;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / 768.0f) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + lane + 32 * i);
+    uint2 pk;
+    pk.x = pack2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+    pk.y = pack2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+    reinterpret_cast<uint2*>(out)[lane + 32 * i] = pk;
+  }
+}
+
+// KV-cache attention of one (row, head), head_dim 192 (DeCap: 4 heads, T <= 32): the arithmetic of
+// decode_attention_bf16_kernel (attention.cu) with coherent loads.  Appends this position's key / value to the cache.
+__device__ __forceinline__ void attn_192(const __nv_bfloat16* __restrict__ qkv_row, __nv_bfloat16* __restrict__ kbase,
+                                         __nv_bfloat16* __restrict__ vbase, __nv_bfloat16* __restrict__ out, int h, int H, int t,
+                                         int lane) {
+  constexpr int HDIM = 192, KB = 8;
+  const float scale = rsqrtf(192.0f);
+  const bool act = lane < HDIM / 8;
+  const __nv_bfloat16* row = qkv_row + h * HDIM + lane * 8;
+  kbase += lane * 8;
+  vbase += lane * 8;
+  float q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  uint4 knew = zero, vnew = zero;
+  if (act) {
+    const uint4 qu = ld_cg16(row);
+    knew = ld_cg16(row + H * HDIM);
+    vnew = ld_cg16(row + 2 * H * HDIM);
+    unpack8(qu, q);
+    *reinterpret_cast<uint4*>(kbase + (long long)t * HDIM) = knew;
+    *reinterpret_cast<uint4*>(vbase + (long long)t * HDIM) = vnew;
+  }
+  const int tl = t > 0 ? t - 1 : 0;
+  float my = -INFINITY;
+  for (int j0 = 0; j0 <= t; j0 += KB) {
+    uint4 ku[KB];
+#pragma unroll
+    for (int u = 0; u < KB; ++u) ku[u] = act ? ld_cg16(kbase + (long long)min(j0 + u, tl) * HDIM) : zero;
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+      const int j = j0 + u;
+      ku[u] = (act && j < t) ? ku[u] : (j == t ? knew : zero);
+    }
+    float sc[KB];
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+      float kf[8];
+      unpack8(ku[u], kf);
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a = fmaf(q[e], kf[e], a);
+      sc[u] = a;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < KB; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
+    }
+#pragma unroll
+    for (int u = 0; u < KB; ++u)
+      if (lane == j0 + u) my = sc[u] * scale;
+  }
+  my = (lane <= t) ? my : -INFINITY;
+  const float mx = warp_max(my);
+  const float pe = (lane <= t) ? __expf(my - mx) : 0.f;
+  const float p = pe * (1.0f / warp_sum(pe));
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j0 = 0; j0 <= t; j0 += KB) {
+    uint4 vu[KB];
+#pragma unroll
+    for (int u = 0; u < KB; ++u) vu[u] = act ? ld_cg16(vbase + (long long)min(j0 + u, tl) * HDIM) : zero;
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+      const int j = j0 + u;
+      const uint4 vv = (j < t) ? vu[u] : (j == t ? vnew : zero);
+      const float pj = __shfl_sync(0xffffffffu, p, j & 31);
+      if (j <= t) {
+        float vf[8];
+        unpack8(vv, vf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vf[e], acc[e]);
+      }
+    }
+  }
+  if (act) {
+    uint4 o;
+    o.x = pack2(acc[0], acc[1]); o.y = pack2(acc[2], acc[3]); o.z = pack2(acc[4], acc[5]); o.w = pack2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(out + h * HDIM + lane * 8) = o;
+  }
+}
+
+// head_dim 64 (GPT-2 small: 12 heads, T <= 128): lane j scores keys j, j+32, j+64, j+96 (the arithmetic of
+// decode_attention_long_kernel); qs = 64 floats of this warp's shared memory
+__device__ __forceinline__ void attn_64(const __nv_bfloat16* __restrict__ qkv_row, __nv_bfloat16* __restrict__ kbase,
+                                        __nv_bfloat16* __restrict__ vbase, __nv_bfloat16* __restrict__ out, int h, int H, int t,
+                                        int lane, float* qs) {
+  constexpr int HDIM = 64, MAXC = 4;
+  const __nv_bfloat16* row = qkv_row + h * HDIM;
+  {
+    const uint32_t qq = ld_cg_u32(row + lane * 2);
+    const float2 q2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq));
+    const uint32_t k2 = ld_cg_u32(row + H * HDIM + lane * 2), v2 = ld_cg_u32(row + 2 * H * HDIM + lane * 2);
+    qs[lane * 2] = q2.x;
+    qs[lane * 2 + 1] = q2.y;
+    *reinterpret_cast<uint32_t*>(kbase + (long long)t * HDIM + lane * 2) = k2;
+    *reinterpret_cast<uint32_t*>(vbase + (long long)t * HDIM + lane * 2) = v2;
+  }
+  __threadfence_block();
+  __syncwarp();  // q and the appended row are visible to the whole warp
+  float sc[MAXC];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int j = lane + 32 * c;
+    sc[c] = -INFINITY;
+    if (j <= t) {
+      const __nv_bfloat16* kr = kbase + (long long)j * HDIM;
+      float a = 0.f;
+#pragma unroll
+      for (int d = 0; d < HDIM; d += 8) {
+        float kf[8];
+        unpack8(ld_cg16(kr + d), kf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a = fmaf(qs[d + e], kf[e], a);
+      }
+      sc[c] = a * 0.125f;
+    }
+    mx = fmaxf(mx, sc[c]);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    sc[c] = (lane + 32 * c <= t) ? __expf(sc[c] - mx) : 0.f;
+    sum += sc[c];
+  }
+  const float inv = 1.0f / warp_sum(sum);
+  float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    if (32 * c > t) break;  // warp-uniform
+    const int n = min(32, t + 1 - 32 * c);
+    for (int jj = 0; jj < n; ++jj) {
+      const float pj = __shfl_sync(0xffffffffu, sc[c], jj);
+      const uint32_t vv = ld_cg_u32(vbase + (long long)(32 * c + jj) * HDIM + lane * 2);
+      const float2 v2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv));
+      a0 = fmaf(pj, v2.x, a0);
+      a1 = fmaf(pj, v2.y, a1);
+    }
+  }
+  *reinterpret_cast<uint32_t*>(out + h * HDIM + lane * 2) = pack2(a0 * inv, a1 * inv);
+  __syncwarp();  // qs is reused by this warp's next unit
+}
+
+// ------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(FT_THREADS, 1)
+decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_att,
+                    const __grid_constant__ CUtensorMap map_f, const FusedParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[4 * MAX_STAGES + 4];
+  __shared__ uint32_t tmem_slot_var;
+  __shared__ float s_bv[4][kFusedMaxRows];  // lm-head: running (max, first index) per TMEM lane quarter and row
+  __shared__ int s_bi[4][kFusedMaxRows];
+  __shared__ float s_q[FT_COMPUTE_WARPS][64];
+  __shared__ int s_ticket;
+
+  const uint32_t bar_base = smem_u32(bars);
+  auto fullW = [&](int s) { return bar_base + 8u * s; };
+  auto emptyW = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto fullA = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto emptyA = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + s); };
+  auto tfull = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + s); };
+  auto tempty = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + 2 + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = P.R, R_pad = P.R_pad, L = P.L, G = P.G;
+  const int PPS = 7 * L + 3;
+  const int a_tile_bytes = R_pad * 128;
+  const uint32_t smemA = smem_base + P.nsw * W_TILE_BYTES;
+  const int gp_begin = P.first_gp, gp_end = min(P.steps * PPS, P.stop_gp);  // [gp_begin, gp_end)
+  Sched S{L, G, R, P.H, (int)blockIdx.x, PPS};
+  Waiter wt{P.abort, false};
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * R_pad) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < P.nsw; ++s) { mbar_init(fullW(s), 1); mbar_init(emptyW(s), 1); }
+    for (int s = 0; s < P.nsa; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), FT_COMPUTE_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(smem_u32(&tmem_slot_var), tmem_cols);
+  for (int i = threadIdx.x; i < 4 * kFusedMaxRows; i += FT_THREADS) {
+    (&s_bv[0][0])[i] = -INFINITY;
+    (&s_bi[0][0])[i] = 0x7fffffff;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_var);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ weight producer: runs ahead of every phase
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int gp = gp_begin; gp < gp_end && !wt.dead; ++gp) {
+        const int p = gp % PPS, pt = S.ptype(p);
+        if (!S.is_gemm(pt)) continue;
+        const int l = p / 7, nu = S.units(pt);
+        const CUtensorMap* map = P.wmaps + (pt == P_LMHEAD ? 4 * L : 4 * l + (pt == P_QKV ? 0 : pt == P_PROJ ? 1 : pt == P_FC ? 2 : 3));
+        for (int u = S.first_unit(gp); u < nu; u += G) {
+          const int tile = pt == P_FC2 ? u % 6 : u, kb0 = pt == P_FC2 ? (u / 6) * KB_PER_UNIT : 0;
+          for (int kb = 0; kb < KB_PER_UNIT; ++kb) {
+            wt.mbar(emptyW(stage), phase ^ 1);
+            if (wt.dead) break;
+            mbar_expect_tx(fullW(stage), W_TILE_BYTES);
+            tma_load_2d(smem_base + stage * W_TILE_BYTES, map, fullW(stage), (kb0 + kb) * 64, tile * 128);
+            if (++stage == P.nsw) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ activation producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int gp = gp_begin; gp < gp_end && !wt.dead; ++gp) {
+        const int p = gp % PPS, pt = S.ptype(p);
+        if (!S.is_gemm(pt)) continue;
+        const int nu = S.units(pt);
+        const int u0 = S.first_unit(gp);
+        if (u0 >= nu) continue;
+        const CUtensorMap* map = pt == P_PROJ ? &map_att : (pt == P_FC2 ? &map_f : &map_h);
+        if (gp > gp_begin) {  // this phase's input rows are complete (and visible to the copy engine)
+          wt.phase(P.phase_cnt + gp - 1, S.participants(S.ptype((gp - 1) % PPS)));
+          fence_proxy_async();
+        }
+        for (int u = u0; u < nu && !wt.dead; u += G) {
+          const int kb0 = pt == P_FC2 ? (u / 6) * KB_PER_UNIT : 0;
+          for (int kb = 0; kb < KB_PER_UNIT; ++kb) {
+            wt.mbar(emptyA(stage), phase ^ 1);
+            if (wt.dead) break;
+            mbar_expect_tx(fullA(stage), a_tile_bytes);
+            tma_load_2d(smemA + stage * a_tile_bytes, map, fullA(stage), (kb0 + kb) * 64, 0);
+            if (++stage == P.nsa) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc(128, R_pad);
+    int sw = 0, sa = 0, it = 0;
+    uint32_t phw = 0, pha = 0;
+    for (int gp = gp_begin; gp < gp_end && !wt.dead; ++gp) {
+      const int p = gp % PPS, pt = S.ptype(p);
+      if (!S.is_gemm(pt)) continue;
+      const int nu = S.units(pt);
+      for (int u = S.first_unit(gp); u < nu && !wt.dead; u += G, ++it) {
+        const int as = it & 1;
+        wt.mbar(tempty(as), ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * R_pad;
+        for (int kb = 0; kb < KB_PER_UNIT; ++kb) {
+          wt.mbar(fullW(sw), phw);
+          wt.mbar(fullA(sa), pha);
+          if (wt.dead) break;
+          tc_fence_after();
+          if (lane == 0) {
+            const uint64_t adesc = make_smem_desc(smem_base + sw * W_TILE_BYTES), bdesc = make_smem_desc(smemA + sa * a_tile_bytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(emptyW(sw));
+            umma_commit(emptyA(sa));
+            if (kb == KB_PER_UNIT - 1) umma_commit(tfull(as));
+          }
+          __syncwarp();
+          if (++sw == P.nsw) { sw = 0; phw ^= 1; }
+          if (++sa == P.nsa) { sa = 0; pha ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ compute warps
+    const int cw = warp - 4, quarter = warp & 3, half = cw >> 2;
+    const int ct = threadIdx.x - 128;  // 0..255 among the compute threads
+    const int n_chunks = R_pad / 16;
+    int it = 0;
+    auto cta_arrive = [&](int gp) {
+      __threadfence();
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ct == 0) red_release_add(P.phase_cnt + gp, 1);
+    };
+    // NB no early exit from this loop: the CTA-wide named barriers need all eight warps.  After a time-out (wt.dead, raised
+    // CTA-wide through the abort flag) a warp keeps walking the schedule but skips every wait and all work.
+    for (int gp = gp_begin; gp < gp_end; ++gp) {
+      const int s = gp / PPS, p = gp % PPS, pt = S.ptype(p), l = p / 7;
+      const int nu = S.units(pt), u0 = S.first_unit(gp);
+      if (u0 >= nu) continue;  // no work for this CTA in this phase (CTA-uniform)
+      const int pos = P.pos_base + s;
+      if (!S.is_gemm(pt)) {
+        if (gp > gp_begin) {
+          if (lane == 0) wt.phase(P.phase_cnt + gp - 1, S.participants(S.ptype((gp - 1) % PPS)));
+          wt.dead = __shfl_sync(0xffffffffu, (int)wt.dead, 0) != 0;
+        }
+        for (int u = u0 + cw * G; u < nu && !wt.dead; u += FT_COMPUTE_WARPS * G) {  // this CTA's units, one warp each
+          if (pt == P_LN1 || pt == P_LN2 || pt == P_LNF) {
+            const float* w = pt == P_LN1 ? P.layers[l].ln1_w : (pt == P_LN2 ? P.layers[l].ln2_w : P.lnf_w);
+            const float* b = pt == P_LN1 ? P.layers[l].ln1_b : (pt == P_LN2 ? P.layers[l].ln2_b : P.lnf_b);
+            ln_row(P.x + (long long)u * gD, w, b, P.h + (long long)u * gD, lane);
+          } else if (pt == P_ATTN) {
+            const int r = u / P.H, hh = u % P.H;
+            __nv_bfloat16* kb_ = P.kc + (long long)l * P.kv_layer + ((long long)(r * P.H + hh) * P.T) * P.hd;
+            __nv_bfloat16* vb_ = P.vc + (long long)l * P.kv_layer + ((long long)(r * P.H + hh) * P.T) * P.hd;
+            if (P.hd == 192) attn_192(P.qkv + (long long)r * 3 * gD, kb_, vb_, P.att + (long long)r * gD, hh, P.H, pos, lane);
+            else attn_64(P.qkv + (long long)r * 3 * gD, kb_, vb_, P.att + (long long)r * gD, hh, P.H, pos, lane, s_q[cw]);
+          } else {  // P_PICK: final arg-max over the per-CTA partials, id out, next token's embedding
+            float best = -INFINITY;
+            int bi = 0x7fffffff;
+            for (int c = lane; c < G; c += 32) {
+              const float v = ld_cg_f(P.pm_val + (long long)c * R_pad + u);
+              const int i = ld_cg_i(P.pm_idx + (long long)c * R_pad + u);
+              if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            const int tok = (bi == 0x7fffffff) ? 0 : bi;  // all-NaN row -> 0, like torch.argmax
+            if (lane == 0) P.out_ids[(long long)u * P.ids_ld + s] = tok;
+            if (s + 1 < P.steps) {
+              const float4* a = reinterpret_cast<const float4*>(P.wte32 + (long long)min(max(tok, 0), gV - 1) * gD);
+              const float4* b = reinterpret_cast<const float4*>(P.wpe + (long long)(pos + 1) * gD);
+              float4* o = reinterpret_cast<float4*>(P.x + (long long)u * gD);
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                const float4 uu = __ldg(a + lane + 32 * i), vv = __ldg(b + lane + 32 * i);
+                o[lane + 32 * i] = make_float4(uu.x + vv.x, uu.y + vv.y, uu.z + vv.z, uu.w + vv.w);
+              }
+            }
+          }
+        }
+        cta_arrive(gp);
+        continue;
+      }
+      // ---- GEMM phase: epilogue of every owned unit
+      const FusedLayer& ly = P.layers[pt == P_LMHEAD ? 0 : l];
+      for (int u = u0; u < nu; u += G, ++it) {
+        const int as = it & 1;
+        const int tile = pt == P_FC2 ? u % 6 : u;
+        const int nl = quarter * 32 + lane, n = tile * 128 + nl;  // this thread's output feature
+        wt.mbar(tfull(as), (it >> 1) & 1);
+        wt.dead = __any_sync(0xffffffffu, wt.dead);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * R_pad + ((uint32_t)(quarter * 32) << 16);
+        float bias = 0.f;
+        if (pt == P_QKV) bias = __ldg(ly.attn_b + n);
+        else if (pt == P_PROJ) bias = __ldg(ly.proj_b + n);
+        else if (pt == P_FC) bias = __ldg(ly.fc_b + n);
+        for (int c = half; c < n_chunks && !wt.dead; c += 2) {
+          uint32_t rr[16];
+          tmem_ld16(tacc + c * 16, rr);
+          tmem_ld_wait();
+          if (pt == P_QKV) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int r = c * 16 + j;
+              if (r < R) P.qkv[(long long)r * (3 * gD) + n] = __float2bfloat16(__uint_as_float(rr[j]) + bias);
+            }
+          } else if (pt == P_PROJ) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int r = c * 16 + j;
+              if (r < R) {
+                float* xp = P.x + (long long)r * gD + n;
+                *xp = ld_cg_f(xp) + (__uint_as_float(rr[j]) + bias);
+              }
+            }
+          } else if (pt == P_FC) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int r = c * 16 + j;
+              if (r < R) P.f[(long long)r * gFF + n] = __float2bfloat16(gelu_new_fast(__uint_as_float(rr[j]) + bias));
+            }
+          } else if (pt == P_FC2) {
+            float* pp = P.part + ((long long)u * R_pad + c * 16) * 128 + nl;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pp[(long long)j * 128] = __uint_as_float(rr[j]);
+          } else {  // P_LMHEAD: arg-max over the 32 vocabulary rows of this warp, per decode row
+            const bool valid = n < gV;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float v = valid ? __uint_as_float(rr[j]) : -INFINITY;
+              int idx = valid ? n : 0x7fffffff;
+              if (!(v == v)) { v = -INFINITY; idx = 0x7fffffff; }  // NaN never wins (torch.argmax semantics handled in PICK)
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+                if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+              }
+              const int r = c * 16 + j;
+              if (lane == (j & 31)) {  // (quarter, row) slots are owned by this warp: no race
+                const float cv = s_bv[quarter][r];
+                const int ci = s_bi[quarter][r];
+                if (v > cv || (v == cv && idx < ci)) { s_bv[quarter][r] = v; s_bi[quarter][r] = idx; }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty(as));
+        if (pt == P_FC2) {
+          // split-K fix-up: the unit that arrives last at its tile's counter sums the 4 partials in split order (so the result
+          // does not depend on arrival order), adds bias and the residual, and owns the x update
+          __threadfence();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (ct == 0) s_ticket = atomicAdd(P.tile_cnt + ((long long)s * L + l) * 6 + tile, 1);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (s_ticket == kFusedFc2Splits - 1 && !wt.dead) {
+            __threadfence();
+            const float b2 = __ldg(ly.fc2_b + n);
+            for (int c = half; c < n_chunks; c += 2) {
+#pragma unroll 4
+              for (int j = 0; j < 16; ++j) {
+                const int r = c * 16 + j;
+                if (r >= R) break;
+                float acc = 0.f;
+#pragma unroll
+                for (int sp = 0; sp < kFusedFc2Splits; ++sp)
+                  acc += ld_cg_f(P.part + ((long long)(sp * 6 + tile) * R_pad + r) * 128 + nl);
+                float* xp = P.x + (long long)r * gD + n;
+                *xp = ld_cg_f(xp) + (acc + b2);
+              }
+            }
+          }
+        }
+      }
+      if (pt == P_LMHEAD) {
+        // fold the four lane quarters and publish this CTA's partial (max, first index) per row; reset for the next step
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int r = ct; r < R_pad; r += 256) {
+          float v = s_bv[0][r];
+          int i = s_bi[0][r];
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            const float ov = s_bv[q][r];
+            const int oi = s_bi[q][r];
+            if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+          }
+          P.pm_val[(long long)blockIdx.x * R_pad + r] = v;
+          P.pm_idx[(long long)blockIdx.x * R_pad + r] = i;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { s_bv[q][r] = -INFINITY; s_bi[q][r] = 0x7fffffff; }
+        }
+      }
+      cta_arrive(gp);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ host side
+bool decode_fused_eligible(const PioDecoder* h, int R, bool want_logprob) {
+  const char* sw = getenv("PIO_DECODE_FUSED");  // read per call: tests and A/B runs flip it inside one process
+  const bool on = !(sw && sw[0] == '0');
+  if (!on || want_logprob || h->mode != PIO_BF16 || h->fused_wmaps == nullptr) return false;
+  if (!((h->H == 4) || (h->H == 12))) return false;
+  int max_rows = kFusedMaxRows;
+  if (const char* e = getenv("PIO_DECODE_FUSED_MAX_ROWS")) max_rows = std::min(kFusedMaxRows, atoi(e));
+  return R >= 1 && R <= max_rows;
+}
+
+int decode_fused_build(PioDecoder* h, cudaStream_t st) {
+  if (h->mode != PIO_BF16) return PIO_OK;
+  const int L = h->L;
+  std::vector<CUtensorMap> maps(4 * L + 1);
+  std::vector<FusedLayer> layers(L);
+  for (int i = 0; i < L; ++i) {
+    const PioDecoder::Blk& b = h->blk[i];
+    PIO_TRY(make_map_2d(&maps[4 * i + 0], b.attn_w, 3 * gD, gD, gD, 128, 64));
+    PIO_TRY(make_map_2d(&maps[4 * i + 1], b.proj_w, gD, gD, gD, 128, 64));
+    PIO_TRY(make_map_2d(&maps[4 * i + 2], b.fc_w, gFF, gD, gD, 128, 64));
+    PIO_TRY(make_map_2d(&maps[4 * i + 3], b.fc2_w, gD, gFF, gFF, 128, 64));
+    layers[i] = FusedLayer{b.ln1_w, b.ln1_b, b.attn_b, b.proj_b, b.ln2_w, b.ln2_b, b.fc_b, b.fc2_b};
+  }
+  PIO_TRY(make_map_2d(&maps[4 * L], h->wte, gV, gD, gD, 128, 64));
+  void* dm = nullptr;
+  void* dl = nullptr;
+  PIO_CUDA(cudaMalloc(&dm, maps.size() * sizeof(CUtensorMap)));
+  h->owned.push_back(dm);
+  PIO_CUDA(cudaMalloc(&dl, layers.size() * sizeof(FusedLayer)));
+  h->owned.push_back(dl);
+  // synchronous copies: the host vectors die with this frame
+  PIO_CUDA(cudaMemcpy(dm, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  PIO_CUDA(cudaMemcpy(dl, layers.data(), layers.size() * sizeof(FusedLayer), cudaMemcpyHostToDevice));
+  (void)st;
+  h->fused_wmaps = dm;
+  h->fused_layers = (FusedLayer*)dl;
+  return PIO_OK;
+}
+
+int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int pos_base, bool start_at_pick, int* out_ids,
+                 cudaStream_t st) {
+  const int L = h->L, PPS = 7 * L + 3;
+  const int R_pad = std::max(16, (R + 15) / 16 * 16);
+  PIO_CHECK(R_pad <= kFusedMaxRows && steps >= 1, "decode_fused: %d rows / %d steps outside the built range", R, steps);
+  int dev = 0, sms = 0;
+  PIO_CUDA(cudaGetDevice(&dev));
+  PIO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int G = std::min(sms, kFusedCtas);
+  if (const char* e = getenv("PIO_DECODE_FUSED_CTAS")) G = std::max(1, std::min(G, atoi(e)));
+  PIO_CHECK(T <= (h->H == 4 ? 32 : 128), "decode_fused: a cache of %d positions exceeds what the attention routines walk", T);
+  // rings: 16 KB weight stages + R_pad x 128 B activation stages inside ~200 KB
+  const int a_tile = R_pad * 128;
+  int nsa = std::max(2, std::min(MAX_STAGES, (R_pad <= 32 ? 32 : (R_pad <= 64 ? 48 : (R_pad <= 128 ? 64 : 96))) * 1024 / a_tile));
+  int nsw = std::min(MAX_STAGES, (200 * 1024 - nsa * a_tile) / W_TILE_BYTES);
+  const size_t smem = (size_t)nsw * W_TILE_BYTES + (size_t)nsa * a_tile + 1024;
+
+  FusedParams P;
+  memset(&P, 0, sizeof(P));
+  P.wmaps = (const CUtensorMap*)h->fused_wmaps;
+  P.layers = h->fused_layers;
+  P.lnf_w = h->lnf_w; P.lnf_b = h->lnf_b; P.wte32 = h->wte32; P.wpe = h->wpe;
+  P.x = w.x; P.h = (__nv_bfloat16*)w.hb; P.qkv = (__nv_bfloat16*)w.qkv; P.att = (__nv_bfloat16*)w.att; P.f = (__nv_bfloat16*)w.f;
+  P.kc = (__nv_bfloat16*)w.kc; P.vc = (__nv_bfloat16*)w.vc; P.kv_layer = (long long)(w.kv_layer / 2);
+  P.part = w.part; P.pm_val = w.pm_val; P.pm_idx = w.pm_idx;
+  PIO_CHECK(fused_counter_ints(L, steps) * sizeof(int) <= w.counters_bytes, "decode_fused: counter region too small for %d steps", steps);
+  P.phase_cnt = w.counters;
+  P.tile_cnt = w.counters + (size_t)steps * PPS;
+  P.abort = w.counters + (size_t)steps * PPS + (size_t)steps * L * 6;
+  P.out_ids = out_ids; P.ids_ld = steps;
+  P.L = L; P.H = h->H; P.hd = gD / h->H; P.T = T; P.R = R; P.R_pad = R_pad; P.steps = steps; P.pos_base = pos_base;
+  P.first_gp = start_at_pick ? 7 * L : 0;
+  P.G = G; P.nsw = nsw; P.nsa = nsa;
+  P.stop_gp = 1 << 30;
+  if (const char* e = getenv("PIO_FUSED_STOP_PHASE")) P.stop_gp = atoi(e) + 1;  // debug: run global phases [first, stop]
+
+  CUtensorMap mh, ma, mf;
+  PIO_TRY(make_map_2d(&mh, w.hb, R, gD, gD, R_pad, 64));
+  PIO_TRY(make_map_2d(&ma, w.att, R, gD, gD, R_pad, 64));
+  PIO_TRY(make_map_2d(&mf, w.f, R, gFF, gFF, R_pad, 64));
+  PIO_CUDA(cudaMemsetAsync(w.counters, 0, fused_counter_ints(L, steps) * sizeof(int), st));
+  static SmemAttrOnce once;
+  PIO_CUDA(once.ensure(decode_fused_kernel, 227 * 1024));
+  int per_sm = 0;
+  PIO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_fused_kernel, FT_THREADS, smem));
+  PIO_CHECK(per_sm >= 1, "decode_fused: the kernel does not fit an SM (%zu bytes of shared memory)", smem);
+  void* args[] = {(void*)&mh, (void*)&ma, (void*)&mf, (void*)&P};
+  PIO_CUDA(cudaLaunchCooperativeKernel((const void*)decode_fused_kernel, dim3(G), dim3(FT_THREADS), args, smem, st));
+  PIO_LAUNCHED();
+  if (getenv("PIO_FUSED_CHECK")) {  // debug: surface a drained (timed-out) kernel right away
+    int flag = 0;
+    PIO_CUDA(cudaStreamSynchronize(st));
+    PIO_CUDA(cudaMemcpy(&flag, P.abort, sizeof(int), cudaMemcpyDeviceToHost));
+    PIO_CHECK(flag == 0, "decode_fused: a wait inside the kernel timed out (abort flag raised)");
+  }
+  return PIO_OK;
+}
+
+}  // namespace pio

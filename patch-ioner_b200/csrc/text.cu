@@ -1,7 +1,7 @@
 // text.cu -- the DeCap text side: caption-memory projection and the KV-cached greedy prefix decoder.
 //   pio_project*        replaces Im2TxtProjector.project   (im2txtprojection.py:353-385)
 //   pio_decode_greedy   replaces decoding_batched          (src/decap/decap.py:116-160)
-#include "common.cuh"
+#include "decoder.cuh"
 #include <stdlib.h>
 #include <vector>
 
@@ -664,22 +664,7 @@ int pio_project_finish(float* O, const float* l, int R, int D, int normalize, vo
 }
 
 // ==========================================================================================
-namespace pio {
-constexpr int gD = 768, gV = 50257, gVld = 50264, gFF = 3072;
-}
-// L blocks x H heads; T = positions the KV cache of one call may hold (DeCap: 4 x 4 x 32; GPT-2 small for ViECap: 12 x 12 x 128)
-struct PioDecoder {
-  int mode, act_dt, prefix_size, L, H, T;
-  std::vector<void*> owned;
-  const float *wte32, *wpe, *lnf_w, *lnf_b, *prefix_b0;  // prefix_b0 = prefix bias + wpe[0]
-  const void *wte, *prefix_w;                             // act dtype
-  struct Blk {
-    const float *ln1_w, *ln1_b, *attn_b, *proj_b, *ln2_w, *ln2_b, *fc_b, *fc2_b;
-    const void *attn_w, *proj_w, *fc_w, *fc2_w;  // act dtype, transposed to [out, in]
-  };
-  std::vector<Blk> blk;
-};
-
+// struct PioDecoder, the workspace layout and the fused-decode entry points: decoder.cuh
 namespace pio {
 namespace {
 int d_own(PioDecoder* h, void** p, size_t bytes) {
@@ -751,6 +736,7 @@ static int decoder_build(PioDecoder** out, const float* wte, const float* wpe, c
       PIO_TRY(d_matT(h, &d.fc_w, s.fc_w, gD, gFF, st));
       PIO_TRY(d_matT(h, &d.fc2_w, s.fc2_w, gFF, gD, st));
     }
+    PIO_TRY(decode_fused_build(h, st));  // tensor maps + layer table of the persistent small-batch decode kernel (bf16 mode)
     return PIO_OK;
   };
   int rc = go();
@@ -784,30 +770,8 @@ void pio_decoder_destroy(PioDecoder* h) {
 }
 
 namespace {
-struct DecodeWs {
-  float* x; void* hb; void* qkv; void* f; float* logits; char* kc; char* vc; void* pfx; size_t kv_layer, total;
-};
-// carve the decode workspace for R rows and a KV cache of T positions (same layout for sizing and for use)
-// `rows` >= R: rows of the token buffers (R for single-position steps, R * prompt_len for a batched prompt prefill)
-DecodeWs decode_ws(const PioDecoder* h, char* base, int R, int T, size_t tail_elems, size_t rows = 0) {
-  using namespace pio;
-  const size_t e = h->act_dt == PIO_DT_F32 ? 4 : 2;
-  DecodeWs w;
-  char* ws = base;
-  if (rows < (size_t)R) rows = R;
-  w.kv_layer = (size_t)R * T * gD * e;
-  w.x = (float*)ws;      ws += align_up(rows * gD * 4, 1024);
-  w.hb = ws;             ws += align_up(rows * gD * e, 1024);
-  w.qkv = ws;            ws += align_up(rows * 3 * gD * e, 1024);
-  w.f = ws;              ws += align_up(rows * gFF * e, 1024);
-  w.logits = (float*)ws; ws += align_up((size_t)R * gVld * 4, 1024);
-  w.kc = ws;             ws += align_up(h->L * w.kv_layer, 1024);
-  w.vc = ws;             ws += align_up(h->L * w.kv_layer, 1024);
-  w.pfx = ws;            ws += align_up(tail_elems * e, 1024);
-  w.total = (size_t)(ws - base) + 4096;
-  return w;
-}
-
+using pio::DecodeWs;
+using pio::decode_ws;
 // all transformer blocks for the single new position t (KV cache of T positions per head)
 int decode_blocks(PioDecoder* h, const DecodeWs& w, int R, int T, int t, cudaStream_t st) {
   using namespace pio;
@@ -855,6 +819,17 @@ int decode_pick(PioDecoder* h, const DecodeWs& w, int R, int* out_ids, int ids_l
 }
 }  // namespace
 
+int pio_decode_debug_layout(const PioDecoder* h, int R, long long* offsets, int n) {
+  using namespace pio;
+  PIO_CHECK(h && offsets && n >= 8, "decode_debug_layout: need room for 8 offsets");
+  const DecodeWs w = decode_ws(h, nullptr, R, h->T, (size_t)R * h->prefix_size);
+  const char* b = nullptr;
+  offsets[0] = (const char*)w.x - b; offsets[1] = (const char*)w.hb - b; offsets[2] = (const char*)w.qkv - b;
+  offsets[3] = (const char*)w.f - b; offsets[4] = (const char*)w.att - b; offsets[5] = (const char*)w.kc - b;
+  offsets[6] = (const char*)w.vc - b; offsets[7] = (const char*)w.pm_val - b;
+  return PIO_OK;
+}
+
 size_t pio_decode_workspace_bytes(const PioDecoder* h, int R, int steps) {
   (void)steps;
   return decode_ws(h, nullptr, R, h->T, (size_t)R * h->prefix_size).total;
@@ -879,6 +854,9 @@ int pio_decode_greedy(PioDecoder* h, const float* prefix, int R, int steps, int*
   PIO_TRY(linear(mode, pA, h->prefix_w, w.x, R, gD, h->prefix_size, h->prefix_size, h->prefix_size, gD, adt, PIO_DT_F32,
                  h->prefix_b0, nullptr, PIO_ACT_NONE, st));
   if (out_logprob_sum) PIO_CUDA(cudaMemsetAsync(out_logprob_sum, 0, (size_t)R * 4, st));
+
+  // small batches: the whole loop below as ONE persistent kernel (decode_fused_sm100.cu) instead of ~32 launches per position
+  if (decode_fused_eligible(h, R, out_logprob_sum != nullptr)) return decode_fused(h, w, R, T, steps, 0, false, out_ids, st);
 
   for (int t = 0; t < steps; ++t) {
     PIO_TRY(decode_blocks(h, w, R, T, t, st));
@@ -951,6 +929,9 @@ int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prom
       PIO_TRY(decode_blocks(h, w, R, T, p, st));
     }
   }
+  // generation: pick(0) on the last prompt position's residual stream, then embed -> blocks -> pick per new position --
+  // one persistent kernel at small batch (decode_fused_sm100.cu)
+  if (decode_fused_eligible(h, R, out_logprob_sum != nullptr)) return decode_fused(h, w, R, T, steps, prompt_len - 1, true, out_ids, st);
   for (int s = 0; s < steps; ++s) {
     PIO_TRY(decode_pick(h, w, R, out_ids, steps, s, out_logprob_sum, st));
     if (s + 1 < steps) {
