@@ -31,6 +31,7 @@
 
 #include <algorithm>
 #include <stdlib.h>
+#include <vector>
 
 namespace pio {
 using namespace tc;
@@ -61,6 +62,7 @@ struct FusedParams {
   int* phase_cnt;             // [steps * PPS]
   int* tile_cnt;              // [steps * L * 6]
   int* abort;
+  unsigned long long* timeline;  // debug (PIO_FUSED_TIMELINE): 4 globaltimer stamps per (phase, CTA), or NULL
   int* out_ids;
   int ids_ld;
   int L, H, hd, T, R, R_pad, steps, pos_base, first_gp, G, nsw, nsa, stop_gp;
@@ -81,6 +83,8 @@ __device__ __forceinline__ void red_release_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// __threadfence() is membar.gl == fence.sc.gpu; release / acquire ordering is all the phase protocol needs
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ uint4 ld_cg16(const void* p) {
   uint4 v;
   asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -508,11 +512,16 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
     const int ct = threadIdx.x - 128;  // 0..255 among the compute threads
     const int n_chunks = R_pad / 16;
     int it = 0;
+    auto stamp = [&](int gp, int k) {
+      if (P.timeline && ct == 0) P.timeline[((long long)(gp - gp_begin) * G + blockIdx.x) * 4 + k] = gtime_ns();
+    };
     auto cta_arrive = [&](int gp) {
-      __threadfence();
+      stamp(gp, 2);
+      fence_acq_rel_gpu();
       fence_proxy_async();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (ct == 0) red_release_add(P.phase_cnt + gp, 1);
+      stamp(gp, 3);
     };
     // NB no early exit from this loop: the CTA-wide named barriers need all eight warps.  After a time-out (wt.dead, raised
     // CTA-wide through the abort flag) a warp keeps walking the schedule but skips every wait and all work.
@@ -521,11 +530,13 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
       const int nu = S.units(pt), u0 = S.first_unit(gp);
       if (u0 >= nu) continue;  // no work for this CTA in this phase (CTA-uniform)
       const int pos = P.pos_base + s;
+      stamp(gp, 0);
       if (!S.is_gemm(pt)) {
         if (gp > gp_begin) {
           if (lane == 0) wt.phase(P.phase_cnt + gp - 1, S.participants(S.ptype((gp - 1) % PPS)));
           wt.dead = __shfl_sync(0xffffffffu, (int)wt.dead, 0) != 0;
         }
+        stamp(gp, 1);
         for (int u = u0 + cw * G; u < nu && !wt.dead; u += FT_COMPUTE_WARPS * G) {  // this CTA's units, one warp each
           if (pt == P_LN1 || pt == P_LN2 || pt == P_LNF) {
             const float* w = pt == P_LN1 ? P.layers[l].ln1_w : (pt == P_LN2 ? P.layers[l].ln2_w : P.lnf_w);
@@ -576,6 +587,7 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         const int nl = quarter * 32 + lane, n = tile * 128 + nl;  // this thread's output feature
         wt.mbar(tfull(as), (it >> 1) & 1);
         wt.dead = __any_sync(0xffffffffu, wt.dead);
+        if (u == u0) stamp(gp, 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * R_pad + ((uint32_t)(quarter * 32) << 16);
         float bias = 0.f;
@@ -639,12 +651,12 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         if (pt == P_FC2) {
           // split-K fix-up: the unit that arrives last at its tile's counter sums the 4 partials in split order (so the result
           // does not depend on arrival order), adds bias and the residual, and owns the x update
-          __threadfence();
+          fence_acq_rel_gpu();
           asm volatile("bar.sync 1, 256;" ::: "memory");
           if (ct == 0) s_ticket = atomicAdd(P.tile_cnt + ((long long)s * L + l) * 6 + tile, 1);
           asm volatile("bar.sync 1, 256;" ::: "memory");
           if (s_ticket == kFusedFc2Splits - 1 && !wt.dead) {
-            __threadfence();
+            fence_acq_rel_gpu();
             const float b2 = __ldg(ly.fc2_b + n);
             for (int c = half; c < n_chunks; c += 2) {
 #pragma unroll 4
@@ -776,13 +788,31 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   PIO_TRY(make_map_2d(&mf, w.f, R, gFF, gFF, R_pad, 64));
   PIO_CUDA(cudaMemsetAsync(w.counters, 0, fused_counter_ints(L, steps) * sizeof(int), st));
   static SmemAttrOnce once;
-  PIO_CUDA(once.ensure(decode_fused_kernel, 227 * 1024));
+  PIO_CUDA(once.ensure(decode_fused_kernel, 210 * 1024));  // + 10.7 KB static: inside the 227 KB an SM offers
   int per_sm = 0;
   PIO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_fused_kernel, FT_THREADS, smem));
   PIO_CHECK(per_sm >= 1, "decode_fused: the kernel does not fit an SM (%zu bytes of shared memory)", smem);
+  const char* tl_path = getenv("PIO_FUSED_TIMELINE");  // debug: per-(phase, CTA) time stamps -> binary file
+  const size_t tl_n = tl_path ? (size_t)(steps * PPS) * G * 4 : 0;
+  if (tl_path) {
+    PIO_CUDA(cudaMalloc((void**)&P.timeline, tl_n * 8));
+    PIO_CUDA(cudaMemsetAsync(P.timeline, 0, tl_n * 8, st));
+  }
   void* args[] = {(void*)&mh, (void*)&ma, (void*)&mf, (void*)&P};
   PIO_CUDA(cudaLaunchCooperativeKernel((const void*)decode_fused_kernel, dim3(G), dim3(FT_THREADS), args, smem, st));
   PIO_LAUNCHED();
+  if (tl_path) {
+    std::vector<unsigned long long> host(tl_n);
+    PIO_CUDA(cudaStreamSynchronize(st));
+    PIO_CUDA(cudaMemcpy(host.data(), P.timeline, tl_n * 8, cudaMemcpyDeviceToHost));
+    PIO_CUDA(cudaFree(P.timeline));
+    if (FILE* f = fopen(tl_path, "wb")) {
+      const int hdr[8] = {steps, PPS, G, P.first_gp, L, R, 4, 0};
+      fwrite(hdr, sizeof(int), 8, f);
+      fwrite(host.data(), 8, tl_n, f);
+      fclose(f);
+    }
+  }
   if (getenv("PIO_FUSED_CHECK")) {  // debug: surface a drained (timed-out) kernel right away
     int flag = 0;
     PIO_CUDA(cudaStreamSynchronize(st));
