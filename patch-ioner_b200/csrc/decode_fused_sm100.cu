@@ -60,7 +60,7 @@ struct FusedParams {
   float* pm_val;              // [G][R_pad]
   int* pm_idx;
   int* phase_cnt;             // [steps * PPS]
-  int* tile_cnt;              // [steps * L * 6]
+  int* tile_cnt;              // [steps * L * 6] (spare: the split-K fix-up of v1 used it)
   int* abort;
   unsigned long long* timeline;  // debug (PIO_FUSED_TIMELINE): 4 globaltimer stamps per (phase, CTA), or NULL
   int* out_ids;
@@ -77,6 +77,11 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void red_release_add(int* p, int v) {
@@ -189,7 +194,7 @@ struct Waiter {
     if (dead) return;
     unsigned long long t0 = 0;
     for (unsigned it = 0;; ++it) {
-      if (ld_acquire(cnt) >= target) return;
+      if (ld_relaxed(cnt) >= target) { fence_acq_rel_gpu(); return; }  // relaxed polls, one acquire fence at the end
       if ((it & 63) == 63) {
         const unsigned long long now = gtime_ns();
         if (t0 == 0) t0 = now;
@@ -200,16 +205,35 @@ struct Waiter {
 };
 
 // ------------------------------------------------------------------------------------------ row-wise pieces (one warp per row / unit)
-// LayerNorm of x[r] (fp32, 768) -> h[r] (bf16); eps 1e-5 (GPT-2)
-__device__ __forceinline__ void ln_row(const float* __restrict__ xrow, const float* __restrict__ w, const float* __restrict__ b,
-                                       __nv_bfloat16* __restrict__ out, int lane) {
+// LayerNorm of x[r] (fp32, 768) -> h[r] (bf16); eps 1e-5 (GPT-2).
+// part != NULL: the previous block's fc2 left its 4 split-K partial tiles unreduced -- this warp first forms
+//   x[r] += (p0 + p1 + p2 + p3) + fc2_b   (fixed order: deterministic), stores the row back, then normalises it.
+// Lane l owns the float4 at column 4 (l + 32 i), i < 6: output tile i of the [6 x 128]-column layout, offset 4 l.
+__device__ __forceinline__ void ln_row(float* __restrict__ xrow, const float* __restrict__ w, const float* __restrict__ b,
+                                       __nv_bfloat16* __restrict__ out, int lane, const float* __restrict__ part, int r, int R_pad,
+                                       const float* __restrict__ fc2_b) {
   float4 v[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) v[i] = ld_cg_f4(xrow + 4 * (lane + 32 * i));
+  if (part != nullptr) {
+    float4 pp[6][kFusedFc2Splits];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int sp = 0; sp < kFusedFc2Splits; ++sp) pp[i][sp] = ld_cg_f4(part + ((long long)(sp * 6 + i) * R_pad + r) * 128 + 4 * lane);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      float4 a = pp[i][0];
+#pragma unroll
+      for (int sp = 1; sp < kFusedFc2Splits; ++sp) { a.x += pp[i][sp].x; a.y += pp[i][sp].y; a.z += pp[i][sp].z; a.w += pp[i][sp].w; }
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(fc2_b) + lane + 32 * i);
+      v[i].x += a.x + bb.x; v[i].y += a.y + bb.y; v[i].z += a.z + bb.z; v[i].w += a.w + bb.w;
+      reinterpret_cast<float4*>(xrow)[lane + 32 * i] = v[i];
+    }
+  }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    v[i] = ld_cg_f4(xrow + 4 * (lane + 32 * i));
-    s += v[i].x + v[i].y + v[i].z + v[i].w;
-  }
+  for (int i = 0; i < 6; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
   const float mean = warp_sum(s) * (1.0f / 768.0f);
   float q = 0.f;
 #pragma unroll
@@ -227,6 +251,94 @@ __device__ __forceinline__ void ln_row(const float* __restrict__ xrow, const flo
     pk.y = pack2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
     reinterpret_cast<uint2*>(out)[lane + 32 * i] = pk;
   }
+}
+
+// KV-cache attention of one (row, head), head_dim 192, by the EIGHT compute warps of a CTA (DeCap: T <= 32 positions):
+// warp w scores keys w, w + 8, w + 16, w + 24 (all its key / value rows are requested at once: one L2 round trip), keeps a
+// local (max, sum, weighted value sum) and the warps meet in shared memory.  Appends this position's key / value to the cache.
+// scratch: 8 x (192 + 2) floats.  Must be called by all 256 compute threads (named barrier 1).
+__device__ __forceinline__ void attn_192_cta(const __nv_bfloat16* __restrict__ qkv_row, __nv_bfloat16* __restrict__ kbase,
+                                             __nv_bfloat16* __restrict__ vbase, __nv_bfloat16* __restrict__ out, int h, int H, int t,
+                                             int cw, int lane, int ct, float* scratch) {
+  constexpr int HDIM = 192, NK = 4;
+  const float scale = rsqrtf(192.0f);
+  const bool act = lane < HDIM / 8;
+  const __nv_bfloat16* row = qkv_row + h * HDIM + lane * 8;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  uint4 qu = zero, knew = zero, vnew = zero, ku[NK], vu[NK];
+#pragma unroll
+  for (int u = 0; u < NK; ++u) {
+    const int j = cw + 8 * u;
+    const bool ld = act && j < t;
+    ku[u] = ld ? ld_cg16(kbase + (long long)j * HDIM + lane * 8) : zero;
+    vu[u] = ld ? ld_cg16(vbase + (long long)j * HDIM + lane * 8) : zero;
+  }
+  if (act) {
+    qu = ld_cg16(row);
+    if ((t & 7) == cw) {  // the warp that owns key t takes it from the qkv row and appends it to the cache
+      knew = ld_cg16(row + H * HDIM);
+      vnew = ld_cg16(row + 2 * H * HDIM);
+      *reinterpret_cast<uint4*>(kbase + (long long)t * HDIM + lane * 8) = knew;
+      *reinterpret_cast<uint4*>(vbase + (long long)t * HDIM + lane * 8) = vnew;
+    }
+  }
+  float q[8];
+  unpack8(qu, q);
+  float sc[NK];
+#pragma unroll
+  for (int u = 0; u < NK; ++u) {
+    const int j = cw + 8 * u;
+    if (j == t) { ku[u] = knew; vu[u] = vnew; }
+    float kf[8];
+    unpack8(ku[u], kf);
+    float a = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a = fmaf(q[e], kf[e], a);
+    sc[u] = a;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int u = 0; u < NK; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);
+  }
+  float mw = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < NK; ++u) {
+    sc[u] = (cw + 8 * u <= t) ? sc[u] * scale : -INFINITY;
+    mw = fmaxf(mw, sc[u]);
+  }
+  float lw = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int u = 0; u < NK; ++u) {
+    const float pj = (cw + 8 * u <= t) ? __expf(sc[u] - mw) : 0.f;  // mw = -inf only when this warp has no key at all
+    lw += pj;
+    float vf[8];
+    unpack8(vu[u], vf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(pj, vf[e], acc[e]);
+  }
+  float* sm = scratch + cw * (HDIM + 2);
+  if (act) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm[lane * 8 + e] = acc[e];
+  }
+  if (lane == 0) { sm[HDIM] = mw; sm[HDIM + 1] = lw; }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (ct < HDIM) {
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) M = fmaxf(M, scratch[w * (HDIM + 2) + HDIM]);
+    float den = 0.f, num = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float mwv = scratch[w * (HDIM + 2) + HDIM];
+      const float f = (mwv == -INFINITY) ? 0.f : __expf(mwv - M);
+      den = fmaf(f, scratch[w * (HDIM + 2) + HDIM + 1], den);
+      num = fmaf(f, scratch[w * (HDIM + 2) + ct], num);
+    }
+    out[h * HDIM + ct] = __float2bfloat16(num / den);
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");  // scratch is free for the next unit
 }
 
 // KV-cache attention of one (row, head), head_dim 192 (DeCap: 4 heads, T <= 32): the arithmetic of
@@ -381,10 +493,6 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[4 * MAX_STAGES + 4];
   __shared__ uint32_t tmem_slot_var;
-  __shared__ float s_bv[4][kFusedMaxRows];  // lm-head: running (max, first index) per TMEM lane quarter and row
-  __shared__ int s_bi[4][kFusedMaxRows];
-  __shared__ float s_q[FT_COMPUTE_WARPS][64];
-  __shared__ int s_ticket;
 
   const uint32_t bar_base = smem_u32(bars);
   auto fullW = [&](int s) { return bar_base + 8u * s; };
@@ -399,6 +507,12 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
   const int PPS = 7 * L + 3;
   const int a_tile_bytes = R_pad * 128;
   const uint32_t smemA = smem_base + P.nsw * W_TILE_BYTES;
+  // generic-proxy scratch behind the two rings: lm-head running (max, first index) per TMEM lane quarter and row
+  // [4][R_pad] x 2, then the attention scratch (8 x 194 floats)
+  uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw)) + P.nsw * W_TILE_BYTES + P.nsa * a_tile_bytes;
+  float* s_bv = reinterpret_cast<float*>(gen);              // [q * R_pad + r]
+  int* s_bi = reinterpret_cast<int*>(gen + 16 * R_pad);
+  float* s_att = reinterpret_cast<float*>(gen + 32 * R_pad);
   const int gp_begin = P.first_gp, gp_end = min(P.steps * PPS, P.stop_gp);  // [gp_begin, gp_end)
   Sched S{L, G, R, P.H, (int)blockIdx.x, PPS};
   Waiter wt{P.abort, false};
@@ -412,9 +526,9 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(smem_u32(&tmem_slot_var), tmem_cols);
-  for (int i = threadIdx.x; i < 4 * kFusedMaxRows; i += FT_THREADS) {
-    (&s_bv[0][0])[i] = -INFINITY;
-    (&s_bi[0][0])[i] = 0x7fffffff;
+  for (int i = threadIdx.x; i < 4 * R_pad; i += FT_THREADS) {
+    s_bv[i] = -INFINITY;
+    s_bi[i] = 0x7fffffff;
   }
   tc_fence_before();
   __syncthreads();
@@ -456,9 +570,12 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         const int u0 = S.first_unit(gp);
         if (u0 >= nu) continue;
         const CUtensorMap* map = pt == P_PROJ ? &map_att : (pt == P_FC2 ? &map_f : &map_h);
+        unsigned long long* tl = P.timeline ? P.timeline + ((long long)(gp - gp_begin) * G + blockIdx.x) * 8 : nullptr;
         if (gp > gp_begin) {  // this phase's input rows are complete (and visible to the copy engine)
           wt.phase(P.phase_cnt + gp - 1, S.participants(S.ptype((gp - 1) % PPS)));
+          if (tl) tl[4] = gtime_ns();
           fence_proxy_async();
+          if (tl) tl[5] = gtime_ns();
         }
         for (int u = u0; u < nu && !wt.dead; u += G) {
           const int kb0 = pt == P_FC2 ? (u / 6) * KB_PER_UNIT : 0;
@@ -469,6 +586,7 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
             tma_load_2d(smemA + stage * a_tile_bytes, map, fullA(stage), (kb0 + kb) * 64, 0);
             if (++stage == P.nsa) { stage = 0; phase ^= 1; }
           }
+          if (tl && u == u0) tl[6] = gtime_ns();
         }
       }
     }
@@ -489,6 +607,7 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         const uint32_t tmem_d = tmem_base + as * R_pad;
         for (int kb = 0; kb < KB_PER_UNIT; ++kb) {
           wt.mbar(fullW(sw), phw);
+          if (P.timeline && lane == 0 && kb == 0 && u == S.first_unit(gp)) P.timeline[((long long)(gp - gp_begin) * G + blockIdx.x) * 8 + 7] = gtime_ns();
           wt.mbar(fullA(sa), pha);
           if (wt.dead) break;
           tc_fence_after();
@@ -513,14 +632,18 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
     const int n_chunks = R_pad / 16;
     int it = 0;
     auto stamp = [&](int gp, int k) {
-      if (P.timeline && ct == 0) P.timeline[((long long)(gp - gp_begin) * G + blockIdx.x) * 4 + k] = gtime_ns();
+      if (P.timeline && ct == 0) P.timeline[((long long)(gp - gp_begin) * G + blockIdx.x) * 8 + k] = gtime_ns();
     };
+    // the CTA's arrival at a phase: its eight compute warps meet, then ONE thread publishes -- the barrier orders the other
+    // threads' writes before that thread's gpu-scope release (cumulativity; the pattern of a cooperative-groups grid sync)
     auto cta_arrive = [&](int gp) {
       stamp(gp, 2);
-      fence_acq_rel_gpu();
-      fence_proxy_async();
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (ct == 0) red_release_add(P.phase_cnt + gp, 1);
+      if (ct == 0) {
+        fence_acq_rel_gpu();
+        fence_proxy_async();
+        red_release_add(P.phase_cnt + gp, 1);
+      }
       stamp(gp, 3);
     };
     // NB no early exit from this loop: the CTA-wide named barriers need all eight warps.  After a time-out (wt.dead, raised
@@ -537,17 +660,31 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
           wt.dead = __shfl_sync(0xffffffffu, (int)wt.dead, 0) != 0;
         }
         stamp(gp, 1);
+        if (pt == P_ATTN && P.hd == 192 && nu <= 2 * G) {
+          // few (row, head) units: all eight warps work on one unit at a time (one L2 round trip instead of a chain of them)
+          for (int u = u0; u < nu; u += G) {
+            const int r = u / P.H, hh = u % P.H;
+            __nv_bfloat16* kb_ = P.kc + (long long)l * P.kv_layer + ((long long)(r * P.H + hh) * P.T) * P.hd;
+            __nv_bfloat16* vb_ = P.vc + (long long)l * P.kv_layer + ((long long)(r * P.H + hh) * P.T) * P.hd;
+            if (!wt.dead) attn_192_cta(P.qkv + (long long)r * 3 * gD, kb_, vb_, P.att + (long long)r * gD, hh, P.H, pos, cw, lane, ct, s_att);
+          }
+          cta_arrive(gp);
+          continue;
+        }
         for (int u = u0 + cw * G; u < nu && !wt.dead; u += FT_COMPUTE_WARPS * G) {  // this CTA's units, one warp each
           if (pt == P_LN1 || pt == P_LN2 || pt == P_LNF) {
             const float* w = pt == P_LN1 ? P.layers[l].ln1_w : (pt == P_LN2 ? P.layers[l].ln2_w : P.lnf_w);
             const float* b = pt == P_LN1 ? P.layers[l].ln1_b : (pt == P_LN2 ? P.layers[l].ln2_b : P.lnf_b);
-            ln_row(P.x + (long long)u * gD, w, b, P.h + (long long)u * gD, lane);
+            // the fc2 of the block before left its split-K partials unreduced: LN1 of blocks 1.., and ln_f (unless the kernel starts there)
+            const bool pending = (pt == P_LN1 && l > 0) || (pt == P_LNF && gp > gp_begin);
+            const float* fb = pending ? P.layers[pt == P_LN1 ? l - 1 : L - 1].fc2_b : nullptr;
+            ln_row(P.x + (long long)u * gD, w, b, P.h + (long long)u * gD, lane, pending ? P.part : nullptr, u, R_pad, fb);
           } else if (pt == P_ATTN) {
             const int r = u / P.H, hh = u % P.H;
             __nv_bfloat16* kb_ = P.kc + (long long)l * P.kv_layer + ((long long)(r * P.H + hh) * P.T) * P.hd;
             __nv_bfloat16* vb_ = P.vc + (long long)l * P.kv_layer + ((long long)(r * P.H + hh) * P.T) * P.hd;
             if (P.hd == 192) attn_192(P.qkv + (long long)r * 3 * gD, kb_, vb_, P.att + (long long)r * gD, hh, P.H, pos, lane);
-            else attn_64(P.qkv + (long long)r * 3 * gD, kb_, vb_, P.att + (long long)r * gD, hh, P.H, pos, lane, s_q[cw]);
+            else attn_64(P.qkv + (long long)r * 3 * gD, kb_, vb_, P.att + (long long)r * gD, hh, P.H, pos, lane, s_att + cw * 64);
           } else {  // P_PICK: final arg-max over the per-CTA partials, id out, next token's embedding
             float best = -INFINITY;
             int bi = 0x7fffffff;
@@ -605,13 +742,13 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
               if (r < R) P.qkv[(long long)r * (3 * gD) + n] = __float2bfloat16(__uint_as_float(rr[j]) + bias);
             }
           } else if (pt == P_PROJ) {
+            float xv[16];  // all residual loads first (one round trip), then the stores
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xv[j] = (c * 16 + j < R) ? ld_cg_f(P.x + (long long)(c * 16 + j) * gD + n) : 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int r = c * 16 + j;
-              if (r < R) {
-                float* xp = P.x + (long long)r * gD + n;
-                *xp = ld_cg_f(xp) + (__uint_as_float(rr[j]) + bias);
-              }
+              if (r < R) P.x[(long long)r * gD + n] = xv[j] + (__uint_as_float(rr[j]) + bias);
             }
           } else if (pt == P_FC) {
 #pragma unroll
@@ -638,9 +775,9 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
               }
               const int r = c * 16 + j;
               if (lane == (j & 31)) {  // (quarter, row) slots are owned by this warp: no race
-                const float cv = s_bv[quarter][r];
-                const int ci = s_bi[quarter][r];
-                if (v > cv || (v == cv && idx < ci)) { s_bv[quarter][r] = v; s_bi[quarter][r] = idx; }
+                const float cv = s_bv[quarter * R_pad + r];
+                const int ci = s_bi[quarter * R_pad + r];
+                if (v > cv || (v == cv && idx < ci)) { s_bv[quarter * R_pad + r] = v; s_bi[quarter * R_pad + r] = idx; }
               }
             }
           }
@@ -648,48 +785,25 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(as));
-        if (pt == P_FC2) {
-          // split-K fix-up: the unit that arrives last at its tile's counter sums the 4 partials in split order (so the result
-          // does not depend on arrival order), adds bias and the residual, and owns the x update
-          fence_acq_rel_gpu();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (ct == 0) s_ticket = atomicAdd(P.tile_cnt + ((long long)s * L + l) * 6 + tile, 1);
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (s_ticket == kFusedFc2Splits - 1 && !wt.dead) {
-            fence_acq_rel_gpu();
-            const float b2 = __ldg(ly.fc2_b + n);
-            for (int c = half; c < n_chunks; c += 2) {
-#pragma unroll 4
-              for (int j = 0; j < 16; ++j) {
-                const int r = c * 16 + j;
-                if (r >= R) break;
-                float acc = 0.f;
-#pragma unroll
-                for (int sp = 0; sp < kFusedFc2Splits; ++sp)
-                  acc += ld_cg_f(P.part + ((long long)(sp * 6 + tile) * R_pad + r) * 128 + nl);
-                float* xp = P.x + (long long)r * gD + n;
-                *xp = ld_cg_f(xp) + (acc + b2);
-              }
-            }
-          }
-        }
+        // P_FC2: the four split-K partial tiles stay unreduced; the next LayerNorm phase (LN1 of the following block or ln_f)
+        // sums them in split order, adds bias and residual and owns the x update (ln_row) -- no in-phase ticket round trip
       }
       if (pt == P_LMHEAD) {
         // fold the four lane quarters and publish this CTA's partial (max, first index) per row; reset for the next step
         asm volatile("bar.sync 1, 256;" ::: "memory");
         for (int r = ct; r < R_pad; r += 256) {
-          float v = s_bv[0][r];
-          int i = s_bi[0][r];
+          float v = s_bv[r];
+          int i = s_bi[r];
 #pragma unroll
           for (int q = 1; q < 4; ++q) {
-            const float ov = s_bv[q][r];
-            const int oi = s_bi[q][r];
+            const float ov = s_bv[q * R_pad + r];
+            const int oi = s_bi[q * R_pad + r];
             if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
           }
           P.pm_val[(long long)blockIdx.x * R_pad + r] = v;
           P.pm_idx[(long long)blockIdx.x * R_pad + r] = i;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) { s_bv[q][r] = -INFINITY; s_bi[q][r] = 0x7fffffff; }
+          for (int q = 0; q < 4; ++q) { s_bv[q * R_pad + r] = -INFINITY; s_bi[q * R_pad + r] = 0x7fffffff; }
         }
       }
       cta_arrive(gp);
@@ -757,11 +871,18 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   int G = std::min(sms, kFusedCtas);
   if (const char* e = getenv("PIO_DECODE_FUSED_CTAS")) G = std::max(1, std::min(G, atoi(e)));
   PIO_CHECK(T <= (h->H == 4 ? 32 : 128), "decode_fused: a cache of %d positions exceeds what the attention routines walk", T);
-  // rings: 16 KB weight stages + R_pad x 128 B activation stages inside ~200 KB
+  // Shared memory: the weight ring should hold a WHOLE unit (12 x 16 KB) -- with a shorter ring the tail of every unit is
+  // fetched on the critical path, after the phase has started (v1: ~3.5 us per GEMM phase) -- then a few R_pad x 128 B
+  // activation stages, the arg-max slots (32 B per row) and the attention scratch; 222 KB of dynamic memory at most
+  // (+ ~0.5 KB static inside the 227 KB an SM offers).
   const int a_tile = R_pad * 128;
-  int nsa = std::max(2, std::min(MAX_STAGES, (R_pad <= 32 ? 32 : (R_pad <= 64 ? 48 : (R_pad <= 128 ? 64 : 96))) * 1024 / a_tile));
-  int nsw = std::min(MAX_STAGES, (200 * 1024 - nsa * a_tile) / W_TILE_BYTES);
-  const size_t smem = (size_t)nsw * W_TILE_BYTES + (size_t)nsa * a_tile + 1024;
+  const int gen_bytes = 32 * R_pad + 8 * 194 * 4;
+  const int cap = 222 * 1024 - 1024 - gen_bytes;
+  int nsa = R_pad <= 32 ? 4 : 2;
+  if (const char* e = getenv("PIO_DECODE_FUSED_ASTAGES")) nsa = std::max(2, std::min(MAX_STAGES, atoi(e)));  // A/B runs
+  int nsw = std::min(MAX_STAGES, (cap - nsa * a_tile) / W_TILE_BYTES);
+  if (const char* e = getenv("PIO_DECODE_FUSED_WSTAGES")) nsw = std::max(2, std::min(nsw, atoi(e)));
+  const size_t smem = (size_t)nsw * W_TILE_BYTES + (size_t)nsa * a_tile + gen_bytes + 1024;
 
   FusedParams P;
   memset(&P, 0, sizeof(P));
@@ -788,12 +909,12 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   PIO_TRY(make_map_2d(&mf, w.f, R, gFF, gFF, R_pad, 64));
   PIO_CUDA(cudaMemsetAsync(w.counters, 0, fused_counter_ints(L, steps) * sizeof(int), st));
   static SmemAttrOnce once;
-  PIO_CUDA(once.ensure(decode_fused_kernel, 210 * 1024));  // + 10.7 KB static: inside the 227 KB an SM offers
+  PIO_CUDA(once.ensure(decode_fused_kernel, 222 * 1024));
   int per_sm = 0;
   PIO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_fused_kernel, FT_THREADS, smem));
   PIO_CHECK(per_sm >= 1, "decode_fused: the kernel does not fit an SM (%zu bytes of shared memory)", smem);
   const char* tl_path = getenv("PIO_FUSED_TIMELINE");  // debug: per-(phase, CTA) time stamps -> binary file
-  const size_t tl_n = tl_path ? (size_t)(steps * PPS) * G * 4 : 0;
+  const size_t tl_n = tl_path ? (size_t)(steps * PPS) * G * 8 : 0;
   if (tl_path) {
     PIO_CUDA(cudaMalloc((void**)&P.timeline, tl_n * 8));
     PIO_CUDA(cudaMemsetAsync(P.timeline, 0, tl_n * 8, st));
@@ -807,7 +928,7 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
     PIO_CUDA(cudaMemcpy(host.data(), P.timeline, tl_n * 8, cudaMemcpyDeviceToHost));
     PIO_CUDA(cudaFree(P.timeline));
     if (FILE* f = fopen(tl_path, "wb")) {
-      const int hdr[8] = {steps, PPS, G, P.first_gp, L, R, 4, 0};
+      const int hdr[8] = {steps, PPS, G, P.first_gp, L, R, 8, 0};
       fwrite(hdr, sizeof(int), 8, f);
       fwrite(host.data(), 8, tl_n, f);
       fclose(f);

@@ -19,7 +19,7 @@ NAMES = ["LN1", "QKV", "ATTN", "PROJ", "LN2", "FC", "FC2"]
 def load(path):
     raw = open(path, "rb").read()
     steps, pps, G, first, L, R, k, _ = struct.unpack("8i", raw[:32])
-    t = np.frombuffer(raw[32:], dtype=np.uint64).reshape(steps * pps, G, 4).astype(np.int64)
+    t = np.frombuffer(raw[32:], dtype=np.uint64).reshape(steps * pps, G, k).astype(np.int64)
     return dict(steps=steps, pps=pps, G=G, first=first, L=L, R=R), t
 
 
@@ -40,12 +40,18 @@ def analyse(meta, t, step):
         work = (a[part, 2] - a[part, 1]).max()
         arr = (a[part, 3] - a[part, 2]).max()
         dur = (done - prev_done) if prev_done is not None else 0
-        rows.append((name, int(part.sum()), dur, (ready - prev_done) if prev_done is not None else 0, work, arr, enter - (prev_done or enter)))
+        extra = ""
+        if a.shape[1] >= 8 and prev_done is not None and (a[part, 4] > 0).any():
+            # GEMM phases: act producer saw the phase (4), after the proxy fence (5), first unit's act loads issued (6); MMA warp: first weight tile present (7)
+            c = int(np.argmax(np.where(part, a[:, 1], 0)))  # the CTA whose accumulator was ready last
+            extra = "  [slowest CTA: detect %d  +proxy fence %d  +TMA issued %d  | W tile there at %d | acc ready %d]" % (
+                a[c, 4] - prev_done, a[c, 5] - a[c, 4], a[c, 6] - a[c, 5], a[c, 7] - prev_done, a[c, 1] - prev_done)
+        rows.append((name, int(part.sum()), dur, (ready - prev_done) if prev_done is not None else 0, work, arr, enter - (prev_done or enter), extra))
         prev_done = done
     print(f"{'phase':10s} {'ctas':>4s} {'total':>8s} {'->ready':>8s} {'work':>8s} {'arrive':>8s} {'late-enter':>10s}   (ns; total = last arrival of this phase - last arrival of the previous)")
     tot = 0
-    for name, n, dur, rdy, work, arr, late in rows:
-        print(f"{name:10s} {n:4d} {dur:8d} {rdy:8d} {work:8d} {arr:8d} {late:10d}")
+    for name, n, dur, rdy, work, arr, late, extra in rows:
+        print(f"{name:10s} {n:4d} {dur:8d} {rdy:8d} {work:8d} {arr:8d} {late:10d}{extra}")
         tot += dur
     print(f"step total {tot / 1e3:.1f} us")
 
