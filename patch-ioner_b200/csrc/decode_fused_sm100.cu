@@ -1,4 +1,4 @@
-// decode_fused_sm100.cu -- the whole KV-cached greedy decode at small batch (R <= 256 rows) as ONE persistent, cooperative
+// decode_fused_sm100.cu -- the whole KV-cached greedy decode at small batch (R <= 64 rows) as ONE persistent, cooperative
 // kernel: the north star's "kernels fused per decode step".  Replaces the ~32 dependent launches per position of text.cu
 // (decoding_batched, src/decap/decap.py:130-155; greedy_search, src/viecap/search.py:108-191) whose fixed cost -- launch,
 // TMEM allocation, barrier init, tensor-map fetch, first TMA round trip, grid completion -- was ~8 us each (8 % of the HBM
@@ -7,24 +7,29 @@
 // One CTA per SM (cooperative launch: the grid-wide phase counters below need co-residency).  A decode step is a sequence of
 // PHASES; a phase is done when every CTA that has work in it has added 1 to the phase's counter in global memory (release),
 // and whoever needs its results polls that counter (acquire):
-//     per block:  LN1 | QKV | ATTN | PROJ(+res) | LN2 | FC(gelu_new) | FC2(+res, split-K 4 with an in-phase fix-up)
-//     then:       LN_f | LM-HEAD (per-CTA arg-max partials) | PICK (final arg-max, ids, next embedding)
+//     block 0   :         QKV* | ATTN | PROJ(+res) | FC*(gelu_new) | FC2 (split-K 4, partials left unreduced)
+//     blocks 1..:  LN1r | QKV  | ATTN | PROJ(+res) | FC*(gelu_new) | FC2
+//     then      :  LNFr | LM-HEAD (per-CTA arg-max partials) | PICK (final arg-max, ids, next embedding -> x)
+//   * = the LayerNorm in front of the layer is applied while the CTA loads its activations (x fp32 -> normalised bf16 tile);
+//   r = the LayerNorm phase first reduces the previous fc2's split-K partials into x (fixed order: deterministic).
 // Dense layers run on the tensor cores with the operands SWAPPED with respect to gemm_sm100.cu: a work unit is 128 OUTPUT
 // FEATURES (the UMMA M dimension, rows of the [out, in] weight matrix) x 12 k-blocks of 64, against all R rows (the UMMA N
 // dimension, R padded to a multiple of 16): D^T[128, R] = W_tile[128, 768] . X[R, 768]^T accumulated in TMEM.  Every unit of
 // every layer is 196 KB of weights; unit u of phase g belongs to CTA (u + 41 g) mod G, so consecutive phases land on
 // different SMs and -- because weights never change -- warp 0 of every CTA streams the weight tiles of its FUTURE units
-// into a shared-memory ring as fast as slots free up, across phase and step boundaries.  The HBM/L2 weight stream is
-// therefore never interrupted by the phase latencies; only the (small, L2-resident) activation tiles wait for a phase.
+// into a shared-memory ring as fast as slots free up, across phase and step boundaries: the weight stream from HBM never
+// waits for a phase.  The activations of a phase (R x 768 bf16, L2 resident) are fetched by the eight compute warps with
+// ordinary 16-byte loads straight into the 128B-swizzled UMMA layout -- NOT by TMA: measured (profiles/r02f_*), activation
+// TMA loads queue behind the 16 KB weight prefetches in the SM's copy engine (3.7 us per phase); the LSU path is one L2
+// round trip.
 //   warp 0        weight producer   : cp.async.bulk.tensor of 128 x 64 weight tiles (128B swizzle), runs ahead
-//   warp 1        activation producer: waits for the previous phase, then TMA-loads R_pad x 64 activation tiles
 //   warp 2        MMA issuer        : tcgen05.mma (UMMA 128 x R_pad x 16), accumulator double-buffered in TMEM
-//   warps 4..11   compute warps     : epilogues (tcgen05.ld: lane = output feature, column = row), LayerNorm, KV-cache
-//                                     attention, arg-max; they also post the CTA's phase arrivals
-// Cross-CTA data (x, h, qkv, attention rows, gelu rows, KV cache, partials) is written with ordinary stores + fences and read
-// either by TMA or with ld.global.cg (never the non-coherent path: the data changes inside the launch).
+//   warps 4..11   compute warps     : activation loads (+ fused LayerNorm), epilogues (tcgen05.ld: lane = output feature,
+//                                     column = row), LayerNorm / reduce rows, KV-cache attention, arg-max, phase arrivals
+// Cross-CTA data (x, h, qkv, attention rows, gelu rows, KV cache, partials) is written with ordinary stores and read with
+// ld.global.cg (never the non-coherent path: the data changes inside the launch).
 // Every wait is bounded (~2 s): on expiry the kernel raises `abort` in global memory and all roles drain, so a logic error
-// ends as PIO_ECUDA on the host instead of a hung GPU.
+// ends as an error on the host instead of a hung GPU.
 #include "tc_ptx.cuh"
 #include "decoder.cuh"
 #include "gemm_epilogue.cuh"
@@ -36,7 +41,7 @@
 namespace pio {
 using namespace tc;
 
-size_t fused_counter_ints(int L, int steps) { return (size_t)steps * (7 * L + 3) + (size_t)steps * L * 6 + 64; }
+size_t fused_counter_ints(int L, int steps) { return (size_t)steps * (6 * L + 3) + 64; }
 
 namespace {
 
@@ -46,7 +51,8 @@ constexpr int W_TILE_BYTES = 128 * 64 * 2;
 constexpr int KB_PER_UNIT = 12;          // 768 / 64
 constexpr int MAX_STAGES = 12;
 
-enum PhaseType { P_LN1 = 0, P_QKV, P_ATTN, P_PROJ, P_LN2, P_FC, P_FC2, P_LNF, P_LMHEAD, P_PICK };
+enum PhaseType { P_LN1 = 0, P_QKV, P_ATTN, P_PROJ, P_FC, P_FC2, P_LNF, P_LMHEAD, P_PICK };
+constexpr int MAX_PHASES = 6 * 12 + 3;  // phases of one step for up to 12 blocks
 
 struct FusedParams {
   const CUtensorMap* wmaps;   // [4 L + 1]
@@ -60,12 +66,12 @@ struct FusedParams {
   float* pm_val;              // [G][R_pad]
   int* pm_idx;
   int* phase_cnt;             // [steps * PPS]
-  int* tile_cnt;              // [steps * L * 6] (spare: the split-K fix-up of v1 used it)
   int* abort;
-  unsigned long long* timeline;  // debug (PIO_FUSED_TIMELINE): 4 globaltimer stamps per (phase, CTA), or NULL
+  unsigned long long* timeline;  // debug (PIO_FUSED_TIMELINE): 8 globaltimer stamps per (phase, CTA), or NULL
   int* out_ids;
   int ids_ld;
-  int L, H, hd, T, R, R_pad, steps, pos_base, first_gp, G, nsw, nsa, stop_gp;
+  int L, H, hd, T, R, R_pad, steps, pos_base, first_gp, G, nsw, stop_gp, PPS;
+  signed char ptype[MAX_PHASES], player[MAX_PHASES];  // the phases of one step: type and block index
 };
 
 // ------------------------------------------------------------------------------------------ small PTX helpers
@@ -137,81 +143,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// ------------------------------------------------------------------------------------------ schedule (same arithmetic in every role)
-struct Sched {
-  int L, G, R, H, cta, PPS;
-  __device__ __forceinline__ int ptype(int p) const { return p < 7 * L ? p % 7 : P_LNF + (p - 7 * L); }
-  __device__ __forceinline__ int units(int pt) const {
-    switch (pt) {
-      case P_QKV: return 18;
-      case P_PROJ: return 6;
-      case P_FC: return 24;
-      case P_FC2: return 6 * kFusedFc2Splits;
-      case P_LMHEAD: return (gV + 127) / 128;
-      case P_ATTN: return R * H;
-      default: return R;  // LN1, LN2, LNF, PICK: one warp per row
-    }
-  }
-  __device__ __forceinline__ bool is_gemm(int pt) const { return pt == P_QKV || pt == P_PROJ || pt == P_FC || pt == P_FC2 || pt == P_LMHEAD; }
-  __device__ __forceinline__ int rot(int gp) const { return (int)(((long long)gp * 41) % G); }  // 41: coprime with 148
-  // first unit of phase gp owned by this CTA; its further units follow at stride G
-  __device__ __forceinline__ int first_unit(int gp) const { return (cta - rot(gp) + G) % G; }
-  __device__ __forceinline__ int participants(int pt) const { return min(G, units(pt)); }
-};
-
-struct Waiter {
-  int* abort;
-  bool dead;
-  __device__ __forceinline__ void fail() {
-    dead = true;
-    atomicExch(abort, 1);
-  }
-  // bounded mbarrier wait
-  __device__ __forceinline__ void mbar(uint32_t bar, uint32_t parity) {
-    if (dead) return;
-    uint32_t done = 0;
-    unsigned long long t0 = 0;
-    for (unsigned it = 0;; ++it) {
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t"
-          "}"
-          : "=r"(done)
-          : "r"(bar), "r"(parity)
-          : "memory");
-      if (done) return;
-      if ((it & 255) == 255) {
-        const unsigned long long now = gtime_ns();
-        if (t0 == 0) t0 = now;
-        if (now - t0 > 2000000000ull || ld_acquire(abort) != 0) { fail(); return; }
-      }
-    }
-  }
-  // bounded wait for a phase counter
-  __device__ __forceinline__ void phase(const int* cnt, int target) {
-    if (dead) return;
-    unsigned long long t0 = 0;
-    for (unsigned it = 0;; ++it) {
-      if (ld_relaxed(cnt) >= target) { fence_acq_rel_gpu(); return; }  // relaxed polls, one acquire fence at the end
-      if ((it & 63) == 63) {
-        const unsigned long long now = gtime_ns();
-        if (t0 == 0) t0 = now;
-        if (now - t0 > 2000000000ull || ld_acquire(abort) != 0) { fail(); return; }
-      }
-    }
-  }
-};
-
 // ------------------------------------------------------------------------------------------ row-wise pieces (one warp per row / unit)
-// LayerNorm of x[r] (fp32, 768) -> h[r] (bf16); eps 1e-5 (GPT-2).
+// LayerNorm of x[r] (fp32, 768) -> bf16, eps 1e-5 (GPT-2): to the global row `out` and / or into the CTA's shared-memory
+// activation tiles (the B operand of the following UMMAs: 12 k-block tiles of [R_pad rows x 128 bytes], 128B swizzle).
 // part != NULL: the previous block's fc2 left its 4 split-K partial tiles unreduced -- this warp first forms
 //   x[r] += (p0 + p1 + p2 + p3) + fc2_b   (fixed order: deterministic), stores the row back, then normalises it.
 // Lane l owns the float4 at column 4 (l + 32 i), i < 6: output tile i of the [6 x 128]-column layout, offset 4 l.
 __device__ __forceinline__ void ln_row(float* __restrict__ xrow, const float* __restrict__ w, const float* __restrict__ b,
                                        __nv_bfloat16* __restrict__ out, int lane, const float* __restrict__ part, int r, int R_pad,
-                                       const float* __restrict__ fc2_b) {
+                                       const float* __restrict__ fc2_b, uint8_t* sm_tiles = nullptr, int tile_bytes = 0) {
   float4 v[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) v[i] = ld_cg_f4(xrow + 4 * (lane + 32 * i));
@@ -249,7 +189,13 @@ __device__ __forceinline__ void ln_row(float* __restrict__ xrow, const float* __
     uint2 pk;
     pk.x = pack2((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
     pk.y = pack2((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
-    reinterpret_cast<uint2*>(out)[lane + 32 * i] = pk;
+    if (out != nullptr) reinterpret_cast<uint2*>(out)[lane + 32 * i] = pk;
+    if (sm_tiles != nullptr) {
+      // columns 4 (lane + 32 i) .. + 3 of row r in the UMMA operand layout: k-block 2 i + lane / 16, 16-byte chunk
+      // (lane % 16) / 2 XOR-swizzled with the row (128B swizzle), low or high half of the chunk
+      const int kb = 2 * i + (lane >> 4), chunk = (lane & 15) >> 1;
+      *reinterpret_cast<uint2*>(sm_tiles + (size_t)kb * tile_bytes + r * 128 + ((chunk ^ (r & 7)) << 4) + (lane & 1) * 8) = pk;
+    }
   }
 }
 
@@ -485,44 +431,139 @@ __device__ __forceinline__ void attn_64(const __nv_bfloat16* __restrict__ qkv_ro
   __syncwarp();  // qs is reused by this warp's next unit
 }
 
+// ------------------------------------------------------------------------------------------ schedule (same arithmetic in every role)
+struct Sched {
+  int G, R, H, cta, PPS;
+  const signed char* pt;
+  __device__ __forceinline__ int ptype(int p) const { return pt[p]; }
+  __device__ __forceinline__ int units(int t) const {
+    switch (t) {
+      case P_QKV: return 18;
+      case P_PROJ: return 6;
+      case P_FC: return 24;
+      case P_FC2: return 6 * kFusedFc2Splits;
+      case P_LMHEAD: return (gV + 127) / 128;
+      case P_ATTN: return R * H;
+      default: return R;  // LN1, LNF, PICK: one warp per row
+    }
+  }
+  __device__ __forceinline__ bool is_gemm(int t) const { return t == P_QKV || t == P_PROJ || t == P_FC || t == P_FC2 || t == P_LMHEAD; }
+  __device__ __forceinline__ int rot(int gp) const { return (int)(((long long)gp * 41) % G); }  // 41: coprime with 148
+  // first unit of phase gp owned by this CTA; its further units follow at stride G
+  __device__ __forceinline__ int first_unit(int gp) const { return (cta - rot(gp) + G) % G; }
+  __device__ __forceinline__ int participants(int t) const { return min(G, units(t)); }
+};
+
+struct Waiter {
+  int* abort;
+  bool dead;
+  __device__ __forceinline__ void fail() {
+    dead = true;
+    atomicExch(abort, 1);
+  }
+  // bounded mbarrier wait
+  __device__ __forceinline__ void mbar(uint32_t bar, uint32_t parity) {
+    if (dead) return;
+    uint32_t done = 0;
+    unsigned long long t0 = 0;
+    for (unsigned it = 0;; ++it) {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity)
+          : "memory");
+      if (done) return;
+      if ((it & 255) == 255) {
+        const unsigned long long now = gtime_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 2000000000ull || ld_acquire(abort) != 0) { fail(); return; }
+      }
+    }
+  }
+  // bounded wait for a phase counter (acquire loads: the data loads that follow are ordered after the one that succeeds)
+  __device__ __forceinline__ void phase(const int* cnt, int target) {
+    if (dead) return;
+    unsigned long long t0 = 0;
+    for (unsigned it = 0;; ++it) {
+      if (ld_acquire(cnt) >= target) return;
+      if ((it & 63) == 63) {
+        const unsigned long long now = gtime_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 2000000000ull || ld_acquire(abort) != 0) { fail(); return; }
+      }
+    }
+  }
+};
+
+// generic-proxy writes to shared memory that the tensor core (async proxy) will read
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// rows [0, R) x columns [k0, k0 + 768) of a bf16 matrix -> the CTA's activation tiles (12 k-blocks of [R_pad x 128 B], 128B
+// swizzle), by all 256 compute threads: 16-byte chunks, every thread's loads issued before its first store (one L2 round trip)
+__device__ __forceinline__ void load_acts(const __nv_bfloat16* __restrict__ src, int ld, int k0, int R, uint8_t* sm_tiles, int tile_bytes,
+                                          int ct) {
+  const int total = R * 96;  // 96 chunks of 8 bf16 per row
+  for (int q0 = ct; q0 < total; q0 += 256 * 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = q0 + 256 * i;
+      if (q < total) {
+        const int r = q / 96, cc = q - r * 96;
+        v[i] = ld_cg16(src + (long long)r * ld + k0 + cc * 8);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = q0 + 256 * i;
+      if (q < total) {
+        const int r = q / 96, cc = q - r * 96, kb = cc >> 3, c = cc & 7;
+        *reinterpret_cast<uint4*>(sm_tiles + (size_t)kb * tile_bytes + r * 128 + ((c ^ (r & 7)) << 4)) = v[i];
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(FT_THREADS, 1)
-decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_att,
-                    const __grid_constant__ CUtensorMap map_f, const FusedParams P) {
+__global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const FusedParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ __align__(8) uint64_t bars[4 * MAX_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 6];
   __shared__ uint32_t tmem_slot_var;
 
   const uint32_t bar_base = smem_u32(bars);
   auto fullW = [&](int s) { return bar_base + 8u * s; };
   auto emptyW = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
-  auto fullA = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
-  auto emptyA = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + s); };
-  auto tfull = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + s); };
-  auto tempty = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + 2 + s); };
+  auto tfull = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
+  auto tempty = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
+  const uint32_t acts_full = bar_base + 8u * (2 * MAX_STAGES + 4);  // the activation tiles of a GEMM phase are in shared memory
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int R = P.R, R_pad = P.R_pad, L = P.L, G = P.G;
-  const int PPS = 7 * L + 3;
+  const int R = P.R, R_pad = P.R_pad, L = P.L, G = P.G, PPS = P.PPS;
   const int a_tile_bytes = R_pad * 128;
+  // dynamic shared memory: weight ring | 12 activation tiles | lm-head running (max, first index) per TMEM lane quarter and
+  // row [4][R_pad] x 2 | attention scratch (8 x 194 floats)
+  uint8_t* dyn = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t smemA = smem_base + P.nsw * W_TILE_BYTES;
-  // generic-proxy scratch behind the two rings: lm-head running (max, first index) per TMEM lane quarter and row
-  // [4][R_pad] x 2, then the attention scratch (8 x 194 floats)
-  uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw)) + P.nsw * W_TILE_BYTES + P.nsa * a_tile_bytes;
-  float* s_bv = reinterpret_cast<float*>(gen);              // [q * R_pad + r]
+  uint8_t* acts = dyn + P.nsw * W_TILE_BYTES;
+  uint8_t* gen = acts + KB_PER_UNIT * a_tile_bytes;
+  float* s_bv = reinterpret_cast<float*>(gen);  // [q * R_pad + r]
   int* s_bi = reinterpret_cast<int*>(gen + 16 * R_pad);
   float* s_att = reinterpret_cast<float*>(gen + 32 * R_pad);
   const int gp_begin = P.first_gp, gp_end = min(P.steps * PPS, P.stop_gp);  // [gp_begin, gp_end)
-  Sched S{L, G, R, P.H, (int)blockIdx.x, PPS};
+  Sched S{G, R, P.H, (int)blockIdx.x, PPS, P.ptype};
   Waiter wt{P.abort, false};
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * R_pad) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < P.nsw; ++s) { mbar_init(fullW(s), 1); mbar_init(emptyW(s), 1); }
-    for (int s = 0; s < P.nsa; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), FT_COMPUTE_WARPS); }
+    mbar_init(acts_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(smem_u32(&tmem_slot_var), tmem_cols);
@@ -543,7 +584,7 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
       for (int gp = gp_begin; gp < gp_end && !wt.dead; ++gp) {
         const int p = gp % PPS, pt = S.ptype(p);
         if (!S.is_gemm(pt)) continue;
-        const int l = p / 7, nu = S.units(pt);
+        const int l = P.player[p], nu = S.units(pt);
         const CUtensorMap* map = P.wmaps + (pt == P_LMHEAD ? 4 * L : 4 * l + (pt == P_QKV ? 0 : pt == P_PROJ ? 1 : pt == P_FC ? 2 : 3));
         for (int u = S.first_unit(gp); u < nu; u += G) {
           const int tile = pt == P_FC2 ? u % 6 : u, kb0 = pt == P_FC2 ? (u / 6) * KB_PER_UNIT : 0;
@@ -558,70 +599,36 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ activation producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int gp = gp_begin; gp < gp_end && !wt.dead; ++gp) {
-        const int p = gp % PPS, pt = S.ptype(p);
-        if (!S.is_gemm(pt)) continue;
-        const int nu = S.units(pt);
-        const int u0 = S.first_unit(gp);
-        if (u0 >= nu) continue;
-        const CUtensorMap* map = pt == P_PROJ ? &map_att : (pt == P_FC2 ? &map_f : &map_h);
-        unsigned long long* tl = P.timeline ? P.timeline + ((long long)(gp - gp_begin) * G + blockIdx.x) * 8 : nullptr;
-        if (gp > gp_begin) {  // this phase's input rows are complete (and visible to the copy engine)
-          wt.phase(P.phase_cnt + gp - 1, S.participants(S.ptype((gp - 1) % PPS)));
-          if (tl) tl[4] = gtime_ns();
-          fence_proxy_async();
-          if (tl) tl[5] = gtime_ns();
-        }
-        for (int u = u0; u < nu && !wt.dead; u += G) {
-          const int kb0 = pt == P_FC2 ? (u / 6) * KB_PER_UNIT : 0;
-          for (int kb = 0; kb < KB_PER_UNIT; ++kb) {
-            wt.mbar(emptyA(stage), phase ^ 1);
-            if (wt.dead) break;
-            mbar_expect_tx(fullA(stage), a_tile_bytes);
-            tma_load_2d(smemA + stage * a_tile_bytes, map, fullA(stage), (kb0 + kb) * 64, 0);
-            if (++stage == P.nsa) { stage = 0; phase ^= 1; }
-          }
-          if (tl && u == u0) tl[6] = gtime_ns();
-        }
-      }
-    }
-    __syncwarp();
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc(128, R_pad);
-    int sw = 0, sa = 0, it = 0;
-    uint32_t phw = 0, pha = 0;
+    int sw = 0, it = 0, nphase = 0;
+    uint32_t phw = 0;
     for (int gp = gp_begin; gp < gp_end && !wt.dead; ++gp) {
       const int p = gp % PPS, pt = S.ptype(p);
       if (!S.is_gemm(pt)) continue;
-      const int nu = S.units(pt);
-      for (int u = S.first_unit(gp); u < nu && !wt.dead; u += G, ++it) {
+      const int nu = S.units(pt), u0 = S.first_unit(gp);
+      if (u0 >= nu) continue;
+      wt.mbar(acts_full, nphase & 1);  // the compute warps have placed this phase's activation tiles (kept for all its units)
+      ++nphase;
+      for (int u = u0; u < nu && !wt.dead; u += G, ++it) {
         const int as = it & 1;
         wt.mbar(tempty(as), ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * R_pad;
         for (int kb = 0; kb < KB_PER_UNIT; ++kb) {
           wt.mbar(fullW(sw), phw);
-          if (P.timeline && lane == 0 && kb == 0 && u == S.first_unit(gp)) P.timeline[((long long)(gp - gp_begin) * G + blockIdx.x) * 8 + 7] = gtime_ns();
-          wt.mbar(fullA(sa), pha);
           if (wt.dead) break;
           tc_fence_after();
           if (lane == 0) {
-            const uint64_t adesc = make_smem_desc(smem_base + sw * W_TILE_BYTES), bdesc = make_smem_desc(smemA + sa * a_tile_bytes);
+            const uint64_t adesc = make_smem_desc(smem_base + sw * W_TILE_BYTES), bdesc = make_smem_desc(smemA + kb * a_tile_bytes);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
             umma_commit(emptyW(sw));
-            umma_commit(emptyA(sa));
             if (kb == KB_PER_UNIT - 1) umma_commit(tfull(as));
           }
           __syncwarp();
           if (++sw == P.nsw) { sw = 0; phw ^= 1; }
-          if (++sa == P.nsa) { sa = 0; pha ^= 1; }
         }
       }
     }
@@ -639,27 +646,23 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
     auto cta_arrive = [&](int gp) {
       stamp(gp, 2);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (ct == 0) {
-        fence_acq_rel_gpu();
-        fence_proxy_async();
-        red_release_add(P.phase_cnt + gp, 1);
-      }
+      if (ct == 0) red_release_add(P.phase_cnt + gp, 1);
       stamp(gp, 3);
     };
     // NB no early exit from this loop: the CTA-wide named barriers need all eight warps.  After a time-out (wt.dead, raised
     // CTA-wide through the abort flag) a warp keeps walking the schedule but skips every wait and all work.
     for (int gp = gp_begin; gp < gp_end; ++gp) {
-      const int s = gp / PPS, p = gp % PPS, pt = S.ptype(p), l = p / 7;
+      const int s = gp / PPS, p = gp % PPS, pt = S.ptype(p), l = P.player[p];
       const int nu = S.units(pt), u0 = S.first_unit(gp);
       if (u0 >= nu) continue;  // no work for this CTA in this phase (CTA-uniform)
       const int pos = P.pos_base + s;
       stamp(gp, 0);
+      if (gp > gp_begin) {  // the previous phase -- the producer of this phase's input -- is complete
+        if (lane == 0) wt.phase(P.phase_cnt + gp - 1, S.participants(S.ptype((gp - 1) % PPS)));
+        wt.dead = __shfl_sync(0xffffffffu, (int)wt.dead, 0) != 0;
+      }
+      stamp(gp, 1);
       if (!S.is_gemm(pt)) {
-        if (gp > gp_begin) {
-          if (lane == 0) wt.phase(P.phase_cnt + gp - 1, S.participants(S.ptype((gp - 1) % PPS)));
-          wt.dead = __shfl_sync(0xffffffffu, (int)wt.dead, 0) != 0;
-        }
-        stamp(gp, 1);
         if (pt == P_ATTN && P.hd == 192 && nu <= 2 * G) {
           // few (row, head) units: all eight warps work on one unit at a time (one L2 round trip instead of a chain of them)
           for (int u = u0; u < nu; u += G) {
@@ -672,13 +675,13 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
           continue;
         }
         for (int u = u0 + cw * G; u < nu && !wt.dead; u += FT_COMPUTE_WARPS * G) {  // this CTA's units, one warp each
-          if (pt == P_LN1 || pt == P_LN2 || pt == P_LNF) {
-            const float* w = pt == P_LN1 ? P.layers[l].ln1_w : (pt == P_LN2 ? P.layers[l].ln2_w : P.lnf_w);
-            const float* b = pt == P_LN1 ? P.layers[l].ln1_b : (pt == P_LN2 ? P.layers[l].ln2_b : P.lnf_b);
-            // the fc2 of the block before left its split-K partials unreduced: LN1 of blocks 1.., and ln_f (unless the kernel starts there)
-            const bool pending = (pt == P_LN1 && l > 0) || (pt == P_LNF && gp > gp_begin);
+          if (pt == P_LN1 || pt == P_LNF) {
+            // the fc2 of the block before left its split-K partials unreduced (always for LN1: blocks 1..; for ln_f unless the
+            // kernel starts there)
+            const bool pending = pt == P_LN1 || gp > gp_begin;
             const float* fb = pending ? P.layers[pt == P_LN1 ? l - 1 : L - 1].fc2_b : nullptr;
-            ln_row(P.x + (long long)u * gD, w, b, P.h + (long long)u * gD, lane, pending ? P.part : nullptr, u, R_pad, fb);
+            ln_row(P.x + (long long)u * gD, pt == P_LN1 ? P.layers[l].ln1_w : P.lnf_w, pt == P_LN1 ? P.layers[l].ln1_b : P.lnf_b,
+                   P.h + (long long)u * gD, lane, pending ? P.part : nullptr, u, R_pad, fb);
           } else if (pt == P_ATTN) {
             const int r = u / P.H, hh = u % P.H;
             __nv_bfloat16* kb_ = P.kc + (long long)l * P.kv_layer + ((long long)(r * P.H + hh) * P.T) * P.hd;
@@ -716,15 +719,36 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         cta_arrive(gp);
         continue;
       }
-      // ---- GEMM phase: epilogue of every owned unit
+      // ---- GEMM phase.  (1) this CTA's activation tiles: every MMA that read the previous contents has completed (the epilogue
+      // of the CTA's last unit waited for its accumulator), so the tiles can be overwritten right away
       const FusedLayer& ly = P.layers[pt == P_LMHEAD ? 0 : l];
+      if (!wt.dead) {
+        if (pt == P_QKV && l == 0) {         // LN1 of block 0 applied on the way in (x is complete: prefix embedding / PICK)
+          for (int r = cw; r < R; r += FT_COMPUTE_WARPS)
+            ln_row(P.x + (long long)r * gD, ly.ln1_w, ly.ln1_b, nullptr, lane, nullptr, r, R_pad, nullptr, acts, a_tile_bytes);
+        } else if (pt == P_FC) {             // LN2 applied on the way in (x is complete after PROJ)
+          for (int r = cw; r < R; r += FT_COMPUTE_WARPS)
+            ln_row(P.x + (long long)r * gD, ly.ln2_w, ly.ln2_b, nullptr, lane, nullptr, r, R_pad, nullptr, acts, a_tile_bytes);
+        } else if (pt == P_PROJ) {
+          load_acts(P.att, gD, 0, R, acts, a_tile_bytes, ct);
+        } else if (pt == P_FC2) {            // this CTA's K slice of the gelu rows
+          load_acts(P.f, gFF, (u0 / 6) * (KB_PER_UNIT * 64), R, acts, a_tile_bytes, ct);
+        } else {                             // QKV of blocks 1.., lm-head: the LayerNorm rows a phase wrote
+          load_acts(P.h, gD, 0, R, acts, a_tile_bytes, ct);
+        }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (ct == 0) mbar_arrive(acts_full);
+      stamp(gp, 4);
+      // (2) epilogue of every owned unit
       for (int u = u0; u < nu; u += G, ++it) {
         const int as = it & 1;
         const int tile = pt == P_FC2 ? u % 6 : u;
         const int nl = quarter * 32 + lane, n = tile * 128 + nl;  // this thread's output feature
         wt.mbar(tfull(as), (it >> 1) & 1);
         wt.dead = __any_sync(0xffffffffu, wt.dead);
-        if (u == u0) stamp(gp, 1);
+        if (u == u0) stamp(gp, 5);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * R_pad + ((uint32_t)(quarter * 32) << 16);
         float bias = 0.f;
@@ -757,6 +781,8 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
               if (r < R) P.f[(long long)r * gFF + n] = __float2bfloat16(gelu_new_fast(__uint_as_float(rr[j]) + bias));
             }
           } else if (pt == P_FC2) {
+            // the four split-K partial tiles stay unreduced: the next LayerNorm phase (LN1 of the following block or ln_f) sums
+            // them in split order, adds bias and residual and owns the x update (ln_row)
             float* pp = P.part + ((long long)u * R_pad + c * 16) * 128 + nl;
 #pragma unroll
             for (int j = 0; j < 16; ++j) pp[(long long)j * 128] = __uint_as_float(rr[j]);
@@ -785,8 +811,6 @@ decode_fused_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty(as));
-        // P_FC2: the four split-K partial tiles stay unreduced; the next LayerNorm phase (LN1 of the following block or ln_f)
-        // sums them in split order, adds bias and residual and owns the x update (ln_row) -- no in-phase ticket round trip
       }
       if (pt == P_LMHEAD) {
         // fold the four lane quarters and publish this CTA's partial (max, first index) per row; reset for the next step
@@ -825,7 +849,7 @@ bool decode_fused_eligible(const PioDecoder* h, int R, bool want_logprob) {
   const char* sw = getenv("PIO_DECODE_FUSED");  // read per call: tests and A/B runs flip it inside one process
   const bool on = !(sw && sw[0] == '0');
   if (!on || want_logprob || h->mode != PIO_BF16 || h->fused_wmaps == nullptr) return false;
-  if (!((h->H == 4) || (h->H == 12))) return false;
+  if (!((h->H == 4) || (h->H == 12)) || h->L > 12) return false;
   int max_rows = kFusedMaxRows;
   if (const char* e = getenv("PIO_DECODE_FUSED_MAX_ROWS")) max_rows = std::min(kFusedMaxRows, atoi(e));
   return R >= 1 && R <= max_rows;
@@ -862,27 +886,25 @@ int decode_fused_build(PioDecoder* h, cudaStream_t st) {
 
 int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int pos_base, bool start_at_pick, int* out_ids,
                  cudaStream_t st) {
-  const int L = h->L, PPS = 7 * L + 3;
+  const int L = h->L, PPS = 6 * L + 2;
   const int R_pad = std::max(16, (R + 15) / 16 * 16);
-  PIO_CHECK(R_pad <= kFusedMaxRows && steps >= 1, "decode_fused: %d rows / %d steps outside the built range", R, steps);
+  PIO_CHECK(R_pad <= kFusedMaxRows && steps >= 1 && L <= 12, "decode_fused: %d rows / %d steps / %d blocks outside the built range", R, steps, L);
+  PIO_CHECK(T <= (h->H == 4 ? 32 : 128), "decode_fused: a cache of %d positions exceeds what the attention routines walk", T);
   int dev = 0, sms = 0;
   PIO_CUDA(cudaGetDevice(&dev));
   PIO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int G = std::min(sms, kFusedCtas);
   if (const char* e = getenv("PIO_DECODE_FUSED_CTAS")) G = std::max(1, std::min(G, atoi(e)));
-  PIO_CHECK(T <= (h->H == 4 ? 32 : 128), "decode_fused: a cache of %d positions exceeds what the attention routines walk", T);
-  // Shared memory: the weight ring should hold a WHOLE unit (12 x 16 KB) -- with a shorter ring the tail of every unit is
-  // fetched on the critical path, after the phase has started (v1: ~3.5 us per GEMM phase) -- then a few R_pad x 128 B
-  // activation stages, the arg-max slots (32 B per row) and the attention scratch; 222 KB of dynamic memory at most
-  // (+ ~0.5 KB static inside the 227 KB an SM offers).
+  PIO_CHECK(G >= 6 * kFusedFc2Splits, "decode_fused: %d CTAs; every fc2 unit needs its own (the activation tiles are per K slice)", G);
+  // Shared memory: weight ring (16 KB stages; 12 = a whole unit, so that nothing of a unit is fetched after its phase has
+  // started) | the 12 activation tiles of a phase (R_pad x 1536 B, resident for all units of the phase) | arg-max slots |
+  // attention scratch; 222 KB of dynamic memory at most (+ ~0.3 KB static inside the 227 KB an SM offers).
   const int a_tile = R_pad * 128;
   const int gen_bytes = 32 * R_pad + 8 * 194 * 4;
-  const int cap = 222 * 1024 - 1024 - gen_bytes;
-  int nsa = R_pad <= 32 ? 4 : 2;
-  if (const char* e = getenv("PIO_DECODE_FUSED_ASTAGES")) nsa = std::max(2, std::min(MAX_STAGES, atoi(e)));  // A/B runs
-  int nsw = std::min(MAX_STAGES, (cap - nsa * a_tile) / W_TILE_BYTES);
-  if (const char* e = getenv("PIO_DECODE_FUSED_WSTAGES")) nsw = std::max(2, std::min(nsw, atoi(e)));
-  const size_t smem = (size_t)nsw * W_TILE_BYTES + (size_t)nsa * a_tile + gen_bytes + 1024;
+  int nsw = std::min(MAX_STAGES, (222 * 1024 - 1024 - gen_bytes - KB_PER_UNIT * a_tile) / W_TILE_BYTES);
+  if (const char* e = getenv("PIO_DECODE_FUSED_WSTAGES")) nsw = std::max(2, std::min(nsw, atoi(e)));  // A/B runs
+  PIO_CHECK(nsw >= 4, "decode_fused: %d rows leave no room for the weight ring", R);
+  const size_t smem = (size_t)nsw * W_TILE_BYTES + (size_t)KB_PER_UNIT * a_tile + gen_bytes + 1024;
 
   FusedParams P;
   memset(&P, 0, sizeof(P));
@@ -894,19 +916,23 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   P.part = w.part; P.pm_val = w.pm_val; P.pm_idx = w.pm_idx;
   PIO_CHECK(fused_counter_ints(L, steps) * sizeof(int) <= w.counters_bytes, "decode_fused: counter region too small for %d steps", steps);
   P.phase_cnt = w.counters;
-  P.tile_cnt = w.counters + (size_t)steps * PPS;
-  P.abort = w.counters + (size_t)steps * PPS + (size_t)steps * L * 6;
+  P.abort = w.counters + (size_t)steps * PPS;
   P.out_ids = out_ids; P.ids_ld = steps;
   P.L = L; P.H = h->H; P.hd = gD / h->H; P.T = T; P.R = R; P.R_pad = R_pad; P.steps = steps; P.pos_base = pos_base;
-  P.first_gp = start_at_pick ? 7 * L : 0;
-  P.G = G; P.nsw = nsw; P.nsa = nsa;
+  P.G = G; P.nsw = nsw; P.PPS = PPS;
+  // the phases of one step (see the header comment)
+  int np = 0, lnf_at = 0;
+  for (int l = 0; l < L; ++l) {
+    if (l > 0) { P.ptype[np] = P_LN1; P.player[np++] = (signed char)l; }
+    for (int t : {(int)P_QKV, (int)P_ATTN, (int)P_PROJ, (int)P_FC, (int)P_FC2}) { P.ptype[np] = (signed char)t; P.player[np++] = (signed char)l; }
+  }
+  lnf_at = np;
+  for (int t : {(int)P_LNF, (int)P_LMHEAD, (int)P_PICK}) { P.ptype[np] = (signed char)t; P.player[np++] = (signed char)L; }
+  PIO_CHECK(np == PPS, "decode_fused: phase table of %d entries, expected %d", np, PPS);
+  P.first_gp = start_at_pick ? lnf_at : 0;
   P.stop_gp = 1 << 30;
   if (const char* e = getenv("PIO_FUSED_STOP_PHASE")) P.stop_gp = atoi(e) + 1;  // debug: run global phases [first, stop]
 
-  CUtensorMap mh, ma, mf;
-  PIO_TRY(make_map_2d(&mh, w.hb, R, gD, gD, R_pad, 64));
-  PIO_TRY(make_map_2d(&ma, w.att, R, gD, gD, R_pad, 64));
-  PIO_TRY(make_map_2d(&mf, w.f, R, gFF, gFF, R_pad, 64));
   PIO_CUDA(cudaMemsetAsync(w.counters, 0, fused_counter_ints(L, steps) * sizeof(int), st));
   static SmemAttrOnce once;
   PIO_CUDA(once.ensure(decode_fused_kernel, 222 * 1024));
@@ -919,7 +945,7 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
     PIO_CUDA(cudaMalloc((void**)&P.timeline, tl_n * 8));
     PIO_CUDA(cudaMemsetAsync(P.timeline, 0, tl_n * 8, st));
   }
-  void* args[] = {(void*)&mh, (void*)&ma, (void*)&mf, (void*)&P};
+  void* args[] = {(void*)&P};
   PIO_CUDA(cudaLaunchCooperativeKernel((const void*)decode_fused_kernel, dim3(G), dim3(FT_THREADS), args, smem, st));
   PIO_LAUNCHED();
   if (tl_path) {
@@ -928,8 +954,9 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
     PIO_CUDA(cudaMemcpy(host.data(), P.timeline, tl_n * 8, cudaMemcpyDeviceToHost));
     PIO_CUDA(cudaFree(P.timeline));
     if (FILE* f = fopen(tl_path, "wb")) {
-      const int hdr[8] = {steps, PPS, G, P.first_gp, L, R, 8, 0};
-      fwrite(hdr, sizeof(int), 8, f);
+      int hdr[8 + MAX_PHASES] = {steps, PPS, G, P.first_gp, L, R, 8, MAX_PHASES};
+      for (int i = 0; i < MAX_PHASES; ++i) hdr[8 + i] = i < PPS ? P.ptype[i] * 16 + P.player[i] : -1;
+      fwrite(hdr, sizeof(int), 8 + MAX_PHASES, f);
       fwrite(host.data(), 8, tl_n, f);
       fclose(f);
     }

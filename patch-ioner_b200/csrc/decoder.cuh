@@ -37,7 +37,7 @@ struct DecodeWs {
   void* att; float* part; float* pm_val; int* pm_idx; int* counters; size_t counters_bytes;
   size_t kv_layer, total;
 };
-constexpr int kFusedMaxRows = 256;     // rows one fused launch handles (TMEM: 2 x R_pad columns)
+constexpr int kFusedMaxRows = 64;      // rows one fused launch handles (their 12 activation tiles stay in shared memory)
 constexpr int kFusedCtas = kNumSMs;    // upper bound of its grid
 constexpr int kFusedFc2Splits = 4;     // K = 3072 cut into 4 x 12 k-blocks: every GEMM unit is 128 rows x 12 k-blocks
 size_t fused_counter_ints(int L, int steps);

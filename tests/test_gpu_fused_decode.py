@@ -42,15 +42,17 @@ def gelu_new(x):
 
 
 def emulate_step0(w, prefix):
-    """expected workspace contents after each global phase of step 0 (position 0): list of (name, [(region, tensor), ...]).
-    The fc2 phase leaves its split-K partials unreduced: x is brought up to date by the NEXT LayerNorm phase."""
+    """expected workspace contents after each global phase of step 0 (position 0): list of (name, [(region, tensor), ...]) in the
+    kernel's phase order -- block 0: QKV* ATTN PROJ FC* FC2; blocks 1..: LN1r QKV ATTN PROJ FC* FC2; then LNFr LMHEAD (PICK).
+    (* LayerNorm applied while loading: no h rows in memory; fc2 leaves split-K partials that the NEXT LayerNorm phase folds into x.)"""
     T = "decoder.transformer."
     out = []
     x = bf(prefix) @ bf(w["clip_project.model.0.weight"]).T + w["clip_project.model.0.bias"] + w[T + "wpe.weight"][0]
     for i in range(4):
         p = f"{T}h.{i}."
         h = bf(F.layer_norm(x, (768,), w[p + "ln_1.weight"], w[p + "ln_1.bias"], eps=1e-5))
-        out.append((f"L{i}.ln1", [("h", h), ("x", x)]))
+        if i > 0:
+            out.append((f"L{i}.ln1", [("h", h), ("x", x)]))
         qkv = bf(h @ bf(w[p + "attn.c_attn.weight"]) + w[p + "attn.c_attn.bias"])
         out.append((f"L{i}.qkv", [("qkv", qkv)]))
         att = qkv[:, 1536:]                      # one key: softmax = 1, output = v
@@ -58,7 +60,6 @@ def emulate_step0(w, prefix):
         x = x + att @ bf(w[p + "attn.c_proj.weight"]) + w[p + "attn.c_proj.bias"]
         out.append((f"L{i}.proj", [("x", x)]))
         h = bf(F.layer_norm(x, (768,), w[p + "ln_2.weight"], w[p + "ln_2.bias"], eps=1e-5))
-        out.append((f"L{i}.ln2", [("h", h)]))
         f = bf(gelu_new(h @ bf(w[p + "mlp.c_fc.weight"]) + w[p + "mlp.c_fc.bias"]))
         out.append((f"L{i}.fc", [("f", f)]))
         x = x + f @ bf(w[p + "mlp.c_proj.weight"]) + w[p + "mlp.c_proj.bias"]
@@ -129,7 +130,7 @@ def _prefix(R, dev, seed=9):
     return (p / p.norm(dim=-1, keepdim=True)).to(dev)
 
 
-@pytest.mark.parametrize("R", [1, 7, 32, 64, 100, 256])
+@pytest.mark.parametrize("R", [1, 7, 16, 32, 33, 64])
 def test_fused_decode_matches_kernel_per_op_decode(dev, ops, dec_w, R, monkeypatch):
     """Same arithmetic, different summation order inside the tensor cores / split-K: the two bf16 paths agree on nearly all
     captions (random-init logit margins are tiny), and the fused one repeats bit for bit."""
@@ -186,7 +187,7 @@ def test_fused_decode_nan_row_and_scores_fallback(dev, ops, dec_w, monkeypatch):
 def test_fused_decode_speed_report(dev, ops, dec_w, monkeypatch):
     """Not a pass/fail bar: prints us per decode step of both paths for the BASELINE small-batch sizes."""
     dec = ops.Decoder(dec_w, dev, "bf16")
-    for R in (32, 64, 256):
+    for R in (8, 32, 64):
         prefix = _prefix(R, dev, seed=12)
         res = {}
         for flag in ("1", "0"):

@@ -13,47 +13,45 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-NAMES = ["LN1", "QKV", "ATTN", "PROJ", "LN2", "FC", "FC2"]
+TYPES = ["LN1r", "QKV", "ATTN", "PROJ", "FC", "FC2", "LNFr", "LMHEAD", "PICK"]
 
 
 def load(path):
     raw = open(path, "rb").read()
-    steps, pps, G, first, L, R, k, _ = struct.unpack("8i", raw[:32])
-    t = np.frombuffer(raw[32:], dtype=np.uint64).reshape(steps * pps, G, k).astype(np.int64)
-    return dict(steps=steps, pps=pps, G=G, first=first, L=L, R=R), t
+    steps, pps, G, first, L, R, k, nph = struct.unpack("8i", raw[:32])
+    table = struct.unpack(f"{nph}i", raw[32:32 + 4 * nph])
+    t = np.frombuffer(raw[32 + 4 * nph:], dtype=np.uint64).reshape(steps * pps, G, k).astype(np.int64)
+    names = [(f"L{v % 16}." if v // 16 < 6 else "") + TYPES[v // 16] for v in table[:pps]]
+    return dict(steps=steps, pps=pps, G=G, first=first, L=L, R=R, names=names), t
 
 
 def analyse(meta, t, step):
-    pps, L = meta["pps"], meta["L"]
+    """stamps per (phase, CTA): 0 enters the phase, 1 previous phase seen complete, 4 activation tiles in shared memory (GEMM
+    phases), 5 first accumulator ready (GEMM phases), 2 work done, 3 arrival posted"""
+    pps = meta["pps"]
     prev_done = None
-    rows = []
+    tot = 0
+    print(f"{'phase':10s} {'ctas':>4s} {'total':>7s} {'detect':>7s} {'acts':>6s} {'mma':>6s} {'work':>6s} {'arrive':>6s}   (ns; slowest CTA of each phase; total = last arrival - last arrival of the previous phase)")
     for p in range(pps):
         gp = step * pps + p - meta["first"]
         a = t[gp]
         part = a[:, 3] > 0
         if not part.any():
             continue
-        name = (f"L{p // 7}." + NAMES[p % 7]) if p < 7 * L else ["LNF", "LMHEAD", "PICK"][p - 7 * L]
         done = a[part, 3].max()
-        ready = a[part, 1].max()
-        enter = a[part, 0].max()
-        work = (a[part, 2] - a[part, 1]).max()
-        arr = (a[part, 3] - a[part, 2]).max()
-        dur = (done - prev_done) if prev_done is not None else 0
-        extra = ""
-        if a.shape[1] >= 8 and prev_done is not None and (a[part, 4] > 0).any():
-            # GEMM phases: act producer saw the phase (4), after the proxy fence (5), first unit's act loads issued (6); MMA warp: first weight tile present (7)
-            c = int(np.argmax(np.where(part, a[:, 1], 0)))  # the CTA whose accumulator was ready last
-            extra = "  [slowest CTA: detect %d  +proxy fence %d  +TMA issued %d  | W tile there at %d | acc ready %d]" % (
-                a[c, 4] - prev_done, a[c, 5] - a[c, 4], a[c, 6] - a[c, 5], a[c, 7] - prev_done, a[c, 1] - prev_done)
-        rows.append((name, int(part.sum()), dur, (ready - prev_done) if prev_done is not None else 0, work, arr, enter - (prev_done or enter), extra))
+        c = int(np.argmax(np.where(part, a[:, 3], 0)))  # the CTA that arrived last
+        gemm = a[c, 5] > 0
+        if prev_done is not None:
+            detect = a[c, 1] - prev_done
+            acts = (a[c, 4] - a[c, 1]) if gemm else 0
+            mma = (a[c, 5] - a[c, 4]) if gemm else 0
+            work = a[c, 2] - (a[c, 5] if gemm else a[c, 1])
+            arr = a[c, 3] - a[c, 2]
+            dur = done - prev_done
+            tot += dur
+            print(f"{meta['names'][p]:10s} {int(part.sum()):4d} {dur:7d} {detect:7d} {acts:6d} {mma:6d} {work:6d} {arr:6d}")
         prev_done = done
-    print(f"{'phase':10s} {'ctas':>4s} {'total':>8s} {'->ready':>8s} {'work':>8s} {'arrive':>8s} {'late-enter':>10s}   (ns; total = last arrival of this phase - last arrival of the previous)")
-    tot = 0
-    for name, n, dur, rdy, work, arr, late, extra in rows:
-        print(f"{name:10s} {n:4d} {dur:8d} {rdy:8d} {work:8d} {arr:8d} {late:10d}{extra}")
-        tot += dur
-    print(f"step total {tot / 1e3:.1f} us")
+    print(f"step total (without its first phase) {tot / 1e3:.1f} us")
 
 
 def main():
