@@ -50,6 +50,7 @@ constexpr int FT_COMPUTE_WARPS = 8;      // warps 4..11
 constexpr int W_TILE_BYTES = 128 * 64 * 2;
 constexpr int KB_PER_UNIT = 12;          // 768 / 64
 constexpr int MAX_STAGES = 12;
+constexpr int NACC = 4;                 // independent accumulators per unit (see the kernel); the epilogue is written for 4
 
 enum PhaseType { P_LN1 = 0, P_QKV, P_ATTN, P_PROJ, P_FC, P_FC2, P_LNF, P_LMHEAD, P_PICK };
 constexpr int MAX_PHASES = 6 * 12 + 3;  // phases of one step for up to 12 blocks
@@ -70,7 +71,7 @@ struct FusedParams {
   unsigned long long* timeline;  // debug (PIO_FUSED_TIMELINE): 8 globaltimer stamps per (phase, CTA), or NULL
   int* out_ids;
   int ids_ld;
-  int L, H, hd, T, R, R_pad, steps, pos_base, first_gp, G, nsw, stop_gp, PPS;
+  int L, H, hd, T, R, R_pad, steps, pos_base, first_gp, G, nsw, gs, stop_gp, PPS, mma_mode, pace_ns;  // gs: ring stages per release group
   signed char ptype[MAX_PHASES], player[MAX_PHASES];  // the phases of one step: type and block index
 };
 
@@ -149,28 +150,13 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // part != NULL: the previous block's fc2 left its 4 split-K partial tiles unreduced -- this warp first forms
 //   x[r] += (p0 + p1 + p2 + p3) + fc2_b   (fixed order: deterministic), stores the row back, then normalises it.
 // Lane l owns the float4 at column 4 (l + 32 i), i < 6: output tile i of the [6 x 128]-column layout, offset 4 l.
-__device__ __forceinline__ void ln_row(float* __restrict__ xrow, const float* __restrict__ w, const float* __restrict__ b,
-                                       __nv_bfloat16* __restrict__ out, int lane, const float* __restrict__ part, int r, int R_pad,
-                                       const float* __restrict__ fc2_b, uint8_t* sm_tiles = nullptr, int tile_bytes = 0) {
-  float4 v[6];
+__device__ __forceinline__ void ln_load(const float* __restrict__ xrow, int lane, float4 (&v)[6]) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) v[i] = ld_cg_f4(xrow + 4 * (lane + 32 * i));
-  if (part != nullptr) {
-    float4 pp[6][kFusedFc2Splits];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int sp = 0; sp < kFusedFc2Splits; ++sp) pp[i][sp] = ld_cg_f4(part + ((long long)(sp * 6 + i) * R_pad + r) * 128 + 4 * lane);
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      float4 a = pp[i][0];
-#pragma unroll
-      for (int sp = 1; sp < kFusedFc2Splits; ++sp) { a.x += pp[i][sp].x; a.y += pp[i][sp].y; a.z += pp[i][sp].z; a.w += pp[i][sp].w; }
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(fc2_b) + lane + 32 * i);
-      v[i].x += a.x + bb.x; v[i].y += a.y + bb.y; v[i].z += a.z + bb.z; v[i].w += a.w + bb.w;
-      reinterpret_cast<float4*>(xrow)[lane + 32 * i] = v[i];
-    }
-  }
+}
+// normalise the row held in v (lane l: float4 at column 4 (l + 32 i)) and write it out
+__device__ __forceinline__ void ln_core(const float4 (&v)[6], const float* __restrict__ w, const float* __restrict__ b,
+                                        __nv_bfloat16* __restrict__ out, int lane, int r, uint8_t* sm_tiles, int tile_bytes) {
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 6; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
@@ -198,12 +184,76 @@ __device__ __forceinline__ void ln_row(float* __restrict__ xrow, const float* __
     }
   }
 }
+// LayerNorm of rows cw, cw + 8, ... of x straight into the CTA's activation tiles; the next row's loads are in flight while a
+// row is normalised (a row is one L2 round trip + two warp reductions: serialised, four rows cost 5.8 us -- measured)
+__device__ __noinline__ void ln_rows_to_tiles(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                 int R, int cw, int lane, uint8_t* sm_tiles, int tile_bytes) {
+  float4 nxt[6], cur[6];
+  if (cw < R) ln_load(x + (long long)cw * gD, lane, nxt);
+  for (int r = cw; r < R; r += FT_COMPUTE_WARPS) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) cur[i] = nxt[i];
+    if (r + FT_COMPUTE_WARPS < R) ln_load(x + (long long)(r + FT_COMPUTE_WARPS) * gD, lane, nxt);
+    ln_core(cur, w, b, nullptr, lane, r, sm_tiles, tile_bytes);
+  }
+}
+
+// One row, all eight compute warps (the LayerNorm PHASES: LN1r, LNFr -- at most one row per CTA up to 148 rows):
+//   x[r] += (p0 + p1 + p2 + p3) + fc2_b  when `part` is given (the previous fc2's split-K partial tiles, summed in split order),
+//   then h[r] = LayerNorm(x[r]) in bf16.  Warp w owns columns [96 w, 96 w + 96): 24 lanes x one float4, so the whole row is ONE
+//   L2 round trip; the two row statistics meet in shared memory (scratch: 16 floats).  Called by all 256 compute threads.
+__device__ __noinline__ void ln_row_cta(float* __restrict__ xrow, const float* __restrict__ w, const float* __restrict__ b,
+                                           __nv_bfloat16* __restrict__ out, int cw, int lane, const float* __restrict__ part, int r,
+                                           int R_pad, const float* __restrict__ fc2_b, float* scratch) {
+  const bool act = lane < 24;
+  const int c = 96 * cw + 4 * lane;  // first of this lane's four columns
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act) {
+    v = ld_cg_f4(xrow + c);
+    if (part != nullptr) {
+      const int tile = c >> 7, nl = c & 127;
+      float4 pp[kFusedFc2Splits];
+#pragma unroll
+      for (int sp = 0; sp < kFusedFc2Splits; ++sp) pp[sp] = ld_cg_f4(part + ((long long)(sp * 6 + tile) * R_pad + r) * 128 + nl);
+      float4 a = pp[0];
+#pragma unroll
+      for (int sp = 1; sp < kFusedFc2Splits; ++sp) { a.x += pp[sp].x; a.y += pp[sp].y; a.z += pp[sp].z; a.w += pp[sp].w; }
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(fc2_b + c));
+      v.x += a.x + bb.x; v.y += a.y + bb.y; v.z += a.z + bb.z; v.w += a.w + bb.w;
+      *reinterpret_cast<float4*>(xrow + c) = v;
+    }
+  }
+  float s = warp_sum(act ? v.x + v.y + v.z + v.w : 0.f);
+  if (lane == 0) scratch[cw] = s;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += scratch[i];  // same order in every thread
+  const float mean = tot * (1.0f / 768.0f);
+  const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+  float q = warp_sum(act ? d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 : 0.f);
+  if (lane == 0) scratch[8 + cw] = q;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  float qt = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qt += scratch[8 + i];
+  const float rstd = rsqrtf(qt * (1.0f / 768.0f) + 1e-5f);
+  if (act) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+    uint2 pk;
+    pk.x = pack2(d0 * rstd * g.x + bb.x, d1 * rstd * g.y + bb.y);
+    pk.y = pack2(d2 * rstd * g.z + bb.z, d3 * rstd * g.w + bb.w);
+    *reinterpret_cast<uint2*>(out + c) = pk;
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");  // scratch is free for the next row
+}
 
 // KV-cache attention of one (row, head), head_dim 192, by the EIGHT compute warps of a CTA (DeCap: T <= 32 positions):
 // warp w scores keys w, w + 8, w + 16, w + 24 (all its key / value rows are requested at once: one L2 round trip), keeps a
 // local (max, sum, weighted value sum) and the warps meet in shared memory.  Appends this position's key / value to the cache.
 // scratch: 8 x (192 + 2) floats.  Must be called by all 256 compute threads (named barrier 1).
-__device__ __forceinline__ void attn_192_cta(const __nv_bfloat16* __restrict__ qkv_row, __nv_bfloat16* __restrict__ kbase,
+__device__ __noinline__ void attn_192_cta(const __nv_bfloat16* __restrict__ qkv_row, __nv_bfloat16* __restrict__ kbase,
                                              __nv_bfloat16* __restrict__ vbase, __nv_bfloat16* __restrict__ out, int h, int H, int t,
                                              int cw, int lane, int ct, float* scratch) {
   constexpr int HDIM = 192, NK = 4;
@@ -289,7 +339,7 @@ __device__ __forceinline__ void attn_192_cta(const __nv_bfloat16* __restrict__ q
 
 // KV-cache attention of one (row, head), head_dim 192 (DeCap: 4 heads, T <= 32): the arithmetic of
 // decode_attention_bf16_kernel (attention.cu) with coherent loads.  Appends this position's key / value to the cache.
-__device__ __forceinline__ void attn_192(const __nv_bfloat16* __restrict__ qkv_row, __nv_bfloat16* __restrict__ kbase,
+__device__ __noinline__ void attn_192(const __nv_bfloat16* __restrict__ qkv_row, __nv_bfloat16* __restrict__ kbase,
                                          __nv_bfloat16* __restrict__ vbase, __nv_bfloat16* __restrict__ out, int h, int H, int t,
                                          int lane) {
   constexpr int HDIM = 192, KB = 8;
@@ -370,7 +420,7 @@ __device__ __forceinline__ void attn_192(const __nv_bfloat16* __restrict__ qkv_r
 
 // head_dim 64 (GPT-2 small: 12 heads, T <= 128): lane j scores keys j, j+32, j+64, j+96 (the arithmetic of
 // decode_attention_long_kernel); qs = 64 floats of this warp's shared memory
-__device__ __forceinline__ void attn_64(const __nv_bfloat16* __restrict__ qkv_row, __nv_bfloat16* __restrict__ kbase,
+__device__ __noinline__ void attn_64(const __nv_bfloat16* __restrict__ qkv_row, __nv_bfloat16* __restrict__ kbase,
                                         __nv_bfloat16* __restrict__ vbase, __nv_bfloat16* __restrict__ out, int h, int H, int t,
                                         int lane, float* qs) {
   constexpr int HDIM = 64, MAXC = 4;
@@ -461,8 +511,10 @@ struct Waiter {
     dead = true;
     atomicExch(abort, 1);
   }
-  // bounded mbarrier wait
-  __device__ __forceinline__ void mbar(uint32_t bar, uint32_t parity) {
+  // bounded mbarrier wait.  NOT inlined, like every larger piece of this kernel: the persistent kernel runs each code path
+  // once per phase, i.e. instruction-cache cold -- at 222 KB of SASS (everything inlined) instruction fetch, not data, set the
+  // pace of every phase (profiles/r02l, r02n: 48 UMMAs took 5 us to ISSUE)
+  __device__ __noinline__ void mbar(uint32_t bar, uint32_t parity) {
     if (dead) return;
     uint32_t done = 0;
     unsigned long long t0 = 0;
@@ -484,8 +536,22 @@ struct Waiter {
       }
     }
   }
+  // fast path inline (one try_wait; a call into the bounded loop costs ~100 ns even when the barrier has completed)
+  __device__ __forceinline__ void mbar_fast(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done) mbar(bar, parity);
+  }
   // bounded wait for a phase counter (acquire loads: the data loads that follow are ordered after the one that succeeds)
-  __device__ __forceinline__ void phase(const int* cnt, int target) {
+  __device__ __noinline__ void phase(const int* cnt, int target) {
     if (dead) return;
     unsigned long long t0 = 0;
     for (unsigned it = 0;; ++it) {
@@ -504,13 +570,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 // rows [0, R) x columns [k0, k0 + 768) of a bf16 matrix -> the CTA's activation tiles (12 k-blocks of [R_pad x 128 B], 128B
 // swizzle), by all 256 compute threads: 16-byte chunks, every thread's loads issued before its first store (one L2 round trip)
-__device__ __forceinline__ void load_acts(const __nv_bfloat16* __restrict__ src, int ld, int k0, int R, uint8_t* sm_tiles, int tile_bytes,
+__device__ __noinline__ void load_acts(const __nv_bfloat16* __restrict__ src, int ld, int k0, int R, uint8_t* sm_tiles, int tile_bytes,
                                           int ct) {
   const int total = R * 96;  // 96 chunks of 8 bf16 per row
-  for (int q0 = ct; q0 < total; q0 += 256 * 8) {
-    uint4 v[8];
+  constexpr int NB = 12;  // 32 rows = 12 chunks per thread: one batch, one round trip
+  for (int q0 = ct; q0 < total; q0 += 256 * NB) {
+    uint4 v[NB];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NB; ++i) {
       const int q = q0 + 256 * i;
       if (q < total) {
         const int r = q / 96, cc = q - r * 96;
@@ -518,7 +585,7 @@ __device__ __forceinline__ void load_acts(const __nv_bfloat16* __restrict__ src,
       }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < NB; ++i) {
       const int q = q0 + 256 * i;
       if (q < total) {
         const int r = q / 96, cc = q - r * 96, kb = cc >> 3, c = cc & 7;
@@ -534,6 +601,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 6];
   __shared__ uint32_t tmem_slot_var;
+  __shared__ int s_dead;
 
   const uint32_t bar_base = smem_u32(bars);
   auto fullW = [&](int s) { return bar_base + 8u * s; };
@@ -557,10 +625,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
   const int gp_begin = P.first_gp, gp_end = min(P.steps * PPS, P.stop_gp);  // [gp_begin, gp_end)
   Sched S{G, R, P.H, (int)blockIdx.x, PPS, P.ptype};
   Waiter wt{P.abort, false};
+  // A unit's 48 UMMAs would form ONE dependent chain on a single accumulator: at N = R_pad <= 64 that chain is latency bound
+  // (measured 3.8 us per unit at N = 32, ~150 clk per instruction instead of the 16 clk the data path needs).  Hence NACC
+  // independent accumulators -- k-step j of every k-block adds into accumulator j -- summed by the epilogue in a fixed order.
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * R_pad) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * NACC * R_pad) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
+    s_dead = 0;
     for (int s = 0; s < P.nsw; ++s) { mbar_init(fullW(s), 1); mbar_init(emptyW(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), FT_COMPUTE_WARPS); }
     mbar_init(acts_full, 1);
@@ -575,6 +647,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_var);
+  unsigned long long* tl_tail = P.timeline ? P.timeline + (long long)(P.steps * PPS) * G * 16 : nullptr;  // SM clock vs wall clock
+  if (tl_tail && blockIdx.x == 0 && threadIdx.x == 0) { tl_tail[0] = clock64(); tl_tail[1] = gtime_ns(); }
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight producer: runs ahead of every phase
@@ -588,11 +662,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
         const CUtensorMap* map = P.wmaps + (pt == P_LMHEAD ? 4 * L : 4 * l + (pt == P_QKV ? 0 : pt == P_PROJ ? 1 : pt == P_FC ? 2 : 3));
         for (int u = S.first_unit(gp); u < nu; u += G) {
           const int tile = pt == P_FC2 ? u % 6 : u, kb0 = pt == P_FC2 ? (u / 6) * KB_PER_UNIT : 0;
+          // the ring is filled and released in GROUPS of gs stages: one (empty, full) barrier pair per group, so that the MMA
+          // warp pays one wait and one commit per group instead of per stage (each costs it 100-200 ns, more than the UMMAs
+          // of a k-block at N <= 64)
           for (int kb = 0; kb < KB_PER_UNIT; ++kb) {
-            wt.mbar(emptyW(stage), phase ^ 1);
-            if (wt.dead) break;
-            mbar_expect_tx(fullW(stage), W_TILE_BYTES);
-            tma_load_2d(smem_base + stage * W_TILE_BYTES, map, fullW(stage), (kb0 + kb) * 64, tile * 128);
+            const int grp = stage / P.gs;
+            if (stage % P.gs == 0) {
+              wt.mbar(emptyW(grp), phase ^ 1);
+              if (wt.dead) break;
+              mbar_expect_tx(fullW(grp), P.gs * W_TILE_BYTES);
+            }
+            tma_load_2d(smem_base + stage * W_TILE_BYTES, map, fullW(grp), (kb0 + kb) * 64, tile * 128);
             if (++stage == P.nsw) { stage = 0; phase ^= 1; }
           }
         }
@@ -601,7 +681,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
     __syncwarp();
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer
+    // The whole warp walks the schedule with warp-uniform values (so that descriptors live in uniform registers) and ONE elected
+    // lane issues.  Instruction count per UMMA matters here: a single warp issues ~1 dependent instruction per 5 ns, and a
+    // UMMA at N <= 64 is short -- with ~60 instructions of address arithmetic per UMMA (runtime modulo, per-lane election
+    // loops) issuing the 48 UMMAs of a unit took 5-8 us (profiles/r02l, r02o).  Descriptors advance by constant strides.
     const uint32_t idesc = make_idesc(128, R_pad);
+    uint32_t leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(leader));
+    const uint64_t adesc0 = make_smem_desc(smem_base), bdesc0 = make_smem_desc(smemA);
+    const uint32_t b_stride = (uint32_t)a_tile_bytes >> 4;  // descriptor start-address units (16 B) per activation k-block
     int sw = 0, it = 0, nphase = 0;
     uint32_t phw = 0;
     for (int gp = gp_begin; gp < gp_end && !wt.dead; ++gp) {
@@ -609,27 +697,41 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
       if (!S.is_gemm(pt)) continue;
       const int nu = S.units(pt), u0 = S.first_unit(gp);
       if (u0 >= nu) continue;
-      wt.mbar(acts_full, nphase & 1);  // the compute warps have placed this phase's activation tiles (kept for all its units)
+      wt.mbar_fast(acts_full, nphase & 1);  // the compute warps have placed this phase's activation tiles (kept for all its units)
       ++nphase;
+      unsigned long long* tl = (P.timeline && lane == 0) ? P.timeline + ((long long)(gp - gp_begin) * G + blockIdx.x) * 16 : nullptr;
+      if (tl) tl[6] = gtime_ns();
       for (int u = u0; u < nu && !wt.dead; u += G, ++it) {
         const int as = it & 1;
-        wt.mbar(tempty(as), ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * R_pad;
-        for (int kb = 0; kb < KB_PER_UNIT; ++kb) {
-          wt.mbar(fullW(sw), phw);
+        wt.mbar_fast(tempty(as), ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+        const uint32_t tmem_d = tmem_base + as * (NACC * R_pad);
+        uint64_t bdesc = bdesc0;
+        for (int kb0 = 0; kb0 < KB_PER_UNIT; kb0 += P.gs) {  // gs divides 12 and nsw: a group never wraps
+          wt.mbar_fast(fullW(sw / P.gs), phw);
           if (wt.dead) break;
           tc_fence_after();
-          if (lane == 0) {
-            const uint64_t adesc = make_smem_desc(smem_base + sw * W_TILE_BYTES), bdesc = make_smem_desc(smemA + kb * a_tile_bytes);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(emptyW(sw));
-            if (kb == KB_PER_UNIT - 1) umma_commit(tfull(as));
+          uint64_t adesc = adesc0 + (uint64_t)(sw * (W_TILE_BYTES >> 4));
+          const uint32_t acc = kb0 != 0;
+#pragma unroll 1
+          for (int j = 0; j < P.gs; ++j) {
+            if (leader) {
+              umma_f16(tmem_d, adesc, bdesc, idesc, acc | (uint32_t)j);
+              umma_f16(tmem_d + R_pad, adesc + 2, bdesc + 2, idesc, acc | (uint32_t)j);
+              umma_f16(tmem_d + 2 * R_pad, adesc + 4, bdesc + 4, idesc, acc | (uint32_t)j);
+              umma_f16(tmem_d + 3 * R_pad, adesc + 6, bdesc + 6, idesc, acc | (uint32_t)j);
+            }
+            adesc += W_TILE_BYTES >> 4;
+            bdesc += b_stride;
+          }
+          if (leader) {
+            umma_commit(emptyW(sw / P.gs));  // the group of ring stages just consumed
+            if (kb0 + P.gs >= KB_PER_UNIT) umma_commit(tfull(as));
           }
           __syncwarp();
-          if (++sw == P.nsw) { sw = 0; phw ^= 1; }
+          sw += P.gs;
+          if (sw >= P.nsw) { sw = 0; phw ^= 1; }
         }
+        if (tl && u == u0) tl[7] = gtime_ns();
       }
     }
   } else if (warp >= 4) {
@@ -639,7 +741,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
     const int n_chunks = R_pad / 16;
     int it = 0;
     auto stamp = [&](int gp, int k) {
-      if (P.timeline && ct == 0) P.timeline[((long long)(gp - gp_begin) * G + blockIdx.x) * 8 + k] = gtime_ns();
+      if (P.timeline && ct == 0) P.timeline[((long long)(gp - gp_begin) * G + blockIdx.x) * 16 + k] = gtime_ns();
     };
     // the CTA's arrival at a phase: its eight compute warps meet, then ONE thread publishes -- the barrier orders the other
     // threads' writes before that thread's gpu-scope release (cumulativity; the pattern of a cooperative-groups grid sync)
@@ -658,8 +760,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
       const int pos = P.pos_base + s;
       stamp(gp, 0);
       if (gp > gp_begin) {  // the previous phase -- the producer of this phase's input -- is complete
-        if (lane == 0) wt.phase(P.phase_cnt + gp - 1, S.participants(S.ptype((gp - 1) % PPS)));
-        wt.dead = __shfl_sync(0xffffffffu, (int)wt.dead, 0) != 0;
+        // ONE polling thread per CTA: with every warp polling, ~1000 pollers hammered one L2 line and a poll round trip grew to
+        // ~0.6 us (it also delayed the arrivals queued behind them)
+        if (ct == 0) {
+          wt.phase(P.phase_cnt + gp - 1, S.participants(S.ptype((gp - 1) % PPS)));
+          s_dead = wt.dead ? 1 : 0;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        wt.dead = wt.dead || (*(volatile int*)&s_dead != 0);
       }
       stamp(gp, 1);
       if (!S.is_gemm(pt)) {
@@ -674,15 +782,20 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
           cta_arrive(gp);
           continue;
         }
+        if (pt == P_LN1 || pt == P_LNF) {
+          // the fc2 of the block before left its split-K partials unreduced (always for LN1: blocks 1..; for ln_f unless the
+          // kernel starts there); one row at a time, all eight warps on it
+          const bool pending = pt == P_LN1 || gp > gp_begin;
+          const float* fb = pending ? P.layers[pt == P_LN1 ? l - 1 : L - 1].fc2_b : nullptr;
+          for (int u = u0; u < nu; u += G)
+            if (!wt.dead)
+              ln_row_cta(P.x + (long long)u * gD, pt == P_LN1 ? P.layers[l].ln1_w : P.lnf_w, pt == P_LN1 ? P.layers[l].ln1_b : P.lnf_b,
+                         P.h + (long long)u * gD, cw, lane, pending ? P.part : nullptr, u, R_pad, fb, s_att);
+          cta_arrive(gp);
+          continue;
+        }
         for (int u = u0 + cw * G; u < nu && !wt.dead; u += FT_COMPUTE_WARPS * G) {  // this CTA's units, one warp each
-          if (pt == P_LN1 || pt == P_LNF) {
-            // the fc2 of the block before left its split-K partials unreduced (always for LN1: blocks 1..; for ln_f unless the
-            // kernel starts there)
-            const bool pending = pt == P_LN1 || gp > gp_begin;
-            const float* fb = pending ? P.layers[pt == P_LN1 ? l - 1 : L - 1].fc2_b : nullptr;
-            ln_row(P.x + (long long)u * gD, pt == P_LN1 ? P.layers[l].ln1_w : P.lnf_w, pt == P_LN1 ? P.layers[l].ln1_b : P.lnf_b,
-                   P.h + (long long)u * gD, lane, pending ? P.part : nullptr, u, R_pad, fb);
-          } else if (pt == P_ATTN) {
+          if (pt == P_ATTN) {
             const int r = u / P.H, hh = u % P.H;
             __nv_bfloat16* kb_ = P.kc + (long long)l * P.kv_layer + ((long long)(r * P.H + hh) * P.T) * P.hd;
             __nv_bfloat16* vb_ = P.vc + (long long)l * P.kv_layer + ((long long)(r * P.H + hh) * P.T) * P.hd;
@@ -724,11 +837,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
       const FusedLayer& ly = P.layers[pt == P_LMHEAD ? 0 : l];
       if (!wt.dead) {
         if (pt == P_QKV && l == 0) {         // LN1 of block 0 applied on the way in (x is complete: prefix embedding / PICK)
-          for (int r = cw; r < R; r += FT_COMPUTE_WARPS)
-            ln_row(P.x + (long long)r * gD, ly.ln1_w, ly.ln1_b, nullptr, lane, nullptr, r, R_pad, nullptr, acts, a_tile_bytes);
+          ln_rows_to_tiles(P.x, ly.ln1_w, ly.ln1_b, R, cw, lane, acts, a_tile_bytes);
         } else if (pt == P_FC) {             // LN2 applied on the way in (x is complete after PROJ)
-          for (int r = cw; r < R; r += FT_COMPUTE_WARPS)
-            ln_row(P.x + (long long)r * gD, ly.ln2_w, ly.ln2_b, nullptr, lane, nullptr, r, R_pad, nullptr, acts, a_tile_bytes);
+          ln_rows_to_tiles(P.x, ly.ln2_w, ly.ln2_b, R, cw, lane, acts, a_tile_bytes);
         } else if (pt == P_PROJ) {
           load_acts(P.att, gD, 0, R, acts, a_tile_bytes, ct);
         } else if (pt == P_FC2) {            // this CTA's K slice of the gelu rows
@@ -750,15 +861,26 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
         wt.dead = __any_sync(0xffffffffu, wt.dead);
         if (u == u0) stamp(gp, 5);
         tc_fence_after();
-        const uint32_t tacc = tmem_base + as * R_pad + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t tacc = tmem_base + as * (NACC * R_pad) + ((uint32_t)(quarter * 32) << 16);
         float bias = 0.f;
         if (pt == P_QKV) bias = __ldg(ly.attn_b + n);
         else if (pt == P_PROJ) bias = __ldg(ly.proj_b + n);
         else if (pt == P_FC) bias = __ldg(ly.fc_b + n);
         for (int c = half; c < n_chunks && !wt.dead; c += 2) {
           uint32_t rr[16];
-          tmem_ld16(tacc + c * 16, rr);
-          tmem_ld_wait();
+          {
+            uint32_t ra[2][16];  // two accumulators at a time (register budget); fixed order: ((a0 + a1) + a2) + a3
+            tmem_ld16(tacc + c * 16, ra[0]);
+            tmem_ld16(tacc + R_pad + c * 16, ra[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint(__uint_as_float(ra[0][j]) + __uint_as_float(ra[1][j]));
+            tmem_ld16(tacc + 2 * R_pad + c * 16, ra[0]);
+            tmem_ld16(tacc + 3 * R_pad + c * 16, ra[1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = __float_as_uint((__uint_as_float(rr[j]) + __uint_as_float(ra[0][j])) + __uint_as_float(ra[1][j]));
+          }
           if (pt == P_QKV) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -836,6 +958,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
 
   tc_fence_before();
   __syncthreads();
+  if (tl_tail && blockIdx.x == 0 && threadIdx.x == 0) { tl_tail[2] = clock64(); tl_tail[3] = gtime_ns(); }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -904,6 +1027,10 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   int nsw = std::min(MAX_STAGES, (222 * 1024 - 1024 - gen_bytes - KB_PER_UNIT * a_tile) / W_TILE_BYTES);
   if (const char* e = getenv("PIO_DECODE_FUSED_WSTAGES")) nsw = std::max(2, std::min(nsw, atoi(e)));  // A/B runs
   PIO_CHECK(nsw >= 4, "decode_fused: %d rows leave no room for the weight ring", R);
+  // the ring is two release groups (see the producer): gs stages each, gs a divisor of the 12 k-blocks of a unit
+  int gs = nsw >= 12 ? 6 : (nsw >= 8 ? 4 : (nsw >= 6 ? 3 : 2));
+  if (const char* e = getenv("PIO_DECODE_FUSED_GROUP")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 3 || g == 4 || g == 6) gs = std::min(g, gs); }
+  nsw = std::min(nsw / gs, 12 / gs) * gs;
   const size_t smem = (size_t)nsw * W_TILE_BYTES + (size_t)KB_PER_UNIT * a_tile + gen_bytes + 1024;
 
   FusedParams P;
@@ -919,7 +1046,7 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   P.abort = w.counters + (size_t)steps * PPS;
   P.out_ids = out_ids; P.ids_ld = steps;
   P.L = L; P.H = h->H; P.hd = gD / h->H; P.T = T; P.R = R; P.R_pad = R_pad; P.steps = steps; P.pos_base = pos_base;
-  P.G = G; P.nsw = nsw; P.PPS = PPS;
+  P.G = G; P.nsw = nsw; P.gs = gs; P.PPS = PPS;
   // the phases of one step (see the header comment)
   int np = 0, lnf_at = 0;
   for (int l = 0; l < L; ++l) {
@@ -931,6 +1058,8 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   PIO_CHECK(np == PPS, "decode_fused: phase table of %d entries, expected %d", np, PPS);
   P.first_gp = start_at_pick ? lnf_at : 0;
   P.stop_gp = 1 << 30;
+  if (const char* e = getenv("PIO_FUSED_MMA_MODE")) P.mma_mode = atoi(e);
+  if (const char* e = getenv("PIO_DECODE_FUSED_PACE_NS")) P.pace_ns = atoi(e);
   if (const char* e = getenv("PIO_FUSED_STOP_PHASE")) P.stop_gp = atoi(e) + 1;  // debug: run global phases [first, stop]
 
   PIO_CUDA(cudaMemsetAsync(w.counters, 0, fused_counter_ints(L, steps) * sizeof(int), st));
@@ -940,7 +1069,7 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   PIO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_fused_kernel, FT_THREADS, smem));
   PIO_CHECK(per_sm >= 1, "decode_fused: the kernel does not fit an SM (%zu bytes of shared memory)", smem);
   const char* tl_path = getenv("PIO_FUSED_TIMELINE");  // debug: per-(phase, CTA) time stamps -> binary file
-  const size_t tl_n = tl_path ? (size_t)(steps * PPS) * G * 8 : 0;
+  const size_t tl_n = tl_path ? (size_t)(steps * PPS) * G * 16 + 4 : 0;
   if (tl_path) {
     PIO_CUDA(cudaMalloc((void**)&P.timeline, tl_n * 8));
     PIO_CUDA(cudaMemsetAsync(P.timeline, 0, tl_n * 8, st));
@@ -954,7 +1083,7 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
     PIO_CUDA(cudaMemcpy(host.data(), P.timeline, tl_n * 8, cudaMemcpyDeviceToHost));
     PIO_CUDA(cudaFree(P.timeline));
     if (FILE* f = fopen(tl_path, "wb")) {
-      int hdr[8 + MAX_PHASES] = {steps, PPS, G, P.first_gp, L, R, 8, MAX_PHASES};
+      int hdr[8 + MAX_PHASES] = {steps, PPS, G, P.first_gp, L, R, 16, MAX_PHASES};
       for (int i = 0; i < MAX_PHASES; ++i) hdr[8 + i] = i < PPS ? P.ptype[i] * 16 + P.player[i] : -1;
       fwrite(hdr, sizeof(int), 8 + MAX_PHASES, f);
       fwrite(host.data(), 8, tl_n, f);

@@ -203,3 +203,51 @@ def test_fused_decode_speed_report(dev, ops, dec_w, monkeypatch):
             torch.cuda.synchronize()
             res[flag] = e0.elapsed_time(e1) / 10
         print(f"R={R}: fused {res['1']:.3f} ms ({res['1'] / 30 * 1e3:.1f} us/step), kernel-per-op {res['0']:.3f} ms ({res['0'] / 30 * 1e3:.1f} us/step)")
+
+
+@pytest.mark.parametrize("R,P,steps,layers", [(64, 18, 16, 2), (5, 28, 64, 12), (33, 3, 40, 12)])
+def test_fused_prompt_decode_matches_kernel_per_op(dev, ops, R, P, steps, layers, monkeypatch):
+    """ViECap's language model (greedy_search, src/viecap/search.py:108-191): GPT-2 (12 heads x 64) continuing a prompt -- the
+    generation loop after the batched prefill runs in the persistent kernel (start at ln_f of the last prompt position,
+    head_dim-64 attention over up to 128 cached positions).  Against the kernel-per-op bf16 path and for repeatability."""
+    from oracle import viecap as ov
+
+    monkeypatch.setenv("PIO_FUSED_CHECK", "1")
+    w = ov.make_weights(seed=77, n_layer_gpt=layers, n_layer_map=1)
+    dec = ops.Gpt2Decoder(w, dev, "bf16")
+    g = torch.Generator().manual_seed(21)
+    prompt = (torch.randn(R, P, 768, generator=g) * 0.3).to(dev)
+    monkeypatch.setenv("PIO_DECODE_FUSED", "1")
+    a = dec.decode(prompt, steps).clone()
+    b = dec.decode(prompt, steps).clone()
+    assert torch.equal(a, b), "fused prompt decode is not repeatable"
+    monkeypatch.setenv("PIO_DECODE_FUSED", "0")
+    c = dec.decode(prompt, steps).clone()
+    same = (a == c)
+    prefix_len = same.long().cumprod(dim=1).sum(dim=1).float().mean().item()
+    print(f"R={R} P={P} steps={steps} L={layers}: first token {same[:, 0].float().mean().item():.3f}, mean common prefix {prefix_len:.1f}/{steps}")
+    assert a.min() >= 0 and a.max() < 50257
+    assert same[:, 0].float().mean().item() >= 0.9 and prefix_len >= 0.5 * steps
+
+
+def test_fused_prompt_decode_speed_report(dev, ops, monkeypatch):
+    """prints us per generated position of GPT-2 small at the ViECap bench batch (64 rows, 64 tokens)"""
+    from oracle import viecap as ov
+
+    w = ov.make_weights(seed=77, n_layer_gpt=12, n_layer_map=1)
+    dec = ops.Gpt2Decoder(w, dev, "bf16")
+    prompt = (torch.randn(64, 24, 768, generator=torch.Generator().manual_seed(3)) * 0.3).to(dev)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PIO_DECODE_FUSED", flag)
+        for _ in range(2):
+            dec.decode(prompt, 64)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            dec.decode(prompt, 64)
+        e1.record()
+        torch.cuda.synchronize()
+        res[flag] = e0.elapsed_time(e1) / 5
+    print(f"GPT-2 small, 64 rows, 24-token prompt + 64 tokens: fused {res['1']:.2f} ms, kernel-per-op {res['0']:.2f} ms")

@@ -20,7 +20,11 @@ def load(path):
     raw = open(path, "rb").read()
     steps, pps, G, first, L, R, k, nph = struct.unpack("8i", raw[:32])
     table = struct.unpack(f"{nph}i", raw[32:32 + 4 * nph])
-    t = np.frombuffer(raw[32 + 4 * nph:], dtype=np.uint64).reshape(steps * pps, G, k).astype(np.int64)
+    flat = np.frombuffer(raw[32 + 4 * nph:], dtype=np.uint64).astype(np.int64)
+    t = flat[:steps * pps * G * k].reshape(steps * pps, G, k)
+    tail = flat[steps * pps * G * k:]
+    if tail.size >= 4 and tail[3] > tail[1]:
+        print(f"SM clock during the kernel: {(tail[2] - tail[0]) / (tail[3] - tail[1]) * 1e3:.0f} MHz ({(tail[3] - tail[1]) / 1e3:.0f} us)")
     names = [(f"L{v % 16}." if v // 16 < 6 else "") + TYPES[v // 16] for v in table[:pps]]
     return dict(steps=steps, pps=pps, G=G, first=first, L=L, R=R, names=names), t
 
@@ -49,7 +53,11 @@ def analyse(meta, t, step):
             arr = a[c, 3] - a[c, 2]
             dur = done - prev_done
             tot += dur
-            print(f"{meta['names'][p]:10s} {int(part.sum()):4d} {dur:7d} {detect:7d} {acts:6d} {mma:6d} {work:6d} {arr:6d}")
+            if gemm and a.shape[1] >= 16 and a[c, 8] > 0:
+                rel = [int(a[c, i] - a[c, 6]) for i in range(8, 15)]
+                print(f"{'':10s} MMA warp after waking: accumulator free +{rel[0]}; weights of group 0/1/2 present +{rel[1]}/+{rel[2]}/+{rel[3]}; group issued +{rel[4]}/+{rel[5]}/+{rel[6]}")
+            extra = f"   [MMA warp: wakes +{a[c, 6] - a[c, 4]}, all issued +{a[c, 7] - a[c, 6]}, accumulator seen +{a[c, 5] - a[c, 7]}]" if gemm and a[c, 6] > 0 else ""
+            print(f"{meta['names'][p]:10s} {int(part.sum()):4d} {dur:7d} {detect:7d} {acts:6d} {mma:6d} {work:6d} {arr:6d}{extra}")
         prev_done = done
     print(f"step total (without its first phase) {tot / 1e3:.1f} us")
 
