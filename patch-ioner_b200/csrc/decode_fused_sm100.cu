@@ -973,7 +973,11 @@ bool decode_fused_eligible(const PioDecoder* h, int R, bool want_logprob) {
   const bool on = !(sw && sw[0] == '0');
   if (!on || want_logprob || h->mode != PIO_BF16 || h->fused_wmaps == nullptr) return false;
   if (!((h->H == 4) || (h->H == 12)) || h->L > 12) return false;
-  int max_rows = kFusedMaxRows;
+  // Measured (tests/test_gpu_fused_decode.py::test_fused_decode_speed_report, B200): 163 / 184 us per step at 8 / 32 rows against
+  // 213 / 224 for the kernel-per-op path, but 268 against 243 at 64 rows -- there the 12 activation tiles (96 KB) leave only half
+  // a unit of weight ring and the fused LayerNorm does 8 rows per warp.  Default: up to 32 rows; PIO_DECODE_FUSED_MAX_ROWS raises
+  // it (at most kFusedMaxRows) for experiments.
+  int max_rows = 32;
   if (const char* e = getenv("PIO_DECODE_FUSED_MAX_ROWS")) max_rows = std::min(kFusedMaxRows, atoi(e));
   return R >= 1 && R <= max_rows;
 }
@@ -1029,7 +1033,7 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   PIO_CHECK(nsw >= 4, "decode_fused: %d rows leave no room for the weight ring", R);
   // the ring is two release groups (see the producer): gs stages each, gs a divisor of the 12 k-blocks of a unit
   int gs = nsw >= 12 ? 6 : (nsw >= 8 ? 4 : (nsw >= 6 ? 3 : 2));
-  if (const char* e = getenv("PIO_DECODE_FUSED_GROUP")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 3 || g == 4 || g == 6) gs = std::min(g, gs); }
+  if (const char* e = getenv("PIO_DECODE_FUSED_GROUP")) { const int g = atoi(e); if (g == 1 || g == 2 || g == 3 || g == 4 || g == 6) gs = std::min(g, nsw); }
   nsw = std::min(nsw / gs, 12 / gs) * gs;
   const size_t smem = (size_t)nsw * W_TILE_BYTES + (size_t)KB_PER_UNIT * a_tile + gen_bytes + 1024;
 

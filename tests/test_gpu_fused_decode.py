@@ -135,6 +135,7 @@ def test_fused_decode_matches_kernel_per_op_decode(dev, ops, dec_w, R, monkeypat
     """Same arithmetic, different summation order inside the tensor cores / split-K: the two bf16 paths agree on nearly all
     captions (random-init logit margins are tiny), and the fused one repeats bit for bit."""
     monkeypatch.setenv("PIO_FUSED_CHECK", "1")
+    monkeypatch.setenv("PIO_DECODE_FUSED_MAX_ROWS", "64")  # the default route stops at 32 rows (where the fused kernel is faster)
     dec = ops.Decoder(dec_w, dev, "bf16")
     prefix = _prefix(R, dev)
     monkeypatch.setenv("PIO_DECODE_FUSED", "1")
@@ -153,6 +154,7 @@ def test_fused_decode_matches_kernel_per_op_decode(dev, ops, dec_w, R, monkeypat
 def test_fused_decode_against_fp32_oracle(dev, ops, dec_w, monkeypatch):
     """bf16 fused decode vs the CPU oracle (fp32): agreement of the same order as the kernel-per-op bf16 path."""
     monkeypatch.setenv("PIO_FUSED_CHECK", "1")
+    monkeypatch.setenv("PIO_DECODE_FUSED_MAX_ROWS", "64")
     R = 48
     dec = ops.Decoder(dec_w, dev, "bf16")
     prefix = _prefix(R, dev, seed=10)
@@ -186,6 +188,7 @@ def test_fused_decode_nan_row_and_scores_fallback(dev, ops, dec_w, monkeypatch):
 
 def test_fused_decode_speed_report(dev, ops, dec_w, monkeypatch):
     """Not a pass/fail bar: prints us per decode step of both paths for the BASELINE small-batch sizes."""
+    monkeypatch.setenv("PIO_DECODE_FUSED_MAX_ROWS", "64")
     dec = ops.Decoder(dec_w, dev, "bf16")
     for R in (8, 32, 64):
         prefix = _prefix(R, dev, seed=12)
@@ -213,6 +216,7 @@ def test_fused_prompt_decode_matches_kernel_per_op(dev, ops, R, P, steps, layers
     from oracle import viecap as ov
 
     monkeypatch.setenv("PIO_FUSED_CHECK", "1")
+    monkeypatch.setenv("PIO_DECODE_FUSED_MAX_ROWS", "64")
     w = ov.make_weights(seed=77, n_layer_gpt=layers, n_layer_map=1)
     dec = ops.Gpt2Decoder(w, dev, "bf16")
     g = torch.Generator().manual_seed(21)
@@ -234,6 +238,7 @@ def test_fused_prompt_decode_speed_report(dev, ops, monkeypatch):
     """prints us per generated position of GPT-2 small at the ViECap bench batch (64 rows, 64 tokens)"""
     from oracle import viecap as ov
 
+    monkeypatch.setenv("PIO_DECODE_FUSED_MAX_ROWS", "64")
     w = ov.make_weights(seed=77, n_layer_gpt=12, n_layer_map=1)
     dec = ops.Gpt2Decoder(w, dev, "bf16")
     prompt = (torch.randn(64, 24, 768, generator=torch.Generator().manual_seed(3)) * 0.3).to(dev)
