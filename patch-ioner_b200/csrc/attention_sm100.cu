@@ -381,7 +381,7 @@ int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int 
   do {                                                                                                                            \
     static SmemAttrOnce once;                                                                                                     \
     PIO_CUDA(once.ensure(vit_attention_tc_kernel<POLY, BKVV>, AttCfg<BKVV>::SMEM));                                                \
-    launch_pdl(vit_attention_tc_kernel<POLY, BKVV>, grid, dim3(ATT_THREADS), AttCfg<BKVV>::SMEM, st, mqk, mkv, (__nv_bfloat16*)out, N, H, \
+    launch_pdl_k(PDL_KIND_ATTN, vit_attention_tc_kernel<POLY, BKVV>, grid, dim3(ATT_THREADS), AttCfg<BKVV>::SMEM, st, mqk, mkv, (__nv_bfloat16*)out, N, H, \
                scale_log2e);                                                                                                      \
   } while (0)
   if (bkv == 64) { if (poly == 0) PIO_ATT_LAUNCH(0, 64); else PIO_ATT_LAUNCH(3, 64); }

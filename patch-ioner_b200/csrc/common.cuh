@@ -81,8 +81,29 @@ struct SmemAttrOnce {
 // overwrites anything a predecessor reads).  Everything ahead of pdl_wait() -- barrier init, tensor-memory allocation,
 // tensor-map prefetch -- then overlaps the predecessor's tail.  PIO_PDL=0 restores plain stream order.
 bool pdl_enabled();  // elementwise.cu
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_kind_enabled(int kind);  // debugging aid: PIO_PDL_OFF=<bit mask of kinds> launches those kernels fully serialised
+enum { PDL_KIND_OTHER = 0, PDL_KIND_LN = 1, PDL_KIND_GEMM = 2, PDL_KIND_GEMM2 = 3, PDL_KIND_ATTN = 4 };
+// griddepcontrol.wait makes the predecessor's writes visible to this grid's ordinary (generic-proxy) accesses; the TMA engine reads
+// through the async proxy, which needs its own fence.  Without it a kernel that TMA-loads what its predecessor wrote with
+// st.global (LayerNorm rows, the 256-wide GEMM tile's direct stores) raced under programmatic dependent launch: the bf16 ViT
+// at 4 x 224 px differed from run to run in 12 of 29 forwards (max |diff| 0.06), 0 of 29 with the attention kernel launched
+// fully serialised (profiles/r02y_*, r02z_*) -- and 0 of 29 with this fence.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n\tfence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_k(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled() && pdl_kind_enabled(kind)) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

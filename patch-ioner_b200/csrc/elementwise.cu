@@ -12,6 +12,16 @@ bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("PIO_PDL"); return !(e && e[0] == '0'); }();
   return on;
 }
+// Kernel kinds launched fully serialised (bit mask over PDL_KIND_*; PIO_PDL_OFF overrides).  Default: the tcgen05 ViT attention.
+// Launched as a programmatic dependent of the qkv GEMM it made the bf16 ViT irreproducible at 4 x 224 px (12 of 29 forwards
+// differed from the first, max |diff| 0.06; 0 of 29 with this kernel serialised, also with every other kind still overlapped:
+// profiles/r02y_*, r02z_*, r02ab_*).  The async-proxy fence now inside pdl_wait() removed the share of the race that came
+// from st.global writes read back by TMA (29/29 -> 0/29 with direct-store epilogues) but not all of it; the cost of
+// serialising 12 launches of a 0.24-0.65 ms kernel is not measurable.
+bool pdl_kind_enabled(int kind) {
+  static const int off = [] { const char* e = getenv("PIO_PDL_OFF"); return e ? atoi(e) : (1 << PDL_KIND_ATTN); }();
+  return ((off >> kind) & 1) == 0;
+}
 
 namespace {
 
@@ -31,7 +41,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    v[i] = xr[lane + 32 * i];
+    v[i] = __ldcg(xr + lane + 32 * i);  // L2, not L1: under programmatic dependent launch this CTA may share its SM (and its L1) with the producer
     s += v[i].x + v[i].y + v[i].z + v[i].w;
   }
   const float mean = warp_sum(s) * (1.0f / DIM);
@@ -231,7 +241,7 @@ int layernorm(const float* x, int ldx, const float* w, const float* b, void* out
   const int blocks = cdiv((long long)rows * 32, 256);
 #define LN_CASE(V)                                                                                   \
   case V:                                                                                            \
-    launch_pdl(layernorm_kernel<V>, dim3(blocks), dim3(256), 0, st, x, ldx, w, b, out, out_dt, ldo, rows, eps); \
+    launch_pdl_k(PDL_KIND_LN, layernorm_kernel<V>, dim3(blocks), dim3(256), 0, st, x, ldx, w, b, out, out_dt, ldo, rows, eps); \
     break;
   switch (dim / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)

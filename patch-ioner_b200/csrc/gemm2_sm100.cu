@@ -240,7 +240,7 @@ int linear_tc2(const PioLinear& p, cudaStream_t st) {
   PIO_CUDA(once.ensure(gemm_tc2_kernel, SMEM2_BYTES));
   const int tiles = cdiv(p.M, 2 * BM2) * cdiv(p.N, BN2);
   const int pairs = tiles < kNumSMs / 2 ? tiles : kNumSMs / 2;
-  launch_pdl(gemm_tc2_kernel, dim3(2 * pairs), dim3(NUM_THREADS2), SMEM2_BYTES, st, ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc,
+  launch_pdl_k(PDL_KIND_GEMM2, gemm_tc2_kernel, dim3(2 * pairs), dim3(NUM_THREADS2), SMEM2_BYTES, st, ma, mw, mc, store_mode, p.C, p.M, p.N, p.K, p.ldc,
              p.c_dt, make_epilogue(p), p.w_static ? 1 : 0);
   PIO_LAUNCHED();
   return PIO_OK;

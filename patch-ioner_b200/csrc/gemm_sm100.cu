@@ -333,7 +333,7 @@ int launch(const PioLinear& p, cudaStream_t st) {
   }
   const int work = tiles * k_splits;
   const int grid = work < kNumSMs ? work : kNumSMs;
-  launch_pdl(gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), cfg::SMEM_BYTES, st, ma, mw, mc, mode, p.C, p.M, p.N, p.K, p.ldc,
+  launch_pdl_k(PDL_KIND_GEMM, gemm_tc_kernel<BN>, dim3(grid), dim3(NUM_THREADS), cfg::SMEM_BYTES, st, ma, mw, mc, mode, p.C, p.M, p.N, p.K, p.ldc,
              p.c_dt, epi, k_splits, p.w_static ? 1 : 0);
   PIO_LAUNCHED();
   return PIO_OK;
