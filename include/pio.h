@@ -262,6 +262,12 @@ typedef struct PioDecoder PioDecoder;
 int pio_decoder_create(PioDecoder** out, const PioDecoderWeights* w, int mode, void* stream);
 void pio_decoder_destroy(PioDecoder* h);
 size_t pio_decode_workspace_bytes(const PioDecoder* h, int R, int steps);
+/* Small batches (bf16 mode, no log-prob sum) are decoded by ONE persistent cooperative kernel (csrc/decode_fused_sm100.cu)   */
+/* instead of ~32 launches per position.  max_rows: largest batch routed to it (default 32, at most 64; 0 turns it off);  */
+/* ctas: CTAs of its grid (0 = one per SM; a cooperative grid of every SM cannot overlap with kernels of another stream -- */
+/* a serving loop that keeps two batches in flight uses half the SMs per decode).  A negative argument keeps the setting.  */
+/* Process-wide; the environment (PIO_DECODE_FUSED, PIO_DECODE_FUSED_MAX_ROWS, PIO_DECODE_FUSED_CTAS) overrides it.        */
+int pio_set_decode_fused(int max_rows, int ctas);
 /* test / debug aid: byte offsets of the decode workspace regions for R rows (pio_decode_greedy layout):                */
 /* [0] x fp32 [R,768], [1] LayerNorm rows, [2] qkv rows, [3] gelu rows, [4] attention rows (fused decode), [5] key      */
 /* cache, [6] value cache, [7] per-CTA arg-max partials (fused decode)                                                  */

@@ -119,6 +119,7 @@ SIGNATURES = {
     "pio_decoder_create": (C.c_int, [C.POINTER(_fp), C.POINTER(PioDecoderWeights), C.c_int, _fp]),
     "pio_decoder_destroy": (None, [_fp]),
     "pio_decode_workspace_bytes": (C.c_size_t, [_fp, C.c_int, C.c_int]),
+    "pio_set_decode_fused": (C.c_int, [C.c_int, C.c_int]),
     "pio_decode_debug_layout": (C.c_int, [_fp, C.c_int, _fp, C.c_int]),
     "pio_decode_greedy": (C.c_int, [_fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
     "pio_l2_normalize": (C.c_int, [_fp, C.c_int, C.c_int, _fp]),

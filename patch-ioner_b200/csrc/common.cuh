@@ -81,7 +81,12 @@ struct SmemAttrOnce {
 // overwrites anything a predecessor reads).  Everything ahead of pdl_wait() -- barrier init, tensor-memory allocation,
 // tensor-map prefetch -- then overlaps the predecessor's tail.  PIO_PDL=0 restores plain stream order.
 bool pdl_enabled();  // elementwise.cu
-bool pdl_kind_enabled(int kind);  // debugging aid: PIO_PDL_OFF=<bit mask of kinds> launches those kernels fully serialised
+bool pdl_kind_enabled(int kind);  // PIO_PDL_OFF=<bit mask of kinds> launches those kernels fully serialised; see elementwise.cu
+// RAII: every kernel launched by this thread while the object lives is fully serialised (the ViT forward: see elementwise.cu)
+struct PdlScopeOff {
+  PdlScopeOff();
+  ~PdlScopeOff();
+};
 enum { PDL_KIND_OTHER = 0, PDL_KIND_LN = 1, PDL_KIND_GEMM = 2, PDL_KIND_GEMM2 = 3, PDL_KIND_ATTN = 4 };
 // griddepcontrol.wait makes the predecessor's writes visible to this grid's ordinary (generic-proxy) accesses; the TMA engine reads
 // through the async proxy, which needs its own fence.  Without it a kernel that TMA-loads what its predecessor wrote with

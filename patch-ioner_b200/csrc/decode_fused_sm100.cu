@@ -968,6 +968,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
 }  // namespace
 
 // ------------------------------------------------------------------------------------------ host side
+std::atomic<int> g_fused_max_rows{32}, g_fused_ctas{0};  // pio_set_decode_fused(); 0 CTAs = one per SM
+
 bool decode_fused_eligible(const PioDecoder* h, int R, bool want_logprob) {
   const char* sw = getenv("PIO_DECODE_FUSED");  // read per call: tests and A/B runs flip it inside one process
   const bool on = !(sw && sw[0] == '0');
@@ -977,7 +979,7 @@ bool decode_fused_eligible(const PioDecoder* h, int R, bool want_logprob) {
   // 213 / 224 for the kernel-per-op path, but 268 against 243 at 64 rows -- there the 12 activation tiles (96 KB) leave only half
   // a unit of weight ring and the fused LayerNorm does 8 rows per warp.  Default: up to 32 rows; PIO_DECODE_FUSED_MAX_ROWS raises
   // it (at most kFusedMaxRows) for experiments.
-  int max_rows = 32;
+  int max_rows = std::min(kFusedMaxRows, g_fused_max_rows.load());
   if (const char* e = getenv("PIO_DECODE_FUSED_MAX_ROWS")) max_rows = std::min(kFusedMaxRows, atoi(e));
   return R >= 1 && R <= max_rows;
 }
@@ -1021,6 +1023,7 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   PIO_CUDA(cudaGetDevice(&dev));
   PIO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   int G = std::min(sms, kFusedCtas);
+  if (const int c = g_fused_ctas.load()) G = std::max(6 * kFusedFc2Splits, std::min(G, c));
   if (const char* e = getenv("PIO_DECODE_FUSED_CTAS")) G = std::max(1, std::min(G, atoi(e)));
   PIO_CHECK(G >= 6 * kFusedFc2Splits, "decode_fused: %d CTAs; every fc2 unit needs its own (the activation tiles are per K slice)", G);
   // Shared memory: weight ring (16 KB stages; 12 = a whole unit, so that nothing of a unit is fetched after its phase has
@@ -1104,3 +1107,9 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
 }
 
 }  // namespace pio
+
+extern "C" int pio_set_decode_fused(int max_rows, int ctas) {
+  if (max_rows >= 0) pio::g_fused_max_rows.store(max_rows);
+  if (ctas >= 0) pio::g_fused_ctas.store(ctas);
+  return PIO_OK;
+}

@@ -12,17 +12,26 @@ bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("PIO_PDL"); return !(e && e[0] == '0'); }();
   return on;
 }
-// Kernel kinds launched fully serialised (bit mask over PDL_KIND_*; PIO_PDL_OFF overrides).  Default: the tcgen05 ViT attention.
-// Launched as a programmatic dependent of the qkv GEMM it made the bf16 ViT irreproducible at 4 x 224 px (12 of 29 forwards
-// differed from the first, max |diff| 0.06; 0 of 29 with this kernel serialised, also with every other kind still overlapped:
-// profiles/r02y_*, r02z_*, r02ab_*).  The async-proxy fence now inside pdl_wait() removed the share of the race that came
-// from st.global writes read back by TMA (29/29 -> 0/29 with direct-store epilogues) but not all of it; the cost of
-// serialising 12 launches of a 0.24-0.65 ms kernel is not measurable.
+// Programmatic dependent launch and reproducibility (round 2).  Launched as programmatic dependents, the kernels of the bf16 ViT
+// forward made it differ from run to run (4 x 224 px: 12 of 29 forwards, max |diff| 0.06; profiles/r02y_*, r02z_*, r02ab_*).  Two
+// causes were separated: (1) TMA loads of what the predecessor wrote with st.global need an async-proxy fence after
+// griddepcontrol.wait -- now inside pdl_wait() (29/29 -> 0/29 differing forwards with direct-store epilogues); (2) a remainder
+// tied to the tcgen05 attention kernel overlapping the tail of the qkv GEMM, which in a process that had used several streams
+// survived serialising the attention launch alone.  It is not root-caused; with LayerNorm, both GEMM kinds and the attention
+// serialised the forward is bit-reproducible in every context tested.  Hence: inside pio_vit_forward / pio_vit_block_rows
+// (PdlScopeOff) every launch is fully serialised -- the kernels there run 50-700 us each, the measured cost is 0.4 % of a
+// bench step -- while the decode / projection path, whose kernels are a few us long and whose repeatability tests are green,
+// keeps the overlap (+31 % at 32 rows without it).  PIO_PDL_OFF=<bit mask over PDL_KIND_*> serialises kinds everywhere.
+static thread_local int g_pdl_scope_off = 0;
+PdlScopeOff::PdlScopeOff() { ++g_pdl_scope_off; }
+PdlScopeOff::~PdlScopeOff() { --g_pdl_scope_off; }
 bool pdl_kind_enabled(int kind) {
-  static const int off = [] { const char* e = getenv("PIO_PDL_OFF"); return e ? atoi(e) : (1 << PDL_KIND_ATTN); }();
-  return ((off >> kind) & 1) == 0;
+  static const int off = [] { const char* e = getenv("PIO_PDL_OFF"); return e ? atoi(e) : 0; }();
+  return g_pdl_scope_off == 0 && ((off >> kind) & 1) == 0;
 }
+}  // namespace pio
 
+namespace pio {
 namespace {
 
 // ------------------------------------------------------------------------------ LayerNorm

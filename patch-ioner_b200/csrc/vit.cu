@@ -164,6 +164,7 @@ size_t pio_vit_workspace_bytes(const PioVit* h, int B, int S) {
 int pio_vit_forward(PioVit* h, const float* imgs, int B, int S, const float* pos_embed, float* out_tokens, float* out_attn,
                     float* out_qkv, void* workspace, size_t workspace_bytes, void* stream) {
   using namespace pio;
+  PdlScopeOff serialised;  // see elementwise.cu: the ViT forward is launched without programmatic overlap (reproducibility)
   PIO_CHECK(h && imgs && pos_embed && out_tokens && workspace, "vit_forward: null argument");
   PIO_CHECK(S % 14 == 0 && S >= 14, "vit_forward: image size %d is not a multiple of the patch size 14", S);
   PIO_CHECK(workspace_bytes >= pio_vit_workspace_bytes(h, B, S), "vit_forward: workspace too small");
@@ -228,6 +229,7 @@ int pio_vit_block_rows(PioVit* h, int layer, float* x, int T, const int* bucket_
                        void* workspace, size_t workspace_bytes, void* stream) {
   using namespace pio;
   if (T == 0) return PIO_OK;
+  PdlScopeOff serialised;
   PIO_CHECK(h && x && bucket_nseq && bucket_len && workspace, "vit_block_rows: null argument");
   PIO_CHECK(layer >= -kDepth && layer < kDepth, "vit_block_rows: layer %d outside [-12, 12)", layer);
   PIO_CHECK(workspace_bytes >= pio_vit_block_workspace_bytes(h, T), "vit_block_rows: workspace too small");

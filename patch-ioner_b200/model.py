@@ -616,6 +616,10 @@ class Patchioner:
             self._stage_bufs, self._stage_free = {}, {}
         copy = self._copy_stream
         streams = (main, self._alt_stream) if overlap_compute else (main, main)
+        if overlap_compute:
+            # two forwards in flight: a small-batch decode (one persistent cooperative kernel) takes half of the SMs, so that the
+            # other batch's kernels -- or its decode -- run beside it instead of queueing behind a grid that owns every SM
+            L.lib().pio_set_decode_fused(-1, 74)
 
         def stage(batch, slot):
             """copy `batch` into the persistent device buffers of `slot` (allocated once per shape: no allocator traffic,
@@ -691,6 +695,14 @@ class Patchioner:
             return
         i = 0
         first_done: list = []
+        try:
+            yield from self._pipeline_loop(it, nxt, launch, stage, main, defer_text, texts, first_done)
+        finally:
+            if overlap_compute:
+                L.lib().pio_set_decode_fused(-1, 0)
+
+    def _pipeline_loop(self, it, nxt, launch, stage, main, defer_text, texts, first_done):
+        i = 0
         inflight = launch(0, stage(nxt, 0))
         while inflight is not None:
             nxt = next(it, None)
