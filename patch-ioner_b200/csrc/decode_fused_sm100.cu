@@ -71,7 +71,7 @@ struct FusedParams {
   unsigned long long* timeline;  // debug (PIO_FUSED_TIMELINE): 8 globaltimer stamps per (phase, CTA), or NULL
   int* out_ids;
   int ids_ld;
-  int L, H, hd, T, R, R_pad, steps, pos_base, first_gp, G, nsw, gs, stop_gp, PPS, mma_mode, pace_ns;  // gs: ring stages per release group
+  int L, H, hd, T, R, R_pad, steps, pos_base, first_gp, G, nsw, gs, stop_gp, PPS, mma_mode, pace_ns, l2_prefetch;  // gs: ring stages per release group
   signed char ptype[MAX_PHASES], player[MAX_PHASES];  // the phases of one step: type and block index
 };
 
@@ -568,27 +568,29 @@ struct Waiter {
 // generic-proxy writes to shared memory that the tensor core (async proxy) will read
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// rows [0, R) x columns [k0, k0 + 768) of a bf16 matrix -> the CTA's activation tiles (12 k-blocks of [R_pad x 128 B], 128B
-// swizzle), by all 256 compute threads: 16-byte chunks, every thread's loads issued before its first store (one L2 round trip)
+// rows [0, R) x columns [k0 + 64 kb0, k0 + 64 (kb0 + nkb)) of a bf16 matrix -> k-blocks [kb0, kb0 + nkb) of the CTA's activation
+// tiles (12 k-blocks of [R_pad x 128 B], 128B swizzle), by all 256 compute threads: 16-byte chunks, every thread's loads issued
+// before its first store (one L2 round trip per batch of 6: half a unit at 32 rows)
 __device__ __noinline__ void load_acts(const __nv_bfloat16* __restrict__ src, int ld, int k0, int R, uint8_t* sm_tiles, int tile_bytes,
-                                          int ct) {
-  const int total = R * 96;  // 96 chunks of 8 bf16 per row
-  constexpr int NB = 12;  // 32 rows = 12 chunks per thread: one batch, one round trip
+                                       int ct, int kb0, int nkb) {
+  const int per_row = nkb * 8;  // chunks of 8 bf16 per row in this k range
+  const int total = R * per_row;
+  constexpr int NB = 6;
   for (int q0 = ct; q0 < total; q0 += 256 * NB) {
     uint4 v[NB];
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
       const int q = q0 + 256 * i;
       if (q < total) {
-        const int r = q / 96, cc = q - r * 96;
-        v[i] = ld_cg16(src + (long long)r * ld + k0 + cc * 8);
+        const int r = q / per_row, cc = q - r * per_row;
+        v[i] = ld_cg16(src + (long long)r * ld + k0 + (kb0 * 8 + cc) * 8);
       }
     }
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
       const int q = q0 + 256 * i;
       if (q < total) {
-        const int r = q / 96, cc = q - r * 96, kb = cc >> 3, c = cc & 7;
+        const int r = q / per_row, cc = q - r * per_row, kb = kb0 + (cc >> 3), c = cc & 7;
         *reinterpret_cast<uint4*>(sm_tiles + (size_t)kb * tile_bytes + r * 128 + ((c ^ (r & 7)) << 4)) = v[i];
       }
     }
@@ -608,7 +610,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
   auto emptyW = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   auto tfull = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
   auto tempty = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 2 + s); };
-  const uint32_t acts_full = bar_base + 8u * (2 * MAX_STAGES + 4);  // the activation tiles of a GEMM phase are in shared memory
+  // the activation tiles of a GEMM phase are in shared memory: k-blocks 0..5 / 6..11 (the UMMAs of the first half run while
+  // the second half is still being fetched)
+  auto acts_full = [&](int half) { return bar_base + 8u * (2 * MAX_STAGES + 4 + half); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = P.R, R_pad = P.R_pad, L = P.L, G = P.G, PPS = P.PPS;
@@ -635,7 +639,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
     s_dead = 0;
     for (int s = 0; s < P.nsw; ++s) { mbar_init(fullW(s), 1); mbar_init(emptyW(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull(s), 1); mbar_init(tempty(s), FT_COMPUTE_WARPS); }
-    mbar_init(acts_full, 1);
+    mbar_init(acts_full(0), 1);
+    mbar_init(acts_full(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) tmem_alloc(smem_u32(&tmem_slot_var), tmem_cols);
@@ -697,9 +702,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
       if (!S.is_gemm(pt)) continue;
       const int nu = S.units(pt), u0 = S.first_unit(gp);
       if (u0 >= nu) continue;
-      wt.mbar_fast(acts_full, nphase & 1);  // the compute warps have placed this phase's activation tiles (kept for all its units)
+      const uint32_t acts_parity = nphase & 1;  // activation tiles are placed once per phase and kept for all its units
       ++nphase;
+      bool acts_seen[2] = {false, false};
       unsigned long long* tl = (P.timeline && lane == 0) ? P.timeline + ((long long)(gp - gp_begin) * G + blockIdx.x) * 16 : nullptr;
+      wt.mbar_fast(acts_full(0), acts_parity);
+      acts_seen[0] = true;
       if (tl) tl[6] = gtime_ns();
       for (int u = u0; u < nu && !wt.dead; u += G, ++it) {
         const int as = it & 1;
@@ -707,6 +715,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
         const uint32_t tmem_d = tmem_base + as * (NACC * R_pad);
         uint64_t bdesc = bdesc0;
         for (int kb0 = 0; kb0 < KB_PER_UNIT; kb0 += P.gs) {  // gs divides 12 and nsw: a group never wraps
+          const int half_ = kb0 >= KB_PER_UNIT / 2 ? 1 : 0;  // groups never straddle the halves (gs divides 6 or is 12 -> both)
+          if (!acts_seen[half_]) { wt.mbar_fast(acts_full(half_), acts_parity); acts_seen[half_] = true; }
+          if (kb0 + P.gs > KB_PER_UNIT / 2 && !acts_seen[1]) { wt.mbar_fast(acts_full(1), acts_parity); acts_seen[1] = true; }
           wt.mbar_fast(fullW(sw / P.gs), phw);
           if (wt.dead) break;
           tc_fence_after();
@@ -840,17 +851,25 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
           ln_rows_to_tiles(P.x, ly.ln1_w, ly.ln1_b, R, cw, lane, acts, a_tile_bytes);
         } else if (pt == P_FC) {             // LN2 applied on the way in (x is complete after PROJ)
           ln_rows_to_tiles(P.x, ly.ln2_w, ly.ln2_b, R, cw, lane, acts, a_tile_bytes);
-        } else if (pt == P_PROJ) {
-          load_acts(P.att, gD, 0, R, acts, a_tile_bytes, ct);
-        } else if (pt == P_FC2) {            // this CTA's K slice of the gelu rows
-          load_acts(P.f, gFF, (u0 / 6) * (KB_PER_UNIT * 64), R, acts, a_tile_bytes, ct);
-        } else {                             // QKV of blocks 1.., lm-head: the LayerNorm rows a phase wrote
-          load_acts(P.h, gD, 0, R, acts, a_tile_bytes, ct);
         }
       }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (ct == 0) mbar_arrive(acts_full);
+      const bool fused_ln = (pt == P_QKV && l == 0) || pt == P_FC;
+      if (fused_ln) {
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (ct == 0) { mbar_arrive(acts_full(0)); mbar_arrive(acts_full(1)); }
+      } else {
+        // plain rows (attention output, gelu rows of this CTA's K slice, LayerNorm rows): two halves of six k-blocks
+        const __nv_bfloat16* src = pt == P_PROJ ? P.att : (pt == P_FC2 ? P.f : P.h);
+        const int ld = pt == P_FC2 ? gFF : gD, k0 = pt == P_FC2 ? (u0 / 6) * (KB_PER_UNIT * 64) : 0;
+#pragma unroll 1
+        for (int half_ = 0; half_ < 2; ++half_) {
+          if (!wt.dead) load_acts(src, ld, k0, R, acts, a_tile_bytes, ct, half_ * (KB_PER_UNIT / 2), KB_PER_UNIT / 2);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (ct == 0) mbar_arrive(acts_full(half_));
+        }
+      }
       stamp(gp, 4);
       // (2) epilogue of every owned unit
       for (int u = u0; u < nu; u += G, ++it) {
@@ -953,6 +972,17 @@ __global__ void __launch_bounds__(FT_THREADS, 1) decode_fused_kernel(const Fused
         }
       }
       cta_arrive(gp);
+      if (pt == P_LMHEAD && P.l2_prefetch && s + 1 < P.steps) {
+        // The lm-head is 57 % of a step's weight bytes and the only phase that streams more than the ring holds: its units
+        // beyond the first are fetched during the phase, from HBM (13.5 us of the 20 us phase).  Ask the L2 for them now, a whole
+        // step ahead -- the blocks' weights in between are prefetched into shared memory anyway, so what the L2 evicts of
+        // THEM costs nothing.  One 16 KB tile per thread.
+        const int gpn = gp + PPS, un0 = S.first_unit(gpn) + G;  // the ring takes this CTA's first unit of the next step
+        const int t_ = ct / KB_PER_UNIT, kb_ = ct - t_ * KB_PER_UNIT, un = un0 + t_ * G;
+        if (un < nu && ct < 4 * KB_PER_UNIT)
+          asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(P.wmaps + 4 * L), "r"(kb_ * 64), "r"(un * 128)
+                       : "memory");
+      }
     }
   }
 
@@ -1067,6 +1097,8 @@ int decode_fused(PioDecoder* h, const DecodeWs& w, int R, int T, int steps, int 
   P.stop_gp = 1 << 30;
   if (const char* e = getenv("PIO_FUSED_MMA_MODE")) P.mma_mode = atoi(e);
   if (const char* e = getenv("PIO_DECODE_FUSED_PACE_NS")) P.pace_ns = atoi(e);
+  P.l2_prefetch = 0;  // measured: no effect (lm-head phase 20.2 vs 20.4 us at 32 rows, profiles/r02al_*): the phase is bound by HBM + the ring refill cadence, and the L2 does not keep 58 MB for a whole step
+  if (const char* e = getenv("PIO_DECODE_FUSED_L2PF")) P.l2_prefetch = atoi(e);
   if (const char* e = getenv("PIO_FUSED_STOP_PHASE")) P.stop_gp = atoi(e) + 1;  // debug: run global phases [first, stop]
 
   PIO_CUDA(cudaMemsetAsync(w.counters, 0, fused_counter_ints(L, steps) * sizeof(int), st));
