@@ -107,24 +107,70 @@ __device__ __forceinline__ void stage_drain(int lane) {
 
 // Activations of the bf16 tensor-core path.  The exact erff / tanhf of the fp32 path cost 25-30 instructions per element,
 // more than the MMA time of the tile they follow; these use the SFU (rcp / ex2 / tanh.approx) instead.
-//   erf: Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 (far below the bf16 rounding of the result)
+//   erf: Abramowitz-Stegun 7.1.28 (one rcp), |gelu error| <= 9e-7 (far below the bf16 rounding of the result)
 //   tanh.approx.f32: relative error 2^-11, below the bf16 rounding (2^-9) of the activation it feeds
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Exact-erf GELU with ONE special-function op per element (round 2; the Abramowitz-Stegun 7.1.26 form of round 1 needed two --
+// rcp and ex2 -- and made the fc1 epilogue SFU-bound: ncu xu_realtime 85.7 %, profiles/r01e_ncu_gemm_tc2_fc1.txt).
+//   A&S 7.1.28:  erf(z) = 1 - 1 / (1 + a1 z + ... + a6 z^6)^16,  |error| <= 3e-7 for z >= 0;
+//   gelu(x) = max(x, 0) - 0.5 |x| r  with  r = 1 - erf(|x| / sqrt 2) = (...)^-16   (no cancellation in the negative tail).
+// Measured against float64 erf over [-12, 12] in fp32 arithmetic: |gelu error| <= 9e-7 (far below the bf16 rounding of the result);
+// for |x| >~ 13 the sixteenth power overflows to +inf, rcp gives 0 and gelu saturates to max(x, 0), as it should.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float ax = fabsf(x), z = ax * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float p = fmaf(t, 1.061405429f, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float erf_abs = fmaf(-p, ex2_approx(-1.4426950408889634f * z * z), 1.0f);  // erf(|x| / sqrt 2)
-  return 0.5f * fmaf(ax, erf_abs, x);                                              // 0.5 x (1 + sign(x) erf_abs)
+  float t = fmaf(0.0000430638f, z, 0.0002765672f);
+  t = fmaf(t, z, 0.0001520143f);
+  t = fmaf(t, z, 0.0092705272f);
+  t = fmaf(t, z, 0.0422820123f);
+  t = fmaf(t, z, 0.0705230784f);
+  t = fmaf(t, z, 1.0f);
+  t *= t; t *= t; t *= t; t *= t;
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return fmaf(-0.5f * ax, r, fmaxf(x, 0.0f));
+}
+// The same formula on TWO elements per instruction (fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2): the GELU epilogue issues
+// 12 packed + 6 scalar instructions per pair instead of 2 x 17 -- the epilogue warps (two per scheduler) are the critical path of
+// fc1, not the tensor pipe (B200: fc1 + GELU 1035 -> 1163 TFLOP/s, profiles/r02ap_gemm_probe_gelu_f32x2.txt).
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t gelu_erf_fast2(uint64_t x) {
+  // coefficients of 7.1.28 times 2^(1/16): the sixteenth power comes out doubled, its reciprocal is r / 2; with nax = -|x|
+  // gelu = max(x, 0) + nax (r / 2): one packed multiply less.  |gelu error| <= 7.1e-7 in fp32 arithmetic over [-14, 14].
+  float x0, x1;
+  unpack2(x, x0, x1);
+  const uint64_t nax = pack2(-fabsf(x0), -fabsf(x1));
+  const uint64_t z = mul2(nax, pack2(-0.70710678118654752440f, -0.70710678118654752440f));
+  uint64_t t = fma2(pack2(4.497039844864048e-05f, 4.497039844864048e-05f), z, pack2(0.0002888118615373969f, 0.0002888118615373969f));
+  t = fma2(t, z, pack2(0.0001587445440236479f, 0.0001587445440236479f));
+  t = fma2(t, z, pack2(0.009680968709290028f, 0.009680968709290028f));
+  t = fma2(t, z, pack2(0.04415399581193924f, 0.04415399581193924f));
+  t = fma2(t, z, pack2(0.07364540547132492f, 0.07364540547132492f));
+  t = fma2(t, z, pack2(1.0442737340927124f, 1.0442737340927124f));
+  t = mul2(t, t); t = mul2(t, t); t = mul2(t, t); t = mul2(t, t);
+  float t0, t1, r0, r1;
+  unpack2(t, t0, t1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(t0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(t1));
+  return fma2(nax, pack2(r0, r1), pack2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
 }
 __device__ __forceinline__ float gelu_new_fast(float x) {
   const float u = 0.79788456080286535588f * fmaf(0.044715f * x * x, x, x);
@@ -184,14 +230,24 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_acc, int quarter, in
       if (use_bias) bi = *reinterpret_cast<const float4*>(s_bias + c + i);
       if (use_gamma) ga = *reinterpret_cast<const float4*>(s_gamma + c + i);
       const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, biv[4] = {bi.x, bi.y, bi.z, bi.w}, gav[4] = {ga.x, ga.y, ga.z, ga.w};
+      if constexpr (ACT != PIO_ACT_GELU_NEW && !(HAS_RES && STORE == STORE_DIRECT)) {  // two elements per instruction
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float t = fmaf(__uint_as_float(r[i + j]), scv[j], biv[j]);
-        if constexpr (ACT == PIO_ACT_GELU_ERF) t = gelu_erf_fast(t);
-        if constexpr (ACT == PIO_ACT_GELU_NEW) t = gelu_new_fast(t);
-        t *= gav[j];
-        if constexpr (HAS_RES && STORE == STORE_DIRECT) t = fmaf(res[i + j], rs, t);
-        v[i + j] = t;
+        for (int j = 0; j < 4; j += 2) {
+          uint64_t t = fma2(pack2(__uint_as_float(r[i + j]), __uint_as_float(r[i + j + 1])), pack2(scv[j], scv[j + 1]), pack2(biv[j], biv[j + 1]));
+          if constexpr (ACT == PIO_ACT_GELU_ERF) t = gelu_erf_fast2(t);
+          t = mul2(t, pack2(gav[j], gav[j + 1]));
+          unpack2(t, v[i + j], v[i + j + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = fmaf(__uint_as_float(r[i + j]), scv[j], biv[j]);
+          if constexpr (ACT == PIO_ACT_GELU_ERF) t = gelu_erf_fast(t);
+          if constexpr (ACT == PIO_ACT_GELU_NEW) t = gelu_new_fast(t);
+          t *= gav[j];
+          if constexpr (HAS_RES && STORE == STORE_DIRECT) t = fmaf(res[i + j], rs, t);
+          v[i + j] = t;
+        }
       }
     }
     if constexpr (STORE == STORE_DIRECT) {
