@@ -16,6 +16,8 @@ from __future__ import annotations
 import math
 from typing import List, Optional, Sequence, Tuple
 
+import random
+
 import torch
 
 # ----------------------------------------------------------------------------
@@ -130,9 +132,10 @@ def extract_bboxes_feats(
     or, in box-set mode, [B,D].  ``attention_map`` [B,P] is COPIED here (the
     reference mutates the caller's CPU copy in place, bbox_utils.py:46-48 -- the
     sequential, order-dependent rescaling *within* one call is reproduced).
-    ``gaussian_bbox_variance == 0`` (python ``random`` centre, :62-71) is not
-    restated: it is RNG-order dependent and unused by the shipped experiment
-    matrices.
+    ``gaussian_bbox_variance == 0`` (:62-71): one-hot on the central patch; for an
+    even span python's ``random.choice`` picks one of the two central indices --
+    restated with the same calls in the same order (y then x, box by box), so a
+    caller that seeds ``random`` gets the reference's picks.
     """
     B, P, D = patch_embeddings.shape
     R = bboxes.shape[1]
@@ -141,8 +144,6 @@ def extract_bboxes_feats(
     pu = boxes_to_patch_units(bboxes, patch_size)
     tok = patch_embeddings.reshape(B, g, g, D).float()
     amap = attention_map.clone().reshape(B, g, g).float() if attention_map is not None else None
-    if gaussian_avg and gaussian_bbox_variance == 0 and amap is None:
-        raise NotImplementedError("variance 0 picks a python-random centre; not part of the oracle")
     total = torch.zeros(B, g, g)
     weights_dbg = torch.zeros(B, R, g, g)
     means = []
@@ -161,7 +162,13 @@ def extract_bboxes_feats(
                 mean = (region * w.unsqueeze(-1)).sum(dim=(0, 1))
                 weights_dbg[i, j, y0:y1, x0:x1] = w
             elif gaussian_avg:
-                w = gaussian_weights(hs, ws, gaussian_bbox_variance)
+                if gaussian_bbox_variance == 0:
+                    w = torch.zeros(hs, ws)
+                    cy = random.choice([hs // 2] if hs % 2 == 1 else [hs // 2 - 1, hs // 2])
+                    cx = random.choice([ws // 2] if ws % 2 == 1 else [ws // 2 - 1, ws // 2])
+                    w[cy, cx] = 1.0
+                else:
+                    w = gaussian_weights(hs, ws, gaussian_bbox_variance)
                 mean = (region * w.unsqueeze(-1)).sum(dim=(0, 1))
                 total[i, y0:y1, x0:x1] += w
                 weights_dbg[i, j, y0:y1, x0:x1] = w
@@ -223,12 +230,18 @@ def grid_pool(patch_tokens: torch.Tensor, weights: torch.Tensor) -> torch.Tensor
 
 
 def compute_region_means(patch_embeddings: torch.Tensor, variance: float) -> torch.Tensor:
-    """model.py:45-94 (variance 0 = python-random centre: not restated)."""
+    """model.py:45-94 (variance 0: one-hot at a python-``random`` central patch per image, :71-79, same call order)."""
     B, P, D = patch_embeddings.shape
     g = int(P ** 0.5)
     tok = patch_embeddings.reshape(B, g, g, D)
     if variance == 0:
-        raise NotImplementedError("variance 0 picks a python-random centre")
+        opts = [g // 2] if g % 2 == 1 else [g // 2 - 1, g // 2]
+        w = torch.zeros(B, g, g)
+        for i in range(B):
+            cy = random.choice(opts)
+            cx = random.choice(opts)
+            w[i, cy, cx] = 1.0
+        return (tok * w.unsqueeze(-1)).sum(dim=(1, 2))
     if variance >= 100:
         w = torch.full((g, g), 1 / (g * g))
     else:

@@ -441,8 +441,11 @@ class Patchioner:
         if get_avg_self_attn_capt:  # model.py:869
             emit("avg_self_attn_capt", avg_self_attn_token)
         if get_avg_patch_capt:      # model.py:45-94
-            w = ops.region_mean_weights(g, gaussian_img_variance, patch.device)
-            emit("avg_patch_capt", ops.pool_grid(patch, w.reshape(1, 1, P).expand(bs, 1, P), 1.0)[:, 0])
+            if gaussian_img_variance == 0:  # model.py:71-79: one-hot at a (python-random, for an even grid) central patch
+                emit("avg_patch_capt", ops.region_centre_rows(patch))
+            else:
+                w = ops.region_mean_weights(g, gaussian_img_variance, patch.device)
+                emit("avg_patch_capt", ops.pool_grid(patch, w.reshape(1, 1, P).expand(bs, 1, P), 1.0)[:, 0])
         if get_attn_heads_capt:     # model.py:871-872, 950-960: one embedding per "head" map (16 x 48-channel re-cut, sic)
             maps = ops.cls_head_attention(qkv_last, self.num_global_tokens, self.num_attn_heads, 0.125)
             emit("attn_heads_capts", ops.pool_grid(patch_orig, maps, 1.0 / P).reshape(-1, D), group=self.num_attn_heads)

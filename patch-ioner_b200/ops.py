@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import random
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -298,6 +299,8 @@ def pool_boxes(patch_tokens: torch.Tensor, bboxes: torch.Tensor, patch_size: int
     B, P, D = patch_tokens.shape
     g = int(P ** 0.5)
     R = bboxes.shape[1]
+    if gaussian_avg and gaussian_bbox_variance == 0 and attention_map is None:
+        return _pool_boxes_centre(patch_tokens, bboxes, patch_size, get_single_embedding_per_image, return_bounds)
     if bboxes.dtype.is_floating_point:
         bx, bdt = bboxes.to(patch_tokens.device, torch.float32).contiguous(), L.DT_F32
     else:
@@ -313,6 +316,86 @@ def pool_boxes(patch_tokens: torch.Tensor, bboxes: torch.Tensor, patch_size: int
                                    float(gaussian_bbox_variance), _ptr(amap), int(get_single_embedding_per_image),
                                    out.data_ptr(), _ptr(bounds), ws.data_ptr(), nbytes, _stream()))
     return (out, bounds) if return_bounds else out
+
+
+def _centre_pick(span: int) -> int:
+    """bbox_utils.py:65-69 / model.py:74-79: the central index; python ``random`` decides between the two of an even span."""
+    return random.choice([span // 2] if span % 2 == 1 else [span // 2 - 1, span // 2])
+
+
+def _row_index_base(patch_tokens: torch.Tensor):
+    """The [B,P,D] token view as one strided 2-D matrix (row b * rows_per_image + p), when the strides allow it."""
+    if patch_tokens.stride(0) % patch_tokens.stride(1) != 0:
+        return None, 0
+    rpi = patch_tokens.stride(0) // patch_tokens.stride(1)
+    flat = torch.as_strided(patch_tokens, ((patch_tokens.shape[0] - 1) * rpi + patch_tokens.shape[1], patch_tokens.shape[2]),
+                            (patch_tokens.stride(1), 1))
+    return flat, rpi
+
+
+def _pool_boxes_centre(patch_tokens: torch.Tensor, bboxes: torch.Tensor, patch_size: int, set_mode: bool, return_bounds: bool):
+    """``gaussian_avg`` with ``gaussian_bbox_variance == 0`` (bbox_utils.py:62-71): the weight is a one-hot on the central patch of
+    the box; for an even span the reference lets python's ``random.choice`` pick one of the two central indices.  The picks are made
+    here on the host with the same calls in the same order (image by image, box by box, y then x; dummy boxes of the box-set mode
+    are skipped before any call), so a caller that seeds ``random`` like the reference gets the reference's picks.  The slice bounds
+    are the device's (bit-exact, ``box_bounds_kernel``); the pooled row is then a plain gather (one-hot x tokens is exact)."""
+    B, P, D = patch_tokens.shape
+    g = int(P ** 0.5)
+    R = bboxes.shape[1]
+    _, bounds = pool_boxes(patch_tokens, bboxes, patch_size, False, 0.5, None, False, return_bounds=True)
+    bh = bounds.cpu().tolist()
+    dummy = ((bboxes.detach().cpu() // patch_size).int().sum(-1) < 0).tolist() if set_mode else None  # bbox_utils.py:19-20, 40
+    idx: List[int] = []
+    owner: List[int] = []
+    for i in range(B):
+        for j in range(R):
+            if set_mode and dummy[i][j]:
+                continue
+            y0, y1, x0, x1 = bh[i][j]
+            hs, ws = y1 - y0, x1 - x0
+            if hs <= 0 or ws <= 0:
+                raise IndexError(f"pool_boxes: box {j} of image {i} selects no patch (the reference indexes an empty weight map here)")
+            cy = _centre_pick(hs)
+            cx = _centre_pick(ws)
+            idx.append((y0 + cy) * g + (x0 + cx))
+            owner.append(i)
+    dev = patch_tokens.device
+    if set_mode:
+        total = torch.zeros(B, P, dtype=torch.float32)
+        if idx:
+            total.index_put_((torch.tensor(owner), torch.tensor(idx)), torch.ones(len(idx)), accumulate=True)
+        total /= total.sum(dim=1, keepdim=True)                 # bbox_utils.py:100 (an image with only dummy boxes: 0/0 = NaN, as there)
+        out = pool_grid(patch_tokens, total.to(dev).reshape(B, 1, P), 1.0)[:, 0]
+    else:
+        flat, rpi = _row_index_base(patch_tokens)
+        if flat is not None:
+            rows = torch.tensor([o * rpi + p for o, p in zip(owner, idx)], dtype=torch.int32, device=dev)
+            out = gather_rows(flat, rows).reshape(B, R, D)
+        else:
+            w = torch.zeros(B * R, P, dtype=torch.float32)
+            w[torch.arange(B * R), torch.tensor(idx)] = 1.0
+            out = pool_grid(patch_tokens, w.to(dev).reshape(B, R, P), 1.0)
+    return (out, bounds) if return_bounds else out
+
+
+def region_centre_rows(patch_tokens: torch.Tensor) -> torch.Tensor:
+    """compute_region_means with ``variance == 0`` (model.py:71-79): per image, the token of a central patch (python ``random`` picks
+    among the two central indices of an even grid, y then x, image by image) -> [B,D]."""
+    _need_cuda(patch_tokens)
+    B, P, D = patch_tokens.shape
+    g = int(P ** 0.5)
+    idx = []
+    for _ in range(B):
+        cy = _centre_pick(g)
+        cx = _centre_pick(g)
+        idx.append(cy * g + cx)
+    flat, rpi = _row_index_base(patch_tokens)
+    if flat is not None:
+        rows = torch.tensor([i * rpi + p for i, p in enumerate(idx)], dtype=torch.int32, device=patch_tokens.device)
+        return gather_rows(flat, rows)
+    w = torch.zeros(B, P, dtype=torch.float32)
+    w[torch.arange(B), torch.tensor(idx)] = 1.0
+    return pool_grid(patch_tokens, w.to(patch_tokens.device).reshape(B, 1, P), 1.0)[:, 0]
 
 
 def pool_grid(patch_tokens: torch.Tensor, weights: torch.Tensor, scale: float) -> torch.Tensor:

@@ -707,6 +707,38 @@ def test_caption_surface_maps_onto_forward(dev):
     assert m.preprocess(pil, keep_img_ratio=True).shape == (2, 3, 224, 224) and m.preprocess(pil, keep_img_ratio=False).shape == (2, 3, 224, 224)
 
 
+def test_variance_zero_centre_patch_against_reference_golden(dev, ops, golden):
+    """gaussian variance 0 (bbox_utils.py:62-71, model.py:71-79): one-hot on a central patch, python ``random`` decides for even
+    spans.  With ``random`` seeded like the generator (tests/golden/make_golden_centre.py, unmodified reference) the device path
+    returns the reference's rows: dense mode is a gather (bit-exact), box-set mode a weighted sum (fp32 round-off)."""
+    import random
+
+    from oracle import pooling as o_pool
+
+    centre = _golden_script("make_golden_centre")
+    rec_all = golden("centre")
+    for name in ("g16", "g37"):
+        rec = rec_all[name]
+        B, g, R, D = rec["shape"]
+        tok, bd, bs = centre.inputs(g, B, R, D)
+        assert float(tok.double().sum()) == rec["in_tok_sum"]
+        t = tok.to(dev)
+        random.seed(rec_all["seed"])
+        got = ops.pool_boxes(t, bd.to(dev), 14, True, 0.0).cpu()
+        assert torch.equal(got, rec["dense"])
+        random.seed(rec_all["seed"])
+        assert torch.equal(o_pool.extract_bboxes_feats(tok, bd, True, 0.0), rec["dense"])
+        random.seed(rec_all["seed"])
+        got = ops.pool_boxes(t, bs.to(dev), 14, True, 0.0, get_single_embedding_per_image=True).cpu()
+        torch.testing.assert_close(got, rec["set"], rtol=2e-5, atol=2e-6)
+        random.seed(rec_all["seed"])
+        assert torch.equal(ops.region_centre_rows(t).cpu(), rec["region_means_0"])
+        # a strided view (patch tokens behind cls + registers, as the forward hands them over)
+        full = torch.cat([torch.zeros(B, 5, D), tok], dim=1).to(dev)
+        random.seed(rec_all["seed"])
+        assert torch.equal(ops.pool_boxes(full[:, 5:], bd.to(dev), 14, True, 0.0).cpu(), rec["dense"])
+
+
 def test_cabi_rejects_bad_arguments(dev, ops):
     """Error behaviour of the C ABI: status code + message through PioError, nothing launched, no crash."""
     from patchioner_b200 import PioError
@@ -714,7 +746,7 @@ def test_cabi_rejects_bad_arguments(dev, ops):
     x = torch.randn(4, 5 * 5, 768, device=dev)
     boxes = torch.tensor([[[0.0, 0.0, 28.0, 28.0]]] * 4, device=dev)
     with pytest.raises(PioError, match="variance 0"):
-        ops.pool_boxes(x, boxes, 14, True, 0.0)                      # python-random centre: not reproduced
+        ops.region_mean_weights(5, 0.0, dev)                         # the C entry has no weight form for the python-random centre (ops.region_centre_rows is the path)
     A = torch.randn(64, 100, device=dev).bfloat16()                   # K = 100: 200-byte rows, not a legal TMA stride
     W = torch.randn(32, 100, device=dev).bfloat16()
     with pytest.raises(PioError, match="multiples of 8"):

@@ -65,6 +65,25 @@ def test_pooling_matches_reference(golden, name):
         torch.testing.assert_close(o_pool.compute_region_means(tok, v), rec[key], **tol)
 
 
+@pytest.mark.parametrize("name", ["g16", "g37"])
+def test_variance_zero_centre_patch_matches_reference(golden, name):
+    """variance 0: the reference's python-``random`` centre picks, reproduced call for call (tests/golden/make_golden_centre.py)."""
+    import random
+
+    centre = _golden_script("make_golden_centre")
+    rec_all = golden("centre")
+    rec = rec_all[name]
+    B, g, R, D = rec["shape"]
+    tok, bd, bs = centre.inputs(g, B, R, D)
+    assert csum(tok) == rec["in_tok_sum"]
+    random.seed(rec_all["seed"])
+    assert torch.equal(o_pool.extract_bboxes_feats(tok, bd, True, 0), rec["dense"])
+    random.seed(rec_all["seed"])
+    torch.testing.assert_close(o_pool.extract_bboxes_feats(tok, bs, True, 0, True), rec["set"], rtol=2e-5, atol=2e-6)
+    random.seed(rec_all["seed"])
+    assert torch.equal(o_pool.compute_region_means(tok, 0), rec["region_means_0"])
+
+
 def test_attention_mutation_is_order_dependent(golden):
     """Q2: the in-place rescale makes overlapping boxes see modified weights -- the oracle must differ
     from an 'independent boxes' computation exactly where the reference does."""
