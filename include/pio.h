@@ -299,6 +299,16 @@ int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prom
 /* compute_scores of the ViECap path (entrypoint.py:164-177): mean negative log-likelihood of every right-padded token row  */
 /* ids int32 [R,n] (lens int32 [R] tokens each) under the language model = GPT2LMHeadModel(input_ids, labels=input_ids).loss  */
 /* of that sentence; the perplexity is exp() of it.  NaN for rows with fewer than two tokens.  n <= 128.                     */
+/* beam_search (viecap/search.py:193-285; the reference's default, entrypoint.py:77,139-143 -- one call per region there, all   */
+/* R regions x beam_width beams as one batch here): prompt fp32 [R,prompt_len,768]; at most `steps` new tokens (max_len);      */
+/* eos0 / eos1 = the two end-of-sentence token ids (search.py:218); temperature divides the logits (:232; <= 0 means 1).       */
+/* out_ids int32 [R,beam_width,steps], out_len int32 [R,beam_width] (tokens of each beam that count, search.py:280),            */
+/* out_score fp32 [R,beam_width] (length-normalised log-probability), beams best first (:281-283).  *out_steps_run (host int,   */
+/* may be NULL) = steps executed before every beam had ended (:275-276); the call synchronises the stream every fourth step.    */
+size_t pio_decode_beam_workspace_bytes(const PioDecoder* h, int R, int prompt_len, int steps, int beam_width);
+int pio_decode_beam_prompt(PioDecoder* h, const float* prompt, int R, int prompt_len, int steps, int beam_width, int eos0, int eos1,
+                           float temperature, int* out_ids, int* out_len, float* out_score, int* out_steps_run, void* workspace,
+                           size_t workspace_bytes, void* stream);
 size_t pio_gpt2_score_workspace_bytes(const PioDecoder* h, int R, int n);
 int pio_gpt2_score_tokens(PioDecoder* h, const int* ids, const int* lens, int R, int n, float* out_nll_mean, void* workspace,
                           size_t workspace_bytes, void* stream);

@@ -11,6 +11,8 @@ Restates, functionally on the reference's state-dict key names,
   * ``compose_discrete_prompts``  Patch-ioner/src/viecap/utils.py:55-74
   * ``greedy_search``             Patch-ioner/src/viecap/search.py:108-191 (arg-max on the LOGITS, 64 tokens, no early exit
                                   for batches > 1, sentence cut after the first '.' / ' .' token)
+  * ``beam_search``               Patch-ioner/src/viecap/search.py:193-285 (the reference's default, entrypoint.py:77,139-143:
+                                  one call per region, width 5, length-normalised scores, stopped beams frozen)
 GPT-2 itself is third-party (``transformers``, 4.46.3 pinned by the reference, 5.5.0 here): the same arithmetic as
 ``oracle/decap.py`` with 12 heads.  Pinned by ``tests/golden/make_golden_viecap.py``, which loads the seeded weights
 below into the UNMODIFIED reference classes (and ``transformers.GPT2LMHeadModel``) and stores their outputs in
@@ -210,6 +212,81 @@ def greedy_ids(w, prompt: torch.Tensor, steps: int = MAX_LEN, return_margin: boo
         seq = torch.cat([seq, wte[nxt][:, None, :]], dim=1)
     ids = torch.stack(toks, dim=1)
     return (ids, torch.stack(margins, dim=1)) if return_margin else ids
+
+
+def stopping_weights(w: Dict[str, torch.Tensor], eos: Sequence[int], seed: int = 77, start: int = 24, slope: float = 0.35,
+                     gain: float = 3.0) -> Dict[str, torch.Tensor]:
+    """A copy of ``w`` whose language model drifts towards the end-of-sentence tokens as the position grows, so that beam search
+    on seeded random weights actually STOPS (different beams at different steps): the position embeddings gain a component
+    along a fixed unit direction u that grows linearly from position ``start`` on, and the tied embedding rows of the
+    end-of-sentence tokens are moved along u.  Test scaffolding only (used by tests/golden/make_golden_viecap_beam.py and the
+    tests that rebuild its inputs)."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.randn(N_EMBD, generator=g)
+    u = u / u.norm()
+    out = dict(w)
+    wpe = w["gpt.transformer.wpe.weight"].clone()
+    pos = torch.arange(N_POS, dtype=torch.float32)
+    wpe += (slope * (pos - start).clamp(min=0))[:, None] * u[None, :]
+    out["gpt.transformer.wpe.weight"] = wpe
+    wte = w["gpt.transformer.wte.weight"].clone()
+    for k, e in enumerate(eos):
+        wte[int(e)] += (gain - 0.4 * k) * u
+    out["gpt.transformer.wte.weight"] = wte
+    if "gpt.lm_head.weight" in out:  # tied in GPT2LMHeadModel: a state dict that carries both must carry the same tensor
+        out["gpt.lm_head.weight"] = wte
+    return out
+
+
+@torch.no_grad()
+def beam_search_ids(w, prompt: torch.Tensor, eos: Sequence[int], beam_width: int = 5, steps: int = MAX_LEN,
+                    temperature: float = 1.0):
+    """search.py:193-285 for ONE prompt [1,P,768] (entrypoint.py:139-143 calls it region by region): returns
+    (tokens [W, n] int64, seq_lengths [W] float, scores / seq_lengths [W]) in the reference's final beam order BEFORE its
+    ``argsort`` -- the caller sorts like :281-283.  No KV cache (the reference re-runs the whole sequence per step); stopped
+    beams keep their score (all of their mass on token 0, :250-251) and their length; the length-normalised scores pick the
+    top ``beam_width`` of the ``W x vocab`` continuations (:252-257); the loop ends when every beam has emitted '.' / ' .'."""
+    wte = w["gpt.transformer.wte.weight"]
+    W = beam_width
+    generated = prompt.float()
+    scores = None
+    tokens = None
+    seq_lengths = torch.ones(W)
+    is_stopped = torch.zeros(W, dtype=torch.bool)
+    for _ in range(steps):
+        logits = gpt2_hidden(w, generated)[:, -1] @ wte.T
+        logits = logits / (temperature if temperature > 0 else 1.0)
+        logits = logits.softmax(-1).log()
+        if scores is None:
+            scores, next_tokens = logits.topk(W, -1)
+            generated = generated.expand(W, *generated.shape[1:])
+            next_tokens, scores = next_tokens.permute(1, 0), scores.squeeze(0)
+            tokens = next_tokens
+        else:
+            logits[is_stopped] = -float("inf")
+            logits[is_stopped, 0] = 0
+            scores_sum = scores[:, None] + logits
+            seq_lengths[~is_stopped] += 1
+            avg = scores_sum / seq_lengths[:, None]
+            avg, next_tokens = avg.view(-1).topk(W, -1)
+            src = torch.div(next_tokens, scores_sum.shape[1], rounding_mode="trunc")
+            seq_lengths = seq_lengths[src]
+            next_tokens = (next_tokens % scores_sum.shape[1]).unsqueeze(1)
+            tokens = torch.cat((tokens[src], next_tokens), dim=1)
+            generated = generated[src]
+            scores = avg * seq_lengths
+            is_stopped = is_stopped[src]
+        generated = torch.cat((generated, wte[next_tokens.squeeze()].view(W, 1, -1)), dim=1)
+        is_stopped = is_stopped + (next_tokens.eq(eos[0]) | next_tokens.eq(eos[1])).squeeze()
+        if is_stopped.all():
+            break
+    return tokens, seq_lengths, scores / seq_lengths
+
+
+def beam_sentences(tokens: torch.Tensor, seq_lengths: torch.Tensor, avg_scores: torch.Tensor) -> List[List[int]]:
+    """search.py:279-283: every beam cut at its length, best length-normalised score first."""
+    outs = [[int(t) for t in row[:int(n)]] for row, n in zip(tokens.tolist(), seq_lengths.tolist())]
+    return [outs[i] for i in avg_scores.argsort(descending=True).tolist()]
 
 
 @torch.no_grad()

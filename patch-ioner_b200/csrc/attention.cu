@@ -362,7 +362,10 @@ template <> __device__ __forceinline__ void store2f<__nv_bfloat16>(__nv_bfloat16
 
 template <typename T>
 __global__ void __launch_bounds__(128) decode_attention_long_kernel(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
-                                                                    T* __restrict__ out, int R, int H, int Tmax, int t, float scale) {
+                                                                    T* __restrict__ out, int R, int H, int Tmax, int t, float scale,
+                                                                    const int* __restrict__ anc) {
+  // anc (beam search, or NULL): anc[r * Tmax + j] = the cache row that holds position j of row r's history -- beams are
+  // re-ordered by copying this small table, never the cache; a row appends position t to ITS OWN cache row.
   constexpr int HDIM = 64, MAXC = 4;
   __shared__ float qs[4][HDIM];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -382,13 +385,16 @@ __global__ void __launch_bounds__(128) decode_attention_long_kernel(const T* __r
   }
   __syncwarp();  // the appended row and q are visible to the whole warp
   float sc[MAXC];
+  int arow[MAXC];
   float mx = -INFINITY;
 #pragma unroll
   for (int c = 0; c < MAXC; ++c) {
     const int j = lane + 32 * c;
     sc[c] = -INFINITY;
+    arow[c] = r;
     if (j <= t) {
-      const T* kr = kbase + (long long)j * HDIM;
+      if (anc != nullptr && j < t) arow[c] = __ldg(anc + (long long)r * Tmax + j);
+      const T* kr = kc + (((long long)arow[c] * H + h) * Tmax + j) * HDIM;
       float a = 0.f;
 #pragma unroll
       for (int d = 0; d < HDIM; d += 8) {
@@ -417,7 +423,8 @@ __global__ void __launch_bounds__(128) decode_attention_long_kernel(const T* __r
 #pragma unroll 4
     for (int jj = 0; jj < n; ++jj) {
       const float pj = __shfl_sync(0xffffffffu, sc[c], jj);
-      const float2 v2 = load2f<T>(vbase + (long long)(32 * c + jj) * HDIM + lane * 2);
+      const int rj = __shfl_sync(0xffffffffu, arow[c], jj);
+      const float2 v2 = load2f<T>(vc + (((long long)rj * H + h) * Tmax + 32 * c + jj) * HDIM + lane * 2);
       a0 = fmaf(pj, v2.x, a0);
       a1 = fmaf(pj, v2.y, a1);
     }
@@ -507,16 +514,17 @@ int small_attention(const void* q, long long ldq, const void* kv, long long ldkv
   return PIO_OK;
 }
 
-int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int R, int H, int T, int t, cudaStream_t st) {
+int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int R, int H, int T, int t, cudaStream_t st, const int* anc) {
+  PIO_CHECK(anc == nullptr || H == 12, "decode attention: the cache-row table is only built for the 12 x 64 kernel");
   if (H == 12) {  // GPT-2 small: 12 heads x 64
     PIO_CHECK(t < T && T <= 128, "decode attention: position %d outside cache of %d (max 128)", t, T);
     const int blocks = cdiv((long long)R * H, 4);
     if (dt == PIO_DT_F32)
       launch_pdl(decode_attention_long_kernel<float>, dim3(blocks), dim3(128), 0, st, (const float*)qkv, (float*)kc, (float*)vc, (float*)out,
-                 R, H, T, t, 0.125f);
+                 R, H, T, t, 0.125f, anc);
     else
       launch_pdl(decode_attention_long_kernel<__nv_bfloat16>, dim3(blocks), dim3(128), 0, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)kc,
-                 (__nv_bfloat16*)vc, (__nv_bfloat16*)out, R, H, T, t, 0.125f);
+                 (__nv_bfloat16*)vc, (__nv_bfloat16*)out, R, H, T, t, 0.125f, anc);
     PIO_LAUNCHED();
     return PIO_OK;
   }

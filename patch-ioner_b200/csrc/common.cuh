@@ -235,7 +235,8 @@ int cls_attention(const void* qkv, int dt, int B, int N, int D, int ng, float* o
 int vit_attention(const void* qkv, void* out, int dt, int B, int N, int H, cudaStream_t st);
 size_t vit_attention_tc_workspace(int B, int N, int H);
 int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int H, cudaStream_t st);  // attention_sm100.cu
-int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int R, int H, int T, int t, cudaStream_t st);
+int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int R, int H, int T, int t, cudaStream_t st,
+                     const int* anc = nullptr);  // anc: per-(row, position) cache-row table of the beam search (12 x 64 kernel only)
 // bidirectional (or causal) attention over n <= 64 tokens; kc / vc != null also writes positions 0..n-1 of a KV cache [R][H][Tmax][hd]
 int small_attention(const void* q, long long ldq, const void* kv, long long ldkv, void* out, long long ldo, int dt, int R, int n, int H,
                     int hd, bool causal, void* kc, void* vc, int Tmax, cudaStream_t st);

@@ -772,8 +772,169 @@ void pio_decoder_destroy(PioDecoder* h) {
 namespace {
 using pio::DecodeWs;
 using pio::decode_ws;
+// ------------------------------------------------------------------------------------------ beam search (viecap/search.py:193-285)
+constexpr int kBeamMax = 8;
+// One CTA per row of the fp32 logits: the W largest log-probabilities log softmax(logits / temperature) (descending; equal
+// values: lower token id first) and their token ids.  Pass 1: every thread keeps the top W of its strided share in registers
+// together with an online (max, sum of exponentials); pass 2: W rounds of a block-wide arg-max over the threads' list heads.
+__global__ void __launch_bounds__(256) beam_topk_kernel(const float* __restrict__ logits, int ld, int V, int W, float inv_temp,
+                                                        float* __restrict__ cand_lp, int* __restrict__ cand_id) {
+  __shared__ float s_val[8];
+  __shared__ int s_idx[8], s_thr[8];
+  __shared__ float s_red[8], s_red2[8];
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float* x = logits + (long long)row * ld;
+  float tv[kBeamMax];
+  int ti[kBeamMax];
+#pragma unroll
+  for (int k = 0; k < kBeamMax; ++k) { tv[k] = -INFINITY; ti[k] = 0x7fffffff; }
+  float mx = -INFINITY, sum = 0.f;
+  for (int i = tid; i < V; i += 256) {
+    const float v = x[i] * inv_temp;
+    if (v > mx) { sum = sum * __expf(mx - v) + 1.f; mx = v; } else sum += __expf(v - mx);
+    if (v > tv[kBeamMax - 1]) {  // strict: an equal value with a higher index never displaces (indices ascend per thread)
+      tv[kBeamMax - 1] = v; ti[kBeamMax - 1] = i;
+#pragma unroll
+      for (int k = kBeamMax - 1; k > 0; --k) {
+        if (tv[k] > tv[k - 1]) { const float a = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = a; const int b = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = b; }
+      }
+    }
+  }
+  // block (max, sum)
+  float bm = pio::warp_max(mx);
+  if (lane == 0) s_red[wid] = bm;
+  __syncthreads();
+  bm = s_red[0];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) bm = fmaxf(bm, s_red[k]);
+  float bs = pio::warp_sum(mx == -INFINITY ? 0.f : sum * __expf(mx - bm));
+  if (lane == 0) s_red2[wid] = bs;
+  __syncthreads();
+  bs = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) bs += s_red2[k];
+  const float lse = bm + logf(bs);
+  int head = 0;  // this thread's next unconsumed list entry
+  for (int k = 0; k < W; ++k) {
+    float v = -INFINITY;
+    int idx = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < kBeamMax; ++q)
+      if (q == head) { v = tv[q]; idx = ti[q]; }
+    int thr = tid;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, idx, o), t2 = __shfl_xor_sync(0xffffffffu, thr, o);
+      if (v2 > v || (v2 == v && i2 < idx)) { v = v2; idx = i2; thr = t2; }
+    }
+    if (lane == 0) { s_val[wid] = v; s_idx[wid] = idx; s_thr[wid] = thr; }
+    __syncthreads();
+    v = s_val[0]; idx = s_idx[0]; thr = s_thr[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q)
+      if (s_val[q] > v || (s_val[q] == v && s_idx[q] < idx)) { v = s_val[q]; idx = s_idx[q]; thr = s_thr[q]; }
+    if (tid == thr) ++head;
+    if (tid == 0) { cand_lp[(long long)row * W + k] = v - lse; cand_id[(long long)row * W + k] = idx; }
+    __syncthreads();
+  }
+}
+
+struct BeamState {
+  float* scores; float* seqlen; int* stopped; int* tok;  // [R * W]
+  int* ids[2];   // [R * W, steps] generated tokens, ping-pong
+  int* anc[2];   // [R * W, T] cache-row table, ping-pong
+  int* active;   // [steps] live beams after each step
+};
+
+// One thread per region: step 0 opens the W beams from the region's single prompt row (search.py:234-243); later steps choose the
+// W best of the W x W candidate continuations by length-normalised score (:244-262).  Writes the NEXT ids / cache-row tables.
+__global__ void beam_select_kernel(BeamState b, int cur, const float* __restrict__ cand_lp, const int* __restrict__ cand_id, int R,
+                                   int W, int steps, int T, int P, int s, int eos0, int eos1) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int* ids_in = b.ids[cur];
+  int* ids_out = b.ids[cur ^ 1];
+  const int* anc_in = b.anc[cur];
+  int* anc_out = b.anc[cur ^ 1];
+  int live = 0;
+  if (s == 0) {
+    for (int k = 0; k < W; ++k) {
+      const int j = r * W + k, id = cand_id[(long long)r * W + k];
+      b.scores[j] = cand_lp[(long long)r * W + k];
+      b.seqlen[j] = 1.f;
+      const int stop = (id == eos0 || id == eos1);
+      b.stopped[j] = stop;
+      live += !stop;
+      b.tok[j] = id;
+      ids_out[(long long)j * steps] = id;
+      for (int p = 0; p < P; ++p) anc_out[(long long)j * T + p] = r;  // the prompt lives in cache row r (prefill of R rows)
+      if (P < T) anc_out[(long long)j * T + P] = j;
+    }
+    atomicAdd(b.active + s, live);
+    return;
+  }
+  float sc[kBeamMax], sl[kBeamMax];
+  int st[kBeamMax];
+  for (int k = 0; k < W; ++k) { const int j = r * W + k; sc[k] = b.scores[j]; st[k] = b.stopped[j]; sl[k] = b.seqlen[j] + (st[k] ? 0.f : 1.f); }
+  // selection: W rounds of arg-max over the candidates not taken yet (flattened index beam * V + token breaks ties)
+  unsigned long long taken = 0ull;
+  for (int k = 0; k < W; ++k) {
+    float best = -INFINITY;
+    int bb = -1, bc = -1, bid = 0;
+    for (int q = 0; q < W; ++q) {
+      const int nc = st[q] ? 1 : W;  // a stopped beam has one continuation: token 0 with log-probability 0 (:250-251)
+      for (int c = 0; c < nc; ++c) {
+        if (taken >> (q * kBeamMax + c) & 1ull) continue;
+        const float lp = st[q] ? 0.f : cand_lp[((long long)r * W + q) * W + c];
+        const int id = st[q] ? 0 : cand_id[((long long)r * W + q) * W + c];
+        const float avg = (sc[q] + lp) / sl[q];
+        if (avg > best || (avg == best && bb >= 0 && (q < bb || (q == bb && id < bid)))) { best = avg; bb = q; bc = c; bid = id; }
+      }
+    }
+    if (bb < 0) { bb = 0; bc = 0; bid = 0; best = -INFINITY; }  // fewer than W finite candidates cannot happen (W live continuations or W stopped beams)
+    taken |= 1ull << (bb * kBeamMax + bc);
+    const int j = r * W + k, src = r * W + bb;
+    b.seqlen[j] = sl[bb];
+    b.scores[j] = best * sl[bb];
+    const int stop = st[bb] | (bid == eos0 || bid == eos1);
+    b.stopped[j] = stop;
+    live += !stop;
+    b.tok[j] = bid;
+    for (int i = 0; i < s; ++i) ids_out[(long long)j * steps + i] = ids_in[(long long)src * steps + i];
+    ids_out[(long long)j * steps + s] = bid;
+    const int npos = min(T, P + s);
+    for (int p = 0; p < npos; ++p) anc_out[(long long)j * T + p] = anc_in[(long long)src * T + p];
+    if (P + s < T) anc_out[(long long)j * T + P + s] = j;
+  }
+  atomicAdd(b.active + s, live);
+}
+
+// search.py:278-283: length-normalised scores, beams best first (equal scores keep their beam order)
+__global__ void beam_finish_kernel(BeamState b, int cur, int R, int W, int steps, int n_done, int* __restrict__ out_ids,
+                                   int* __restrict__ out_len, float* __restrict__ out_score) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float avg[kBeamMax];
+  int ord[kBeamMax];
+  for (int k = 0; k < W; ++k) { avg[k] = b.scores[r * W + k] / b.seqlen[r * W + k]; ord[k] = k; }
+  for (int i = 1; i < W; ++i) {
+    const int o = ord[i];
+    int q = i - 1;
+    while (q >= 0 && avg[ord[q]] < avg[o]) { ord[q + 1] = ord[q]; --q; }
+    ord[q + 1] = o;
+  }
+  const int* ids = b.ids[cur];
+  for (int k = 0; k < W; ++k) {
+    const int src = r * W + ord[k], j = r * W + k;
+    for (int i = 0; i < steps; ++i) out_ids[(long long)j * steps + i] = i < n_done ? ids[(long long)src * steps + i] : 0;
+    out_len[j] = (int)b.seqlen[src];
+    out_score[j] = avg[ord[k]];
+  }
+}
+
 // all transformer blocks for the single new position t (KV cache of T positions per head)
-int decode_blocks(PioDecoder* h, const DecodeWs& w, int R, int T, int t, cudaStream_t st) {
+int decode_blocks(PioDecoder* h, const DecodeWs& w, int R, int T, int t, cudaStream_t st, const int* anc = nullptr) {
   using namespace pio;
   const int adt = h->act_dt, mode = h->mode;
   float* x = w.x;
@@ -781,7 +942,7 @@ int decode_blocks(PioDecoder* h, const DecodeWs& w, int R, int T, int t, cudaStr
     const PioDecoder::Blk& b = h->blk[i];
     PIO_TRY(layernorm(x, gD, b.ln1_w, b.ln1_b, w.hb, adt, gD, R, gD, 1e-5f, st));
     PIO_TRY(linear(mode, w.hb, b.attn_w, w.qkv, R, 3 * gD, gD, gD, gD, 3 * gD, adt, adt, b.attn_b, nullptr, PIO_ACT_NONE, st));
-    PIO_TRY(decode_attention(w.qkv, w.kc + i * w.kv_layer, w.vc + i * w.kv_layer, w.hb, adt, R, h->H, T, t, st));
+    PIO_TRY(decode_attention(w.qkv, w.kc + i * w.kv_layer, w.vc + i * w.kv_layer, w.hb, adt, R, h->H, T, t, st, anc));
     PIO_TRY(linear(mode, w.hb, b.proj_w, x, R, gD, gD, gD, gD, gD, adt, PIO_DT_F32, b.proj_b, x, PIO_ACT_NONE, st));
     PIO_TRY(layernorm(x, gD, b.ln2_w, b.ln2_b, w.hb, adt, gD, R, gD, 1e-5f, st));
     PIO_TRY(linear(mode, w.hb, b.fc_w, w.f, R, gFF, gD, gD, gD, gFF, adt, adt, b.fc_b, nullptr, PIO_ACT_GELU_NEW, st));
@@ -941,6 +1102,123 @@ int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prom
       PIO_TRY(decode_blocks(h, w, R, T, prompt_len + s, st));
     }
   }
+  return PIO_OK;
+}
+
+namespace {
+struct BeamLayout { size_t staging, cand_lp, cand_id, scores, seqlen, stopped, tok, ids0, ids1, anc0, anc1, active, total; };
+BeamLayout beam_layout(int R, int W, int steps, int T) {
+  BeamLayout l;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { const size_t at = o; o += pio::align_up(bytes, 256); return at; };
+  const size_t rows = (size_t)R * W;
+  l.staging = take((size_t)R * pio::gD * 4);
+  l.cand_lp = take(rows * W * 4); l.cand_id = take(rows * W * 4);
+  l.scores = take(rows * 4); l.seqlen = take(rows * 4); l.stopped = take(rows * 4); l.tok = take(rows * 4);
+  l.ids0 = take(rows * steps * 4); l.ids1 = take(rows * steps * 4);
+  l.anc0 = take(rows * T * 4); l.anc1 = take(rows * T * 4);
+  l.active = take((size_t)steps * 4);
+  l.total = o;
+  return l;
+}
+}  // namespace
+
+size_t pio_decode_beam_workspace_bytes(const PioDecoder* h, int R, int prompt_len, int steps, int beam_width) {
+  const int T = prompt_len + steps - 1;
+  const size_t e = h->act_dt == PIO_DT_F32 ? 4 : 2;
+  const size_t rows = std::max((size_t)R * beam_width, (size_t)R * prompt_len);
+  return pio::decode_ws(h, nullptr, R * beam_width, T, (beam_layout(R, beam_width, steps, T).total + e - 1) / e, rows).total;
+}
+
+// beam_search (viecap/search.py:193-285) for R prompts at once: W beams per prompt, every step decodes all R * W beam rows as one
+// batch with a KV cache (the reference re-runs the whole sequence of each beam, one region at a time).  Beams are re-ordered
+// through a per-(row, position) cache-row table instead of copying the cache; per-row top-W candidates come from beam_topk_kernel.
+int pio_decode_beam_prompt(PioDecoder* h, const float* prompt, int R, int prompt_len, int steps, int beam_width, int eos0, int eos1,
+                           float temperature, int* out_ids, int* out_len, float* out_score, int* out_steps_run, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  using namespace pio;
+  if (out_steps_run) *out_steps_run = 0;
+  if (R == 0) return PIO_OK;
+  PIO_CHECK(h && prompt && out_ids && out_len && out_score && workspace, "decode_beam_prompt: null argument");
+  PIO_CHECK(h->H == 12, "decode_beam_prompt: built for the 12-head GPT-2 decoder (pio_decoder_create_gpt2)");
+  PIO_CHECK(beam_width >= 1 && beam_width <= kBeamMax, "decode_beam_prompt: beam width %d outside [1,%d]", beam_width, kBeamMax);
+  const int T = prompt_len + steps - 1, W = beam_width, rows = R * W;
+  PIO_CHECK(prompt_len >= 1 && steps >= 1 && T <= h->T, "decode_beam_prompt: %d prompt + %d new positions exceed the cache of %d",
+            prompt_len, steps, h->T);
+  PIO_CHECK(workspace_bytes >= pio_decode_beam_workspace_bytes(h, R, prompt_len, steps, W), "decode_beam_prompt: workspace too small");
+  PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "decode_beam_prompt: workspace must be 1024-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  const int adt = h->act_dt, mode = h->mode, P = prompt_len;
+  const size_t e = adt == PIO_DT_F32 ? 4 : 2;
+  const BeamLayout lay = beam_layout(R, W, steps, T);
+  const DecodeWs w = decode_ws(h, (char*)workspace, rows, T, (lay.total + e - 1) / e, std::max((size_t)rows, (size_t)R * P));
+  char* tail = (char*)w.pfx;
+  float* cand_lp = (float*)(tail + lay.cand_lp);
+  int* cand_id = (int*)(tail + lay.cand_id);
+  BeamState bs;
+  bs.scores = (float*)(tail + lay.scores); bs.seqlen = (float*)(tail + lay.seqlen); bs.stopped = (int*)(tail + lay.stopped);
+  bs.tok = (int*)(tail + lay.tok);
+  bs.ids[0] = (int*)(tail + lay.ids0); bs.ids[1] = (int*)(tail + lay.ids1);
+  bs.anc[0] = (int*)(tail + lay.anc0); bs.anc[1] = (int*)(tail + lay.anc1);
+  bs.active = (int*)(tail + lay.active);
+  PIO_CUDA(cudaMemsetAsync(bs.active, 0, (size_t)steps * 4, st));
+  const float inv_temp = 1.0f / (temperature > 0.f ? temperature : 1.0f);  // search.py:232
+
+  // prefill: all prompt positions of the R prompts in one pass; their keys / values go to cache rows 0..R-1
+  {
+    const int prow = R * P;
+    prompt_embed_all_kernel<<<cdiv((long long)prow * 32, 256), 256, 0, st>>>(prompt, P, h->wpe, w.x, prow, gD);
+    PIO_LAUNCHED();
+    if (P >= 2 && small_attention_smem(P, gD / h->H) <= 48 * 1024) {
+      for (int i = 0; i < h->L; ++i) {
+        const PioDecoder::Blk& b = h->blk[i];
+        PIO_TRY(layernorm(w.x, gD, b.ln1_w, b.ln1_b, w.hb, adt, gD, prow, gD, 1e-5f, st));
+        PIO_TRY(linear(mode, w.hb, b.attn_w, w.qkv, prow, 3 * gD, gD, gD, gD, 3 * gD, adt, adt, b.attn_b, nullptr, PIO_ACT_NONE, st));
+        PIO_TRY(small_attention(w.qkv, 3 * gD, (char*)w.qkv + (size_t)gD * e, 3 * gD, w.hb, gD, adt, R, P, h->H, gD / h->H, true,
+                                w.kc + i * w.kv_layer, w.vc + i * w.kv_layer, T, st));
+        PIO_TRY(linear(mode, w.hb, b.proj_w, w.x, prow, gD, gD, gD, gD, gD, adt, PIO_DT_F32, b.proj_b, w.x, PIO_ACT_NONE, st));
+        PIO_TRY(layernorm(w.x, gD, b.ln2_w, b.ln2_b, w.hb, adt, gD, prow, gD, 1e-5f, st));
+        PIO_TRY(linear(mode, w.hb, b.fc_w, w.f, prow, gFF, gD, gD, gD, gFF, adt, adt, b.fc_b, nullptr, PIO_ACT_GELU_NEW, st));
+        PIO_TRY(linear(mode, w.f, b.fc2_w, w.x, prow, gD, gFF, gFF, gFF, gD, adt, PIO_DT_F32, b.fc2_b, w.x, PIO_ACT_NONE, st));
+      }
+      float* last = (float*)(tail + lay.staging);
+      PIO_CUDA(cudaMemcpy2DAsync(last, (size_t)gD * 4, w.x + (size_t)(P - 1) * gD, (size_t)P * gD * 4, (size_t)gD * 4, R,
+                                 cudaMemcpyDeviceToDevice, st));
+      PIO_CUDA(cudaMemcpyAsync(w.x, last, (size_t)R * gD * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+      for (int p = 0; p < P; ++p) {  // position by position through the single-position blocks (cache rows 0..R-1 of the R * W-row cache)
+        prompt_embed_kernel<<<cdiv((long long)R * 32, 256), 256, 0, st>>>(prompt, P, p, h->wpe, w.x, R, gD);
+        PIO_LAUNCHED();
+        PIO_TRY(decode_blocks(h, w, R, T, p, st));
+      }
+    }
+  }
+  int cur = 0, done = 0;
+  for (int s = 0; s < steps; ++s) {
+    const int m = s == 0 ? R : rows;
+    if (s > 0) {
+      embed_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, st>>>(h->wte32, h->wpe, bs.tok, 1, 0, P + s - 1, w.x, rows, gD);
+      PIO_LAUNCHED();
+      PIO_TRY(decode_blocks(h, w, rows, T, P + s - 1, st, bs.anc[cur]));
+    }
+    PIO_TRY(layernorm(w.x, gD, h->lnf_w, h->lnf_b, w.hb, adt, gD, m, gD, 1e-5f, st));
+    PIO_TRY(linear(mode, w.hb, h->wte, w.logits, m, gV, gD, gD, gD, gVld, adt, PIO_DT_F32, nullptr, nullptr, PIO_ACT_NONE, st));
+    beam_topk_kernel<<<m, 256, 0, st>>>(w.logits, gVld, gV, W, inv_temp, cand_lp, cand_id);
+    PIO_LAUNCHED();
+    beam_select_kernel<<<cdiv(R, 64), 64, 0, st>>>(bs, cur, cand_lp, cand_id, R, W, steps, T, P, s, eos0, eos1);
+    PIO_LAUNCHED();
+    cur ^= 1;
+    done = s + 1;
+    if ((s & 3) == 3 || s + 1 == steps) {  // search.py:275-276: stop once every beam has ended (checked every fourth step: one small sync)
+      int live = 0;
+      PIO_CUDA(cudaMemcpyAsync(&live, bs.active + s, sizeof(int), cudaMemcpyDeviceToHost, st));
+      PIO_CUDA(cudaStreamSynchronize(st));
+      if (live == 0) break;
+    }
+  }
+  beam_finish_kernel<<<cdiv(R, 64), 64, 0, st>>>(bs, cur, R, W, steps, done, out_ids, out_len, out_score);
+  PIO_LAUNCHED();
+  if (out_steps_run) *out_steps_run = done;
   return PIO_OK;
 }
 

@@ -620,6 +620,26 @@ class Gpt2Decoder:
                                                  ws.data_ptr(), nbytes, _stream()))
         return (ids, lp) if compute_scores else ids
 
+    def beam_search(self, prompt: torch.Tensor, eos: Sequence[int], beam_width: int = 5, steps: int = 64, temperature: float = 1.0):
+        """beam_search (viecap/search.py:193-285) for all prompts at once: prompt fp32 [R,P,768] -> (ids int32 [R,W,steps],
+        lengths int32 [R,W], length-normalised scores fp32 [R,W]), beams best first; ``self.beam_steps_run`` = steps executed."""
+        _need_cuda(prompt)
+        prompt = prompt.float().contiguous()
+        R, P, D = prompt.shape
+        assert D == 768 and len(eos) == 2  # search.py:273 ("hack"): exactly two end-of-sentence tokens
+        W = int(beam_width)
+        ids = torch.empty(R, W, steps, dtype=torch.int32, device=prompt.device)
+        lens = torch.empty(R, W, dtype=torch.int32, device=prompt.device)
+        score = torch.empty(R, W, dtype=torch.float32, device=prompt.device)
+        nbytes = L.lib().pio_decode_beam_workspace_bytes(self._h, R, P, steps, W)
+        ws = workspace(nbytes, prompt.device, "decode_beam")
+        ran = C.c_int(0)
+        L.check(L.lib().pio_decode_beam_prompt(self._h, prompt.data_ptr(), R, P, steps, W, int(eos[0]), int(eos[1]), float(temperature),
+                                               ids.data_ptr(), lens.data_ptr(), score.data_ptr(), C.byref(ran), ws.data_ptr(), nbytes,
+                                               _stream()))
+        self.beam_steps_run = ran.value
+        return ids, lens, score
+
     def score_tokens(self, ids: torch.Tensor, lens: torch.Tensor) -> torch.Tensor:
         """Mean negative log-likelihood per right-padded token row (int32 ids [R,n], int32 lens [R]) -> fp32 [R]."""
         _need_cuda(ids, lens)

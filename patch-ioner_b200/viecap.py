@@ -1,7 +1,8 @@
 """ViECap captioner on the pooled region embeddings (BASELINE config 4's second model).
 
 Mirror of ``VieCap`` (Patch-ioner/src/viecap/entrypoint.py:15-162) for the configuration the reference ships
-(``configs/mlp.viecap.k.yaml``: GPT-2 language model, greedy search):
+(``configs/mlp.viecap.k.yaml``: GPT-2 language model, greedy search; beam search -- the reference's default -- when
+``using_greedy_search`` is false):
 
     feats --L2 normalise in place (:108)--> mapping network (ClipCap.py:122-153)     -> 10 soft-prompt embeddings
           --softmax(q.E^T / T), top-k >= threshold (retrieval_categories.py:87-115)  -> entity names
@@ -60,9 +61,9 @@ class VieCap:
             raise L.PioError("patchioner_b200 runs on CUDA (sm_100a) only: there is no CPU fallback")
         if "gpt" not in cfg["language_model"]:
             raise NotImplementedError("only the GPT-2 language model is built (opt_search, search.py:16-105, is not)")
-        if not cfg["using_greedy_search"]:
-            raise NotImplementedError("beam search (search.py:193-285) is not built; set using_greedy_search: True "
-                                      "as configs/mlp.viecap.k.yaml does")
+        self.beam_width = int(cfg["beam_width"])
+        if not cfg["using_greedy_search"] and not 1 <= self.beam_width <= 8:
+            raise ValueError(f"beam_width {self.beam_width}: the device beam search is built for 1..8 beams")
         self.clip_hidden_size = cfg.get("clip_hidden_size") or (640 if "RN" in (clip_name or "") else 512)  # entrypoint.py:24-29
 
         sd = cfg.get("state_dict")
@@ -214,9 +215,11 @@ class VieCap:
             return out
         feats = self._normalised(feats)
         cont = torch.cat([self.mapper.forward(feats[s:s + chunk]) for s in range(0, R, chunk)], 0)
+        if not self.args["using_greedy_search"]:
+            chunk = max(1, chunk // self.beam_width)  # the cache holds beam_width rows per region
         if not self.args["using_hard_prompt"]:
             for s in range(0, R, chunk):
-                out[s:s + chunk] = self.gpt.decode(cont[s:s + chunk], MAX_LEN)
+                out[s:s + chunk] = self._search(cont[s:s + chunk])
             return out
         toks = self.hard_prompt_token_lists(feats)
         G = R if not pad_group else int(pad_group)
@@ -230,12 +233,24 @@ class VieCap:
                 hard = self._pad([toks[i] for i in part], length)
                 whole = len(part) == R
                 idx = None if whole else torch.tensor(part, dtype=torch.long, device=self.device)
-                ids = self.gpt.decode(self._join(cont if whole else cont[idx], hard), MAX_LEN)
+                ids = self._search(self._join(cont if whole else cont[idx], hard))
                 if whole:
                     out = ids
                 else:
                     out[idx] = ids
         return out
+
+    def _search(self, prompt: torch.Tensor) -> torch.Tensor:
+        """int32 [R,64] ids of the chosen sentence per prompt.  Greedy search (search.py:108-191) when the config says so, else the
+        reference's default (entrypoint.py:77,139-143): beam search of ``beam_width`` beams, best beam returned.  The reference
+        keeps ``tokens[:length]`` of that beam (search.py:280); here the positions from ``length`` on are overwritten with the
+        end-of-sentence id, so that ``cut`` (the same rule greedy search uses) yields exactly those ``length`` tokens."""
+        if self.args["using_greedy_search"]:
+            return self.gpt.decode(prompt, MAX_LEN)
+        ids, lens, _ = self.gpt.beam_search(prompt, self.eos, self.beam_width, MAX_LEN)
+        best, n = ids[:, 0], lens[:, 0:1]
+        pos = torch.arange(MAX_LEN, device=best.device, dtype=torch.int32)[None, :]
+        return torch.where(pos < n, best, torch.full_like(best, int(self.eos[0])))
 
     def cut(self, ids: Sequence[int]) -> List[int]:
         """search.py:184-190: keep up to and including the first end-of-sentence token."""

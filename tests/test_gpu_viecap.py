@@ -144,8 +144,8 @@ def test_viecap_forward_against_reference_golden(dev, golden, weights):
                                  only_hard_prompt=extra.get("only_hard_prompt", False), steps=10)
         got = v2.gpt.decode(v2.prompt_embeddings(g["feats"].clone().to(dev)), 10).cpu().long()
         assert (got == want[1]).all(dim=1).float().mean() >= 0.8
-    with pytest.raises(NotImplementedError):
-        VieCap({**cfg, "using_greedy_search": False}, dev, "ViT-B/16")
+    with pytest.raises(ValueError, match="beam_width"):
+        VieCap({**cfg, "using_greedy_search": False, "beam_width": 9}, dev, "ViT-B/16")
 
 
 def test_patchioner_with_viecap_region_sets(dev, golden, weights):
@@ -330,3 +330,82 @@ def test_viecap_padding_follows_the_reference_calls(dev, golden, weights):
             want += ov.viecap_forward(weights, emb[s:s + per_call].clone(), g["entities"], g["ent_emb"], tok)[0]
         out = m(imgs, get_cls_capt=False, bboxes=boxes.clone(), bs_factor=bs_factor)["bbox_capts"]
         assert [c for row in out for c in row] == want, bs_factor
+
+
+def _golden_script(name):
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".py")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_beam_search_against_reference_golden(dev, ops, golden):
+    """pio_decode_beam_prompt (all prompts x 5 beams as one KV-cached batch, beams re-ordered through the cache-row table) against
+    the sentences the UNMODIFIED reference beam_search (search.py:193-285) produced prompt by prompt without a cache
+    (tests/golden/make_golden_viecap_beam.py): every beam of every prompt, token for token, in the reference's order; lengths and
+    length-normalised scores against the oracle transcript of the same loop."""
+    bm = _golden_script("make_golden_viecap_beam")
+    rec = golden("viecap_beam")
+    w, prompts, eos = bm.inputs()
+    assert float(prompts.double().sum()) == rec["prompt_sum"] and eos == rec["eos"]
+    dec = ops.Gpt2Decoder(w, dev, "fp32")
+    ids, lens, score = dec.beam_search(prompts.to(dev), eos, rec["W"], rec["steps"])
+    ids, lens, score = ids.cpu(), lens.cpu(), score.cpu()
+    assert dec.beam_steps_run < rec["steps"]                 # every beam ended: the loop stopped early (search.py:275-276)
+    for r, reg in enumerate(rec["regions"]):
+        got = [ids[r, k, :int(lens[r, k])].tolist() for k in range(rec["W"])]
+        assert got == reg["sentences"], (r, got, reg["sentences"])
+        order = reg["oracle_avg"].argsort(descending=True)
+        torch.testing.assert_close(score[r], reg["oracle_avg"][order], rtol=1e-4, atol=1e-4)
+        assert lens[r].tolist() == [int(v) for v in reg["oracle_lens"][order].tolist()]
+    # a single prompt, and a width-1 search (= greedy until the first end-of-sentence token)
+    one, l1, _ = dec.beam_search(prompts[2:3].to(dev), eos, rec["W"], rec["steps"])
+    assert one[0, 0, :int(l1[0, 0])].tolist() == rec["regions"][2]["sentences"][0]
+    w1, lw, _ = dec.beam_search(prompts.to(dev), eos, 1, rec["steps"])
+    greedy = dec.decode(prompts.to(dev), rec["steps"]).cpu()
+    for r in range(prompts.shape[0]):
+        n = int(lw[r, 0])
+        assert w1[r, 0, :n].tolist() == greedy[r, :n].tolist()
+    # steps exhausted before the beams end: lengths stay within the budget, nothing is read past it
+    short, ls, _ = dec.beam_search(prompts.to(dev), eos, rec["W"], 3)
+    assert int(ls.max()) <= 3 and dec.beam_steps_run == 3
+    for r, reg in enumerate(rec["regions"]):
+        toks, sl, avg = ov.beam_search_ids(w, prompts[r:r + 1], eos, rec["W"], 3)
+        want = ov.beam_sentences(toks, sl, avg)
+        assert [short[r, k, :int(ls[r, k])].tolist() for k in range(rec["W"])] == want
+
+
+def test_beam_search_bf16_mostly_agrees(dev, ops, golden):
+    bm = _golden_script("make_golden_viecap_beam")
+    rec = golden("viecap_beam")
+    w, prompts, eos = bm.inputs()
+    dec = ops.Gpt2Decoder(w, dev, "bf16")
+    ids, lens, score = dec.beam_search(prompts.to(dev), eos, rec["W"], rec["steps"])
+    first = [int(ids[r, 0, 0]) == reg["sentences"][0][0] for r, reg in enumerate(rec["regions"])]
+    assert sum(first) >= len(first) - 1, first
+    assert bool(torch.isfinite(score).all()) and int(lens.min()) >= 1
+
+
+def test_viecap_forward_with_beam_search(dev, ops, weights, golden):
+    """VieCap.forward with the reference's default search (using_greedy_search False): mapping network -> entities -> prompt ->
+    device beam search, against the oracle's beam search on the oracle's prompt embeddings, region by region."""
+    from patchioner_b200.viecap import VieCap
+
+    g = golden("viecap")
+    tok = ov.ToyTokenizer()
+    eos = [tok.encode(e)[-1] for e in (".", " .")]
+    ws = ov.stopping_weights(weights, eos)
+    cfg = {"state_dict": ws, "tokenizer": tok, "entities_text": g["entities"], "texts_embeddings": g["ent_emb"], "using_hard_prompt": True,
+           "soft_prompt_first": True, "threshold": 0.4, "clip_hidden_size": 768, "using_greedy_search": False, "beam_width": 5}
+    v = VieCap(cfg, dev, "ViT-B/16", precision="fp32")
+    got = v(g["feats"].clone().to(dev))
+    _, _, emb, _ = ov.viecap_forward(ws, g["feats"].clone(), g["entities"], g["ent_emb"], ov.ToyTokenizer(), steps=1)
+    want = []
+    for r in range(emb.shape[0]):
+        toks, sl, avg = ov.beam_search_ids(ws, emb[r:r + 1], eos, 5, ov.MAX_LEN)
+        want.append(tok.decode(ov.beam_sentences(toks, sl, avg)[0]))
+    assert got == want, (got, want)

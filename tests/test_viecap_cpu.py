@@ -89,3 +89,24 @@ def test_entity_files_are_read_like_the_reference(tmp_path):
     assert VieCap._load_entities(cfg, "ViT-B/16_t2d_")[0] == ["cat", "dog", "person"]
     with pytest.raises(NotImplementedError):
         VieCap._load_entities(dict(cfg, name_of_entities_text="open_image_entities"), "x")
+
+
+def test_oracle_beam_search_matches_reference_golden(golden):
+    """oracle/viecap.py::beam_search_ids against the sentences of the unmodified reference beam_search
+    (tests/golden/make_golden_viecap_beam.py): all five beams of every prompt, in the reference's order."""
+    import importlib.util
+    import os
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden_viecap_beam.py")
+    spec = importlib.util.spec_from_file_location("make_golden_viecap_beam", path)
+    bm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bm)
+    rec = golden("viecap_beam")
+    w, prompts, eos = bm.inputs()
+    assert float(prompts.double().sum()) == rec["prompt_sum"]
+    lens_seen = set()
+    for r in (0, 2, 4):
+        toks, sl, avg = ov.beam_search_ids(w, prompts[r:r + 1], eos, rec["W"], rec["steps"])
+        assert ov.beam_sentences(toks, sl, avg) == rec["regions"][r]["sentences"]
+        lens_seen.update(int(v) for v in sl.tolist())
+    assert len(lens_seen) >= 3   # beams of different lengths: the length normalisation and the frozen stopped beams are exercised
