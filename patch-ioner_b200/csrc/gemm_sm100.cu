@@ -34,6 +34,21 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;          // 2 per TMEM lane quarter, each owning half of the tile's columns
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
 
+// Debug build only (-DPIO_GEMM_TRACE, tools/gemm_trace.py): %globaltimer stamps of the roles of every CTA of the LAST launch.
+#ifdef PIO_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[160 * 16];
+__device__ int g_gemm_trace_nk[2];  // only launches of this (N, K) leave stamps (0, 0: every launch)
+__device__ __forceinline__ void trace_stamp(int slot, int N, int K) {
+  if ((g_gemm_trace_nk[0] | g_gemm_trace_nk[1]) != 0 && (N != g_gemm_trace_nk[0] || K != g_gemm_trace_nk[1])) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  g_gemm_trace[blockIdx.x * 16 + slot] = t;
+}
+#define PIO_TRACE(slot) trace_stamp(slot, N, K)
+#else
+#define PIO_TRACE(slot) ((void)0)
+#endif
+
 template <int BN> struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
@@ -68,6 +83,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t tmem_slot = smem_u32(&tmem_slot_var);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) PIO_TRACE(0);  // kernel entry
   const int m_blocks = (M + BM - 1) / BM, n_blocks = (N + BN - 1) / BN;
   // split-K (k_splits > 1, accumulate-only epilogue through the copy engine's reduce-add): work item w = split * tiles + tile
   // covers k-blocks [split * kbs, min(k_blocks, (split + 1) * kbs)); the host guarantees that no split is empty
@@ -88,6 +104,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_var);
+  if (threadIdx.x == 0) PIO_TRACE(1);  // barriers initialised, tensor memory allocated
   pdl_launch_dependents();  // the next kernel may start its own prologue as soon as this grid's CTAs retire
   // pdl_wait() is per role: with prefetch_w (PioLinear.w_static: W is not written by a kernel still in flight -- weights,
   // bank, wte) the producer fetches WEIGHT tiles first; A and the residual always wait; the epilogue waits before it touches
@@ -109,6 +126,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       pdl_wait();  // the previous kernel's output (our A operand) is complete and visible
+      PIO_TRACE(2);  // producer: the previous grid has completed
       for (int w = blockIdx.x; w < num_tiles; w += gridDim.x) {
         const int tile = w % out_tiles, split = w / out_tiles;
         const int m0 = (tile / n_blocks) * BM, n0 = (tile % n_blocks) * BN;
@@ -125,6 +143,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      PIO_TRACE(3);  // producer: last load issued
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -144,6 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         if (lane == 0) {
+          if (it == 0 && kb == kb0) PIO_TRACE(4);  // MMA: first stage has landed
           const uint32_t sa = smem_base + stage * cfg::STAGE_BYTES, sb = sa + cfg::A_BYTES;
           const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sb);
 #pragma unroll
@@ -152,7 +172,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0) || (k != 0));
           }
           umma_commit(empty_bar(stage));                       // ring slot reusable once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(tfull_bar(as));  // accumulator complete
+          if (kb == kb1 - 1) { umma_commit(tfull_bar(as)); PIO_TRACE(5); }  // accumulator complete (stamp: last commit ISSUED, last tile wins)
         }
         __syncwarp();
         if (++stage == cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -183,6 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
+      if (et == 0) PIO_TRACE(it == 0 ? 6 : 7);  // epilogue: accumulator of the first / a later tile is ready
       const int m = m0 + quarter * 32 + lane;
       const uint32_t tacc = tmem_base + as * BN;
       if (store_mode == STORE_SPLIT_FIXUP) {
@@ -238,8 +259,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (et == 0) PIO_TRACE(8);  // epilogue: tile processed, stores issued (last tile wins)
     }
     stage_drain(lane);
+    if (et == 0) PIO_TRACE(9);    // epilogue: bulk stores have read their staging boxes
   }
 
   tc_fence_before();
@@ -248,6 +271,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, cfg::TMEM_COLS);
   }
+  if (threadIdx.x == 0) PIO_TRACE(10);  // exit
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -463,3 +487,15 @@ int make_map_f32_3d(CUtensorMap* map, const void* ptr, long long d0, long long d
 }  // namespace tc
 
 }  // namespace pio
+
+#ifdef PIO_GEMM_TRACE
+extern "C" int pio_debug_gemm_trace_read(unsigned long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, pio::g_gemm_trace, sizeof(unsigned long long) * (size_t)std::min(n, 160 * 16)) == cudaSuccess ? 0 : -1;
+}
+extern "C" int pio_debug_gemm_trace_clear(int n, int k) {
+  static unsigned long long zeros[160 * 16];
+  const int nk[2] = {n, k};
+  if (cudaMemcpyToSymbol(pio::g_gemm_trace_nk, nk, sizeof(nk)) != cudaSuccess) return -1;
+  return cudaMemcpyToSymbol(pio::g_gemm_trace, zeros, sizeof(zeros)) == cudaSuccess ? 0 : -1;
+}
+#endif
