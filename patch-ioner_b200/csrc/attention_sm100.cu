@@ -28,11 +28,14 @@ namespace pio {
 using namespace tc;
 namespace {
 
+#ifndef PIO_ATTN_WAIT_PV
+#define PIO_ATTN_WAIT_PV 1
+#endif
 constexpr int HD = 64;        // head dim
 constexpr int BQ = 128;       // queries per CTA
 constexpr int KV_STAGES = 2;
 constexpr int Q_BYTES = BQ * HD * 2;            // 16 KB
-constexpr int NUM_BARS = 1 + 2 * KV_STAGES + 3;
+constexpr int NUM_BARS = 1 + 2 * KV_STAGES + 4;
 constexpr int ATT_THREADS = 192;
 // Two tile shapes: 128 keys per step with two CTAs per SM (long sequences: 518 px, N = 1374), and 64 keys per step with three
 // CTAs per SM (short sequences: 224 px, N = 261, where 128-key tiles would pad 261 keys to 384).  Measured: 0.655 vs 0.684 ms
@@ -118,9 +121,12 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// wait_h0 / wait_full (0 = no wait): mbarriers (parity wait_par) that say the previous tile's P V has finished reading the first
+// 64-key sub-tile / the whole P buffer -- waited on right before the first store into each sub-tile, i.e. as late as possible.
 template <bool MASK, int POLY, int BKV>
 __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, int row, int kbase, int N, float scale_log2e,
-                                              float ref, float& tmax) {
+                                              float ref, float& tmax, uint32_t wait_h0 = 0, uint32_t wait_full = 0,
+                                              uint32_t wait_par = 0) {
   float s0 = 0.f, s1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY;
   uint32_t ra[16], rb[16];
   tmem_ld16(s_addr, ra);
@@ -145,6 +151,8 @@ __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, in
       pk[i >> 1] = *reinterpret_cast<uint32_t*>(&q2);
     }
     uint8_t* sub = prow + (c >> 6) * (BQ * 128);
+    if (c == 0 && wait_h0 != 0) mbar_wait(BKV == 64 ? wait_full : wait_h0, wait_par);
+    if (c == 64 && wait_full != 0) mbar_wait(wait_full, wait_par);
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int chunk = (((c & 63) >> 3) + q) ^ (row & 7);
@@ -185,7 +193,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
   auto kv_empty = [&](int s) { return bar0 + 8u * (1 + KV_STAGES + s); };
   const uint32_t s_ready = bar0 + 8u * (1 + 2 * KV_STAGES);
   const uint32_t p_ready = s_ready + 8u;
-  const uint32_t pv_step = s_ready + 16u;  // one phase per key tile; waited on only by a rescale and at the end (never > 1 phase ahead)
+  const uint32_t pv_step = s_ready + 16u;  // one phase per key tile (never > 1 phase ahead)
+  const uint32_t pv_half = s_ready + 24u;  // one phase per key tile: the first 64-key sub-tile of P has been consumed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -200,6 +209,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
     mbar_init(s_ready, 1);
     mbar_init(p_ready, 4);
     mbar_init(pv_step, 1);
+    mbar_init(pv_half, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot_ptr)), TM_COLS);
@@ -258,6 +268,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
           // MN-major V: rows are keys (128 B = 64 dims each), 8-key groups 1024 B apart (SBO); K = 16 keys = 2048 B per step.
           const uint64_t bdesc = make_smem_desc(vbase + k * 2048);
           umma_f16(tmem_base + TM_PV0, adesc, bdesc, idesc_o, (j | k) != 0);  // O accumulates across key tiles
+          if (BKV == 128 && k == 3) umma_commit(pv_half);
         }
         umma_commit(pv_step);
         umma_commit(kv_empty(s));
@@ -305,10 +316,16 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
       } else if (__any_sync(0xffffffffu, fmaf(seen, scale_log2e, -ref) > 8.f)) {
         rescale(j, fmaxf(ref, seen * scale_log2e));
       }
+      // P_{j-1} V_{j-1} -- issued AFTER Q K_j^T, so S_j being ready says nothing about it -- must have finished reading a 64-key
+      // sub-tile of the (single) P buffer before this tile's probabilities overwrite it.  Round 1 relied on the tensor pipe
+      // staying ahead of the P stores; a second CTA's MMAs on the same pipe can delay it.  Round 2: the MMA warp commits after each
+      // half of P V, the softmax warps wait right before their first store into each sub-tile.
+      const uint32_t wh = (j > 0 && PIO_ATTN_WAIT_PV) ? pv_half : 0u, wf = (j > 0 && PIO_ATTN_WAIT_PV) ? pv_step : 0u;
+      const uint32_t wpar = (uint32_t)(j - 1) & 1u;
       float ls;
       for (;;) {
-        ls = mask ? softmax_pass<true, POLY, BKV>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax)
-                  : softmax_pass<false, POLY, BKV>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax);
+        ls = mask ? softmax_pass<true, POLY, BKV>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax, wh, wf, wpar)
+                  : softmax_pass<false, POLY, BKV>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax, wh, wf, wpar);
         // exponent headroom: a row whose tile max sits more than 2^64 above its reference redoes the tile
         if (!__any_sync(0xffffffffu, fmaf(tmax, scale_log2e, -ref) > 64.f)) break;
         rescale(j, fmaxf(ref, tmax * scale_log2e));
@@ -358,6 +375,223 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Round-2 kernel for long sequences: 64-key tiles with S and P DOUBLE-BUFFERED, separate K and V rings.
+//
+// In the kernel above one CTA's loop is a chain: softmax(j) -> P ready -> QK(j+1) issued -> S ready -> softmax(j+1); the
+// softmax warps idle while S = Q K^T of the next tile is produced (ncu r01d: their top stall is the wait for S), and K(j+1) can
+// only be fetched once PV(j-1) has released the shared K/V stage -- about one TMA latency before it is needed.  It also
+// re-uses its single P buffer as soon as S(j+1) is ready, although PV(j) -- issued AFTER QK(j+1) -- may still be reading it:
+// harmless only as long as PV(j) runs ahead of the first P stores of softmax(j+1), which a second CTA's MMAs on the same tensor
+// pipe can break (the run-to-run differences of profiles/r02ab).  Here:
+//   * S lives in two 64-column TMEM buffers: QK(j+2) is issued right after PV(j), two tiles ahead of the softmax that reads it,
+//     so the softmax warps go from tile to tile without waiting for the tensor pipe;
+//   * P lives in two shared-memory buffers; softmax(j) waits for PV(j-2) (mbarrier pv_done) before it overwrites one -- no race;
+//   * K and V have their own rings and barriers: a K stage is released by QK (not by the later PV), so K(j+3) is fetched
+//     three tiles ahead; one producer lane per ring;
+//   * 96 KB of shared memory and 256 TMEM columns (S0 | S1 | O | unused): two CTAs per SM as before.
+constexpr int DB_BKV = 64, DB_KST = 3;
+constexpr int DB_KB = DB_BKV * HD * 2;                     // 8 KB: one K (or V) tile
+constexpr int DB_PB = BQ * DB_BKV * 2;                     // 16 KB: one P buffer
+constexpr int DB_NBARS = 1 + 4 * DB_KST + 6;
+constexpr int DB_SMEM = Q_BYTES + 2 * DB_KST * DB_KB + 2 * DB_PB + DB_NBARS * 8 + 16;
+
+template <int POLY>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+vit_attention_db_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_kv,
+                        __nv_bfloat16* __restrict__ out, int N, int H, float scale_log2e) {
+  constexpr int BKV = DB_BKV, KST = DB_KST;
+  constexpr uint32_t TM_S = 0, TM_O = 2 * BKV, TM_COLS = 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if ((smem_base & 1023u) != 0) __trap();
+  const uint32_t sQ = smem_base;
+  const uint32_t sK = sQ + Q_BYTES;
+  const uint32_t sV = sK + KST * DB_KB;
+  const uint32_t sP = sV + KST * DB_KB;
+  uint8_t* sP_gen = smem_raw + Q_BYTES + 2 * KST * DB_KB;
+  const uint32_t bar0 = sP + 2 * DB_PB;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + Q_BYTES + 2 * KST * DB_KB + 2 * DB_PB + DB_NBARS * 8);
+  const uint32_t q_full = bar0;
+  auto k_full = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bar0 + 8u * (1 + KST + s); };
+  auto v_full = [&](int s) { return bar0 + 8u * (1 + 2 * KST + s); };
+  auto v_empty = [&](int s) { return bar0 + 8u * (1 + 3 * KST + s); };
+  auto s_ready = [&](int b) { return bar0 + 8u * (1 + 4 * KST + b); };
+  auto p_ready = [&](int b) { return bar0 + 8u * (3 + 4 * KST + b); };
+  auto pv_done = [&](int b) { return bar0 + 8u * (5 + 4 * KST + b); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int nt = (N + BKV - 1) / BKV;
+  const int row_base = b * N;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_qk) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(s_ready(i), 1); mbar_init(p_ready(i), 4); mbar_init(pv_done(i), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot_ptr)), TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producers: lane 0 the K ring (+ Q), lane 1 the V ring
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Q_BYTES);
+      tma_load_2d(sQ, &map_qk, q_full, h * HD, row_base + q0);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j % KST;
+        mbar_wait(k_empty(s), ((j / KST) & 1) ^ 1);
+        mbar_expect_tx(k_full(s), DB_KB);
+        tma_load_2d(sK + s * DB_KB, &map_kv, k_full(s), H * HD + h * HD, row_base + j * BKV);
+      }
+    } else if (lane == 1) {
+      for (int j = 0; j < nt; ++j) {
+        const int s = j % KST;
+        mbar_wait(v_empty(s), ((j / KST) & 1) ^ 1);
+        mbar_expect_tx(v_full(s), DB_KB);
+        tma_load_2d(sV + s * DB_KB, &map_kv, v_full(s), 2 * H * HD + h * HD, row_base + j * BKV);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc_s = make_idesc(BQ, BKV);
+    constexpr uint32_t idesc_o = make_idesc(BQ, HD) | (1u << 16);  // V as stored: MN-major B operand
+    auto issue_qk = [&](int j) {  // S[j & 1] = Q K_j^T
+      const int s = j % KST;
+      mbar_wait(k_full(s), (j / KST) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t adesc = make_smem_desc(sQ), bdesc = make_smem_desc(sK + s * DB_KB);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_f16(tmem_base + TM_S + (j & 1) * BKV, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(s_ready(j & 1));
+        umma_commit(k_empty(s));
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    if (nt > 1) issue_qk(1);
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % KST, pb = j & 1;
+      mbar_wait(p_ready(pb), (j >> 1) & 1);   // P_j is in shared memory and S_j has been read
+      mbar_wait(v_full(s), (j / KST) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t adesc = make_smem_desc(sP + pb * DB_PB) + 2 * k;
+          const uint64_t bdesc = make_smem_desc(sV + s * DB_KB + k * 2048);  // 16 keys = 2048 B per K step
+          umma_f16(tmem_base + TM_O, adesc, bdesc, idesc_o, (j | k) != 0);
+        }
+        umma_commit(pv_done(pb));
+        umma_commit(v_empty(s));
+      }
+      __syncwarp();
+      if (j + 2 < nt) issue_qk(j + 2);  // into the S buffer softmax(j) has just drained
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / output (warps 2..5)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t pv_addr = tmem_base + lane_addr + TM_O;
+    float ref = 0.f, l = 0.f, seen = -INFINITY, tmax = -INFINITY;
+    auto wait_pv = [&](int j) { mbar_wait(pv_done(j & 1), (j >> 1) & 1); };  // P_j V_j has landed in O (and P[j & 1] is free)
+    auto rescale = [&](int j, float new_ref) {
+      const float f = ex2_approx(ref - new_ref);
+      if (j > 0) {
+        wait_pv(j - 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < HD; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(pv_addr + c, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+          tmem_st16(pv_addr + c, r);
+        }
+        tmem_st_wait();
+      }
+      l *= f;
+      ref = new_ref;
+    };
+    for (int j = 0; j < nt; ++j) {
+      const int pb = j & 1;
+      const uint32_t s_addr = tmem_base + lane_addr + TM_S + pb * BKV;
+      uint8_t* prow = sP_gen + pb * DB_PB + row * 128;
+      mbar_wait(s_ready(pb), (j >> 1) & 1);
+      tc_fence_after();
+      const bool mask = (j + 1) * BKV > N;
+      const int kbase = j * BKV;
+      if (j == 0) {
+        ref = (mask ? row_max<true, BKV>(s_addr, kbase, N) : row_max<false, BKV>(s_addr, kbase, N)) * scale_log2e;
+      } else if (__any_sync(0xffffffffu, fmaf(seen, scale_log2e, -ref) > 8.f)) {
+        rescale(j, fmaxf(ref, seen * scale_log2e));
+      }
+      if (j >= 2) wait_pv(j - 2);  // the tensor core has finished reading this P buffer
+      float ls;
+      for (;;) {
+        ls = mask ? softmax_pass<true, POLY, BKV>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax)
+                  : softmax_pass<false, POLY, BKV>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax);
+        if (!__any_sync(0xffffffffu, fmaf(tmax, scale_log2e, -ref) > 64.f)) break;
+        rescale(j, fmaxf(ref, tmax * scale_log2e));
+      }
+      seen = fmaxf(seen, tmax);
+      l += ls;
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready(pb));
+    }
+    wait_pv(nt - 1);
+    tc_fence_after();
+    const float inv = 1.0f / l;
+    const int q = q0 + row;
+    __nv_bfloat16* dst = out + ((long long)(row_base + q)) * (H * HD) + h * HD;
+    uint32_t ra[16], rb[16];
+    auto emit = [&](const uint32_t (&r)[16], int c) {
+      if (q >= N) return;
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    };
+    tmem_ld16(pv_addr, ra);
+#pragma unroll
+    for (int c = 0; c < HD; c += 32) {
+      tmem_ld_wait();
+      tmem_ld16(pv_addr + c + 16, rb);
+      emit(ra, c);
+      tmem_ld_wait();
+      if (c + 32 < HD) tmem_ld16(pv_addr + c + 32, ra);
+      emit(rb, c + 16);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
 }  // namespace
 
 size_t vit_attention_tc_workspace(int B, int N, int H) {
@@ -373,6 +607,24 @@ int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int 
   PIO_TRY(make_map_2d(&mqk, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, BQ, HD));
   // tile choice by sequence length: fewer padded keys for short sequences (PIO_ATTN_BKV=64|128 overrides)
   static const int force_bkv = [] { const char* e = getenv("PIO_ATTN_BKV"); return e ? atoi(e) : 0; }();
+  // double-buffered kernel (round 2; measured SLOWER: 0.763 vs 0.666 ms at N = 1374, 0.284 vs 0.244 ms at N = 261, so off by
+  // default): PIO_ATTN_DB = 0 never (default), 1 long sequences only, 2 every sequence length
+  static const int db = [] { const char* e = getenv("PIO_ATTN_DB"); return e ? atoi(e) : 0; }();
+  if (!force_bkv && ((db == 1 && N > 640) || db == 2)) {
+    PIO_TRY(make_map_2d(&mkv, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, DB_BKV, HD));
+    dim3 grid(cdiv(N, BQ), H, B);
+    const float sl2 = 0.125f * 1.4426950408889634f;
+#define PIO_ATT_DB_LAUNCH(POLY)                                                                                                  \
+  do {                                                                                                                           \
+    static SmemAttrOnce once;                                                                                                    \
+    PIO_CUDA(once.ensure(vit_attention_db_kernel<POLY>, DB_SMEM));                                                                \
+    launch_pdl_k(PDL_KIND_ATTN, vit_attention_db_kernel<POLY>, grid, dim3(ATT_THREADS), DB_SMEM, st, mqk, mkv, (__nv_bfloat16*)out, N, H, sl2); \
+  } while (0)
+    if (poly == 0) PIO_ATT_DB_LAUNCH(0); else if (poly == 2) PIO_ATT_DB_LAUNCH(2); else PIO_ATT_DB_LAUNCH(3);
+#undef PIO_ATT_DB_LAUNCH
+    PIO_LAUNCHED();
+    return PIO_OK;
+  }
   const int bkv = force_bkv ? force_bkv : (N <= 640 ? 64 : 128);
   PIO_TRY(make_map_2d(&mkv, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, bkv, HD));
   dim3 grid(cdiv(N, BQ), H, B);
