@@ -360,7 +360,7 @@ template <> __device__ __forceinline__ void store2f<__nv_bfloat16>(__nv_bfloat16
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
 
-template <typename T>
+template <typename T, bool ANC>
 __global__ void __launch_bounds__(128) decode_attention_long_kernel(const T* __restrict__ qkv, T* __restrict__ kc, T* __restrict__ vc,
                                                                     T* __restrict__ out, int R, int H, int Tmax, int t, float scale,
                                                                     const int* __restrict__ anc) {
@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(128) decode_attention_long_kernel(const T* __r
     sc[c] = -INFINITY;
     arow[c] = r;
     if (j <= t) {
-      if (anc != nullptr && j < t) arow[c] = __ldg(anc + (long long)r * Tmax + j);
-      const T* kr = kc + (((long long)arow[c] * H + h) * Tmax + j) * HDIM;
+      if (ANC && j < t) arow[c] = __ldg(anc + (long long)r * Tmax + j);
+      const T* kr = ANC ? kc + (((long long)arow[c] * H + h) * Tmax + j) * HDIM : kbase + (long long)j * HDIM;
       float a = 0.f;
 #pragma unroll
       for (int d = 0; d < HDIM; d += 8) {
@@ -423,8 +423,12 @@ __global__ void __launch_bounds__(128) decode_attention_long_kernel(const T* __r
 #pragma unroll 4
     for (int jj = 0; jj < n; ++jj) {
       const float pj = __shfl_sync(0xffffffffu, sc[c], jj);
-      const int rj = __shfl_sync(0xffffffffu, arow[c], jj);
-      const float2 v2 = load2f<T>(vc + (((long long)rj * H + h) * Tmax + 32 * c + jj) * HDIM + lane * 2);
+      const T* vr = vbase + (long long)(32 * c + jj) * HDIM;
+      if (ANC) {
+        const int rj = __shfl_sync(0xffffffffu, arow[c], jj);
+        vr = vc + (((long long)rj * H + h) * Tmax + 32 * c + jj) * HDIM;
+      }
+      const float2 v2 = load2f<T>(vr + lane * 2);
       a0 = fmaf(pj, v2.x, a0);
       a1 = fmaf(pj, v2.y, a1);
     }
@@ -519,12 +523,12 @@ int decode_attention(const void* qkv, void* kc, void* vc, void* out, int dt, int
   if (H == 12) {  // GPT-2 small: 12 heads x 64
     PIO_CHECK(t < T && T <= 128, "decode attention: position %d outside cache of %d (max 128)", t, T);
     const int blocks = cdiv((long long)R * H, 4);
-    if (dt == PIO_DT_F32)
-      launch_pdl(decode_attention_long_kernel<float>, dim3(blocks), dim3(128), 0, st, (const float*)qkv, (float*)kc, (float*)vc, (float*)out,
-                 R, H, T, t, 0.125f, anc);
-    else
-      launch_pdl(decode_attention_long_kernel<__nv_bfloat16>, dim3(blocks), dim3(128), 0, st, (const __nv_bfloat16*)qkv, (__nv_bfloat16*)kc,
-                 (__nv_bfloat16*)vc, (__nv_bfloat16*)out, R, H, T, t, 0.125f, anc);
+#define PIO_DEC_ATT_LONG(TT, A)                                                                                                        \
+  launch_pdl(decode_attention_long_kernel<TT, A>, dim3(blocks), dim3(128), 0, st, (const TT*)qkv, (TT*)kc, (TT*)vc, (TT*)out, R, H, T, t, \
+             0.125f, anc)
+    if (dt == PIO_DT_F32) { if (anc) PIO_DEC_ATT_LONG(float, true); else PIO_DEC_ATT_LONG(float, false); }
+    else { if (anc) PIO_DEC_ATT_LONG(__nv_bfloat16, true); else PIO_DEC_ATT_LONG(__nv_bfloat16, false); }
+#undef PIO_DEC_ATT_LONG
     PIO_LAUNCHED();
     return PIO_OK;
   }

@@ -23,8 +23,13 @@ bool pdl_enabled() {
 // bench step -- while the decode / projection path, whose kernels are a few us long and whose repeatability tests are green,
 // keeps the overlap (+31 % at 32 rows without it).  PIO_PDL_OFF=<bit mask over PDL_KIND_*> serialises kinds everywhere.
 static thread_local int g_pdl_scope_off = 0;
-PdlScopeOff::PdlScopeOff() { ++g_pdl_scope_off; }
-PdlScopeOff::~PdlScopeOff() { --g_pdl_scope_off; }
+// PIO_VIT_PDL=1 makes the scope inert (A/B runs: the ViT forward with programmatic overlap again)
+static bool pdl_scope_inert() {
+  static const bool v = [] { const char* e = getenv("PIO_VIT_PDL"); return e && e[0] == '1'; }();
+  return v;
+}
+PdlScopeOff::PdlScopeOff() { if (!pdl_scope_inert()) ++g_pdl_scope_off; }
+PdlScopeOff::~PdlScopeOff() { if (!pdl_scope_inert()) --g_pdl_scope_off; }
 bool pdl_kind_enabled(int kind) {
   static const int off = [] { const char* e = getenv("PIO_PDL_OFF"); return e ? atoi(e) : 0; }();
   return g_pdl_scope_off == 0 && ((off >> kind) & 1) == 0;
