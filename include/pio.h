@@ -299,6 +299,11 @@ int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prom
 /* compute_scores of the ViECap path (entrypoint.py:164-177): mean negative log-likelihood of every right-padded token row  */
 /* ids int32 [R,n] (lens int32 [R] tokens each) under the language model = GPT2LMHeadModel(input_ids, labels=input_ids).loss  */
 /* of that sentence; the perplexity is exp() of it.  NaN for rows with fewer than two tokens.  n <= 128.                     */
+/* The same search, stopped once EVERY row has emitted one of the two end-of-sentence ids: the reference runs all `steps`         */
+/* positions for a batch and then keeps each row up to its first '.' (search.py:184-190), so the kept tokens are identical.     */
+/* Columns from *out_steps_run (host int, may be NULL) on are filled with eos0.  Synchronises the stream every eighth step.      */
+int pio_decode_greedy_prompt_eos(PioDecoder* h, const float* prompt, int R, int prompt_len, int steps, int eos0, int eos1, int* out_ids,
+                                 float* out_logprob_sum, int* out_steps_run, void* workspace, size_t workspace_bytes, void* stream);
 /* beam_search (viecap/search.py:193-285; the reference's default, entrypoint.py:77,139-143 -- one call per region there, all   */
 /* R regions x beam_width beams as one batch here): prompt fp32 [R,prompt_len,768]; at most `steps` new tokens (max_len);      */
 /* eos0 / eos1 = the two end-of-sentence token ids (search.py:218); temperature divides the logits (:232; <= 0 means 1).       */

@@ -126,6 +126,8 @@ SIGNATURES = {
     "pio_decoder_create_gpt2": (C.c_int, [C.POINTER(_fp), C.POINTER(PioGpt2Weights), C.c_int, _fp]),
     "pio_decode_prompt_workspace_bytes": (C.c_size_t, [_fp, C.c_int, C.c_int, C.c_int]),
     "pio_decode_greedy_prompt": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, _fp, _fp, _fp, C.c_size_t, _fp]),
+    "pio_decode_greedy_prompt_eos": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp, _fp, C.POINTER(C.c_int), _fp,
+                                               C.c_size_t, _fp]),
     "pio_decode_beam_workspace_bytes": (C.c_size_t, [_fp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pio_decode_beam_prompt": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _fp, _fp, _fp,
                                          C.POINTER(C.c_int), _fp, C.c_size_t, _fp]),

@@ -910,6 +910,28 @@ __global__ void beam_select_kernel(BeamState b, int cur, const float* __restrict
   atomicAdd(b.active + s, live);
 }
 
+// greedy search with an early exit: done[r] latches once row r has emitted an end-of-sentence token; live[s] counts the rows
+// still open after step s (the host reads it every few steps)
+__global__ void eos_track_kernel(const int* __restrict__ ids, int ids_ld, int s, int eos0, int eos1, int* __restrict__ done,
+                                 int* __restrict__ live, int R) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  int open = 0;
+  if (r < R) {
+    const int id = ids[(long long)r * ids_ld + s];
+    const int d = done[r] | (id == eos0 || id == eos1);
+    done[r] = d;
+    open = !d;
+  }
+  open = __reduce_add_sync(0xffffffffu, open);
+  if ((threadIdx.x & 31) == 0 && open) atomicAdd(live + s, open);
+}
+__global__ void fill_cols_kernel(int* __restrict__ ids, int ids_ld, int from, int R, int value) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = ids_ld - from;
+  if (i >= (long long)R * w) return;
+  ids[(i / w) * ids_ld + from + (i % w)] = value;
+}
+
 // search.py:278-283: length-normalised scores, beams best first (equal scores keep their beam order)
 __global__ void beam_finish_kernel(BeamState b, int cur, int R, int W, int steps, int n_done, int* __restrict__ out_ids,
                                    int* __restrict__ out_len, float* __restrict__ out_score) {
@@ -1039,17 +1061,44 @@ bool prompt_prefill_batched(const PioDecoder* h, int prompt_len) {
 }
 }  // namespace
 
+namespace {
+size_t prompt_staging_bytes(int R, bool batched) { return pio::align_up(batched ? (size_t)R * pio::gD * 4 : 0, 256); }
+size_t prompt_tail_elems(const PioDecoder* h, int R, bool batched) {
+  const size_t e = h->act_dt == PIO_DT_F32 ? 4 : 2;
+  return (prompt_staging_bytes(R, batched) + ((size_t)R + 128) * sizeof(int) + e - 1) / e;
+}
+}  // namespace
+
 size_t pio_decode_prompt_workspace_bytes(const PioDecoder* h, int R, int prompt_len, int steps) {
   const bool batched = prompt_prefill_batched(h, prompt_len);
-  // tail: fp32 [R,768] staging row for the last prompt position (prefill) 
-  return decode_ws(h, nullptr, R, prompt_len + steps - 1, batched ? (size_t)R * pio::gD * 2 : 0, batched ? (size_t)R * prompt_len : 0).total;
+  // tail: fp32 [R,768] staging row for the last prompt position (prefill), then the early-exit flags ([R] done + [128] live counters)
+  return decode_ws(h, nullptr, R, prompt_len + steps - 1, prompt_tail_elems(h, R, batched), batched ? (size_t)R * prompt_len : 0).total;
 }
 
 // Greedy continuation of a prompt of P input embeddings per row (ViECap: soft + hard prompt; viecap/search.py:108-191).
 // The prompt is consumed one position at a time through the same single-position blocks as the generation steps.
+static int decode_greedy_prompt_impl(PioDecoder* h, const float* prompt, int R, int prompt_len, int steps, int eos0, int eos1,
+                                     int* out_ids, float* out_logprob_sum, int* out_steps_run, void* workspace, size_t workspace_bytes,
+                                     void* stream);
 int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prompt_len, int steps, int* out_ids,
                              float* out_logprob_sum, void* workspace, size_t workspace_bytes, void* stream) {
+  return decode_greedy_prompt_impl(h, prompt, R, prompt_len, steps, -1, -1, out_ids, out_logprob_sum, nullptr, workspace, workspace_bytes,
+                                   stream);
+}
+// The same search, stopped once EVERY row has emitted an end-of-sentence token: the reference runs all `steps` positions for a batch
+// (search.py:173-176 exits early only at batch 1) and then cuts every row after its first '.' (:184-190), so the tokens it keeps
+// are the same.  Columns from *out_steps_run on are filled with eos0.  The stream is synchronised every eighth step (one 4-byte
+// read-back).  With out_logprob_sum the search runs to the end (the sum covers every step, decap.py:157-160).
+int pio_decode_greedy_prompt_eos(PioDecoder* h, const float* prompt, int R, int prompt_len, int steps, int eos0, int eos1, int* out_ids,
+                                 float* out_logprob_sum, int* out_steps_run, void* workspace, size_t workspace_bytes, void* stream) {
+  return decode_greedy_prompt_impl(h, prompt, R, prompt_len, steps, eos0, eos1, out_ids, out_logprob_sum, out_steps_run, workspace,
+                                   workspace_bytes, stream);
+}
+static int decode_greedy_prompt_impl(PioDecoder* h, const float* prompt, int R, int prompt_len, int steps, int eos0, int eos1,
+                                     int* out_ids, float* out_logprob_sum, int* out_steps_run, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
   using namespace pio;
+  if (out_steps_run) *out_steps_run = 0;
   if (R == 0) return PIO_OK;
   PIO_CHECK(h && prompt && out_ids && workspace, "decode_greedy_prompt: null argument");
   const int T = prompt_len + steps - 1;
@@ -1059,7 +1108,7 @@ int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prom
   PIO_CHECK((((uintptr_t)workspace) & 1023) == 0, "decode_greedy_prompt: workspace must be 1024-byte aligned");
   cudaStream_t st = as_stream(stream);
   const bool batched = prompt_prefill_batched(h, prompt_len);
-  const DecodeWs w = decode_ws(h, (char*)workspace, R, T, batched ? (size_t)R * gD * 2 : 0, batched ? (size_t)R * prompt_len : 0);
+  const DecodeWs w = decode_ws(h, (char*)workspace, R, T, prompt_tail_elems(h, R, batched), batched ? (size_t)R * prompt_len : 0);
   if (out_logprob_sum) PIO_CUDA(cudaMemsetAsync(out_logprob_sum, 0, (size_t)R * 4, st));
   if (batched) {
     // prefill (search.py:150-153): all prompt positions of all rows in one pass, M = R * prompt_len rows per GEMM
@@ -1092,9 +1141,30 @@ int pio_decode_greedy_prompt(PioDecoder* h, const float* prompt, int R, int prom
   }
   // generation: pick(0) on the last prompt position's residual stream, then embed -> blocks -> pick per new position --
   // one persistent kernel at small batch (decode_fused_sm100.cu)
+  if (out_steps_run) *out_steps_run = steps;
   if (decode_fused_eligible(h, R, out_logprob_sum != nullptr)) return decode_fused(h, w, R, T, steps, prompt_len - 1, true, out_ids, st);
+  const bool early = eos0 >= 0 && out_logprob_sum == nullptr && steps > 8;
+  int* done = (int*)((char*)w.pfx + prompt_staging_bytes(R, batched));  // [R] flags, then [steps <= 128] counters
+  int* live = done + R;
+  if (early) PIO_CUDA(cudaMemsetAsync(done, 0, (size_t)(R + steps) * sizeof(int), st));
   for (int s = 0; s < steps; ++s) {
     PIO_TRY(decode_pick(h, w, R, out_ids, steps, s, out_logprob_sum, st));
+    if (early) {
+      eos_track_kernel<<<cdiv(R, 128), 128, 0, st>>>(out_ids, steps, s, eos0, eos1, done, live, R);
+      PIO_LAUNCHED();
+      if ((s & 7) == 7 && s + 1 < steps) {
+        int open = 0;
+        PIO_CUDA(cudaMemcpyAsync(&open, live + s, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PIO_CUDA(cudaStreamSynchronize(st));
+        if (open == 0) {
+          const long long n = (long long)R * (steps - s - 1);
+          fill_cols_kernel<<<cdiv(n, 256), 256, 0, st>>>(out_ids, steps, s + 1, R, eos0);
+          PIO_LAUNCHED();
+          if (out_steps_run) *out_steps_run = s + 1;
+          return PIO_OK;
+        }
+      }
+    }
     if (s + 1 < steps) {
       launch_pdl(embed_kernel, dim3(cdiv((long long)R * 32, 256)), dim3(256), 0, st, h->wte32, h->wpe, (const int*)out_ids, steps, s,
                  prompt_len + s, w.x, R, gD);

@@ -606,8 +606,10 @@ class Gpt2Decoder:
             L._lib.pio_decoder_destroy(h)
             self._h = None
 
-    def decode(self, prompt: torch.Tensor, steps: int = 64, compute_scores: bool = False):
-        """prompt fp32 [R,P,768] input embeddings -> int32 ids [R,steps] (+ sum of log-probs [R])."""
+    def decode(self, prompt: torch.Tensor, steps: int = 64, compute_scores: bool = False, eos: Optional[Sequence[int]] = None):
+        """prompt fp32 [R,P,768] input embeddings -> int32 ids [R,steps] (+ sum of log-probs [R]).  With ``eos`` (two token ids) the
+        search stops once every row has emitted one of them (the columns after that are filled with ``eos[0]``; the tokens up to each
+        row's first end of sentence -- all the reference keeps, search.py:184-190 -- are unchanged); ``self.steps_run`` = steps executed."""
         _need_cuda(prompt)
         prompt = prompt.float().contiguous()
         R, P, D = prompt.shape
@@ -616,8 +618,15 @@ class Gpt2Decoder:
         lp = torch.empty(R, dtype=torch.float32, device=prompt.device) if compute_scores else None
         nbytes = L.lib().pio_decode_prompt_workspace_bytes(self._h, R, P, steps)
         ws = workspace(nbytes, prompt.device, "decode_prompt")
-        L.check(L.lib().pio_decode_greedy_prompt(self._h, prompt.data_ptr(), R, P, steps, ids.data_ptr(), _ptr(lp),
-                                                 ws.data_ptr(), nbytes, _stream()))
+        if eos is None:
+            L.check(L.lib().pio_decode_greedy_prompt(self._h, prompt.data_ptr(), R, P, steps, ids.data_ptr(), _ptr(lp),
+                                                     ws.data_ptr(), nbytes, _stream()))
+            self.steps_run = steps
+        else:
+            ran = C.c_int(0)
+            L.check(L.lib().pio_decode_greedy_prompt_eos(self._h, prompt.data_ptr(), R, P, steps, int(eos[0]), int(eos[1]), ids.data_ptr(),
+                                                         _ptr(lp), C.byref(ran), ws.data_ptr(), nbytes, _stream()))
+            self.steps_run = ran.value
         return (ids, lp) if compute_scores else ids
 
     def beam_search(self, prompt: torch.Tensor, eos: Sequence[int], beam_width: int = 5, steps: int = 64, temperature: float = 1.0):

@@ -246,7 +246,7 @@ class VieCap:
         keeps ``tokens[:length]`` of that beam (search.py:280); here the positions from ``length`` on are overwritten with the
         end-of-sentence id, so that ``cut`` (the same rule greedy search uses) yields exactly those ``length`` tokens."""
         if self.args["using_greedy_search"]:
-            return self.gpt.decode(prompt, MAX_LEN)
+            return self.gpt.decode(prompt, MAX_LEN, eos=self.eos)  # stops once every row has ended; `cut` keeps the same tokens
         ids, lens, _ = self.gpt.beam_search(prompt, self.eos, self.beam_width, MAX_LEN)
         best, n = ids[:, 0], lens[:, 0:1]
         pos = torch.arange(MAX_LEN, device=best.device, dtype=torch.int32)[None, :]

@@ -409,3 +409,26 @@ def test_viecap_forward_with_beam_search(dev, ops, weights, golden):
         toks, sl, avg = ov.beam_search_ids(ws, emb[r:r + 1], eos, 5, ov.MAX_LEN)
         want.append(tok.decode(ov.beam_sentences(toks, sl, avg)[0]))
     assert got == want, (got, want)
+
+
+def test_greedy_search_early_exit_keeps_the_sentences(dev, ops):
+    """pio_decode_greedy_prompt_eos: the search stops once every row has emitted '.' / ' .'; the reference runs all 64 positions for a
+    batch and cuts afterwards (search.py:184-190) -- the kept tokens must be identical, in both arithmetic modes, on the
+    kernel-per-op path (40 rows) and on the persistent-kernel path (8 rows: runs to the end, same sentences)."""
+    tok = ov.ToyTokenizer()
+    eos = [tok.encode(e)[-1] for e in (".", " .")]
+    w = ov.stopping_weights(ov.make_weights(), eos)
+    g = torch.Generator().manual_seed(77)
+    for mode in ("fp32", "bf16"):
+        dec = ops.Gpt2Decoder(w, dev, mode)
+        for R in (40, 8):
+            prompts = (torch.randn(R, 14, 768, generator=g) * 0.3).to(dev)
+            full = dec.decode(prompts, 48).cpu().tolist()
+            early = dec.decode(prompts, 48, eos=eos).cpu().tolist()
+            ran = dec.steps_run
+            cut_full, cut_early = [ov.cut_sentence(r, eos) for r in full], [ov.cut_sentence(r, eos) for r in early]
+            assert cut_full == cut_early
+            assert max(len(c) for c in cut_full) < 48        # every row ends: the early exit has something to skip
+            if R == 40:
+                assert ran < 48 and ran % 8 == 0 and ran >= max(len(c) for c in cut_full)
+                assert all(t == eos[0] for r in early for t in r[ran:])
