@@ -625,7 +625,10 @@ int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int 
     PIO_LAUNCHED();
     return PIO_OK;
   }
-  const int bkv = force_bkv ? force_bkv : (N <= 640 ? 64 : 128);
+  // Round 1 dispatched by sequence length (N <= 640 -> 64-key tiles).  With the P-buffer race closed the 128-key kernel pays for
+  // its waits (0.666 -> 0.717 ms at B = 64, N = 1374) and the 64-key kernel with three CTAs per SM is the faster one at every
+  // length measured (0.698 ms there; profiles/r02be_attention_variants.txt): 64-key tiles everywhere, 128 only when forced.
+  const int bkv = force_bkv ? force_bkv : 64;
   PIO_TRY(make_map_2d(&mkv, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, bkv, HD));
   dim3 grid(cdiv(N, BQ), H, B);
   const float scale_log2e = 0.125f * 1.4426950408889634f;
