@@ -108,19 +108,23 @@ def prefix_embed(w, feats: torch.Tensor) -> torch.Tensor:
 
 @torch.no_grad()
 def decode_greedy(w, feats: torch.Tensor, compute_scores: bool = False, use_cache: bool = True,
-                  steps: int = ENTRY_LENGTH):
+                  steps: int = ENTRY_LENGTH, return_margin: bool = False):
     """decap.py:116-160.  30 fixed steps, no EOS early exit; next token = argmax of the softmax
     PROBABILITIES of the last position (first index wins ties, :136,141); its wte row is appended.
 
     ``use_cache=False`` re-runs the whole growing sequence every step exactly like the reference
     (465 token-positions per region, lm-head applied to the last one only here -- the other
     positions' logits are discarded by the reference, :133); ``use_cache=True`` is the same
-    arithmetic with a KV cache.  Returns tokens [R,30] int64 (and scores [R] = exp(sum log p))."""
+    arithmetic with a KV cache.  Returns tokens [R,30] int64 (and scores [R] = exp(sum log p)).
+    ``return_margin`` (instead of scores) also returns, per step, the gap between the best and the second-best LOGIT [R,steps]
+    and the standard deviation of the logits over the vocabulary [R,steps] -- tests use them to tell a near-tie that reduced
+    precision may flip from a real mismatch."""
     wte = w["decoder.transformer.wte.weight"]
     R = feats.shape[0]
     emb = prefix_embed(w, feats).reshape(R, 1, -1)
     tokens = []
     logps = []
+    margins, spreads = [], []
     kv = [None] * N_LAYER if use_cache else None
     seq = emb
     for t in range(steps):
@@ -131,11 +135,17 @@ def decode_greedy(w, feats: torch.Tensor, compute_scores: bool = False, use_cach
         logits = h @ wte.T
         probs = F.softmax(logits, -1)
         nxt = torch.argmax(probs, -1)
+        if return_margin:
+            top2 = logits.topk(2, dim=-1).values
+            margins.append(top2[:, 0] - top2[:, 1])
+            spreads.append(logits.std(dim=-1))
         if compute_scores:
             logps.append(torch.log(probs).gather(1, nxt[:, None])[:, 0])
         tokens.append(nxt)
         seq = torch.cat([seq, wte[nxt][:, None, :]], dim=1)
     tokens = torch.stack(tokens, dim=1)
+    if return_margin:
+        return tokens, torch.stack(margins, dim=1), torch.stack(spreads, dim=1)
     if compute_scores:
         return tokens, torch.exp(torch.stack(logps, dim=1).sum(dim=-1))
     return tokens

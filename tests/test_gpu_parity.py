@@ -462,6 +462,31 @@ def test_decode_bf16_runs_and_mostly_agrees(dev, ops):
     assert first >= 0.8, first  # bf16 flips near-ties; reported, not a parity claim
 
 
+def test_decode_bf16_differs_from_the_oracle_only_at_near_ties(dev, ops):
+    """What the bf16 mode's caption differences ARE: with random-init weights the logits are nearly flat, and
+    every FIRST position at which a bf16 caption leaves the fp32 oracle's is one where the oracle's best and second-best logit are
+    within a few percent of one standard deviation of the logits (measured on B200: <= 1.6 %, the lowest ~1.5 % of all positions;
+    the median position has a gap of 83 %).  Rows whose 30 positions all have a clear gap decode identically."""
+    w = o_decap.make_weights(seed=1234)
+    R = 256
+    feats = torch.randn(R, 768, generator=torch.Generator().manual_seed(32))
+    feats = feats / feats.norm(dim=-1, keepdim=True)
+    ref, margin, spread = o_decap.decode_greedy(w, feats, use_cache=True, return_margin=True)
+    rel = margin / spread
+    ids = ops.Decoder(w, dev, "bf16").decode(feats.to(dev), 30).cpu().long()
+    differing = 0
+    for r in range(R):
+        ne = (ids[r] != ref[r]).nonzero()
+        if len(ne):
+            differing += 1
+            t = int(ne[0])
+            assert rel[r, t] < 0.04, (r, t, rel[r, t].item())      # a near-tie, never a clear arg-max
+    clear = rel.min(dim=1).values >= 0.04                        # rows without any near-tie
+    assert clear.sum() >= R // 4
+    assert torch.equal(ids[clear], ref[clear])
+    assert differing <= R // 5                                   # ~9 % on B200
+
+
 # ----------------------------------------------------------------------------------------- whole forward
 def _model(dev, precision, with_bank, golden_bank=True):
     from patchioner_b200 import Patchioner

@@ -1,0 +1,21 @@
+import sys, torch
+sys.path.insert(0, '/root/repo')
+from oracle import decap as o_decap
+from patchioner_b200 import ops
+dev = torch.device('cuda:0')
+w = o_decap.make_weights(seed=1234)
+R = 256
+feats = torch.randn(R, 768, generator=torch.Generator().manual_seed(32))
+feats = feats / feats.norm(dim=-1, keepdim=True)
+ref, margin, spread = o_decap.decode_greedy(w, feats, use_cache=True, return_margin=True)
+for mode in ("bf16", "fp32"):
+    ids = ops.Decoder(w, dev, mode).decode(feats.to(dev), 30).cpu().long()
+    div = []
+    for r in range(R):
+        ne = (ids[r] != ref[r]).nonzero()
+        if len(ne):
+            t = int(ne[0])
+            div.append((margin[r, t] / spread[r, t]).item())
+    rel = (margin / spread).flatten()
+    print(mode, "rows differing", len(div), "of", R, "| margin/spread at first divergence: max %.4g median %.4g" % (max(div) if div else 0, sorted(div)[len(div)//2] if div else 0),
+          "| all positions: median %.4g, 5%% quantile %.4g, 1%% quantile %.4g" % (rel.median().item(), rel.quantile(0.05).item(), rel.quantile(0.01).item()))
