@@ -123,7 +123,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
 
 // wait_h0 / wait_full (0 = no wait): mbarriers (parity wait_par) that say the previous tile's P V has finished reading the first
 // 64-key sub-tile / the whole P buffer -- waited on right before the first store into each sub-tile, i.e. as late as possible.
-template <bool MASK, int POLY, int BKV>
+template <bool MASK, int POLY, int BKV, bool PACKED = false>
 __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, int row, int kbase, int N, float scale_log2e,
                                               float ref, float& tmax, uint32_t wait_h0 = 0, uint32_t wait_full = 0,
                                               uint32_t wait_par = 0) {
@@ -131,10 +131,32 @@ __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, in
   uint32_t ra[16], rb[16];
   tmem_ld16(s_addr, ra);
   // 16 keys = 2 chunks of 16 bytes: sub-tile (c / 64), chunk index ((c % 64) / 8 + q) ^ (row % 8)
+  const uint64_t sc2 = pack2(scale_log2e, scale_log2e), nref2 = pack2(-ref, -ref);
+  uint64_t s01 = pack2(0.f, 0.f);
   auto take = [&](const uint32_t (&r)[16], int c) {
     uint32_t pk[8];
+    if constexpr (PACKED) {  // two elements per FFMA2 / FADD2: the 64-key kernel (three CTAs per SM) is short of issue slots
 #pragma unroll
-    for (int i = 0; i < 16; i += 2) {
+      for (int i = 0; i < 16; i += 2) {
+        const float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
+        float x0, x1;
+        unpack2(fma2(pack2(v0, v1), sc2, nref2), x0, x1);
+        float p0 = ex2_approx(x0);
+        float p1 = (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) ? exp2_poly(x1) : ex2_approx(x1);
+        float m0 = v0, m1 = v1;
+        if (MASK) {
+          if (kbase + c + i >= N) { p0 = 0.f; m0 = -INFINITY; }
+          if (kbase + c + i + 1 >= N) { p1 = 0.f; m1 = -INFINITY; }
+        }
+        mx0 = fmaxf(mx0, m0);
+        mx1 = fmaxf(mx1, m1);
+        s01 = add2(s01, pack2(p0, p1));
+        __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
+        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&q2);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < (PACKED ? 0 : 16); i += 2) {
       float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
       const float x0 = fmaf(v0, scale_log2e, -ref), x1 = fmaf(v1, scale_log2e, -ref);
       float p0 = ex2_approx(x0);
@@ -169,10 +191,11 @@ __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, in
     take(rb, c + 16);
   }
   tmax = fmaxf(mx0, mx1);
+  if constexpr (PACKED) unpack2(s01, s0, s1);
   return s0 + s1;
 }
 
-template <int POLY, int BKV>
+template <int POLY, int BKV, bool PACKED = false>
 __global__ void __launch_bounds__(ATT_THREADS, AttCfg<BKV>::CTAS_PER_SM)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_kv,
                         __nv_bfloat16* __restrict__ out, int N, int H, float scale_log2e) {
@@ -324,8 +347,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid
       const uint32_t wpar = (uint32_t)(j - 1) & 1u;
       float ls;
       for (;;) {
-        ls = mask ? softmax_pass<true, POLY, BKV>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax, wh, wf, wpar)
-                  : softmax_pass<false, POLY, BKV>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax, wh, wf, wpar);
+        ls = mask ? softmax_pass<true, POLY, BKV, PACKED>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax, wh, wf, wpar)
+                  : softmax_pass<false, POLY, BKV, PACKED>(s_addr, prow, row, kbase, N, scale_log2e, ref, tmax, wh, wf, wpar);
         // exponent headroom: a row whose tile max sits more than 2^64 above its reference redoes the tile
         if (!__any_sync(0xffffffffu, fmaf(tmax, scale_log2e, -ref) > 64.f)) break;
         rescale(j, fmaxf(ref, tmax * scale_log2e));
@@ -602,7 +625,11 @@ size_t vit_attention_tc_workspace(int B, int N, int H) {
 // qkv bf16 [B,N,3*H*64] -> out bf16 [B,N,H*64]; vt_ws holds the transposed V copy.
 int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int H, cudaStream_t st) {
   (void)vt_ws;
-  static const int poly = [] { const char* e = getenv("PIO_ATTN_POLY"); return e ? atoi(e) : 3; }();  // 0 = every exponential on the SFU; 3 = one in six on the FMA pipe (measured best)
+  // PIO_ATTN_POLY: 0 = every exponential on the SFU; n = one in 2n on the FMA pipe.  Unset: 3 (one in six).  Same-box sweep of the
+  // 64-key kernel at B = 64, N = 1374 (profiles/r02be_attention_variants.txt): scalar arithmetic 0.693 / 0.712 / 0.701 ms at
+  // POLY = 0 / 2 / 3; with x = S c - ref and the row sums on two elements per instruction (PIO_ATTN_PACKED, the default)
+  // 0.706 / 0.681 / 0.674 ms -- the 64-key kernel with three CTAs per SM is short of issue slots, not of SFU throughput
+  static const int poly_env = [] { const char* e = getenv("PIO_ATTN_POLY"); return e ? atoi(e) : -1; }();
   CUtensorMap mqk, mkv;
   PIO_TRY(make_map_2d(&mqk, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, BQ, HD));
   // tile choice by sequence length: fewer padded keys for short sequences (PIO_ATTN_BKV=64|128 overrides)
@@ -620,7 +647,8 @@ int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int 
     PIO_CUDA(once.ensure(vit_attention_db_kernel<POLY>, DB_SMEM));                                                                \
     launch_pdl_k(PDL_KIND_ATTN, vit_attention_db_kernel<POLY>, grid, dim3(ATT_THREADS), DB_SMEM, st, mqk, mkv, (__nv_bfloat16*)out, N, H, sl2); \
   } while (0)
-    if (poly == 0) PIO_ATT_DB_LAUNCH(0); else if (poly == 2) PIO_ATT_DB_LAUNCH(2); else PIO_ATT_DB_LAUNCH(3);
+    const int dbpoly = poly_env >= 0 ? poly_env : 0;
+    if (dbpoly == 0) PIO_ATT_DB_LAUNCH(0); else if (dbpoly == 2) PIO_ATT_DB_LAUNCH(2); else PIO_ATT_DB_LAUNCH(3);
 #undef PIO_ATT_DB_LAUNCH
     PIO_LAUNCHED();
     return PIO_OK;
@@ -629,19 +657,26 @@ int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int 
   // its waits (0.666 -> 0.717 ms at B = 64, N = 1374) and the 64-key kernel with three CTAs per SM is the faster one at every
   // length measured (0.698 ms there; profiles/r02be_attention_variants.txt): 64-key tiles everywhere, 128 only when forced.
   const int bkv = force_bkv ? force_bkv : 64;
+  const int poly = poly_env >= 0 ? poly_env : 3;
   PIO_TRY(make_map_2d(&mkv, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, bkv, HD));
   dim3 grid(cdiv(N, BQ), H, B);
   const float scale_log2e = 0.125f * 1.4426950408889634f;
-#define PIO_ATT_LAUNCH(POLY, BKVV)                                                                                                \
+#define PIO_ATT_LAUNCH3(POLY, BKVV, PK)                                                                                           \
   do {                                                                                                                            \
     static SmemAttrOnce once;                                                                                                     \
-    PIO_CUDA(once.ensure(vit_attention_tc_kernel<POLY, BKVV>, AttCfg<BKVV>::SMEM));                                                \
-    launch_pdl_k(PDL_KIND_ATTN, vit_attention_tc_kernel<POLY, BKVV>, grid, dim3(ATT_THREADS), AttCfg<BKVV>::SMEM, st, mqk, mkv, (__nv_bfloat16*)out, N, H, \
+    PIO_CUDA(once.ensure(vit_attention_tc_kernel<POLY, BKVV, PK>, AttCfg<BKVV>::SMEM));                                            \
+    launch_pdl_k(PDL_KIND_ATTN, vit_attention_tc_kernel<POLY, BKVV, PK>, grid, dim3(ATT_THREADS), AttCfg<BKVV>::SMEM, st, mqk, mkv, (__nv_bfloat16*)out, N, H, \
                scale_log2e);                                                                                                      \
   } while (0)
-  if (bkv == 64) { if (poly == 0) PIO_ATT_LAUNCH(0, 64); else PIO_ATT_LAUNCH(3, 64); }
+#define PIO_ATT_LAUNCH(POLY, BKVV) PIO_ATT_LAUNCH3(POLY, BKVV, false)
+  // PIO_ATTN_PACKED (64-key kernel): x = S c - ref and the row sums on two elements per instruction (fma / add .f32x2)
+  static const int packed_env = [] { const char* e = getenv("PIO_ATTN_PACKED"); return e ? atoi(e) : -1; }();
+  const bool packed = packed_env >= 0 ? packed_env != 0 : true;
+  if (bkv == 64 && packed) { if (poly == 0) PIO_ATT_LAUNCH3(0, 64, true); else if (poly == 2) PIO_ATT_LAUNCH3(2, 64, true); else PIO_ATT_LAUNCH3(3, 64, true); }
+  else if (bkv == 64) { if (poly == 0) PIO_ATT_LAUNCH(0, 64); else if (poly == 2) PIO_ATT_LAUNCH(2, 64); else PIO_ATT_LAUNCH(3, 64); }
   else           { if (poly == 0) PIO_ATT_LAUNCH(0, 128); else if (poly == 2) PIO_ATT_LAUNCH(2, 128); else PIO_ATT_LAUNCH(3, 128); }
 #undef PIO_ATT_LAUNCH
+#undef PIO_ATT_LAUNCH3
   PIO_LAUNCHED();
   return PIO_OK;
 }

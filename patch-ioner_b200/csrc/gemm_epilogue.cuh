@@ -136,22 +136,7 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 // The same formula on TWO elements per instruction (fma.rn.f32x2 / mul.rn.f32x2 -> FFMA2 / FMUL2): the GELU epilogue issues
 // 12 packed + 6 scalar instructions per pair instead of 2 x 17 -- the epilogue warps (two per scheduler) are the critical path of
 // fc1, not the tensor pipe (B200: fc1 + GELU 1035 -> 1163 TFLOP/s, profiles/r02ap_gemm_probe_gelu_f32x2.txt).
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
+// pack2 / unpack2 / fma2 / mul2 / add2: tc_ptx.cuh
 __device__ __forceinline__ uint64_t gelu_erf_fast2(uint64_t x) {
   // coefficients of 7.1.28 times 2^(1/16): the sixteenth power comes out doubled, its reciprocal is r / 2; with nax = -|x|
   // gelu = max(x, 0) + nax (r / 2): one packed multiply less.  |gelu error| <= 7.1e-7 in fp32 arithmetic over [-14, 14].
