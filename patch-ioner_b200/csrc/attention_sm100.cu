@@ -123,6 +123,23 @@ __device__ __forceinline__ float exp2_poly(float x) {
 
 // wait_h0 / wait_full (0 = no wait): mbarriers (parity wait_par) that say the previous tile's P V has finished reading the first
 // 64-key sub-tile / the whole P buffer -- waited on right before the first store into each sub-tile, i.e. as late as possible.
+// the same polynomial on a PAIR of exponents, two lanes per instruction: 10 instructions per pair instead of 2 x 8
+__device__ __forceinline__ uint64_t exp2_poly2(float x0, float x1) {
+  const uint64_t x = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t t = add2(x, pack2(12582912.0f, 12582912.0f));
+  const uint64_t u = add2(t, pack2(-12582912.0f, -12582912.0f));
+  const uint64_t f = fma2(u, pack2(-1.0f, -1.0f), x);
+  uint64_t p = fma2(pack2(0.05517132f, 0.05517132f), f, pack2(0.24261054f, 0.24261054f));
+  p = fma2(p, f, pack2(0.69326097f, 0.69326097f));
+  p = fma2(p, f, pack2(0.99992812f, 0.99992812f));
+  float t0, t1, p0, p1;
+  unpack2(t, t0, t1);
+  unpack2(p, p0, p1);
+  return pack2(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)), __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+}
+
+// POLY: 0 = every exponential on the SFU; 1..9 = the second element of every POLY-th pair on the FMA pipe (one in 2 POLY);
+// 10 + n (packed pass only) = BOTH elements of every n-th pair, evaluated two lanes per instruction (one in n)
 template <bool MASK, int POLY, int BKV, bool PACKED = false>
 __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, int row, int kbase, int N, float scale_log2e,
                                               float ref, float& tmax, uint32_t wait_h0 = 0, uint32_t wait_full = 0,
@@ -141,8 +158,14 @@ __device__ __forceinline__ float softmax_pass(uint32_t s_addr, uint8_t* prow, in
         const float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
         float x0, x1;
         unpack2(fma2(pack2(v0, v1), sc2, nref2), x0, x1);
-        float p0 = ex2_approx(x0);
-        float p1 = (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) ? exp2_poly(x1) : ex2_approx(x1);
+        float p0, p1;
+        constexpr int PN = (POLY >= 10 && POLY < 100) ? POLY - 10 : 1;
+        if ((POLY >= 100 && (((POLY - 100) >> (i >> 1)) & 1)) || (POLY >= 10 && POLY < 100 && ((i >> 1) % PN) == PN - 1)) {  // 100 + mask: pair k of each 16-element chunk if bit k
+          unpack2(exp2_poly2(x0, x1), p0, p1);
+        } else {
+          p0 = ex2_approx(x0);
+          p1 = (POLY > 0 && POLY < 10 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) ? exp2_poly(x1) : ex2_approx(x1);
+        }
         float m0 = v0, m1 = v1;
         if (MASK) {
           if (kbase + c + i >= N) { p0 = 0.f; m0 = -INFINITY; }
@@ -625,7 +648,10 @@ size_t vit_attention_tc_workspace(int B, int N, int H) {
 // qkv bf16 [B,N,3*H*64] -> out bf16 [B,N,H*64]; vt_ws holds the transposed V copy.
 int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int H, cudaStream_t st) {
   (void)vt_ws;
-  // PIO_ATTN_POLY: 0 = every exponential on the SFU; n = one in 2n on the FMA pipe.  Unset: 3 (one in six).  Same-box sweep of the
+  // PIO_ATTN_POLY: 0 = every exponential on the SFU; n < 10 = one in 2n on the FMA pipe; 10 + n = both elements of every n-th pair
+  // by the two-lane polynomial; 100 + mask = the pairs of each 16-element chunk whose bit is set.  Unset: 18 for the 64-key kernel
+  // (the LAST pair of every chunk: 0.648 ms against 0.674 for one-in-six scalar polynomials and 0.705 for none; masks 0xC0 0.646,
+  // 0x81 0.653, two spread pairs 0.66 -- profiles/r02bh_attention_pair_poly.txt), 3 for the 128-key kernel.  Same-box sweep of the
   // 64-key kernel at B = 64, N = 1374 (profiles/r02be_attention_variants.txt): scalar arithmetic 0.693 / 0.712 / 0.701 ms at
   // POLY = 0 / 2 / 3; with x = S c - ref and the row sums on two elements per instruction (PIO_ATTN_PACKED, the default)
   // 0.706 / 0.681 / 0.674 ms -- the 64-key kernel with three CTAs per SM is short of issue slots, not of SFU throughput
@@ -657,7 +683,7 @@ int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int 
   // its waits (0.666 -> 0.717 ms at B = 64, N = 1374) and the 64-key kernel with three CTAs per SM is the faster one at every
   // length measured (0.698 ms there; profiles/r02be_attention_variants.txt): 64-key tiles everywhere, 128 only when forced.
   const int bkv = force_bkv ? force_bkv : 64;
-  const int poly = poly_env >= 0 ? poly_env : 3;
+  const int poly = poly_env >= 0 ? poly_env : (bkv == 64 ? 18 : 3);
   PIO_TRY(make_map_2d(&mkv, qkv, (long long)B * N, 3 * H * HD, 3 * H * HD, bkv, HD));
   dim3 grid(cdiv(N, BQ), H, B);
   const float scale_log2e = 0.125f * 1.4426950408889634f;
@@ -672,7 +698,11 @@ int vit_attention_tc(const void* qkv, void* out, void* vt_ws, int B, int N, int 
   // PIO_ATTN_PACKED (64-key kernel): x = S c - ref and the row sums on two elements per instruction (fma / add .f32x2)
   static const int packed_env = [] { const char* e = getenv("PIO_ATTN_PACKED"); return e ? atoi(e) : -1; }();
   const bool packed = packed_env >= 0 ? packed_env != 0 : true;
-  if (bkv == 64 && packed) { if (poly == 0) PIO_ATT_LAUNCH3(0, 64, true); else if (poly == 2) PIO_ATT_LAUNCH3(2, 64, true); else PIO_ATT_LAUNCH3(3, 64, true); }
+  if (bkv == 64 && packed) {
+    if (poly == 0) PIO_ATT_LAUNCH3(0, 64, true); else if (poly == 2) PIO_ATT_LAUNCH3(2, 64, true); else if (poly == 3) PIO_ATT_LAUNCH3(3, 64, true);
+    else if (poly == 13) PIO_ATT_LAUNCH3(13, 64, true); else if (poly == 100 + 0xC0) PIO_ATT_LAUNCH3(100 + 0xC0, 64, true);
+    else PIO_ATT_LAUNCH3(18, 64, true);
+  }
   else if (bkv == 64) { if (poly == 0) PIO_ATT_LAUNCH(0, 64); else if (poly == 2) PIO_ATT_LAUNCH(2, 64); else PIO_ATT_LAUNCH(3, 64); }
   else           { if (poly == 0) PIO_ATT_LAUNCH(0, 128); else if (poly == 2) PIO_ATT_LAUNCH(2, 128); else PIO_ATT_LAUNCH(3, 128); }
 #undef PIO_ATT_LAUNCH
