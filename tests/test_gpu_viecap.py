@@ -432,3 +432,39 @@ def test_greedy_search_early_exit_keeps_the_sentences(dev, ops):
             if R == 40:
                 assert ran < 48 and ran % 8 == 0 and ran >= max(len(c) for c in cut_full)
                 assert all(t == eos[0] for r in early for t in r[ran:])
+
+
+def test_patchioner_with_viecap_default_search_is_beam_search(dev, golden, weights):
+    """The reference's default (`using_greedy_search` absent -> False, entrypoint.py:77): Patchioner.forward with a ViECap block
+    captions the dense boxes by beam search -- strings, ids (return_ids) and the pipelined serving loop agree with the oracle's
+    beam search on the region embeddings of the same forward."""
+    from oracle import dinov2 as o_vit
+    from oracle import pipeline as o_pipe
+    from patchioner_b200 import Patchioner
+
+    g = golden("viecap")
+    tok = ov.ToyTokenizer()
+    eos = [tok.encode(e)[-1] for e in (".", " .")]
+    ws = ov.stopping_weights(weights, eos)
+    vcfg = {"state_dict": ws, "entities_text": g["entities"], "texts_embeddings": g["ent_emb"], "tokenizer": tok, "clip_hidden_size": 768,
+            "project_length": 10, "temperature": 0.01, "top_k": 3, "threshold": 0.4, "using_hard_prompt": False}  # no search key: beam
+    m = Patchioner.from_config({"prefix_size": 768, "support_memory_size": 0, "dino_model": "dinov2_vitb14_reg", "normalize": False,
+                                "resize_dim": 224, "crop_dim": 224, "dino_weights": o_vit.make_weights(seed=1234),
+                                "clip_model_name": "ViT-B/16", "viecap": vcfg, "precision": "fp32"}, device=dev)
+    assert m.viecap.args["using_greedy_search"] is False and m.viecap.beam_width == 5
+    B, S, R = 2, 224, 3
+    imgs = o_pipe.synth_images(B, S, seed=1)
+    boxes = o_pipe.synth_boxes(B, R, S, seed=1, pad="dense")
+    out = m(imgs, get_cls_capt=False, bboxes=boxes.clone())["bbox_capts"]
+    emb = m.region_embeddings(imgs.to(dev), bboxes=boxes.clone())["bbox"].reshape(-1, 768).cpu()
+    emb = emb / emb.norm(dim=-1, keepdim=True)
+    cont = ov.mapping_network(ws, emb)
+    want = []
+    for r in range(cont.shape[0]):
+        toks, sl, avg = ov.beam_search_ids(ws, cont[r:r + 1], eos, 5, ov.MAX_LEN)
+        want.append(tok.decode(ov.beam_sentences(toks, sl, avg)[0]))
+    assert [s for img in out for s in img] == want
+    ids = m(imgs, get_cls_capt=False, bboxes=boxes.clone(), return_ids=True)["bbox_capts"].reshape(-1, 64)
+    assert [tok.decode(m.viecap.cut(r)) for r in ids.cpu().tolist()] == want
+    piped = list(m.forward_pipelined([{"imgs": imgs, "bboxes": boxes.clone()}] * 2, get_cls_capt=False))
+    assert all([s for img in p["bbox_capts"] for s in img] == want for p in piped)
