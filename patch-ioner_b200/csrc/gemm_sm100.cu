@@ -397,10 +397,23 @@ int linear_tc(const PioLinear& p, cudaStream_t st) {
   // Tile shape: fewest (waves x per-tile MMA time), with a small penalty for the narrower, less efficient tiles.
   // per-SM cost of one tile ~ its width (every CTA owns 128 rows); 74 CTA pairs or 148 CTAs work per wave.
   const long long mt = cdiv(p.M, BM);
-  auto cost = [&](int bn, double penalty) { return (double)cdiv(mt * cdiv(p.N, bn), kNumSMs) * bn * penalty; };
-  const double c2 = (use_2cta && linear_tc2_eligible(p)) ? (double)cdiv((long long)cdiv(p.M, 256) * cdiv(p.N, 256), kNumSMs / 2) * 256 * 0.95 : 1e30;
-  const double c256 = cost(256, 1.0), c192 = slabs256 ? 1e30 : cost(192, 1.03), c128 = slabs256 ? 1e30 : cost(128, 1.10),
-               c64 = slabs256 ? 1e30 : cost(64, 1.30);
+  // Round 2 (second session): the main loop of every tile shape is bound by operand delivery, not by the MMA (tools/gemm_trace.py:
+  // 315 ns per k-block for a 128 x 192 tile against 200 ns of tensor-core time), so a wave costs ~ the bytes a CTA fetches per
+  // k-block -- (128 + BN) rows of 128 bytes, 256 for a CTA of the pair kernel -- not the tile width.  Measured on the shapes this
+  // flips (M = 4096, N = 768 -> the pair kernel instead of 128 x 192 tiles): memory projection 7.66 -> 6.91 ms, dense decode
+  // 25.14 -> 24.86 ms.  PIO_GEMM_COST=old keeps the round-1 model (width x penalty) for A/B runs.
+  static const bool old_cost = [] { const char* e = getenv("PIO_GEMM_COST"); return e && !strcmp(e, "old"); }();
+  auto cost = [&](int bn, double penalty) {
+    return (double)cdiv(mt * cdiv(p.N, bn), kNumSMs) * (old_cost ? (double)bn : (double)(BM + bn)) * penalty;
+  };
+  // (round 1 sent only GEMMs with a full wave of pair tiles to the pair kernel; with the traffic model the cost decides)
+  double c2 = (use_2cta && (linear_tc2_eligible(p) || !old_cost))
+                  ? (double)cdiv((long long)cdiv(p.M, 256) * cdiv(p.N, 256), kNumSMs / 2) * (old_cost ? 256 * 0.95 : 266.0) : 1e30;
+  // long-K GEMMs with a handful of output tiles are cut along K by the 1-CTA kernel (launch<BN>): the pair kernel has no split-K
+  if (!old_cost && cdiv(p.M, BM) * cdiv(p.N, 192) * 2 <= kNumSMs && cdiv(p.K, BK) >= split_min_kblocks()) c2 = 1e30;
+  if (!old_cost && !linear_tc2_eligible(p) && p.M <= BM) c2 = 1e30;  // a pair tile is 256 rows: with <= 128 the second CTA idles
+  const double c256 = cost(256, old_cost ? 1.0 : 1.15), c192 = slabs256 ? 1e30 : cost(192, old_cost ? 1.03 : 1.0),
+               c128 = slabs256 ? 1e30 : cost(128, old_cost ? 1.10 : 1.0), c64 = slabs256 ? 1e30 : cost(64, old_cost ? 1.30 : 1.0);
   const double best = std::min(std::min(std::min(c2, c256), std::min(c192, c128)), c64);
   if (const char* force = getenv("PIO_GEMM_TILE")) {  // A/B testing: 2cta | 256 | 192 | 128 | 64
     if (!strcmp(force, "2cta")) return linear_tc2(p, st);
