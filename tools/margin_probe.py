@@ -1,5 +1,11 @@
-import sys, torch
-sys.path.insert(0, '/root/repo')
+"""Where do bf16 decoder captions leave the fp32 oracle's?  Top-2 logit gap (in units of the logits' standard deviation) at every
+first diverging position, against the distribution of that gap over all positions.  python tools/margin_probe.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import decap as o_decap
 from patchioner_b200 import ops
 dev = torch.device('cuda:0')
