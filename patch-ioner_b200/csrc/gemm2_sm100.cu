@@ -202,7 +202,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
-      epilogue_tile<BN2>(tmem_base + as * BN2, quarter, lane, half, m, M, n0, N, (tile % n_blocks) * 2 + half, C, ldc, c_dt, epi,
+      epilogue_tile<BN2, true>(tmem_base + as * BN2, quarter, lane, half, m, M, n0, N, (tile % n_blocks) * 2 + half, C, ldc, c_dt, epi,
                     s_scale, s_bias, s_gamma, to);
       tc_fence_before();
       __syncwarp();

@@ -168,7 +168,9 @@ __device__ __forceinline__ float gelu_new_fast(float x) {
 // One epilogue warp, one tile: columns [c_begin, c_end) of TMEM lane quarter `quarter`.
 //   out = residual * rowscale + gamma * act(acc * (alpha * colscale) + bias); vectors come from shared memory.
 // STORE_TMA_ADD is the in-place residual (residual == C, no row scale): the value is reduced into C by the copy engine.
-template <int ACT, bool HAS_RES, bool OUT_BF16, int STORE, int NCOLS>
+// PLAIN: no column scale, alpha == 1 and no LayerScale vector (qkv, fc1, fc of the decoder, ...): the per-column defaults are
+// not materialised and not multiplied in -- acc + bias only (bit-identical: x * 1 + b == x + b), ~20 % fewer epilogue instructions
+template <int ACT, bool HAS_RES, bool OUT_BF16, int STORE, int NCOLS, bool PLAIN = false>
 __device__ __forceinline__ void epilogue_cols(uint32_t tmem_acc, int quarter, int lane, int c_begin, int m, int M,
                                               int n0, int N, void* C, int ldc, const Epilogue& epi, const float* s_scale,
                                               const float* s_bias, const float* s_gamma, const TmaOut& to) {
@@ -208,8 +210,32 @@ __device__ __forceinline__ void epilogue_cols(uint32_t tmem_acc, int quarter, in
       }
     }
     float v[32];
+    if constexpr (PLAIN) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
+      for (int i = 0; i < 32; i += 4) {
+        const float4 bi = *reinterpret_cast<const float4*>(s_bias + c + i);  // staged as zeros when there is no bias
+        const float biv[4] = {bi.x, bi.y, bi.z, bi.w};
+        if constexpr (ACT != PIO_ACT_GELU_NEW && !(HAS_RES && STORE == STORE_DIRECT)) {
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            uint64_t t = add2(pack2(__uint_as_float(r[i + j]), __uint_as_float(r[i + j + 1])), pack2(biv[j], biv[j + 1]));
+            if constexpr (ACT == PIO_ACT_GELU_ERF) t = gelu_erf_fast2(t);
+            unpack2(t, v[i + j], v[i + j + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float t = __uint_as_float(r[i + j]) + biv[j];
+            if constexpr (ACT == PIO_ACT_GELU_ERF) t = gelu_erf_fast(t);
+            if constexpr (ACT == PIO_ACT_GELU_NEW) t = gelu_new_fast(t);
+            if constexpr (HAS_RES && STORE == STORE_DIRECT) t = fmaf(res[i + j], rs, t);
+            v[i + j] = t;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < (PLAIN ? 0 : 32); i += 4) {
       float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f), ga = sc;
       if (use_scale) sc = *reinterpret_cast<const float4*>(s_scale + c + i);
       if (use_bias) bi = *reinterpret_cast<const float4*>(s_bias + c + i);
@@ -359,7 +385,9 @@ __device__ __forceinline__ void epilogue_argmax(uint32_t tmem_acc, int quarter, 
 
 
 // One epilogue warp, one tile: dispatch on the (uniform) epilogue kind.  `half` selects this warp's column half.
-template <int BN>
+// ALLOW_PLAIN: also instantiate the bias-only specialisation of epilogue_cols (the pair kernel, where the big GEMMs run; the
+// 1-CTA kernel's four tile widths would double their compile time for launches that are latency-bound anyway)
+template <int BN, bool ALLOW_PLAIN = false>
 __device__ __forceinline__ void epilogue_tile(uint32_t tacc, int quarter, int lane, int half, int m, int M, int n0, int N,
                                               int slab, void* C, int ldc, int c_dt, const Epilogue& epi, const float* s_scale,
                                               const float* s_bias, const float* s_gamma, const TmaOut& to) {
@@ -367,14 +395,20 @@ __device__ __forceinline__ void epilogue_tile(uint32_t tacc, int quarter, int la
   // this warp's columns: half of the tile (the 192-wide tile is cut 128 + 64 for bf16 output: 64-column staging boxes)
   const int cb = half * (BN / 2), ce = cb + BN / 2;
   const bool hr = epi.residual != nullptr;
+  const bool plain = ALLOW_PLAIN && epi.colscale == nullptr && epi.alpha == 1.0f && epi.gamma == nullptr;
   if (epi.argmax_val != nullptr) {
     if (epi.argmax_sumexp != nullptr) epilogue_argmax<true>(tacc, quarter, cb, ce, m, M, n0, N, slab, epi, s_scale, s_bias);
     else epilogue_argmax<false>(tacc, quarter, cb, ce, m, M, n0, N, slab, epi, s_scale, s_bias);
   } else if (epi.exp_ref != nullptr) {
     epilogue_exp(tacc, quarter, lane, cb, ce, m, M, n0, N, slab, C, ldc, epi, s_scale, to);
   } else
-#define PIO_EPI_N(ACTV, HR, BF, ST, NC, CB) \
-  epilogue_cols<ACTV, HR, BF, ST, NC>(tacc, quarter, lane, CB, m, M, n0, N, C, ldc, epi, s_scale, s_bias, s_gamma, to)
+#define PIO_EPI_N(ACTV, HR, BF, ST, NC, CB)                                                                                      \
+  do {                                                                                                                           \
+    if constexpr (ALLOW_PLAIN) {                                                                                                 \
+      if (plain) { epilogue_cols<ACTV, HR, BF, ST, NC, true>(tacc, quarter, lane, CB, m, M, n0, N, C, ldc, epi, s_scale, s_bias, s_gamma, to); break; } \
+    }                                                                                                                            \
+    epilogue_cols<ACTV, HR, BF, ST, NC, false>(tacc, quarter, lane, CB, m, M, n0, N, C, ldc, epi, s_scale, s_bias, s_gamma, to); \
+  } while (0)
 #define PIO_EPI(ACTV, HR, BF, ST)                                                              \
   do {                                                                                         \
     if constexpr (BN == 192 && BF) {                                                           \
