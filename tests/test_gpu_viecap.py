@@ -468,3 +468,27 @@ def test_patchioner_with_viecap_default_search_is_beam_search(dev, golden, weigh
     assert [tok.decode(m.viecap.cut(r)) for r in ids.cpu().tolist()] == want
     piped = list(m.forward_pipelined([{"imgs": imgs, "bboxes": boxes.clone()}] * 2, get_cls_capt=False))
     assert all([s for img in p["bbox_capts"] for s in img] == want for p in piped)
+
+
+def test_beam_search_edge_cases(dev, ops, golden):
+    """Shapes around the edges of pio_decode_beam_prompt: no prompts, a one-position prompt (the position-by-position prefill
+    path), a single step, the widest beam -- against the oracle's beam search prompt by prompt."""
+    bm = _golden_script("make_golden_viecap_beam")
+    w, prompts, eos = bm.inputs()
+    dec = ops.Gpt2Decoder(w, dev, "fp32")
+    ids, lens, score = dec.beam_search(prompts[:0].to(dev), eos, 5, 8)
+    assert ids.shape == (0, 5, 8) and lens.shape == (0, 5) and score.shape == (0, 5)
+    for P, W, steps in ((1, 5, 6), (14, 8, 5), (3, 2, 1), (14, 1, 9)):
+        pr = prompts[:3, :P].contiguous()
+        ids, lens, score = dec.beam_search(pr.to(dev), eos, W, steps)
+        ids, lens, score = ids.cpu(), lens.cpu(), score.cpu()
+        for r in range(pr.shape[0]):
+            toks, sl, avg = ov.beam_search_ids(w, pr[r:r + 1], eos, W, steps)
+            want = ov.beam_sentences(toks, sl, avg)
+            got = [ids[r, k, :int(lens[r, k])].tolist() for k in range(W)]
+            assert got == want, (P, W, steps, r, got, want)
+            torch.testing.assert_close(score[r], avg[avg.argsort(descending=True)], rtol=1e-4, atol=1e-4)
+    with pytest.raises(Exception, match="beam width"):
+        dec.beam_search(prompts[:1].to(dev), eos, 9, 4)
+    with pytest.raises(Exception, match="exceed the cache"):
+        dec.beam_search(prompts[:1].to(dev), eos, 2, 120)
