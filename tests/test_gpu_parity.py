@@ -1096,3 +1096,43 @@ def test_vit_bf16_is_reproducible_run_to_run(dev, ops, vit_w):
         ref = vit.forward(imgs)[0].clone()
         for _ in range(12):
             assert torch.equal(vit.forward(imgs)[0], ref), (B, S)
+
+
+def test_vit_bf16_is_reproducible_under_tensor_pipe_contention(dev, ops, vit_w):
+    """The attention kernel's P buffer is re-used per key tile; round 1 let the softmax overwrite it as soon as S of the next tile
+    was ready, although the tensor core might still be reading it for P V -- harmless only while the tensor pipe keeps ahead, which
+    MMAs of OTHER kernels on the same SMs can break.  With the half-tile commits and waits of round 2 the ViT forward must be
+    bit-identical whether or not a second stream keeps the tensor pipes busy with unrelated GEMMs."""
+    imgs = o_pipe.synth_images(4, 224, seed=31).to(dev)
+    vit = ops.Vit(vit_w, dev, "bf16")
+    ref = vit.forward(imgs)[0].clone()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    A = torch.randn(2048, 768, device=dev).bfloat16()
+    W = torch.randn(2304, 768, device=dev).bfloat16()
+    C = torch.empty(2048, 2304, device=dev, dtype=torch.bfloat16)
+    for _ in range(6):
+        with torch.cuda.stream(side):
+            for _ in range(200):                         # ~20 us each: a steady stream of MMAs next to the attention CTAs
+                ops.linear(A, W, "bf16", out=C)
+        got = [vit.forward(imgs)[0].clone() for _ in range(4)]
+        torch.cuda.synchronize()
+        for t in got:
+            assert torch.equal(t, ref)
+
+
+def test_vit_bf16_is_reproducible_with_programmatic_overlap_back_on(dev):
+    """The discriminating check for the attention kernel's P-buffer race: with programmatic dependent launch re-enabled inside the
+    ViT (PIO_VIT_PDL=1, read once per process -> a fresh interpreter) every forward must still be bit-identical.  A library built
+    with -DPIO_ATTN_WAIT_PV=0 (the round-1 behaviour) fails exactly this (profiles/r02bp_attention_race_root_cause.txt)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PIO_VIT_PDL="1", TAG="pdl_on")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "determinism_probe.py")], env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if "runs differ" in ln]
+    assert len(lines) == 3 and all(" 0/29 runs differ" in ln for ln in lines), out.stdout
