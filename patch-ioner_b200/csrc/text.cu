@@ -541,13 +541,16 @@ int pio_project(PioBank* h, const float* q, int R, float temperature, int normal
     const int slabs_max = argmax_slabs_tc(R, Mf);
     float* psum = (float*)P16;                       // [R, slabs_max]
     float* pmax = psum + (size_t)R * slabs_max;      // [R, slabs_max]   (R*Mc*2 bytes are available: plenty)
-    PIO_CUDA(cudaMemsetAsync(P, 0, (size_t)R * Mf * 2, st));
+    // (round 1 zeroed all of P -- 268 MB at R = 4096 -- per call; only the <= 63 padding columns of the LAST chunk are ever read
+    // without having been written: they are zeroed right before that chunk's similarity GEMM)
     fill_kernel<<<cdiv(R, 256), 256, 0, st>>>(m, log2e * (1.0f / temperature - 70.0f), R); PIO_LAUNCHED();
     fill_kernel<<<cdiv(R, 256), 256, 0, st>>>(alpha, 1.0f, R); PIO_LAUNCHED();
     for (long long c0 = 0; c0 < h->M; c0 += Mf) {
       const int mc = (int)std::min<long long>(Mf, h->M - c0);
       const int mc_pad = (mc + 63) / 64 * 64;
       const int slabs = argmax_slabs_tc(R, mc);
+      if (mc_pad > mc)  // K padding of the recombination GEMM: stale bits there (NaN x 0) would poison O
+        PIO_CUDA(cudaMemset2DAsync(P + mc, (size_t)Mf * 2, 0, (size_t)(mc_pad - mc) * 2, R, st));
       PioLinear p;
       memset(&p, 0, sizeof(p));
       p.A = qn; p.W = (const char*)h->bank + (size_t)c0 * D * e; p.C = P; p.M = R; p.N = mc; p.K = D;

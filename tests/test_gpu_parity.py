@@ -1136,3 +1136,22 @@ def test_vit_bf16_is_reproducible_with_programmatic_overlap_back_on(dev):
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if "runs differ" in ln]
     assert len(lines) == 3 and all(" 0/29 runs differ" in ln for ln in lines), out.stdout
+
+
+def test_project_bf16_ignores_stale_workspace_contents(dev, ops, monkeypatch):
+    """The fused projection no longer zeroes its whole P buffer per call, only the K-padding columns of the last chunk: a workspace
+    full of NaN bit patterns (whatever an earlier call of another size left there) must not reach the result."""
+    monkeypatch.setenv("PIO_PROJECT_MAX_CHUNK", "16384")
+    bank = o_pipe.synth_bank(40013, 768, seed=27, zero_frac=0.001)      # last chunk: 40013 - 32768 rows -> 59 padding columns
+    q = torch.randn(800, 768, generator=torch.Generator().manual_seed(28))   # > 768 queries: the deterministic (no split-K) path
+    ref = o_mem.project(q, o_mem.drop_zero_rows(bank), normalize=True)
+    b16 = ops.Bank(bank, dev, "bf16")
+    first = b16.project(q.to(dev), normalize=True).clone()
+    from patchioner_b200 import _lib as L
+
+    ws = ops.workspace(L.lib().pio_project_workspace_bytes(b16._h, 800), dev, "project")
+    ws.view(torch.int32).fill_(0x7FC07FC0)                               # bf16 / fp32 NaNs everywhere
+    again = b16.project(q.to(dev), normalize=True)
+    assert bool(torch.isfinite(again).all())
+    assert torch.equal(again, first)
+    assert cos_min(again.cpu(), ref) >= 0.999
